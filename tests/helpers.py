@@ -1,0 +1,47 @@
+"""Shared fixtures: rebuild the seeded synthetic model that produced tests/golden/*.npz."""
+from __future__ import annotations
+
+import functools
+import os
+
+import numpy as np
+import torch
+
+from wavtokenizer_b200 import spec
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CONFIG_DIR = os.path.join(ROOT, "wavtokenizer_b200", "configs")
+CONFIGS = {
+    "small600": ("wavtokenizer_smalldata_frame40_3s_nq1_code4096_dim512_kmeans200_attn.yaml", 0),
+    "small320": ("wavtokenizer_smalldata_frame75_3s_nq1_code4096_dim512_kmeans200_attn.yaml", 1),
+    "medium": ("wavtokenizer_mediumdata_music_audio_frame75_3s_nq1_code4096_dim512_kmeans200_attn.yaml", 2),
+}
+TAGS = tuple(CONFIGS)
+
+
+def config_path(tag: str) -> str:
+    return os.path.join(CONFIG_DIR, CONFIGS[tag][0])
+
+
+@functools.lru_cache(maxsize=None)
+def golden(tag: str):
+    return dict(np.load(os.path.join(GOLDEN, f"golden_{tag}.npz")))
+
+
+@functools.lru_cache(maxsize=None)
+def model(tag: str):
+    """(cfg, state_dict) with the golden codebook installed — identical to what
+    oracle/make_golden.py loaded into the reference."""
+    cfg = spec.load_config(config_path(tag))
+    g = golden(tag)
+    sd = spec.synthetic_state_dict(cfg, int(g["weights_seed"]))
+    base = torch.from_numpy(g["codebook_base_bf16"].copy()).view(torch.bfloat16)
+    spec.install_codebook(sd, spec.expand_codebook(base, cfg.vq_bins, seed=5))
+    return cfg, sd
+
+
+def snr_db(ref: torch.Tensor, test: torch.Tensor) -> float:
+    ref = ref.double().flatten()
+    err = (test.double().flatten() - ref)
+    return float(10 * torch.log10(ref.pow(2).sum() / err.pow(2).sum().clamp_min(1e-300)))
