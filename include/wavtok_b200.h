@@ -1,0 +1,131 @@
+/*
+ * wavtok_b200 — C ABI of the B200-native WavTokenizer inference path.
+ *
+ * This is the drop-in boundary for the reference's Python inference API
+ * (reference decoder/pretrained.py:32-239). Every entry point takes plain pointers and
+ * sizes; no torch types cross this boundary. Device pointers are raw CUDA addresses on
+ * the handle's device; `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ * stream). All compute entry points are asynchronous on `stream`.
+ *
+ * Status convention: 0 = ok; non-zero = error, message via wt_last_error() (thread-local).
+ *   WT_ERR_VALUE    (1)  mirrors a Python ValueError   in the reference (bad shape / size)
+ *   WT_ERR_INDEX    (2)  mirrors a Python IndexError   (bandwidth_id or code out of range)
+ *   WT_ERR_TYPE     (3)  mirrors a Python TypeError
+ *   WT_ERR_RUNTIME  (4)  CUDA / allocation / internal failure
+ *
+ * Threading: one handle per GPU/rank; a handle may be used by one host thread at a time
+ * (the reference is single-threaded Python, not re-entrant by design).
+ *
+ * Ownership: the caller owns every input/output buffer; the handle owns the prepared
+ * weights and a workspace arena that grows to the largest (B, T) seen (or wt_reserve'd).
+ */
+#ifndef WAVTOK_B200_H
+#define WAVTOK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WT_OK 0
+#define WT_ERR_VALUE 1
+#define WT_ERR_INDEX 2
+#define WT_ERR_TYPE 3
+#define WT_ERR_RUNTIME 4
+
+typedef struct wt_handle wt_handle;
+
+/* Model hyper-parameters: what the reference resolves from YAML `model.init_args`
+ * (decoder/pretrained.py:81-92) plus the SEANet constants hard-wired in
+ * decoder/feature_extractors.py:71-74. */
+typedef struct wt_config {
+    int32_t strides[4];            /* encoder down-sampling strides in execution order (seanet.py:100) */
+    int32_t n_filters;             /* 32 */
+    int32_t dimension;             /* 512: encoder output / codebook dim */
+    int32_t lstm_layers;           /* 2 */
+    int32_t vq_bins;               /* 4096 */
+    int32_t num_quantizers;        /* codebooks present in the checkpoint (infer uses the first, vq.py:137) */
+    int32_t dim;                   /* 768: backbone width */
+    int32_t intermediate_dim;      /* 2304 */
+    int32_t num_layers;            /* 12 ConvNeXt blocks */
+    int32_t adanorm_num_embeddings;/* 4 bandwidth ids */
+    int32_t n_fft;
+    int32_t hop_length;
+} wt_config;
+
+/* One checkpoint tensor, fp32, HOST memory, named by its reference state_dict key
+ * (decoder/pretrained.py:101-112). Unknown names are ignored (the reference filters by
+ * prefix and the SEANet-decoder keys are dead weight); a missing required name is an error. */
+typedef struct wt_tensor {
+    const char* name;
+    const float* data;
+    int64_t numel;
+} wt_tensor;
+
+/* Replaces WavTokenizer.from_pretrained0802's module construction + load_state_dict
+ * (decoder/pretrained.py:95-114): folds weight-norm, re-lays weights for the kernels,
+ * precomputes ||C||^2 and the windowed inverse-DFT basis, uploads to `device`. */
+int wt_create(const wt_config* cfg, const wt_tensor* tensors, int32_t n_tensors, int32_t device,
+              wt_handle** out);
+int wt_destroy(wt_handle* h);
+
+/* Frames produced for T samples: ceil-divide through the four strides (encoder/modules/conv.py:54-61). */
+int32_t wt_frames_for(const wt_handle* h, int32_t T);
+
+/* Workspace the handle needs for a (B, T) encode+decode; wt_reserve allocates it up front
+ * (otherwise the arena grows on demand, which synchronises the device). */
+int64_t wt_workspace_bytes(const wt_handle* h, int32_t B, int32_t T);
+int wt_reserve(wt_handle* h, int32_t B, int32_t T);
+
+/* WavTokenizer.encode_infer (decoder/pretrained.py:186-189 -> feature_extractors.py:131-142).
+ * wav [B, T] f32 (device) -> features [B, dimension, L] f32, codes [1, B, L] int64. */
+int wt_encode(wt_handle* h, const float* wav, int32_t B, int32_t T, float* features_out,
+              int64_t* codes_out, void* stream);
+
+/* feature_extractor.encodec.encoder(wav[B,1,T]) (encoder/modules/seanet.py:143-144):
+ * the pre-quantisation latent z [B, dimension, L]. */
+int wt_encoder_forward(wt_handle* h, const float* wav, int32_t B, int32_t T, float* z_out, void* stream);
+
+/* WavTokenizer.codes_to_features (decoder/pretrained.py:209-239).
+ * codes [K, B, L] int64 (device) -> features [B, dimension, L] (sum over the K codebooks). */
+int wt_codes_to_features(wt_handle* h, const int64_t* codes, int32_t K, int32_t B, int32_t L,
+                         float* features_out, void* stream);
+
+/* WavTokenizer.decode (decoder/pretrained.py:192-207): features [B, dimension, L] ->
+ * audio [B, L*hop_length]. One bandwidth_id for the whole batch (decoder/modules.py:81-86). */
+int wt_decode(wt_handle* h, const float* features, int32_t B, int32_t L, int32_t bandwidth_id,
+              float* audio_out, void* stream);
+
+/* EuclideanCodebook.quantize + dequantize (encoder/quantization/core_vq.py:175-190) on
+ * row-major frames x [N, dimension] -> codes [N] int64, quantized [N, dimension] (may be NULL). */
+int wt_vq(wt_handle* h, const float* x, int64_t N, int64_t* codes_out, float* quantized_out, void* stream);
+
+/* Whole hot path with HOST buffers (pinned memory recommended): H2D wav, encode, decode of the
+ * quantised features, D2H codes + audio, then synchronises `stream`.
+ * wav_host [B, T]; codes_host [B, L] int64; audio_host [B, L*hop]. */
+int wt_encode_decode_host(wt_handle* h, const float* wav_host, int32_t B, int32_t T, int32_t bandwidth_id,
+                          int64_t* codes_host, float* audio_host, void* stream);
+
+/* Debug taps for per-stage parity tests: after the next encode/decode, the named stage's
+ * output is copied (channels-last [B, T, C]) into dev_buf (capacity in floats). Stage names:
+ * "enc0".."enc15", "dec_embed", "dec_pos0".."dec_pos5", "dec_norm", "dec_cnx0".."dec_cnxN",
+ * "dec_final", "dec_headlin". wt_tap_shape reports the shape seen at the last run. */
+int wt_tap_request(wt_handle* h, const char* stage, float* dev_buf, int64_t capacity);
+int wt_tap_shape(const wt_handle* h, const char* stage, int32_t* B, int32_t* T, int32_t* C);
+int wt_tap_clear(wt_handle* h);
+
+/* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
+int64_t wt_launch_count(const wt_handle* h);
+
+/* Compute plan: 0 = fp32 CUDA-core contractions everywhere (bit-conservative);
+ * 1 = tcgen05 tensor-core contractions with split-fp16 operands where validated. */
+int wt_set_plan(wt_handle* h, int32_t plan);
+
+const char* wt_last_error(void);
+const char* wt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAVTOK_B200_H */

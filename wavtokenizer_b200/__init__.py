@@ -1,0 +1,5 @@
+"""wavtokenizer_b200 — B200-native (sm_100a) WavTokenizer inference path behind the reference API."""
+from .pretrained import WavTokenizer  # noqa: F401
+from .spec import ModelConfig, load_config  # noqa: F401
+
+__all__ = ["WavTokenizer", "ModelConfig", "load_config"]

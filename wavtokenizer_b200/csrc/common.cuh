@@ -1,0 +1,86 @@
+// Shared declarations for the wavtok_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace wt {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define WT_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            throw ::wt::Error(4, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// tap-GEMM: the one contraction shape of this path.
+//   out[m, n] = epi( sum_{j<taps} sum_{c<Cin} pro(A[src(m, j), c]) * W[n, j*Cin + c] )
+// Activations are channels-last rows [B*T, C]; a Conv1d with k taps and stride s is a GEMM
+// whose A row for output (b, t) is the k rows  t*s - pad_left + j  of clip b, resolved with
+// zero or reflect padding in the loader (encoder/modules/conv.py:79-96, 195-211).
+// ---------------------------------------------------------------------------------------
+enum : int { PAD_ZERO = 0, PAD_REFLECT = 1 };
+enum : int { PRO_NONE = 0, PRO_ELU = 1 };
+enum : int { ACT_NONE = 0, ACT_GELU = 1 };
+
+struct TapGemm {
+    const float* A = nullptr;     // [B*Tin, lda]
+    const float* W = nullptr;     // [N, K]   K = taps*Cin
+    const float* bias = nullptr;  // [N] or null
+    const float* gamma = nullptr; // [N] or null: out = res + gamma*(acc + bias)
+    const float* res = nullptr;   // [M, ldres] or null
+    float* out = nullptr;         // [M, ldo]
+    int M = 0, N = 0, K = 0;
+    int Cin = 0, taps = 1, stride = 1, pad_left = 0;
+    int Tin = 0, Tout = 0;        // rows per clip on the input / output side
+    int Trefl = 0;                // reflect length T' = max(Tin, max_pad + 1) (conv.py:86-94)
+    int pad_mode = PAD_ZERO;
+    int pro = PRO_NONE;
+    int act = ACT_NONE;
+    int lda = 0, ldo = 0, ldres = 0;
+};
+
+void launch_tap_gemm_simt(const TapGemm& g, cudaStream_t s);
+
+// encoder
+void launch_conv0(const float* wav, const float* w /*[C,7]*/, const float* bias, float* out, int B, int T, int C,
+                  cudaStream_t s);
+void launch_lstm_pointwise(const float* gates /*row b*ldg, 4H wide*/, float* c /*[B,H]*/, float* y /*row b*ldy*/,
+                           int B, int H, long long ldg, long long ldy, cudaStream_t s);
+void launch_add(const float* a, const float* b, float* out, long long n, cudaStream_t s);
+
+// vq
+void launch_vq_simt(const float* x, const float* codebook, const float* cnorm, long long N, int D, int bins,
+                    long long* codes, cudaStream_t s);
+void launch_gather_rows(const float* codebook, const long long* codes, float* out, long long N, int D, int bins,
+                        int* err_flag, cudaStream_t s);
+// features [B, D, L] (channel-major) = sum_k codebook[k][codes[k, b, t]]
+void launch_codes_to_features(const float* codebooks, const long long* codes, float* out, int K, int B, int L, int D,
+                              int bins, int* err_flag, cudaStream_t s);
+
+// layout
+void launch_transpose_bcl_to_blc(const float* in, float* out, int B, int C, int L, cudaStream_t s);
+void launch_transpose_blc_to_bcl(const float* in, float* out, int B, int L, int C, cudaStream_t s);
+
+// decoder
+void launch_groupnorm(const float* x, const float* w, const float* b, float* out, int B, int L, int C, int groups,
+                      float eps, int swish, cudaStream_t s);
+void launch_layernorm(const float* x, const float* w, const float* b, float* out, long long M, int C, float eps,
+                      cudaStream_t s);
+void launch_dwconv_ln(const float* x, const float* dw /*[C,7]*/, const float* db, const float* scale,
+                      const float* shift, float* out, int B, int L, int C, float eps, cudaStream_t s);
+void launch_attention(const float* qkv /*[B*L, 3C]*/, float* out /*[B*L, C]*/, int B, int L, int C, cudaStream_t s);
+void launch_spectral(const float* z /*[M, 2*half]*/, float* S /*[M, ldS]*/, long long M, int half, int ldS,
+                     cudaStream_t s);
+void launch_overlap_add(const float* frames /*[B*L, n_fft]*/, const float* wsq /*[n_fft]*/, float* audio, int B, int L,
+                        int n_fft, int hop, cudaStream_t s);
+
+}  // namespace wt

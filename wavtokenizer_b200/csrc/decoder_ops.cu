@@ -1,0 +1,282 @@
+// Memory-bound decoder kernels: GroupNorm(+swish), LayerNorm / AdaLayerNorm, depthwise conv fused
+// with AdaLayerNorm, single-head attention, spectral (mag/phase -> re/im) and overlap-add.
+// All tensors are channels-last rows [B*L, C] fp32.
+#include "common.cuh"
+
+namespace wt {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NW>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) t += red[i];
+    return t;
+}
+
+// Normalize = GroupNorm(32, C, eps=1e-6, affine) (+ x*sigmoid(x)) (reference decoder/models.py:10-16,
+// 58-78, 107-110). One block per (clip, group): statistics span all L frames of the clip, two-pass
+// (mean, then centred variance); the clip slice (L*C*4 B) stays in L2 between passes.
+__global__ void __launch_bounds__(256) groupnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bsh, float* __restrict__ out, int L,
+                                                        int C, int cpg, float eps, int swish) {
+    __shared__ float red[8];
+    const int b = blockIdx.y, g = blockIdx.x;
+    const float* xb = x + (long long)b * L * C + g * cpg;
+    float* ob = out + (long long)b * L * C + g * cpg;
+    const int n = L * cpg;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        int t = i / cpg, c = i - t * cpg;
+        s += xb[(long long)t * C + c];
+    }
+    const float mean = block_sum<8>(s, red) / (float)n;
+    float v = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        int t = i / cpg, c = i - t * cpg;
+        float d = xb[(long long)t * C + c] - mean;
+        v = fmaf(d, d, v);
+    }
+    const float var = block_sum<8>(v, red) / (float)n;
+    const float rstd = rsqrtf(var + eps);
+    for (int i = threadIdx.x; i < n; i += 256) {
+        int t = i / cpg, c = i - t * cpg;
+        float y = (xb[(long long)t * C + c] - mean) * rstd * w[g * cpg + c] + bsh[g * cpg + c];
+        if (swish) y = y / (1.f + expf(-y));
+        ob[(long long)t * C + c] = y;
+    }
+}
+
+// layer_norm over C (eps 1e-6) then * w + b, one warp per row. With w = scale[id], b = shift[id] this is
+// AdaLayerNorm (reference decoder/modules.py:81-86); with the affine parameters it is the final
+// nn.LayerNorm (decoder/models.py:195, 234).
+template <int PER>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, float* __restrict__ out,
+                                                        long long M, float eps) {
+    constexpr int C = PER * 32;
+    const int lane = threadIdx.x & 31;
+    long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float* xr = x + row * C;
+    float v[PER];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i] = xr[lane + 32 * i]; s += v[i]; }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    float* orow = out + row * C;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int c = lane + 32 * i;
+        orow[c] = (v[i] - mean) * rstd * w[c] + b[c];
+    }
+}
+
+// ConvNeXt front half: depthwise Conv1d(k=7, pad 3 zeros, groups=C) -> AdaLayerNorm
+// (reference decoder/modules.py:30-33, 49-53). One warp per frame; the seven neighbouring rows are
+// L1/L2 hits, so HBM traffic is one read + one write of the activation.
+template <int PER>
+__global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ dw,
+                                                        const float* __restrict__ db, const float* __restrict__ scale,
+                                                        const float* __restrict__ shift, float* __restrict__ out,
+                                                        int B, int L, float eps) {
+    constexpr int C = PER * 32;
+    const int lane = threadIdx.x & 31;
+    long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= (long long)B * L) return;
+    const int b = (int)(row / L), t = (int)(row - (long long)b * L);
+    float v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) v[i] = db[lane + 32 * i];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        int tj = t - 3 + j;
+        if (tj < 0 || tj >= L) continue;
+        const float* xr = x + ((long long)b * L + tj) * C;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            int c = lane + 32 * i;
+            v[i] = fmaf(dw[c * 7 + j], xr[c], v[i]);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) s += v[i];
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    float* orow = out + row * C;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int c = lane + 32 * i;
+        orow[c] = (v[i] - mean) * rstd * scale[c] + shift[c];
+    }
+}
+
+// AttnBlock core (reference decoder/models.py:115-123): softmax(q k^T * C^-0.5) v, one head of width C
+// over the L frames of a clip. One warp per query row, 8 queries per block; scores live in shared memory.
+template <int PER>
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int L,
+                                                        float scale) {
+    constexpr int C = PER * 32;
+    extern __shared__ float sm[];  // [8][L] scores
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int qi = blockIdx.x * 8 + warp;
+    const float* base = qkv + (long long)b * L * 3 * C;
+    float* sc = sm + warp * L;
+    if (qi >= L) return;
+    float q[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) q[i] = base[(long long)qi * 3 * C + lane + 32 * i];
+    float mx = -INFINITY;
+    for (int j = 0; j < L; ++j) {
+        const float* kr = base + (long long)j * 3 * C + C;
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) d = fmaf(q[i], kr[lane + 32 * i], d);
+        d = warp_sum(d) * scale;
+        if (lane == 0) sc[j] = d;
+        mx = fmaxf(mx, d);
+    }
+    __syncwarp();
+    float den = 0.f;
+    for (int j = lane; j < L; j += 32) {
+        float e = expf(sc[j] - mx);
+        sc[j] = e;
+        den += e;
+    }
+    den = warp_sum(den);
+    __syncwarp();
+    const float inv = 1.f / den;
+    float o[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) o[i] = 0.f;
+    for (int j = 0; j < L; ++j) {
+        const float p = sc[j] * inv;
+        const float* vr = base + (long long)j * 3 * C + 2 * C;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) o[i] = fmaf(p, vr[lane + 32 * i], o[i]);
+    }
+    float* orow = out + ((long long)b * L + qi) * C;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) orow[lane + 32 * i] = o[i];
+}
+
+// ISTFTHead spectral step (reference decoder/heads.py:55-65): z = [log-mag | phase] ->
+// S = [min(exp(m), 100) cos p | min(exp(m), 100) sin p], zero-filled to ldS columns (the K of the iDFT GEMM).
+__global__ void spectral_kernel(const float* __restrict__ z, float* __restrict__ S, long long M, int half, int ldS) {
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= M * ldS) return;
+    long long m = gid / ldS;
+    int c = (int)(gid - m * ldS);
+    float v = 0.f;
+    if (c < 2 * half) {
+        int i = c < half ? c : c - half;
+        float mag = fminf(expf(z[m * 2 * half + i]), 100.f);
+        float sn, cs;
+        sincosf(z[m * 2 * half + half + i], &sn, &cs);
+        v = c < half ? mag * cs : mag * sn;
+    }
+    S[gid] = v;
+}
+
+// ISTFT "same" overlap-add + envelope normalisation (reference decoder/spectral_ops.py:58-73).
+// frames already carry the window (folded into the iDFT basis). Each output sample sums the <= n_fft/hop
+// frames that cover it and divides by the matching sum of squared window samples.
+__global__ void overlap_add_kernel(const float* __restrict__ frames, const float* __restrict__ wsq,
+                                   float* __restrict__ audio, int L, int n_fft, int hop, int pad) {
+    const int b = blockIdx.y;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int len = L * hop;
+    if (n >= len) return;
+    const int p = n + pad;
+    int t_hi = p / hop;
+    int t_lo = (p - n_fft + hop) / hop;  // ceil((p - n_fft + 1) / hop) for p >= n_fft - 1; clipped below
+    if (p - n_fft + 1 <= 0) t_lo = 0;
+    if (t_hi > L - 1) t_hi = L - 1;
+    float acc = 0.f, env = 0.f;
+    for (int t = t_lo; t <= t_hi; ++t) {
+        int k = p - t * hop;
+        acc += frames[((long long)b * L + t) * n_fft + k];
+        env += wsq[k];
+    }
+    audio[(long long)b * len + n] = acc / env;
+}
+
+}  // namespace
+
+void launch_groupnorm(const float* x, const float* w, const float* b, float* out, int B, int L, int C, int groups,
+                      float eps, int swish, cudaStream_t s) {
+    if (B <= 0 || L <= 0) return;
+    dim3 grid(groups, B);
+    groupnorm_kernel<<<grid, 256, 0, s>>>(x, w, b, out, L, C, C / groups, eps, swish);
+    WT_CUDA(cudaGetLastError());
+}
+
+void launch_layernorm(const float* x, const float* w, const float* b, float* out, long long M, int C, float eps,
+                      cudaStream_t s) {
+    if (M <= 0) return;
+    if (C != 768) throw Error(1, "layernorm: backbone dim must be 768");
+    layernorm_kernel<24><<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, w, b, out, M, eps);
+    WT_CUDA(cudaGetLastError());
+}
+
+void launch_dwconv_ln(const float* x, const float* dw, const float* db, const float* scale, const float* shift,
+                      float* out, int B, int L, int C, float eps, cudaStream_t s) {
+    if (B <= 0 || L <= 0) return;
+    if (C != 768) throw Error(1, "dwconv_ln: backbone dim must be 768");
+    long long M = (long long)B * L;
+    dwconv_ln_kernel<24><<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, dw, db, scale, shift, out, B, L, eps);
+    WT_CUDA(cudaGetLastError());
+}
+
+void launch_attention(const float* qkv, float* out, int B, int L, int C, cudaStream_t s) {
+    if (B <= 0 || L <= 0) return;
+    if (C != 768) throw Error(1, "attention: backbone dim must be 768");
+    size_t smem = (size_t)8 * L * sizeof(float);
+    if (smem > 200 * 1024) throw Error(1, "attention: clip too long for the on-chip score buffer (L <= 6400)");
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        WT_CUDA(cudaFuncSetAttribute(attention_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = 200 * 1024;
+    }
+    dim3 grid((L + 7) / 8, B);
+    attention_kernel<24><<<grid, 256, smem, s>>>(qkv, out, L, 1.0f / sqrtf((float)C));
+    WT_CUDA(cudaGetLastError());
+}
+
+void launch_spectral(const float* z, float* S, long long M, int half, int ldS, cudaStream_t s) {
+    if (M <= 0) return;
+    long long n = M * ldS;
+    spectral_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(z, S, M, half, ldS);
+    WT_CUDA(cudaGetLastError());
+}
+
+void launch_overlap_add(const float* frames, const float* wsq, float* audio, int B, int L, int n_fft, int hop,
+                        cudaStream_t s) {
+    if (B <= 0 || L <= 0) return;
+    dim3 grid((L * hop + 255) / 256, B);
+    overlap_add_kernel<<<grid, 256, 0, s>>>(frames, wsq, audio, L, n_fft, hop, (n_fft - hop) / 2);
+    WT_CUDA(cudaGetLastError());
+}
+
+}  // namespace wt

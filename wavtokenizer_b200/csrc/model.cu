@@ -1,0 +1,819 @@
+// Model handle, weight preparation, workspace arena and the C ABI (include/wavtok_b200.h).
+// Host-side orchestration of the hot path: encode_infer -> VQ -> codes_to_features -> decode
+// (reference decoder/pretrained.py:186-239).
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/wavtok_b200.h"
+#include "common.cuh"
+
+namespace wt {
+
+namespace {
+
+thread_local std::string g_last_error;
+
+constexpr int ENC_CHUNK = 16;   // clips per encoder pass (early SEANet tensors are 9.2 MB per clip per tensor)
+constexpr int DEC_CHUNK = 128;  // clips per decoder pass
+
+struct ConvW {
+    float* w = nullptr;  // [cout, k*cin], K index = tap*cin + c
+    float* b = nullptr;  // [cout]
+    int cout = 0, cin = 0, k = 1, stride = 1;
+};
+
+struct TapReq {
+    float* buf = nullptr;
+    int64_t cap = 0;
+    int B = 0, T = 0, C = 0;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+}  // namespace wt
+
+using namespace wt;
+
+struct wt_handle {
+    wt_config cfg{};
+    int device = 0;
+    int plan = 0;
+    int64_t launches = 0;
+    std::vector<void*> owned;  // weight allocations
+
+    // encoder
+    float *conv0_w = nullptr, *conv0_b = nullptr;
+    struct ResBlk { ConvW c1, c2, sc; } rb[4];
+    ConvW down[4];
+    struct Lstm { float *w_ih = nullptr, *w_hh = nullptr, *bias = nullptr; } lstm[4];
+    ConvW enc_last;
+    // vq
+    float* codebooks = nullptr;  // [num_quantizers * bins, D]
+    float* cnorm = nullptr;      // [bins] of codebook 0
+    // decoder
+    ConvW embed;
+    struct Resnet { float *n1w, *n1b, *n2w, *n2b; ConvW c1, c2; } pos[4];
+    struct Attn { float *nw, *nb, *wqkv, *bqkv; ConvW proj; } attn{};
+    float *gn5w = nullptr, *gn5b = nullptr;
+    float *norm_scale = nullptr, *norm_shift = nullptr;  // [E, dim]
+    struct Cnx { float *dw, *db, *scale, *shift, *w1, *b1, *w2, *b2, *gamma; };
+    std::vector<Cnx> cnx;
+    float *fln_w = nullptr, *fln_b = nullptr;
+    float *head_w = nullptr, *head_b = nullptr;
+    float *basis = nullptr, *wsq = nullptr;
+    int Kp = 0;  // padded K of the inverse-DFT GEMM
+
+    // workspace arena (bump allocator, reset per call)
+    char* arena = nullptr;
+    size_t arena_cap = 0, arena_off = 0;
+    // persistent staging for the host-buffer entry point
+    char* stage = nullptr;
+    size_t stage_cap = 0;
+    int* err_flag = nullptr;  // device
+    int* err_host = nullptr;  // pinned
+
+    std::map<std::string, TapReq> taps;
+
+    ~wt_handle() {
+        cudaSetDevice(device);
+        for (void* p : owned) cudaFree(p);
+        if (arena) cudaFree(arena);
+        if (stage) cudaFree(stage);
+        if (err_flag) cudaFree(err_flag);
+        if (err_host) cudaFreeHost(err_host);
+    }
+
+    float* upload(const std::vector<float>& v) {
+        float* d = nullptr;
+        WT_CUDA(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(float)));
+        owned.push_back(d);
+        if (!v.empty()) WT_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+        return d;
+    }
+
+    void ensure_arena(size_t bytes) {
+        if (bytes <= arena_cap) return;
+        WT_CUDA(cudaDeviceSynchronize());
+        if (arena) WT_CUDA(cudaFree(arena));
+        arena = nullptr;
+        arena_cap = 0;
+        WT_CUDA(cudaMalloc(&arena, bytes));
+        arena_cap = bytes;
+    }
+    float* alloc(size_t n_floats) {
+        size_t bytes = align_up(n_floats * sizeof(float), 256);
+        if (arena_off + bytes > arena_cap) throw Error(4, "workspace arena overflow (internal sizing bug)");
+        float* p = reinterpret_cast<float*>(arena + arena_off);
+        arena_off += bytes;
+        return p;
+    }
+
+    void tap(const char* name, const float* src, int B, int T, int C, int b0, cudaStream_t s) {
+        if (taps.empty() || b0 != 0) return;
+        auto it = taps.find(name);
+        if (it == taps.end()) return;
+        it->second.B = B; it->second.T = T; it->second.C = C;
+        int64_t n = (int64_t)B * T * C;
+        if (it->second.buf && n <= it->second.cap)
+            WT_CUDA(cudaMemcpyAsync(it->second.buf, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+};
+
+namespace wt {
+namespace {
+
+// ---------------------------------------------------------------------------------------
+// weight preparation (host)
+// ---------------------------------------------------------------------------------------
+struct Table {
+    std::unordered_map<std::string, std::pair<const float*, int64_t>> m;
+    const float* get(const std::string& name, int64_t numel) const {
+        auto it = m.find(name);
+        if (it == m.end()) throw Error(WT_ERR_VALUE, "missing checkpoint tensor: " + name);
+        if (it->second.second != numel)
+            throw Error(WT_ERR_VALUE, "size mismatch for " + name + ": got " + std::to_string(it->second.second) +
+                                          ", expected " + std::to_string(numel));
+        return it->second.first;
+    }
+};
+
+// [cout, cin, k] -> [cout, k*cin] with K index tap*cin + c
+std::vector<float> relayout_conv(const float* w, int cout, int cin, int k) {
+    std::vector<float> o((size_t)cout * cin * k);
+    for (int n = 0; n < cout; ++n)
+        for (int c = 0; c < cin; ++c)
+            for (int j = 0; j < k; ++j) o[((size_t)n * k + j) * cin + c] = w[((size_t)n * cin + c) * k + j];
+    return o;
+}
+
+// old-style weight_norm fold, w = g * v / ||v|| over (cin, k) (reference encoder/modules/conv.py:25-34, 115)
+std::vector<float> fold_weight_norm(const float* g, const float* v, int cout, int cin, int k) {
+    std::vector<float> w((size_t)cout * cin * k);
+    for (int n = 0; n < cout; ++n) {
+        const float* vn = v + (size_t)n * cin * k;
+        double s = 0;
+        for (int i = 0; i < cin * k; ++i) s += (double)vn[i] * vn[i];
+        float norm = (float)std::sqrt(s);
+        for (int i = 0; i < cin * k; ++i) w[(size_t)n * cin * k + i] = g[n] * vn[i] / norm;
+    }
+    return w;
+}
+
+ConvW load_wn_conv(wt_handle* h, const Table& t, const std::string& p, int cout, int cin, int k, int stride) {
+    const float* g = t.get(p + "conv.conv.weight_g", cout);
+    const float* v = t.get(p + "conv.conv.weight_v", (int64_t)cout * cin * k);
+    const float* b = t.get(p + "conv.conv.bias", cout);
+    auto w = fold_weight_norm(g, v, cout, cin, k);
+    ConvW c;
+    c.cout = cout; c.cin = cin; c.k = k; c.stride = stride;
+    c.w = h->upload(relayout_conv(w.data(), cout, cin, k));
+    c.b = h->upload(std::vector<float>(b, b + cout));
+    return c;
+}
+
+ConvW load_conv(wt_handle* h, const Table& t, const std::string& p, int cout, int cin, int k) {
+    const float* w = t.get(p + "weight", (int64_t)cout * cin * k);
+    const float* b = t.get(p + "bias", cout);
+    ConvW c;
+    c.cout = cout; c.cin = cin; c.k = k; c.stride = 1;
+    c.w = h->upload(relayout_conv(w, cout, cin, k));
+    c.b = h->upload(std::vector<float>(b, b + cout));
+    return c;
+}
+
+float* load_vec(wt_handle* h, const Table& t, const std::string& name, int64_t n) {
+    const float* p = t.get(name, n);
+    return h->upload(std::vector<float>(p, p + n));
+}
+
+void prepare(wt_handle* h, const Table& t) {
+    const wt_config& c = h->cfg;
+    const std::string E = "feature_extractor.encodec.encoder.model.";
+    // ---- encoder (reference encoder/modules/seanet.py:105-141) ----
+    {
+        const int C = c.n_filters;
+        const float* g = t.get(E + "0.conv.conv.weight_g", C);
+        const float* v = t.get(E + "0.conv.conv.weight_v", (int64_t)C * 7);
+        const float* b = t.get(E + "0.conv.conv.bias", C);
+        h->conv0_w = h->upload(fold_weight_norm(g, v, C, 1, 7));
+        h->conv0_b = h->upload(std::vector<float>(b, b + C));
+    }
+    int ch = c.n_filters, idx = 1;
+    for (int i = 0; i < 4; ++i) {
+        std::string p = E + std::to_string(idx) + ".";
+        h->rb[i].c1 = load_wn_conv(h, t, p + "block.1.", ch / 2, ch, 3, 1);
+        h->rb[i].c2 = load_wn_conv(h, t, p + "block.3.", ch, ch / 2, 1, 1);
+        h->rb[i].sc = load_wn_conv(h, t, p + "shortcut.", ch, ch, 1, 1);
+        int s = c.strides[i];
+        h->down[i] = load_wn_conv(h, t, E + std::to_string(idx + 2) + ".", 2 * ch, ch, 2 * s, s);
+        ch *= 2;
+        idx += 3;
+    }
+    if (ch != c.dimension) throw Error(WT_ERR_VALUE, "n_filters * 16 must equal dimension");
+    for (int l = 0; l < c.lstm_layers; ++l) {
+        std::string p = E + std::to_string(idx) + ".lstm.";
+        std::string sfx = "_l" + std::to_string(l);
+        const int64_t D = ch;
+        h->lstm[l].w_ih = load_vec(h, t, p + "weight_ih" + sfx, 4 * D * D);
+        h->lstm[l].w_hh = load_vec(h, t, p + "weight_hh" + sfx, 4 * D * D);
+        const float* bi = t.get(p + "bias_ih" + sfx, 4 * D);
+        const float* bh = t.get(p + "bias_hh" + sfx, 4 * D);
+        std::vector<float> bias(4 * D);
+        for (int64_t i = 0; i < 4 * D; ++i) bias[i] = bi[i] + bh[i];
+        h->lstm[l].bias = h->upload(bias);
+    }
+    h->enc_last = load_wn_conv(h, t, E + std::to_string(idx + 2) + ".", c.dimension, ch, 7, 1);
+
+    // ---- codebooks (reference encoder/quantization/core_vq.py:126-133) ----
+    {
+        const int64_t n = (int64_t)c.vq_bins * c.dimension;
+        std::vector<float> all((size_t)c.num_quantizers * n);
+        for (int q = 0; q < c.num_quantizers; ++q) {
+            const float* e = t.get("feature_extractor.encodec.quantizer.vq.layers." + std::to_string(q) +
+                                       "._codebook.embed", n);
+            std::memcpy(all.data() + (size_t)q * n, e, n * sizeof(float));
+        }
+        h->codebooks = h->upload(all);
+        std::vector<float> cn(c.vq_bins);
+        for (int j = 0; j < c.vq_bins; ++j) {
+            double s = 0;
+            for (int d = 0; d < c.dimension; ++d) { double v = all[(size_t)j * c.dimension + d]; s += v * v; }
+            cn[j] = (float)s;
+        }
+        h->cnorm = h->upload(cn);
+    }
+
+    // ---- backbone (reference decoder/models.py:166-216) ----
+    const int D = c.dim, H = c.intermediate_dim, NE = c.adanorm_num_embeddings;
+    h->embed = load_conv(h, t, "backbone.embed.", D, c.dimension, 7);
+    int slot = 0;
+    for (int i : {0, 1, 3, 4}) {
+        std::string p = "backbone.pos_net." + std::to_string(i) + ".";
+        auto& r = h->pos[slot++];
+        r.n1w = load_vec(h, t, p + "norm1.weight", D); r.n1b = load_vec(h, t, p + "norm1.bias", D);
+        r.n2w = load_vec(h, t, p + "norm2.weight", D); r.n2b = load_vec(h, t, p + "norm2.bias", D);
+        r.c1 = load_conv(h, t, p + "conv1.", D, D, 3);
+        r.c2 = load_conv(h, t, p + "conv2.", D, D, 3);
+    }
+    {
+        std::string p = "backbone.pos_net.2.";
+        h->attn.nw = load_vec(h, t, p + "norm.weight", D);
+        h->attn.nb = load_vec(h, t, p + "norm.bias", D);
+        std::vector<float> w((size_t)3 * D * D), b((size_t)3 * D);
+        int o = 0;
+        for (const char* nm : {"q", "k", "v"}) {
+            const float* wp = t.get(p + nm + ".weight", (int64_t)D * D);
+            const float* bp = t.get(p + nm + ".bias", D);
+            std::memcpy(w.data() + (size_t)o * D * D, wp, (size_t)D * D * sizeof(float));
+            std::memcpy(b.data() + (size_t)o * D, bp, (size_t)D * sizeof(float));
+            ++o;
+        }
+        h->attn.wqkv = h->upload(w);
+        h->attn.bqkv = h->upload(b);
+        h->attn.proj = load_conv(h, t, p + "proj_out.", D, D, 1);
+    }
+    h->gn5w = load_vec(h, t, "backbone.pos_net.5.weight", D);
+    h->gn5b = load_vec(h, t, "backbone.pos_net.5.bias", D);
+    h->norm_scale = load_vec(h, t, "backbone.norm.scale.weight", (int64_t)NE * D);
+    h->norm_shift = load_vec(h, t, "backbone.norm.shift.weight", (int64_t)NE * D);
+    h->cnx.resize(c.num_layers);
+    for (int i = 0; i < c.num_layers; ++i) {
+        std::string p = "backbone.convnext." + std::to_string(i) + ".";
+        auto& x = h->cnx[i];
+        x.dw = load_vec(h, t, p + "dwconv.weight", (int64_t)D * 7);
+        x.db = load_vec(h, t, p + "dwconv.bias", D);
+        x.scale = load_vec(h, t, p + "norm.scale.weight", (int64_t)NE * D);
+        x.shift = load_vec(h, t, p + "norm.shift.weight", (int64_t)NE * D);
+        x.w1 = load_vec(h, t, p + "pwconv1.weight", (int64_t)H * D);
+        x.b1 = load_vec(h, t, p + "pwconv1.bias", H);
+        x.w2 = load_vec(h, t, p + "pwconv2.weight", (int64_t)D * H);
+        x.b2 = load_vec(h, t, p + "pwconv2.bias", D);
+        x.gamma = load_vec(h, t, p + "gamma", D);
+    }
+    h->fln_w = load_vec(h, t, "backbone.final_layer_norm.weight", D);
+    h->fln_b = load_vec(h, t, "backbone.final_layer_norm.bias", D);
+
+    // ---- head + windowed inverse real DFT basis (reference decoder/heads.py:36-40,
+    //      decoder/spectral_ops.py:56-57: irfft(norm="backward") * window) ----
+    const int N = c.n_fft, half = N / 2 + 1;
+    h->head_w = load_vec(h, t, "head.out.weight", (int64_t)(N + 2) * D);
+    h->head_b = load_vec(h, t, "head.out.bias", N + 2);
+    const float* win = t.get("head.istft.window", N);
+    h->Kp = (int)align_up(2 * half, 16);
+    std::vector<float> basis((size_t)N * h->Kp, 0.f), wsq(N);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int n = 0; n < N; ++n) {
+        wsq[n] = win[n] * win[n];
+        for (int k = 0; k < half; ++k) {
+            double wk = (k == 0 || k == N / 2) ? 1.0 : 2.0;
+            long long r = ((long long)k * n) % N;
+            double ang = two_pi * (double)r / (double)N;
+            basis[(size_t)n * h->Kp + k] = (float)(wk * std::cos(ang) / N * (double)win[n]);
+            basis[(size_t)n * h->Kp + half + k] = (float)(-wk * std::sin(ang) / N * (double)win[n]);
+        }
+    }
+    h->basis = h->upload(basis);
+    h->wsq = h->upload(wsq);
+    WT_CUDA(cudaMalloc(&h->err_flag, sizeof(int)));
+    WT_CUDA(cudaMemset(h->err_flag, 0, sizeof(int)));
+    WT_CUDA(cudaMallocHost(&h->err_host, sizeof(int)));
+}
+
+// ---------------------------------------------------------------------------------------
+// shape helpers
+// ---------------------------------------------------------------------------------------
+int frames_for(const wt_config& c, int T) {
+    long long n = T;
+    for (int i = 0; i < 4; ++i) n = (n + c.strides[i] - 1) / c.strides[i];
+    return (int)n;
+}
+
+size_t enc_chunk_floats(const wt_config& c, int Bc, int T) {
+    size_t tot = 0;
+    size_t Tc = T, C = c.n_filters;
+    auto a = [&](size_t n) { tot += align_up(n * sizeof(float), 256) / sizeof(float); };
+    a((size_t)Bc * Tc * C);
+    for (int i = 0; i < 4; ++i) {
+        a((size_t)Bc * Tc * (C / 2));
+        a((size_t)Bc * Tc * C);
+        a((size_t)Bc * Tc * C);
+        size_t Tn = (Tc + c.strides[i] - 1) / c.strides[i];
+        a((size_t)Bc * Tn * 2 * C);
+        Tc = Tn; C *= 2;
+    }
+    const size_t M = (size_t)Bc * Tc, D = c.dimension;
+    a(M * 4 * D);                                    // xin
+    for (int l = 0; l < c.lstm_layers; ++l) a(M * D);  // y_l
+    a((size_t)Bc * 4 * D);                           // gates
+    a((size_t)Bc * D);                               // c
+    a(M * D);                                        // lstm + skip
+    a(M * D);                                        // z
+    a(M * 2);                                        // codes (int64)
+    a(M * D);                                        // transposed z staging
+    return tot;
+}
+
+size_t dec_chunk_floats(const wt_config& c, int Bc, int L, int Kp) {
+    size_t tot = 0;
+    auto a = [&](size_t n) { tot += align_up(n * sizeof(float), 256) / sizeof(float); };
+    const size_t M = (size_t)Bc * L;
+    size_t big = std::max<size_t>(std::max<size_t>(3 * c.dim, c.intermediate_dim), std::max<size_t>(c.n_fft + 2, Kp));
+    a(M * c.dimension);
+    a(M * c.dim); a(M * c.dim); a(M * c.dim);
+    a(M * big); a(M * big);
+    return tot;
+}
+
+size_t workspace_bytes(const wt_handle* h, int B, int T) {
+    const wt_config& c = h->cfg;
+    int L = frames_for(c, T);
+    size_t e = enc_chunk_floats(c, std::min(B, ENC_CHUNK), T);
+    size_t d = dec_chunk_floats(c, std::min(B, DEC_CHUNK), L, h->Kp);
+    return std::max(e, d) * sizeof(float) + 4096;
+}
+
+// ---------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------
+struct Runner {
+    wt_handle* h;
+    cudaStream_t s;
+
+    void gemm(const TapGemm& g) {
+        launch_tap_gemm_simt(g, s);
+        ++h->launches;
+    }
+
+    // Conv1d as tap-GEMM on channels-last rows. `reflect`: SConv1d non-causal padding rule
+    // (reference encoder/modules/conv.py:195-211); otherwise symmetric zero padding (k-1)/2.
+    void conv(const ConvW& w, const float* in, float* out, int Bc, int Tin, bool reflect, int pro, int act = ACT_NONE,
+              const float* res = nullptr, const float* gamma = nullptr) {
+        TapGemm g;
+        const int s_ = w.stride, k = w.k;
+        int left, right_total;
+        int Tout;
+        if (reflect) {
+            int pt = k - s_;
+            int right = pt / 2;
+            left = pt - right;
+            Tout = (Tin + s_ - 1) / s_;
+            int extra = Tout * s_ - Tin;
+            right_total = right + extra;
+        } else {
+            left = (k - 1) / 2;
+            right_total = left;
+            Tout = Tin;
+        }
+        g.A = in; g.W = w.w; g.bias = w.b; g.gamma = gamma; g.res = res; g.out = out;
+        g.M = Bc * Tout; g.N = w.cout; g.K = k * w.cin;
+        g.Cin = w.cin; g.taps = k; g.stride = s_; g.pad_left = left;
+        g.Tin = Tin; g.Tout = Tout;
+        int max_pad = std::max(left, right_total);
+        g.Trefl = std::max(Tin, max_pad + 1);
+        g.pad_mode = reflect ? PAD_REFLECT : PAD_ZERO;
+        g.pro = pro; g.act = act;
+        g.lda = w.cin; g.ldo = w.cout; g.ldres = w.cout;
+        gemm(g);
+    }
+
+    void linear(const float* A, const float* W, const float* bias, float* out, long long M, int N, int K, int act,
+                const float* gamma, const float* res, int lda = 0, int ldo = 0, int ldres = 0) {
+        TapGemm g;
+        g.A = A; g.W = W; g.bias = bias; g.gamma = gamma; g.res = res; g.out = out;
+        g.M = (int)M; g.N = N; g.K = K; g.Cin = K; g.taps = 1; g.stride = 1; g.pad_left = 0;
+        g.Tin = 1; g.Tout = 1; g.Trefl = 1; g.pad_mode = PAD_ZERO; g.pro = PRO_NONE; g.act = act;
+        g.lda = lda ? lda : K; g.ldo = ldo ? ldo : N; g.ldres = ldres ? ldres : N;
+        gemm(g);
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// encoder: SEANetEncoder.forward on a chunk (reference encoder/modules/seanet.py:143-144)
+// returns z rows [Bc*L, D] (channels-last)
+// ---------------------------------------------------------------------------------------
+float* encoder_chunk(wt_handle* h, const float* wav, int Bc, int T, int b0, cudaStream_t s) {
+    const wt_config& c = h->cfg;
+    Runner r{h, s};
+    int Tc = T, C = c.n_filters;
+    float* cur = h->alloc((size_t)Bc * Tc * C);
+    launch_conv0(wav, h->conv0_w, h->conv0_b, cur, Bc, T, C, s);
+    ++h->launches;
+    h->tap("enc0", cur, Bc, Tc, C, b0, s);
+    int idx = 1;
+    for (int i = 0; i < 4; ++i) {
+        // SEANetResnetBlock (seanet.py:45-63): shortcut(x) + conv1x1(ELU(conv_k3(ELU(x))))
+        float* h1 = h->alloc((size_t)Bc * Tc * (C / 2));
+        float* sc = h->alloc((size_t)Bc * Tc * C);
+        float* y = h->alloc((size_t)Bc * Tc * C);
+        r.conv(h->rb[i].c1, cur, h1, Bc, Tc, true, PRO_ELU);
+        r.conv(h->rb[i].sc, cur, sc, Bc, Tc, true, PRO_NONE);
+        r.conv(h->rb[i].c2, h1, y, Bc, Tc, true, PRO_ELU, ACT_NONE, sc);
+        h->tap(("enc" + std::to_string(idx)).c_str(), y, Bc, Tc, C, b0, s);
+        // ELU + strided SConv1d (seanet.py:121-131)
+        int Tn = (Tc + c.strides[i] - 1) / c.strides[i];
+        float* z = h->alloc((size_t)Bc * Tn * 2 * C);
+        r.conv(h->down[i], y, z, Bc, Tc, true, PRO_ELU);
+        h->tap(("enc" + std::to_string(idx + 2)).c_str(), z, Bc, Tn, 2 * C, b0, s);
+        cur = z; Tc = Tn; C *= 2; idx += 3;
+    }
+    // SLSTM (reference encoder/modules/lstm.py:31-39)
+    const int L = Tc, D = C;
+    const long long M = (long long)Bc * L;
+    float* xin = h->alloc((size_t)M * 4 * D);
+    float* ybuf[4];
+    for (int l = 0; l < c.lstm_layers; ++l) ybuf[l] = h->alloc((size_t)M * D);
+    float* gates = h->alloc((size_t)Bc * 4 * D);
+    float* cst = h->alloc((size_t)Bc * D);
+    const float* lin = cur;
+    for (int l = 0; l < c.lstm_layers; ++l) {
+        r.linear(lin, h->lstm[l].w_ih, h->lstm[l].bias, xin, M, 4 * D, D, ACT_NONE, nullptr, nullptr);
+        WT_CUDA(cudaMemsetAsync(cst, 0, (size_t)Bc * D * sizeof(float), s));
+        for (int t = 0; t < L; ++t) {
+            const float* g_in;
+            long long ldg;
+            if (t == 0) {
+                g_in = xin; ldg = (long long)L * 4 * D;  // h_{-1} = 0
+            } else {
+                r.linear(ybuf[l] + (size_t)(t - 1) * D, h->lstm[l].w_hh, nullptr, gates, Bc, 4 * D, D, ACT_NONE, nullptr,
+                         xin + (size_t)t * 4 * D, L * D, 4 * D, L * 4 * D);
+                g_in = gates; ldg = 4 * D;
+            }
+            launch_lstm_pointwise(g_in, cst, ybuf[l] + (size_t)t * D, Bc, D, ldg, (long long)L * D, s);
+            ++h->launches;
+        }
+        lin = ybuf[l];
+    }
+    float* lo = h->alloc((size_t)M * D);
+    launch_add(lin, cur, lo, M * D, s);
+    ++h->launches;
+    h->tap(("enc" + std::to_string(idx)).c_str(), lo, Bc, L, D, b0, s);
+    float* z = h->alloc((size_t)M * D);
+    r.conv(h->enc_last, lo, z, Bc, L, true, PRO_ELU);
+    h->tap(("enc" + std::to_string(idx + 2)).c_str(), z, Bc, L, D, b0, s);
+    return z;
+}
+
+// ---------------------------------------------------------------------------------------
+// decoder: VocosBackbone + ISTFTHead on a chunk (reference decoder/models.py:223-235,
+// decoder/heads.py:42-67)
+// ---------------------------------------------------------------------------------------
+void decoder_chunk(wt_handle* h, const float* features /*[Bc, Din, L]*/, int Bc, int L, int bw, float* audio, int b0,
+                   cudaStream_t s) {
+    const wt_config& c = h->cfg;
+    Runner r{h, s};
+    const int D = c.dim, Hd = c.intermediate_dim, Din = c.dimension;
+    const long long M = (long long)Bc * L;
+    const size_t big = std::max<size_t>(std::max<size_t>(3 * D, Hd), std::max<size_t>(c.n_fft + 2, h->Kp));
+    float* xin = h->alloc((size_t)M * Din);
+    float* x = h->alloc((size_t)M * D);
+    float* t1 = h->alloc((size_t)M * D);
+    float* t2 = h->alloc((size_t)M * D);
+    float* bigA = h->alloc((size_t)M * big);
+    float* bigB = h->alloc((size_t)M * big);
+    auto K1 = [&]() { ++h->launches; };
+    const float eps = 1e-6f;
+
+    launch_transpose_bcl_to_blc(features, xin, Bc, Din, L, s); K1();
+    r.conv(h->embed, xin, x, Bc, L, false, PRO_NONE);
+    h->tap("dec_embed", x, Bc, L, D, b0, s);
+
+    auto resnet = [&](const wt_handle::Resnet& p) {
+        launch_groupnorm(x, p.n1w, p.n1b, t1, Bc, L, D, 32, eps, 1, s); K1();
+        r.conv(p.c1, t1, t2, Bc, L, false, PRO_NONE);
+        launch_groupnorm(t2, p.n2w, p.n2b, t1, Bc, L, D, 32, eps, 1, s); K1();
+        r.conv(p.c2, t1, x, Bc, L, false, PRO_NONE, ACT_NONE, x);
+    };
+    resnet(h->pos[0]); h->tap("dec_pos0", x, Bc, L, D, b0, s);
+    resnet(h->pos[1]); h->tap("dec_pos1", x, Bc, L, D, b0, s);
+    {   // AttnBlock (reference decoder/models.py:107-127)
+        launch_groupnorm(x, h->attn.nw, h->attn.nb, t1, Bc, L, D, 32, eps, 0, s); K1();
+        r.linear(t1, h->attn.wqkv, h->attn.bqkv, bigA, M, 3 * D, D, ACT_NONE, nullptr, nullptr);
+        launch_attention(bigA, t2, Bc, L, D, s); K1();
+        r.linear(t2, h->attn.proj.w, h->attn.proj.b, x, M, D, D, ACT_NONE, nullptr, x);
+        h->tap("dec_pos2", x, Bc, L, D, b0, s);
+    }
+    resnet(h->pos[2]); h->tap("dec_pos3", x, Bc, L, D, b0, s);
+    resnet(h->pos[3]); h->tap("dec_pos4", x, Bc, L, D, b0, s);
+    launch_groupnorm(x, h->gn5w, h->gn5b, t1, Bc, L, D, 32, eps, 0, s); K1();
+    h->tap("dec_pos5", t1, Bc, L, D, b0, s);
+    // AdaLayerNorm keyed by bandwidth_id (reference decoder/modules.py:81-86)
+    launch_layernorm(t1, h->norm_scale + (size_t)bw * D, h->norm_shift + (size_t)bw * D, x, M, D, eps, s); K1();
+    h->tap("dec_norm", x, Bc, L, D, b0, s);
+    for (int i = 0; i < c.num_layers; ++i) {
+        // ConvNeXtBlock (reference decoder/modules.py:43-60)
+        const auto& p = h->cnx[i];
+        launch_dwconv_ln(x, p.dw, p.db, p.scale + (size_t)bw * D, p.shift + (size_t)bw * D, t1, Bc, L, D, eps, s); K1();
+        r.linear(t1, p.w1, p.b1, bigA, M, Hd, D, ACT_GELU, nullptr, nullptr);
+        r.linear(bigA, p.w2, p.b2, x, M, D, Hd, ACT_NONE, p.gamma, x);
+        h->tap(("dec_cnx" + std::to_string(i)).c_str(), x, Bc, L, D, b0, s);
+    }
+    launch_layernorm(x, h->fln_w, h->fln_b, t1, M, D, eps, s); K1();
+    h->tap("dec_final", t1, Bc, L, D, b0, s);
+    const int N = c.n_fft, half = N / 2 + 1;
+    r.linear(t1, h->head_w, h->head_b, bigA, M, N + 2, D, ACT_NONE, nullptr, nullptr);
+    h->tap("dec_headlin", bigA, Bc, L, N + 2, b0, s);
+    launch_spectral(bigA, bigB, M, half, h->Kp, s); K1();
+    r.linear(bigB, h->basis, nullptr, bigA, M, N, h->Kp, ACT_NONE, nullptr, nullptr);
+    launch_overlap_add(bigA, h->wsq, audio, Bc, L, N, c.hop_length, s); K1();
+}
+
+void check_err_flag(wt_handle* h, cudaStream_t s, const char* what) {
+    WT_CUDA(cudaMemcpyAsync(h->err_host, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    WT_CUDA(cudaStreamSynchronize(s));
+    if (*h->err_host) {
+        WT_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(int), s));
+        throw Error(WT_ERR_INDEX, std::string(what) + ": index out of range in self");
+    }
+}
+
+void do_encode(wt_handle* h, const float* wav, int B, int T, float* features_out, int64_t* codes_out, float* z_out,
+               cudaStream_t s) {
+    const wt_config& c = h->cfg;
+    if (B < 0 || T <= 0) throw Error(WT_ERR_VALUE, "encode: expected wav [B, T] with T > 0");
+    h->ensure_arena(workspace_bytes(h, B, T));
+    const int L = frames_for(c, T), D = c.dimension;
+    for (int b0 = 0; b0 < B; b0 += ENC_CHUNK) {
+        const int Bc = std::min(ENC_CHUNK, B - b0);
+        h->arena_off = 0;
+        float* z = encoder_chunk(h, wav + (size_t)b0 * T, Bc, T, b0, s);
+        const long long M = (long long)Bc * L;
+        if (z_out) {
+            launch_transpose_blc_to_bcl(z, z_out + (size_t)b0 * D * L, Bc, L, D, s);
+            ++h->launches;
+        }
+        if (codes_out) {
+            long long* codes = reinterpret_cast<long long*>(codes_out) + (size_t)b0 * L;
+            launch_vq_simt(z, h->codebooks, h->cnorm, M, D, c.vq_bins, codes, s);
+            ++h->launches;
+            if (features_out) {
+                launch_codes_to_features(h->codebooks, codes, features_out + (size_t)b0 * D * L, 1, Bc, L, D, c.vq_bins,
+                                         nullptr, s);
+                ++h->launches;
+            }
+        }
+    }
+}
+
+void do_decode(wt_handle* h, const float* features, int B, int L, int bw, float* audio, cudaStream_t s) {
+    const wt_config& c = h->cfg;
+    if (B < 0 || L <= 0) throw Error(WT_ERR_VALUE, "decode: expected features [B, C, L] with L > 0");
+    if (bw < 0 || bw >= c.adanorm_num_embeddings) throw Error(WT_ERR_INDEX, "index out of range in self (bandwidth_id)");
+    size_t need = dec_chunk_floats(c, std::min(B, DEC_CHUNK), L, h->Kp) * sizeof(float) + 4096;
+    h->ensure_arena(need);
+    for (int b0 = 0; b0 < B; b0 += DEC_CHUNK) {
+        const int Bc = std::min(DEC_CHUNK, B - b0);
+        h->arena_off = 0;
+        decoder_chunk(h, features + (size_t)b0 * c.dimension * L, Bc, L, bw,
+                      audio + (size_t)b0 * L * c.hop_length, b0, s);
+    }
+}
+
+template <typename F>
+int guarded(wt_handle* h, F&& f) {
+    try {
+        if (!h) throw Error(WT_ERR_VALUE, "null handle");
+        WT_CUDA(cudaSetDevice(h->device));
+        f();
+        return WT_OK;
+    } catch (const Error& e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return WT_ERR_RUNTIME;
+    }
+}
+
+}  // namespace
+}  // namespace wt
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+const char* wt_last_error(void) { return g_last_error.c_str(); }
+const char* wt_version(void) { return "wavtok_b200 0.1 (sm_100a)"; }
+
+int wt_create(const wt_config* cfg, const wt_tensor* tensors, int32_t n_tensors, int32_t device, wt_handle** out) {
+    if (out) *out = nullptr;
+    try {
+        if (!cfg || !tensors || !out) throw Error(WT_ERR_VALUE, "wt_create: null argument");
+        if (cfg->n_filters != 32 || cfg->dimension != 512)
+            throw Error(WT_ERR_VALUE, "unsupported encoder geometry (n_filters must be 32, dimension 512)");
+        if (cfg->dim != 768) throw Error(WT_ERR_VALUE, "unsupported backbone width (dim must be 768)");
+        if (cfg->dim % 32 || cfg->intermediate_dim % 16 || cfg->n_fft % 2 || cfg->n_fft % cfg->hop_length)
+            throw Error(WT_ERR_VALUE, "unsupported backbone / head geometry");
+        if (cfg->lstm_layers < 0 || cfg->lstm_layers > 4) throw Error(WT_ERR_VALUE, "lstm_layers must be in [0, 4]");
+        if (cfg->vq_bins % 128 || cfg->num_quantizers < 1) throw Error(WT_ERR_VALUE, "vq_bins must be a multiple of 128");
+        for (int i = 0; i < 4; ++i)
+            if (cfg->strides[i] < 1) throw Error(WT_ERR_VALUE, "strides must be positive");
+        int ndev = 0;
+        WT_CUDA(cudaGetDeviceCount(&ndev));
+        if (device < 0 || device >= ndev) throw Error(WT_ERR_RUNTIME, "invalid CUDA device ordinal");
+        WT_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        WT_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            throw Error(WT_ERR_RUNTIME, std::string("wavtok_b200 is built for sm_100a only; device is ") + prop.name);
+        Table t;
+        for (int i = 0; i < n_tensors; ++i)
+            if (tensors[i].name && tensors[i].data) t.m[tensors[i].name] = {tensors[i].data, tensors[i].numel};
+        std::unique_ptr<wt_handle> h(new wt_handle());
+        h->cfg = *cfg;
+        h->device = device;
+        prepare(h.get(), t);
+        WT_CUDA(cudaDeviceSynchronize());
+        *out = h.release();
+        return WT_OK;
+    } catch (const Error& e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return WT_ERR_RUNTIME;
+    }
+}
+
+int wt_destroy(wt_handle* h) {
+    if (!h) return WT_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    delete h;
+    return WT_OK;
+}
+
+int32_t wt_frames_for(const wt_handle* h, int32_t T) { return h ? frames_for(h->cfg, T) : -1; }
+
+int64_t wt_workspace_bytes(const wt_handle* h, int32_t B, int32_t T) {
+    return h ? (int64_t)workspace_bytes(h, B, T) : -1;
+}
+
+int wt_reserve(wt_handle* h, int32_t B, int32_t T) {
+    return guarded(h, [&] { h->ensure_arena(workspace_bytes(h, B, T)); });
+}
+
+int wt_encode(wt_handle* h, const float* wav, int32_t B, int32_t T, float* features_out, int64_t* codes_out,
+              void* stream) {
+    return guarded(h, [&] {
+        if (!wav || !codes_out) throw Error(WT_ERR_VALUE, "wt_encode: null buffer");
+        do_encode(h, wav, B, T, features_out, codes_out, nullptr, (cudaStream_t)stream);
+    });
+}
+
+int wt_encoder_forward(wt_handle* h, const float* wav, int32_t B, int32_t T, float* z_out, void* stream) {
+    return guarded(h, [&] {
+        if (!wav || !z_out) throw Error(WT_ERR_VALUE, "wt_encoder_forward: null buffer");
+        do_encode(h, wav, B, T, nullptr, nullptr, z_out, (cudaStream_t)stream);
+    });
+}
+
+int wt_codes_to_features(wt_handle* h, const int64_t* codes, int32_t K, int32_t B, int32_t L, float* features_out,
+                         void* stream) {
+    return guarded(h, [&] {
+        if (!codes || !features_out) throw Error(WT_ERR_VALUE, "wt_codes_to_features: null buffer");
+        if (K < 1 || K > h->cfg.num_quantizers)
+            throw Error(WT_ERR_INDEX, "codes_to_features: more code books than the checkpoint holds");
+        cudaStream_t s = (cudaStream_t)stream;
+        launch_codes_to_features(h->codebooks, reinterpret_cast<const long long*>(codes), features_out, K, B, L,
+                                 h->cfg.dimension, h->cfg.vq_bins, h->err_flag, s);
+        ++h->launches;
+        check_err_flag(h, s, "codes_to_features");
+    });
+}
+
+int wt_decode(wt_handle* h, const float* features, int32_t B, int32_t L, int32_t bandwidth_id, float* audio_out,
+              void* stream) {
+    return guarded(h, [&] {
+        if (!features || !audio_out) throw Error(WT_ERR_VALUE, "wt_decode: null buffer");
+        do_decode(h, features, B, L, bandwidth_id, audio_out, (cudaStream_t)stream);
+    });
+}
+
+int wt_vq(wt_handle* h, const float* x, int64_t N, int64_t* codes_out, float* quantized_out, void* stream) {
+    return guarded(h, [&] {
+        if (!x || !codes_out) throw Error(WT_ERR_VALUE, "wt_vq: null buffer");
+        cudaStream_t s = (cudaStream_t)stream;
+        const wt_config& c = h->cfg;
+        launch_vq_simt(x, h->codebooks, h->cnorm, N, c.dimension, c.vq_bins, reinterpret_cast<long long*>(codes_out), s);
+        ++h->launches;
+        if (quantized_out) {
+            launch_gather_rows(h->codebooks, reinterpret_cast<const long long*>(codes_out), quantized_out, N,
+                               c.dimension, c.vq_bins, nullptr, s);
+            ++h->launches;
+        }
+    });
+}
+
+int wt_encode_decode_host(wt_handle* h, const float* wav_host, int32_t B, int32_t T, int32_t bandwidth_id,
+                          int64_t* codes_host, float* audio_host, void* stream) {
+    return guarded(h, [&] {
+        if (!wav_host || !codes_host || !audio_host) throw Error(WT_ERR_VALUE, "wt_encode_decode_host: null buffer");
+        cudaStream_t s = (cudaStream_t)stream;
+        const wt_config& c = h->cfg;
+        const int L = frames_for(c, T);
+        const size_t n_wav = (size_t)B * T, n_feat = (size_t)B * c.dimension * L, n_codes = (size_t)B * L,
+                     n_audio = (size_t)B * L * c.hop_length;
+        size_t need = align_up(n_wav * 4, 256) + align_up(n_feat * 4, 256) + align_up(n_codes * 8, 256) +
+                      align_up(n_audio * 4, 256);
+        if (need > h->stage_cap) {
+            WT_CUDA(cudaDeviceSynchronize());
+            if (h->stage) WT_CUDA(cudaFree(h->stage));
+            h->stage = nullptr; h->stage_cap = 0;
+            WT_CUDA(cudaMalloc(&h->stage, need));
+            h->stage_cap = need;
+        }
+        char* p = h->stage;
+        float* wav = (float*)p; p += align_up(n_wav * 4, 256);
+        float* feat = (float*)p; p += align_up(n_feat * 4, 256);
+        int64_t* codes = (int64_t*)p; p += align_up(n_codes * 8, 256);
+        float* audio = (float*)p;
+        WT_CUDA(cudaMemcpyAsync(wav, wav_host, n_wav * 4, cudaMemcpyHostToDevice, s));
+        do_encode(h, wav, B, T, feat, codes, nullptr, s);
+        do_decode(h, feat, B, L, bandwidth_id, audio, s);
+        WT_CUDA(cudaMemcpyAsync(codes_host, codes, n_codes * 8, cudaMemcpyDeviceToHost, s));
+        WT_CUDA(cudaMemcpyAsync(audio_host, audio, n_audio * 4, cudaMemcpyDeviceToHost, s));
+        WT_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int wt_tap_request(wt_handle* h, const char* stage, float* dev_buf, int64_t capacity) {
+    return guarded(h, [&] {
+        if (!stage) throw Error(WT_ERR_VALUE, "wt_tap_request: null stage");
+        TapReq r;
+        r.buf = dev_buf; r.cap = capacity;
+        h->taps[stage] = r;
+    });
+}
+
+int wt_tap_shape(const wt_handle* h, const char* stage, int32_t* B, int32_t* T, int32_t* C) {
+    if (!h || !stage) return WT_ERR_VALUE;
+    auto it = h->taps.find(stage);
+    if (it == h->taps.end()) return WT_ERR_VALUE;
+    if (B) *B = it->second.B;
+    if (T) *T = it->second.T;
+    if (C) *C = it->second.C;
+    return WT_OK;
+}
+
+int wt_tap_clear(wt_handle* h) {
+    return guarded(h, [&] { h->taps.clear(); });
+}
+
+int64_t wt_launch_count(const wt_handle* h) { return h ? h->launches : -1; }
+
+int wt_set_plan(wt_handle* h, int32_t plan) {
+    return guarded(h, [&] {
+        if (plan != 0) throw Error(WT_ERR_VALUE, "unknown compute plan");
+        h->plan = plan;
+    });
+}
+
+}  // extern "C"

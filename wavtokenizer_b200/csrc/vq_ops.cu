@@ -1,0 +1,223 @@
+// Vector quantiser kernels (plan 0, fp32 CUDA cores) and codebook gathers.
+// Replaces EuclideanCodebook.quantize / dequantize (reference encoder/quantization/core_vq.py:175-190)
+// and WavTokenizer.codes_to_features (decoder/pretrained.py:209-239).
+#include "common.cuh"
+
+namespace wt {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, NT = 256;
+
+// One block owns 128 frames and sweeps the whole codebook: the [frames, bins] score matrix
+// (and the one-hot the reference builds from it, core_vq.py:213) is never materialised.
+// d = (||x||^2 - 2 x.c) + ||c||^2 in the reference's term order; argmin, first index on ties.
+__global__ void __launch_bounds__(NT) vq_simt_kernel(const float* __restrict__ x, const float* __restrict__ cb,
+                                                     const float* __restrict__ cnorm, long long N, int D, int bins,
+                                                     long long* __restrict__ codes) {
+    __shared__ __align__(16) float As[2][BK][BM + 4];
+    __shared__ __align__(16) float Bs[2][BK][BN + 4];
+    __shared__ float xn[BM];
+
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int lane = tid & 31, warp = tid >> 5;
+    const long long m0 = (long long)blockIdx.x * BM;
+
+    // row norms: warp w handles rows w, w+8, ...
+    for (int r = warp; r < BM; r += NT / 32) {
+        long long m = m0 + r;
+        float s = 0.f;
+        if (m < N)
+            for (int c = lane; c < D; c += 32) {
+                float v = x[m * D + c];
+                s = fmaf(v, v, s);
+            }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) xn[r] = s;
+    }
+
+    int a_row[2], a_kq[2];
+    bool a_ok[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        int idx = tid + i * NT;
+        a_row[i] = idx >> 2;
+        a_kq[i] = idx & 3;
+        a_ok[i] = (m0 + a_row[i]) < N;
+    }
+    const int KT = D / BK;
+    const int NTILES = bins / BN;
+    const int total = KT * NTILES;
+    float4 a_reg[2], b_reg[2];
+    auto load_tile = [&](int it) {
+        int nt = it / KT, kt = it - nt * KT;
+        int k0 = kt * BK;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            a_reg[i] = a_ok[i] ? *reinterpret_cast<const float4*>(x + (m0 + a_row[i]) * D + k0 + a_kq[i] * 4)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            int n = nt * BN + a_row[i];
+            b_reg[i] = *reinterpret_cast<const float4*>(cb + (long long)n * D + k0 + a_kq[i] * 4);
+        }
+    };
+    auto store_tile = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            int kk = a_kq[i] * 4;
+            As[buf][kk + 0][a_row[i]] = a_reg[i].x; As[buf][kk + 1][a_row[i]] = a_reg[i].y;
+            As[buf][kk + 2][a_row[i]] = a_reg[i].z; As[buf][kk + 3][a_row[i]] = a_reg[i].w;
+            Bs[buf][kk + 0][a_row[i]] = b_reg[i].x; Bs[buf][kk + 1][a_row[i]] = b_reg[i].y;
+            Bs[buf][kk + 2][a_row[i]] = b_reg[i].z; Bs[buf][kk + 3][a_row[i]] = b_reg[i].w;
+        }
+    };
+
+    float best[8];
+    int besti[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { best[i] = INFINITY; besti[i] = 0; }
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    load_tile(0);
+    store_tile(0);
+    __syncthreads();
+    for (int it = 0; it < total; ++it) {
+        const int buf = it & 1;
+        if (it + 1 < total) load_tile(it + 1);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+            float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+            float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        const int nt = it / KT, kt = it - nt * KT;
+        if (kt == KT - 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = nt * BN + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+                const float cn = cnorm[n];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+                    float d = (xn[r] - 2.f * acc[i][j]) + cn;
+                    if (d < best[i]) { best[i] = d; besti[i] = n; }
+                    acc[i][j] = 0.f;
+                }
+            }
+        }
+        if (it + 1 < total) {
+            store_tile(buf ^ 1);
+            __syncthreads();
+        }
+    }
+    // reduce over the 16 threads (tx) that share each row; ties -> lower index
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float v = best[i];
+        int bi = besti[i];
+#pragma unroll
+        for (int o = 8; o; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov < v || (ov == v && oi < bi)) { v = ov; bi = oi; }
+        }
+        if (tx == 0) {
+            long long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+            if (m < N) codes[m] = bi;
+        }
+    }
+}
+
+// quantized [N, D] = codebook[codes]  (row-major both sides)
+__global__ void gather_rows_kernel(const float4* __restrict__ cb, const long long* __restrict__ codes,
+                                   float4* __restrict__ out, long long N, int D4, int bins, int* err) {
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= N * D4) return;
+    long long m = gid / D4;
+    int c = (int)(gid - m * D4);
+    long long code = codes[m];
+    if (code < 0 || code >= bins) {
+        if (err) atomicExch(err, 1);
+        return;
+    }
+    out[gid] = cb[code * D4 + c];
+}
+
+// features[b, c, t] = sum_k codebooks[k*bins + codes[k, b, t]][c]; tile of 32 frames per block,
+// transposed through shared memory so both the codebook reads and the [B, D, L] writes coalesce.
+__global__ void __launch_bounds__(256) codes_to_features_kernel(const float* __restrict__ cbs,
+                                                                const long long* __restrict__ codes,
+                                                                float* __restrict__ out, int K, int B, int L, int D,
+                                                                int bins, int* err) {
+    extern __shared__ float tile[];  // [32][D + 1]
+    const int b = blockIdx.y, t0 = blockIdx.x * 32;
+    const int ldt = D + 1;
+    for (int i = threadIdx.x; i < 32 * D; i += blockDim.x) {
+        int tt = i / D, c = i - tt * D;
+        int t = t0 + tt;
+        float v = 0.f;
+        if (t < L) {
+            for (int k = 0; k < K; ++k) {
+                long long code = codes[((long long)k * B + b) * L + t];
+                if (code < 0 || code >= bins) {
+                    if (err) atomicExch(err, 1);
+                    code = 0;
+                }
+                v += cbs[((long long)k * bins + code) * D + c];
+            }
+        }
+        tile[tt * ldt + c] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * D; i += blockDim.x) {
+        int c = i >> 5, tt = i & 31;
+        int t = t0 + tt;
+        if (t < L) out[((long long)b * D + c) * L + t] = tile[tt * ldt + c];
+    }
+}
+
+}  // namespace
+
+void launch_vq_simt(const float* x, const float* codebook, const float* cnorm, long long N, int D, int bins,
+                    long long* codes, cudaStream_t s) {
+    if (N <= 0) return;
+    if (D % BK || bins % BN) throw Error(1, "vq: dimension must be a multiple of 16 and bins of 128");
+    vq_simt_kernel<<<(unsigned)((N + BM - 1) / BM), NT, 0, s>>>(x, codebook, cnorm, N, D, bins, codes);
+    WT_CUDA(cudaGetLastError());
+}
+
+void launch_gather_rows(const float* codebook, const long long* codes, float* out, long long N, int D, int bins,
+                        int* err_flag, cudaStream_t s) {
+    if (N <= 0) return;
+    long long n = N * (D / 4);
+    gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float4*)codebook, codes, (float4*)out, N,
+                                                                   D / 4, bins, err_flag);
+    WT_CUDA(cudaGetLastError());
+}
+
+void launch_codes_to_features(const float* codebooks, const long long* codes, float* out, int K, int B, int L, int D,
+                              int bins, int* err_flag, cudaStream_t s) {
+    if (B <= 0 || L <= 0) return;
+    size_t smem = (size_t)32 * (D + 1) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        WT_CUDA(cudaFuncSetAttribute(codes_to_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    dim3 grid((L + 31) / 32, B);
+    codes_to_features_kernel<<<grid, 256, smem, s>>>(codebooks, codes, out, K, B, L, D, bins, err_flag);
+    WT_CUDA(cudaGetLastError());
+}
+
+}  // namespace wt

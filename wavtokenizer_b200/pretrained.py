@@ -1,0 +1,340 @@
+"""Drop-in for the reference inference API (reference decoder/pretrained.py:32-239).
+
+``WavTokenizer`` keeps the reference's constructor class-methods, method names, argument
+meaning, tensor layouts, state-dict key names and error behaviour, and runs every method on
+the hand-written sm_100a library through the C ABI (include/wavtok_b200.h). PyTorch is used
+only for device memory, streams and the nn.Module parameter container. There is no eager
+or CPU fallback: calling a compute method without a CUDA device or without the built
+library raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _native, spec
+from .spec import ModelConfig
+
+
+class _Node(nn.Module):
+    """Plain container used to reproduce the reference's dotted state-dict names."""
+
+
+class _Encoder(_Node):
+    """``model.feature_extractor.encodec.encoder`` — callable on wav [B, 1, T] like the
+    reference SEANetEncoder (reference encoder/modules/seanet.py:143-144; used directly by
+    extract_features.py:46)."""
+
+    def __init__(self, root: "WavTokenizer"):
+        super().__init__()
+        object.__setattr__(self, "_root", root)
+
+    @torch.inference_mode()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        B, C, T = x.shape  # ValueError on a wrong rank, like conv.py:196
+        if C != 1:
+            raise RuntimeError(f"expected input[{B}, {C}, {T}] to have 1 channels")
+        return self._root._encoder_forward(x.reshape(B, T))
+
+
+class _VQLayer(_Node):
+    @property
+    def codebook(self) -> torch.Tensor:  # reference core_vq.py:286-288
+        return self._codebook.embed
+
+
+class WavTokenizer(nn.Module):
+    """B200-native WavTokenizer (inference only)."""
+
+    def __init__(self, cfg: ModelConfig, config_path: Optional[str] = None):
+        super().__init__()
+        self.cfg = cfg
+        self.config_path = config_path
+        self._handle: Optional[_native.Handle] = None
+        self._kinds: Dict[str, str] = {}
+        init = spec.synthetic_state_dict(cfg, seed=0)  # a fresh (random-init) model, like from_hparams0802
+        for name, (shape, kind) in spec.state_spec(cfg).items():
+            self._register(name, init[name], kind)
+        # attributes the reference exposes and callers read (decoder/pretrained.py:230)
+        q = self.feature_extractor.encodec.quantizer
+        q.bins = cfg.vq_bins
+        q.n_q = cfg.num_quantizers
+        q.dimension = cfg.dimension
+        self.feature_extractor.bandwidths = list(cfg.bandwidths)
+        self.feature_extractor.frame_rate = 25  # "not use" (feature_extractors.py:68)
+        self.eval()
+
+    # ------------------------------------------------------------------ module tree
+    def _register(self, name: str, value: torch.Tensor, kind: str) -> None:
+        parts = name.split(".")
+        mod: nn.Module = self
+        path: List[str] = []
+        for p in parts[:-1]:
+            path.append(p)
+            if p not in mod._modules:
+                joined = ".".join(path)
+                if joined == "feature_extractor.encodec.encoder":
+                    child: nn.Module = _Encoder(self)
+                elif joined == "feature_extractor.encodec.quantizer.vq.layers":
+                    child = nn.ModuleList()
+                elif joined.startswith("feature_extractor.encodec.quantizer.vq.layers.") and len(path) == 6:
+                    child = _VQLayer()
+                else:
+                    child = _Node()
+                mod.add_module(p, child)
+            mod = mod._modules[p]
+        if kind == "param":
+            mod.register_parameter(parts[-1], nn.Parameter(value.clone(), requires_grad=False))
+        else:
+            mod.register_buffer(parts[-1], value.clone())
+        self._kinds[name] = kind
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_hparams0802(cls, config_path: str) -> "WavTokenizer":
+        """Build from a reference-style YAML (reference decoder/pretrained.py:81-92)."""
+        return cls(spec.load_config(config_path), config_path)
+
+    @classmethod
+    def from_pretrained0802(cls, config_path: str, model_path: str) -> "WavTokenizer":
+        """Load a Lightning checkpoint (reference decoder/pretrained.py:95-114): keep the
+        ``backbone.`` / ``head.`` / ``feature_extractor.`` keys of ``['state_dict']``."""
+        model = cls.from_hparams0802(config_path)
+        state_dict_raw = torch.load(model_path, map_location="cpu")["state_dict"]
+        state_dict = {k: v for k, v in state_dict_raw.items()
+                      if k.startswith(("backbone.", "head.", "feature_extractor."))}
+        model.load_state_dict(state_dict)
+        model.eval()
+        return model
+
+    @classmethod
+    def from_pretrained0911(cls, config_path: str, model_folder_path: str) -> "WavTokenizer":
+        """Average every checkpoint in a folder (reference decoder/pretrained.py:117-156)."""
+        import os
+        model = cls.from_hparams0802(config_path)
+        models = [os.path.join(model_folder_path, f) for f in os.listdir(model_folder_path)
+                  if f.endswith(".ckpt") or f.endswith(".pt") or f.endswith(".pth")] or \
+                 [os.path.join(model_folder_path, f) for f in os.listdir(model_folder_path)]
+        dicts = []
+        for path in models:
+            raw = torch.load(path, map_location="cpu")["state_dict"]
+            dicts.append({k: v for k, v in raw.items() if k.startswith(("backbone.", "head.", "feature_extractor."))})
+        avg = {k: sum(d[k] for d in dicts) / len(dicts) for k in dicts[0]}
+        model.load_state_dict(avg)
+        model.eval()
+        return model
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        """Strict on the hot-path keys; the SEANet-decoder keys every reference checkpoint
+        carries (feature_extractors.py:76-79) are accepted and ignored."""
+        filtered = {k: v for k, v in state_dict.items() if not k.startswith(spec.UNUSED_PREFIX)}
+        out = super().load_state_dict(filtered, strict=strict, assign=assign)
+        self._invalidate()
+        return out
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        self._invalidate()
+        return out
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("wavtokenizer_b200 implements the inference path only (SURVEY.md section 8)")
+        return super().train(False)
+
+    def _invalidate(self) -> None:
+        if getattr(self, "_handle", None) is not None:
+            self._handle.close()
+        self._handle = None
+
+    # ------------------------------------------------------------------ native plumbing
+    @property
+    def device(self) -> torch.device:
+        return self.head.istft.window.device
+
+    def native(self) -> _native.Handle:
+        """The wt_handle for the current weights/device (built on first use)."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("wavtokenizer_b200 has no CPU path: move the model to a CUDA device "
+                               "(model.to('cuda')) before calling it")
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        if self._handle is None or self._handle.device_index != idx:
+            self._invalidate()
+            inited = self.feature_extractor.encodec.quantizer.vq.layers._modules["0"]._codebook.inited
+            if float(inited.sum()) == 0.0:
+                raise RuntimeError(
+                    "codebook is not initialised (inited == 0): the reference would run k-means inside infer "
+                    "(core_vq.py:140-151); load a checkpoint or install a codebook first")
+            self._handle = _native.Handle(self.cfg, {k: v for k, v in self.state_dict().items()}, idx)
+        return self._handle
+
+    def _stream(self) -> ctypes.c_void_p:
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check_input(self, t: torch.Tensor, what: str) -> None:
+        if t.device != self.device:
+            raise RuntimeError(f"Expected all tensors to be on the same device, but {what} is on {t.device} "
+                               f"and the model on {self.device}")
+
+    def set_plan(self, plan: int) -> None:
+        _native.check(_native.lib().wt_set_plan(self.native().ptr, int(plan)))
+
+    def _bandwidth_index(self, kwargs: Dict[str, Any], need_list_semantics: bool) -> int:
+        if "bandwidth_id" not in kwargs or kwargs["bandwidth_id"] is None:
+            if need_list_semantics:
+                raise TypeError("infer() missing 1 required positional argument: 'bandwidth_id'")
+            raise AssertionError("bandwidth_id is required (adanorm_num_embeddings is set)")  # models.py:227
+        bw = kwargs["bandwidth_id"]
+        if isinstance(bw, torch.Tensor):
+            if bw.numel() != 1:
+                if need_list_semantics:  # list[tensor] needs a single-element integer tensor
+                    raise TypeError("only integer tensors of a single element can be converted to an index")
+                raise RuntimeError("bandwidth_id must hold one id for the whole batch (decoder/modules.py:81-86)")
+            if bw.dtype.is_floating_point or bw.dtype == torch.bool:
+                raise TypeError("only integer tensors of a single element can be converted to an index")
+            i = int(bw.reshape(-1)[0].item())
+        else:
+            i = int(bw)
+        n = len(self.cfg.bandwidths) if need_list_semantics else self.cfg.adanorm_num_embeddings
+        if need_list_semantics and -n <= i < 0:
+            i += n  # Python list indexing accepts negatives
+        if not 0 <= i < n:
+            raise IndexError("list index out of range" if need_list_semantics else "index out of range in self")
+        return i
+
+    def _check_audio(self, audio_input: torch.Tensor) -> Tuple[int, int]:
+        if audio_input.dim() != 2:
+            raise ValueError(f"not enough values to unpack (expected audio [B, T], got {tuple(audio_input.shape)})"
+                             if audio_input.dim() < 2 else
+                             f"too many values to unpack (expected audio [B, T], got {tuple(audio_input.shape)})")
+        if audio_input.dtype != torch.float32:
+            raise RuntimeError(f"Input type ({audio_input.dtype}) and weight type (torch.float32) should be the same")
+        self._check_input(audio_input, "audio_input")
+        B, T = audio_input.shape
+        if T < 1:
+            raise RuntimeError("audio must hold at least one sample")
+        return B, T
+
+    # ------------------------------------------------------------------ public API
+    @torch.inference_mode()
+    def encode_infer(self, audio_input: torch.Tensor, **kwargs: Any) -> Tuple[torch.Tensor, torch.Tensor]:
+        """audio [B, T] -> (features [B, 512, L] f32, codes [1, B, L] int64)
+        (reference decoder/pretrained.py:186-189, feature_extractors.py:131-142)."""
+        h = self.native()
+        B, T = self._check_audio(audio_input)
+        self._bandwidth_index(kwargs, need_list_semantics=True)  # looked up, then ignored (vq.py:126-137)
+        wav = audio_input.contiguous()
+        L = self.cfg.frames_for(T)
+        feats = torch.empty(B, self.cfg.dimension, L, dtype=torch.float32, device=wav.device)
+        codes = torch.empty(1, B, L, dtype=torch.int64, device=wav.device)
+        with torch.cuda.device(wav.device):
+            _native.check(_native.lib().wt_encode(h.ptr, wav.data_ptr(), B, T, feats.data_ptr(), codes.data_ptr(),
+                                                  self._stream()))
+        return feats, codes
+
+    @torch.inference_mode()
+    def encode(self, audio_input: torch.Tensor, **kwargs: Any) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Eval-mode ``feature_extractor.forward`` (reference decoder/pretrained.py:179-182). With one
+        codebook it quantises exactly like ``infer`` (vq.py:84-113 picks n_q <= num_quantizers)."""
+        if self.cfg.num_quantizers != 1:
+            raise NotImplementedError("encode() with several codebooks is the training-time quantiser path")
+        return self.encode_infer(audio_input, **kwargs)
+
+    @torch.inference_mode()
+    def _encoder_forward(self, wav: torch.Tensor) -> torch.Tensor:
+        h = self.native()
+        B, T = self._check_audio(wav)
+        wav = wav.contiguous()
+        z = torch.empty(B, self.cfg.dimension, self.cfg.frames_for(T), dtype=torch.float32, device=wav.device)
+        with torch.cuda.device(wav.device):
+            _native.check(_native.lib().wt_encoder_forward(h.ptr, wav.data_ptr(), B, T, z.data_ptr(), self._stream()))
+        return z
+
+    @torch.inference_mode()
+    def codes_to_features(self, codes: torch.Tensor) -> torch.Tensor:
+        """codes [K, L] or [K, B, L] -> features [B, 512, L] (reference decoder/pretrained.py:209-239)."""
+        h = self.native()
+        if codes.dim() == 2:
+            codes = codes.unsqueeze(1)
+        if codes.dim() != 3:
+            raise RuntimeError(f"codes must be [K, L] or [K, B, L], got {tuple(codes.shape)}")
+        if codes.dtype.is_floating_point or codes.dtype == torch.bool:
+            raise RuntimeError("Expected tensor for argument #1 'indices' to have one of the following scalar "
+                               f"types: Long, Int; but got {codes.dtype} instead")
+        self._check_input(codes, "codes")
+        K, B, L = codes.shape
+        if K > self.cfg.num_quantizers:
+            raise IndexError("index out of range in self")
+        c64 = codes.to(torch.int64).contiguous()
+        feats = torch.empty(B, self.cfg.dimension, L, dtype=torch.float32, device=codes.device)
+        with torch.cuda.device(codes.device):
+            _native.check(_native.lib().wt_codes_to_features(h.ptr, c64.data_ptr(), K, B, L, feats.data_ptr(),
+                                                             self._stream()))
+        return feats
+
+    @torch.inference_mode()
+    def decode(self, features_input: torch.Tensor, **kwargs: Any) -> torch.Tensor:
+        """features [B, 512, L] -> audio [B, L*hop] (reference decoder/pretrained.py:192-207)."""
+        h = self.native()
+        bw = self._bandwidth_index(kwargs, need_list_semantics=False)
+        if features_input.dim() != 3 or features_input.shape[1] != self.cfg.input_channels:
+            raise RuntimeError(f"expected features [B, {self.cfg.input_channels}, L], got {tuple(features_input.shape)}")
+        if features_input.dtype != torch.float32:
+            raise RuntimeError(f"Input type ({features_input.dtype}) and weight type (torch.float32) should be the same")
+        self._check_input(features_input, "features_input")
+        feats = features_input.contiguous()
+        B, _, L = feats.shape
+        audio = torch.empty(B, L * self.cfg.hop_length, dtype=torch.float32, device=feats.device)
+        with torch.cuda.device(feats.device):
+            _native.check(_native.lib().wt_decode(h.ptr, feats.data_ptr(), B, L, bw, audio.data_ptr(), self._stream()))
+        return audio
+
+    @torch.inference_mode()
+    def forward(self, audio_input: torch.Tensor, **kwargs: Any) -> torch.Tensor:
+        """Copy-synthesis audio -> audio (reference decoder/pretrained.py:159-175)."""
+        features, _ = self.encode(audio_input, **kwargs)
+        return self.decode(features, **kwargs)
+
+    # ------------------------------------------------------------------ beyond the reference API
+    @torch.inference_mode()
+    def vq(self, frames: torch.Tensor, return_quantized: bool = True):
+        """EuclideanCodebook.quantize/dequantize on row-major frames [N, 512]
+        (reference encoder/quantization/core_vq.py:175-190) — BASELINE.json's VQ-only sweep."""
+        h = self.native()
+        if frames.dim() != 2 or frames.shape[1] != self.cfg.dimension or frames.dtype != torch.float32:
+            raise ValueError(f"expected float32 frames [N, {self.cfg.dimension}]")
+        self._check_input(frames, "frames")
+        x = frames.contiguous()
+        N = x.shape[0]
+        codes = torch.empty(N, dtype=torch.int64, device=x.device)
+        quant = torch.empty_like(x) if return_quantized else None
+        with torch.cuda.device(x.device):
+            _native.check(_native.lib().wt_vq(h.ptr, x.data_ptr(), N, codes.data_ptr(),
+                                              quant.data_ptr() if quant is not None else None, self._stream()))
+        return codes, quant
+
+    def encode_decode_host(self, wav_host: torch.Tensor, bandwidth_id: int = 0):
+        """Whole hot path on HOST tensors (pinned recommended): H2D, encode, decode, D2H, sync."""
+        h = self.native()
+        if wav_host.device.type != "cpu" or wav_host.dtype != torch.float32 or wav_host.dim() != 2:
+            raise ValueError("expected a float32 CPU tensor [B, T]")
+        wav_host = wav_host.contiguous()
+        B, T = wav_host.shape
+        L = self.cfg.frames_for(T)
+        pin = wav_host.is_pinned()
+        codes = torch.empty(1, B, L, dtype=torch.int64, pin_memory=pin)
+        audio = torch.empty(B, L * self.cfg.hop_length, dtype=torch.float32, pin_memory=pin)
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().wt_encode_decode_host(h.ptr, wav_host.data_ptr(), B, T, int(bandwidth_id),
+                                                              codes.data_ptr(), audio.data_ptr(), self._stream()))
+        return codes, audio
+
+    def reserve(self, B: int, T: int) -> None:
+        _native.check(_native.lib().wt_reserve(self.native().ptr, int(B), int(T)))
+
+    def launch_count(self) -> int:
+        return int(_native.lib().wt_launch_count(self.native().ptr))
