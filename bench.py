@@ -1,0 +1,329 @@
+"""Benchmark of the WavTokenizer hot path (encode_infer -> VQ -> codes_to_features -> decode).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--plan P]
+
+One "step" = one pass of the hot path over one batch of synthetic 24 kHz clips. The workload is
+BASELINE.json configs[1]: WavTokenizer-small-320 (frame75), 256 x 3 s clips per GPU (weak scaling:
+each rank owns its own 256 clips; the only collective is the all-gather of codes). Prints ONE JSON line.
+
+  value        audio-seconds per second, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e          same metric through the host-buffer C-ABI entry (pinned host wav in, codes+audio out)
+  roofline     dominant contraction category, timed live with CUDA events on its stream
+  cpu_baseline the CPU oracle port (oracle/) on a bounded sample of the same workload, host cores
+
+`--impl reference` times the reference algorithm's CPU port (oracle/, torch CPU ops, all host threads)
+on a bounded sample of the same workload: /root/reference is pure Python and does not exist on the GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from wavtokenizer_b200 import spec  # noqa: E402
+
+CONFIG = "wavtokenizer_smalldata_frame75_3s_nq1_code4096_dim512_kmeans200_attn.yaml"
+WORKLOAD = "WavTokenizer-small-320-24k-4096 encode_infer+codes_to_features+decode, 256 x 3 s clips per GPU"
+CLIPS_PER_GPU = 256
+T = 72000
+SR = 24000
+METRIC = "encode+decode audio-sec/sec (24 kHz)"
+UNIT = "audio-s/s"
+CPU_SAMPLE_CLIPS = 4
+# algorithmic FLOPs per frame of the ConvNeXt pointwise GEMMs: 12 x 2 x (2*768*2304)
+CATS = ["enc_conv", "lstm", "vq", "dec_conv", "pwconv", "head_idft", "attention", "memory_bound"]
+
+
+def cfg_path() -> str:
+    return os.path.join(ROOT, "wavtokenizer_b200", "configs", CONFIG)
+
+
+def algorithmic_flops(cfg, L: int) -> dict:
+    """Per 3 s clip, per category (2*MACs; SURVEY.md Appendix A formulas)."""
+    D, H = cfg.dim, cfg.intermediate_dim
+    enc = 0.0
+    Tc, C = T, cfg.n_filters
+    enc += 2.0 * Tc * C * 7
+    for s in cfg.strides:
+        enc += 2.0 * Tc * (3 * C * (C // 2) + (C // 2) * C + C * C)
+        Tn = -(-Tc // s)
+        enc += 2.0 * Tn * (2 * s * C) * (2 * C)
+        Tc, C = Tn, 2 * C
+    enc += 2.0 * L * 7 * C * cfg.dimension
+    lstm = cfg.lstm_layers * L * 16.0 * C * C
+    vq = 2.0 * L * cfg.vq_bins * cfg.dimension
+    dec_conv = 2.0 * L * (7 * cfg.dimension * D + 8 * 3 * D * D + 4 * D * D)
+    pw = cfg.num_layers * 2.0 * L * 2 * D * H
+    head = 2.0 * L * D * (cfg.n_fft + 2)
+    attn = 4.0 * L * L * D
+    return {"enc_conv": enc, "lstm": lstm, "vq": vq, "dec_conv": dec_conv, "pwconv": pw, "head_idft": head,
+            "attention": attn, "memory_bound": 0.0}
+
+
+def make_state(cfg, seed: int, encode_frames):
+    """Random-init weights + a codebook of sampled encoder frames."""
+    sd = spec.synthetic_state_dict(cfg, seed)
+    spec.install_codebook(sd, torch.zeros(cfg.vq_bins, cfg.dimension))  # placeholder so the encoder can run
+    cal = spec.synthetic_audio(4, T, seed=7)
+    z = encode_frames(sd, cal)  # [4, 512, L]
+    frames = z.permute(0, 2, 1).reshape(-1, cfg.dimension).float().cpu()
+    g = torch.Generator().manual_seed(5)
+    base = frames[torch.randperm(frames.shape[0], generator=g)[:512]].to(torch.bfloat16)
+    spec.install_codebook(sd, spec.expand_codebook(base, cfg.vq_bins, seed=5))
+    return sd
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) == 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self) -> dict:
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def oracle_step(sd, cfg, wav, bw):
+    from oracle import wavtok_oracle as O  # CPU baseline leg only
+    with torch.inference_mode():
+        feats, codes = O.encode_infer(sd, cfg, wav, library_lstm=True)
+        audio = O.decode(sd, cfg, O.codes_to_features(sd, cfg, codes), bw)
+    return codes, audio
+
+
+def time_cpu(sd, cfg, clips: int, steps: int, warmup: int) -> dict:
+    torch.set_num_threads(os.cpu_count() or 1)
+    wav = spec.synthetic_audio(clips, T, seed=100)
+    bw = torch.tensor([0])
+    for _ in range(warmup):
+        oracle_step(sd, cfg, wav, bw)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        oracle_step(sd, cfg, wav, bw)
+        ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    return {"value": clips * T / SR / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{clips} x 3 s clips per step of the same workload, {steps} steps after {warmup} warm-up, "
+                      f"oracle/wavtok_oracle.py (torch CPU fp32 ops, nn.LSTM), {sec * 1e3:.0f} ms/step",
+            "ms_per_step": sec * 1e3}
+
+
+def run_reference(args, rank: int) -> None:
+    if rank != 0:
+        return
+    from oracle import wavtok_oracle as O
+    cfg = spec.load_config(cfg_path())
+    torch.set_num_threads(os.cpu_count() or 1)
+
+    def enc(sd, cal):
+        with torch.inference_mode():
+            return O.seanet_encoder(sd, cfg, cal.unsqueeze(1), library_lstm=True)
+    sd = make_state(cfg, 1, enc)
+    r = time_cpu(sd, cfg, CPU_SAMPLE_CLIPS, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample_clips_per_step": CPU_SAMPLE_CLIPS, "device": "host CPU"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_native(args, rank: int, local_rank: int, world: int) -> None:
+    import torch.distributed as dist
+    from wavtokenizer_b200 import WavTokenizer, _native
+    from wavtokenizer_b200.shard import gather_codes
+
+    assert torch.cuda.is_available(), "bench.py (native arm) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = spec.load_config(cfg_path())
+    L = cfg.frames_for(T)
+
+    model = WavTokenizer(cfg)
+
+    def enc(sd, cal):
+        model.load_state_dict(sd)
+        m = model.to(dev)
+        z = m._encoder_forward(cal.to(dev))
+        torch.cuda.synchronize()
+        return z
+    sd = make_state(cfg, 1, enc)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    if args.plan:
+        model.set_plan(args.plan)
+    B = CLIPS_PER_GPU
+    model.reserve(B, T)
+    lib, hptr = _native.lib(), model.native().ptr
+
+    wav_host = spec.synthetic_audio(B, T, seed=1000 + rank).pin_memory()
+    wav = wav_host.to(dev)
+    bw = torch.tensor([0], device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        feats, codes = model.encode_infer(wav, bandwidth_id=bw)
+        audio = model.decode(model.codes_to_features(codes), bandwidth_id=bw)
+        allc = gather_codes(codes, B * world) if world > 1 else codes
+        return allc, audio
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = lib.wt_launch_count(hptr)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        torch.cuda.synchronize()
+        for a, b in evs:
+            flush.zero_()  # evict L2 between timed iterations (outside the event pair)
+            a.record()
+            step()
+            b.record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = (lib.wt_launch_count(hptr) - launches0) // args.steps
+    ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    audio_s = B * world * T / SR
+    value = audio_s / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI entry (pinned host in / out) ----
+    for _ in range(2):
+        model.encode_decode_host(wav_host, 0)
+    e2e_t = []
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        codes_h, audio_h = model.encode_decode_host(wav_host, 0)
+        e2e_t.append(time.perf_counter() - t0)
+    e2e_ms = 1e3 * sum(e2e_t) / len(e2e_t)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {"value": audio_s / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * T * 4,
+           "d2h_bytes_per_step": B * L * 8 + B * L * cfg.hop_length * 4, "ms_per_step": e2e_ms,
+           "api": "wt_encode_decode_host (WavTokenizer.encode_decode_host), pinned host buffers"}
+
+    # ---- per-category breakdown, timed live with CUDA events on the launching stream ----
+    import ctypes
+    _native.check(lib.wt_timing_enable(hptr, 1))
+    step()
+    torch.cuda.synchronize()
+    flops = algorithmic_flops(cfg, L)
+    breakdown = {}
+    for i, name in enumerate(CATS):
+        t_ms, n = ctypes.c_double(), ctypes.c_int64()
+        _native.check(lib.wt_timing_read(hptr, i, ctypes.byref(t_ms), ctypes.byref(n)))
+        breakdown[name] = {"ms": round(t_ms.value, 3), "launches": n.value,
+                           "algorithmic_tflops": round(flops[name] * B / 1e12, 4),
+                           "tflops_per_s": round(flops[name] * B / max(t_ms.value, 1e-9) / 1e9, 2)}
+    _native.check(lib.wt_timing_enable(hptr, 0))
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md sustained)"
+    dom = max((k for k in CATS if flops[k] > 0), key=lambda k: breakdown[k]["ms"])
+    d = breakdown[dom]
+    achieved = flops[dom] * B / (d["ms"] * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 2), "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": round(achieved / peak_tf, 4), "traffic": None, "peak_source": peak_src,
+                "launches_per_step": d["launches"], "avg_launch_ms": round(d["ms"] / max(d["launches"], 1), 4),
+                "note": "algorithmic FLOPs of the category (split-precision passes not counted) / summed CUDA-event "
+                        "time of its launches in one step"}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cpu_r = time_cpu(sd, cfg, CPU_SAMPLE_CLIPS, 2, 1)
+            cpu = {k: cpu_r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "clips_per_gpu": B, "samples_per_clip": T, "frames_per_clip": L,
+                           "plan": args.plan, "l2": "256 MiB flush between timed iterations; activations per step "
+                           "(> 10 GB) exceed the 126 MB L2", "sharding": f"by clip, {world} rank(s), all-gather of codes"},
+                "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "clocks": clocks.summary(), "breakdown": breakdown,
+                "algorithmic_gflop_per_audio_s": round(sum(flops.values()) / 3 / 1e9, 3)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--plan", type=int, default=int(os.environ.get("WT_PLAN", "0")))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_native(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

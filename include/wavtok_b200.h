@@ -118,6 +118,14 @@ int wt_tap_clear(wt_handle* h);
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t wt_launch_count(const wt_handle* h);
 
+/* Per-category kernel timing for roofline reports: when enabled, every kernel launch is bracketed
+ * by CUDA events on its own stream. Categories: 0 encoder convs, 1 LSTM, 2 VQ, 3 decoder convs
+ * (embed / ResnetBlock / attention 1x1), 4 ConvNeXt pointwise GEMMs, 5 head + inverse-DFT GEMMs,
+ * 6 attention core, 7 memory-bound kernels (norms, depthwise conv, transposes, gathers, overlap-add).
+ * wt_timing_enable(h, on) clears the record; wt_timing_read synchronises and sums one category. */
+int wt_timing_enable(wt_handle* h, int32_t on);
+int wt_timing_read(wt_handle* h, int32_t category, double* total_ms, int64_t* n_launches);
+
 /* Compute plan: 0 = fp32 CUDA-core contractions everywhere (bit-conservative);
  * 1 = tcgen05 tensor-core contractions with split-fp16 operands where validated. */
 int wt_set_plan(wt_handle* h, int32_t plan);

@@ -113,7 +113,22 @@ def slstm(sd: Dict[str, Tensor], prefix: str, x: Tensor, layers: int = 2) -> Ten
     return seq.permute(1, 2, 0) + x
 
 
-def seanet_encoder(sd: Dict[str, Tensor], cfg, audio: Tensor) -> Tensor:
+def slstm_library(sd: Dict[str, Tensor], prefix: str, x: Tensor, layers: int = 2) -> Tensor:
+    """Same SLSTM through ``torch.nn.LSTM`` itself — the library op the reference calls
+    (encoder/modules/lstm.py:20) — used when the oracle is timed as the CPU baseline so that the
+    baseline is not slowed down by the explicit Python time loop of ``slstm``."""
+    C = x.shape[1]
+    lstm = torch.nn.LSTM(C, C, layers)
+    with torch.no_grad():
+        for layer in range(layers):
+            for nm in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+                getattr(lstm, f"{nm}_l{layer}").copy_(sd[f"{prefix}lstm.{nm}_l{layer}"])
+    lstm = lstm.to(x.dtype)
+    y, _ = lstm(x.permute(2, 0, 1))
+    return y.permute(1, 2, 0) + x
+
+
+def seanet_encoder(sd: Dict[str, Tensor], cfg, audio: Tensor, library_lstm: bool = False) -> Tensor:
     """SEANetEncoder.forward (encoder/modules/seanet.py:105-144) on audio [B, 1, T];
     returns z [B, 512, L]."""
     x = sconv1d(sd, ENC + "0.", audio)
@@ -122,7 +137,7 @@ def seanet_encoder(sd: Dict[str, Tensor], cfg, audio: Tensor) -> Tensor:
         x = seanet_resblock(sd, f"{ENC}{idx}.", x)
         x = sconv1d(sd, f"{ENC}{idx + 2}.", F.elu(x), stride=s)
         idx += 3
-    x = slstm(sd, f"{ENC}{idx}.", x, cfg.lstm_layers)
+    x = (slstm_library if library_lstm else slstm)(sd, f"{ENC}{idx}.", x, cfg.lstm_layers)
     x = sconv1d(sd, f"{ENC}{idx + 2}.", F.elu(x))
     return x
 
@@ -174,11 +189,11 @@ def codes_to_features(sd: Dict[str, Tensor], cfg, codes: Tensor) -> Tensor:
 
 
 def encode_infer(sd: Dict[str, Tensor], cfg, audio: Tensor, bandwidth_id=None,
-                 dtype=torch.float32) -> Tuple[Tensor, Tensor]:
+                 dtype=torch.float32, library_lstm: bool = False) -> Tuple[Tensor, Tensor]:
     """EncodecFeatures.infer (decoder/feature_extractors.py:131-142) behind
     WavTokenizer.encode_infer (decoder/pretrained.py:186-189). ``bandwidth_id`` only
     indexes a Python list there and the looked-up value is ignored (vq.py:126-137)."""
-    z = seanet_encoder(sd, cfg, audio.to(dtype).unsqueeze(1))
+    z = seanet_encoder(sd, cfg, audio.to(dtype).unsqueeze(1), library_lstm)
     return vq_infer(sd, z)
 
 

@@ -1,0 +1,252 @@
+"""-m gpu: the CUDA path, called through the C ABI (via the reference-shaped Python API), against
+the committed reference goldens and the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): codes bit-identical except near-ties (fp64 distance gap < 1e-5
+relative to ||x||^2 + ||c||^2), reported; features exact codebook rows; waveform SNR >= 60 dB.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wavtok_oracle as O  # checker only
+from tests import helpers
+from tests.gpu_util import Taps, golden_sub, native_model
+from wavtokenizer_b200 import _native, spec
+
+pytestmark = pytest.mark.gpu
+
+PLANS = [0]
+SKIP_TAPS = {"enc2", "enc5", "enc8", "enc11", "enc14"}  # ELU outputs: fused into the next conv's loader
+SNR_BAR_DB = 60.0          # north_star waveform / feature tolerance
+FP32_STAGE_BAR_DB = 100.0  # plan 0 computes in fp32: every stage must agree far beyond the bar
+
+
+def codebook(sd):
+    return sd[spec.CODEBOOK_PREFIX + "0._codebook.embed"]
+
+
+@pytest.fixture(scope="module", params=helpers.TAGS)
+def setup(request):
+    tag = request.param
+    cfg, sd = helpers.model(tag)
+    return tag, cfg, sd, helpers.golden(tag), native_model(tag)
+
+
+def test_loaded_native_library():
+    """The product path is the CUDA library, not a fallback."""
+    lib = _native.lib()
+    assert b"sm_100a" in lib.wt_version()
+    with open("/proc/self/maps") as f:
+        assert "libwavtok_b200.so" in f.read()
+
+
+def test_every_stage_matches_reference_taps(setup):
+    tag, cfg, sd, g, m = setup
+    names = [str(n) for n in g["tap_names"] if str(n) not in SKIP_TAPS]
+    taps = Taps(m, names)
+    wav = spec.synthetic_audio(2, int(g["e2e_T"]), seed=11).cuda()
+    bw = torch.tensor([2]).cuda()
+    launches0 = m.launch_count()
+    feats, codes = m.encode_infer(wav, bandwidth_id=bw)
+    ref_codes = torch.from_numpy(g["e2e_codes"].astype(np.int64))
+    audio = m.decode(m.codes_to_features(ref_codes.cuda()), bandwidth_id=bw)
+    torch.cuda.synchronize()
+    assert m.launch_count() - launches0 > 100
+    worst = (None, 1e9)
+    for n in names:
+        t = taps.get(n)
+        assert tuple(t.shape) == tuple(int(x) for x in g["tapshape_" + n]), n
+        snr = helpers.snr_db(torch.from_numpy(g["tap_" + n]), golden_sub(t))
+        if snr < worst[1]:
+            worst = (n, snr)
+    assert worst[1] >= FP32_STAGE_BAR_DB, worst
+    z = taps.get("enc15")
+    taps.close()
+    assert helpers.snr_db(torch.from_numpy(g["e2e_z"]), z) >= FP32_STAGE_BAR_DB
+    rep = O.vq_tie_report(z.permute(0, 2, 1).reshape(-1, cfg.dimension), codebook(sd), codes.cpu(), ref_codes)
+    assert rep["hard_mismatches"] == 0, rep
+    assert rep["match_pct"] >= 98.0, rep
+    # features are exactly the codebook rows of the returned codes (reference: torch.equal)
+    assert codes.shape == (1, 2, cfg.frames_for(int(g["e2e_T"]))) and codes.dtype == torch.int64
+    assert torch.equal(feats.cpu(), O.codes_to_features(sd, cfg, codes.cpu()))
+    assert audio.shape == g["e2e_audio"].shape
+    assert helpers.snr_db(torch.from_numpy(g["e2e_audio"]), audio.cpu()) >= max(SNR_BAR_DB, FP32_STAGE_BAR_DB)
+
+
+def test_three_second_clip(setup):
+    """BASELINE.json configs[0] shape: one 3 s clip."""
+    tag, cfg, sd, g, m = setup
+    wav = spec.synthetic_audio(1, 72000, seed=12).cuda()
+    bw = torch.tensor([0]).cuda()
+    feats, codes = m.encode_infer(wav, bandwidth_id=bw)
+    ref_codes = torch.from_numpy(g["c3s_codes"].astype(np.int64))
+    with torch.inference_mode():
+        z = O.seanet_encoder(sd, cfg, wav.cpu().unsqueeze(1), library_lstm=True)
+    rep = O.vq_tie_report(z.permute(0, 2, 1).reshape(-1, cfg.dimension), codebook(sd), codes.cpu(), ref_codes)
+    assert rep["hard_mismatches"] == 0 and rep["match_pct"] >= 98.0, rep
+    audio = m.decode(m.codes_to_features(ref_codes.cuda()), bandwidth_id=bw)
+    assert audio.shape == (1, 72000)
+    assert helpers.snr_db(torch.from_numpy(g["c3s_audio_sub16"]), audio.cpu()[:, ::16]) >= SNR_BAR_DB
+    assert abs(float(audio.abs().max()) - float(g["c3s_audio_absmax"])) < 1e-4
+
+
+def test_edge_lengths(setup):
+    """T < pad (L = 1), short clips, T = k*hop + 1; odd batch; 0-dim bandwidth id."""
+    tag, cfg, sd, g, m = setup
+    for T_e in [int(x) for x in g["edge_lengths"]]:
+        w = spec.synthetic_audio(3, T_e, seed=13 + T_e).cuda()
+        feats, codes = m.encode_infer(w, bandwidth_id=torch.tensor([1]).cuda())
+        ref_codes = torch.from_numpy(g[f"edge{T_e}_codes"].astype(np.int64))
+        assert codes.shape == ref_codes.shape
+        with torch.inference_mode():
+            z = O.seanet_encoder(sd, cfg, w.cpu().unsqueeze(1))
+        rep = O.vq_tie_report(z.permute(0, 2, 1).reshape(-1, cfg.dimension), codebook(sd), codes.cpu(), ref_codes)
+        assert rep["hard_mismatches"] == 0, (T_e, rep)
+        audio = m.decode(m.codes_to_features(ref_codes.cuda()), bandwidth_id=torch.tensor(1).cuda())
+        ga = torch.from_numpy(g[f"edge{T_e}_audio"])
+        assert audio.shape == ga.shape == (3, cfg.frames_for(T_e) * cfg.hop_length)
+        assert helpers.snr_db(ga, audio.cpu()) >= SNR_BAR_DB, T_e
+
+
+def test_bandwidth_ids_and_code_forms(setup):
+    tag, cfg, sd, g, m = setup
+    rc = torch.from_numpy(g["bw_codes"].astype(np.int64)).cuda()
+    rf = m.codes_to_features(rc)
+    assert torch.equal(rf.cpu(), O.codes_to_features(sd, cfg, rc.cpu()))
+    assert torch.equal(m.codes_to_features(rc[:, 0])[0], rf[0])                  # 2-D [K, L] form
+    assert torch.equal(m.codes_to_features(rc.to(torch.int32)), rf)             # int32 codes accepted
+    outs = []
+    for b in range(4):
+        a = m.decode(rf, bandwidth_id=torch.tensor([b]).cuda())
+        outs.append(a)
+        assert helpers.snr_db(torch.from_numpy(g[f"bw{b}_audio_sub4"]), a.cpu()[:, ::4]) >= SNR_BAR_DB
+    assert helpers.snr_db(outs[0], outs[1]) < 40  # the id is observable
+
+
+def test_decode_accepts_arbitrary_features(setup):
+    """decode takes any fp32 features, not only codebook rows (the fork feeds enhanced features)."""
+    tag, cfg, sd, g, m = setup
+    gen = torch.Generator().manual_seed(3)
+    f = torch.randn(3, 512, 37, generator=gen) * 0.05
+    bw = torch.tensor([3])
+    with torch.inference_mode():
+        ref = O.decode(sd, cfg, f, bw)
+    got = m.decode(f.cuda(), bandwidth_id=bw.cuda())
+    assert helpers.snr_db(ref, got.cpu()) >= SNR_BAR_DB
+
+
+def test_batch_independence_and_chunking(setup):
+    """Clips are independent: a batch larger than the encoder chunk (16) equals per-clip runs."""
+    tag, cfg, sd, g, m = setup
+    wav = spec.synthetic_audio(19, 3000, seed=5).cuda()
+    bw = torch.tensor([0]).cuda()
+    f_all, c_all = m.encode_infer(wav, bandwidth_id=bw)
+    a_all = m.decode(f_all, bandwidth_id=bw)
+    for i in (0, 15, 16, 18):
+        f1, c1 = m.encode_infer(wav[i:i + 1], bandwidth_id=bw)
+        assert torch.equal(c1[0, 0], c_all[0, i])
+        a1 = m.decode(f1, bandwidth_id=bw)
+        assert helpers.snr_db(a1, a_all[i:i + 1]) >= 100
+
+
+def test_encoder_module_entry(setup):
+    """model.feature_extractor.encodec.encoder(wav[B,1,T]) (reference extract_features.py:46)."""
+    tag, cfg, sd, g, m = setup
+    wav = spec.synthetic_audio(2, int(g["e2e_T"]), seed=11).cuda()
+    z = m.feature_extractor.encodec.encoder(wav.unsqueeze(1))
+    assert helpers.snr_db(torch.from_numpy(g["e2e_z"]), z.cpu()) >= FP32_STAGE_BAR_DB
+
+
+def test_vq_matches_oracle_on_calibration_like_frames():
+    """EuclideanCodebook.quantize on row-major frames (BASELINE.json config 5 path)."""
+    cfg, sd = helpers.model("small600")
+    m = native_model("small600")
+    cb = codebook(sd)
+    gen = torch.Generator().manual_seed(9)
+    x = cb[torch.randint(0, cb.shape[0], (5000,), generator=gen)] + 2e-3 * torch.randn(5000, 512, generator=gen)
+    codes, quant = m.vq(x.cuda())
+    ref = O.vq_quantize(x, cb)
+    rep = O.vq_tie_report(x, cb, codes.cpu(), ref)
+    assert rep["hard_mismatches"] == 0 and rep["match_pct"] >= 98.0, rep
+    assert torch.equal(quant.cpu(), cb[codes.cpu()])
+    # exact ties resolve to the first index like torch.max (core_vq.py:182)
+    cb2 = cb.clone()
+    xt = cb2[7:8].repeat(300, 1)
+    sd2 = dict(sd)
+    dup = cb2.clone()
+    dup[1000] = dup[7]
+    spec.install_codebook(sd2, dup)
+    m.load_state_dict(sd2)
+    m2 = m.to("cuda:0")
+    codes2, _ = m2.vq(xt.cuda())
+    assert int(codes2.max()) == 7 and int(codes2.min()) == 7
+
+
+def test_error_behaviour_mirrors_reference(setup):
+    tag, cfg, sd, g, m = setup
+    bw = torch.tensor([0]).cuda()
+    with pytest.raises(ValueError):
+        m.encode_infer(torch.zeros(100).cuda(), bandwidth_id=bw)            # 1-D audio (conv.py:196)
+    with pytest.raises(ValueError):
+        m.encode_infer(torch.zeros(1, 1, 100).cuda(), bandwidth_id=bw)      # 3-D audio
+    with pytest.raises(RuntimeError):
+        m.encode_infer(torch.zeros(1, 100, dtype=torch.float64).cuda(), bandwidth_id=bw)
+    with pytest.raises(TypeError):
+        m.encode_infer(torch.zeros(1, 100).cuda(), bandwidth_id=torch.tensor([0, 0, 0]).cuda())
+    with pytest.raises(IndexError):
+        m.encode_infer(torch.zeros(1, 100).cuda(), bandwidth_id=torch.tensor([4]).cuda())
+    with pytest.raises(AssertionError):
+        m.decode(torch.zeros(1, 512, 4).cuda())
+    with pytest.raises(IndexError):
+        m.decode(torch.zeros(1, 512, 4).cuda(), bandwidth_id=torch.tensor([4]).cuda())
+    with pytest.raises(IndexError):
+        m.codes_to_features(torch.full((1, 1, 4), 4096, dtype=torch.int64).cuda())
+    # the C ABI itself reports the same classes
+    lib, h = _native.lib(), m.native().ptr
+    buf = torch.zeros(16).cuda()
+    assert lib.wt_decode(h, buf.data_ptr(), 1, 1, 9, buf.data_ptr(), None) == _native.WT_ERR_INDEX
+    assert lib.wt_encode(h, None, 1, 100, None, None, None) == _native.WT_ERR_VALUE
+    # still healthy afterwards
+    f, c = m.encode_infer(torch.zeros(1, 100).cuda(), bandwidth_id=bw)
+    assert c.shape == (1, 1, cfg.frames_for(100))
+
+
+def test_host_buffer_entry_point(setup):
+    tag, cfg, sd, g, m = setup
+    wav = spec.synthetic_audio(3, 5000, seed=21).pin_memory()
+    codes_h, audio_h = m.encode_decode_host(wav, 2)
+    bw = torch.tensor([2]).cuda()
+    f, c = m.encode_infer(wav.cuda(), bandwidth_id=bw)
+    a = m.decode(f, bandwidth_id=bw)
+    assert torch.equal(codes_h, c.cpu()) and torch.equal(audio_h, a.cpu())
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[1] size (small-320, 256 x 3 s): size-independent properties — features are
+    exact codebook rows of the codes, decoding is deterministic and batch-order equivariant, and a
+    sampled subset of clips matches the oracle."""
+    cfg, sd = helpers.model("small320")
+    m = native_model("small320")
+    B = 256
+    wav = spec.synthetic_audio(B, 72000, seed=77).cuda()
+    bw = torch.tensor([0]).cuda()
+    feats, codes = m.encode_infer(wav, bandwidth_id=bw)
+    assert codes.shape == (1, B, 225) and int(codes.min()) >= 0 and int(codes.max()) < 4096
+    assert torch.equal(m.codes_to_features(codes), feats)
+    audio = m.decode(feats, bandwidth_id=bw)
+    assert audio.shape == (B, 72000) and bool(torch.isfinite(audio).all())
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).cuda()
+    f2, c2 = m.encode_infer(wav[perm], bandwidth_id=bw)
+    assert torch.equal(c2[0], codes[0][perm])
+    a2 = m.decode(f2, bandwidth_id=bw)
+    assert helpers.snr_db(audio[perm], a2) >= 100
+    idx = [0, 100, 255]
+    with torch.inference_mode():
+        z = O.seanet_encoder(sd, cfg, wav[idx].cpu().unsqueeze(1), library_lstm=True)
+        _, c_ref = O.vq_infer(sd, z)
+        a_ref = O.decode(sd, cfg, O.codes_to_features(sd, cfg, codes[:, idx].cpu()), torch.tensor([0]))
+    rep = O.vq_tie_report(z.permute(0, 2, 1).reshape(-1, 512), codebook(sd), codes[:, idx].cpu(), c_ref)
+    assert rep["hard_mismatches"] == 0 and rep["match_pct"] >= 98.0, rep
+    assert helpers.snr_db(a_ref, audio[idx].cpu()) >= SNR_BAR_DB

@@ -53,6 +53,8 @@ SYMBOLS = {
     "wt_tap_clear": (ctypes.c_int, [_P]),
     "wt_launch_count": (_I64, [_P]),
     "wt_set_plan": (ctypes.c_int, [_P, _I32]),
+    "wt_timing_enable": (ctypes.c_int, [_P, _I32]),
+    "wt_timing_read": (ctypes.c_int, [_P, _I32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64)]),
     "wt_last_error": (ctypes.c_char_p, []),
     "wt_version": (ctypes.c_char_p, []),
 }

@@ -19,6 +19,7 @@ namespace {
 thread_local std::string g_last_error;
 
 constexpr int ENC_CHUNK = 16;   // clips per encoder pass (early SEANet tensors are 9.2 MB per clip per tensor)
+constexpr int ENC_GROUP = 1024; // clips per LSTM / final-conv / VQ pass (the recurrent GEMM's M)
 constexpr int DEC_CHUNK = 128;  // clips per decoder pass
 
 struct ConvW {
@@ -81,8 +82,22 @@ struct wt_handle {
 
     std::map<std::string, TapReq> taps;
 
+    // optional per-category kernel timing (CUDA events on the launching stream; bench.py's roofline)
+    bool timing = false;
+    struct Ev { cudaEvent_t a, b; int cat; };
+    std::vector<Ev> evs;
+    std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t get_event() {
+        if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+        cudaEvent_t e;
+        WT_CUDA(cudaEventCreate(&e));
+        return e;
+    }
+
     ~wt_handle() {
         cudaSetDevice(device);
+        for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        for (auto e : ev_pool) cudaEventDestroy(e);
         for (void* p : owned) cudaFree(p);
         if (arena) cudaFree(arena);
         if (stage) cudaFree(stage);
@@ -335,7 +350,7 @@ int frames_for(const wt_config& c, int T) {
     return (int)n;
 }
 
-size_t enc_chunk_floats(const wt_config& c, int Bc, int T) {
+size_t enc_front_floats(const wt_config& c, int Bc, int T) {
     size_t tot = 0;
     size_t Tc = T, C = c.n_filters;
     auto a = [&](size_t n) { tot += align_up(n * sizeof(float), 256) / sizeof(float); };
@@ -348,15 +363,20 @@ size_t enc_chunk_floats(const wt_config& c, int Bc, int T) {
         a((size_t)Bc * Tn * 2 * C);
         Tc = Tn; C *= 2;
     }
-    const size_t M = (size_t)Bc * Tc, D = c.dimension;
-    a(M * 4 * D);                                    // xin
+    return tot;
+}
+
+size_t enc_back_floats(const wt_config& c, int Bg, int L) {
+    size_t tot = 0;
+    auto a = [&](size_t n) { tot += align_up(n * sizeof(float), 256) / sizeof(float); };
+    const size_t M = (size_t)Bg * L, D = c.dimension;
+    a(M * D);                                          // pre-LSTM rows of the group
+    a(M * 4 * D);                                      // xin
     for (int l = 0; l < c.lstm_layers; ++l) a(M * D);  // y_l
-    a((size_t)Bc * 4 * D);                           // gates
-    a((size_t)Bc * D);                               // c
-    a(M * D);                                        // lstm + skip
-    a(M * D);                                        // z
-    a(M * 2);                                        // codes (int64)
-    a(M * D);                                        // transposed z staging
+    a((size_t)Bg * 4 * D);                             // gates
+    a((size_t)Bg * D);                                 // c
+    a(M * D);                                          // lstm + skip
+    a(M * D);                                          // z
     return tot;
 }
 
@@ -374,7 +394,8 @@ size_t dec_chunk_floats(const wt_config& c, int Bc, int L, int Kp) {
 size_t workspace_bytes(const wt_handle* h, int B, int T) {
     const wt_config& c = h->cfg;
     int L = frames_for(c, T);
-    size_t e = enc_chunk_floats(c, std::min(B, ENC_CHUNK), T);
+    size_t e = enc_back_floats(c, std::min(B, ENC_GROUP), L) +
+               std::max(enc_front_floats(c, std::min(B, ENC_CHUNK), T), (size_t)0);
     size_t d = dec_chunk_floats(c, std::min(B, DEC_CHUNK), L, h->Kp);
     return std::max(e, d) * sizeof(float) + 4096;
 }
@@ -382,13 +403,35 @@ size_t workspace_bytes(const wt_handle* h, int B, int T) {
 // ---------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------
+enum Cat : int { CAT_ENC_CONV = 0, CAT_LSTM, CAT_VQ, CAT_DEC_CONV, CAT_PWCONV, CAT_HEAD, CAT_ATTN, CAT_MEM, CAT_COUNT };
+
+// Counts one kernel launch and, when timing is on, brackets it with CUDA events on its stream.
+struct Scope {
+    wt_handle* h;
+    cudaStream_t s;
+    int idx = -1;
+    Scope(wt_handle* h_, int cat, cudaStream_t s_) : h(h_), s(s_) {
+        ++h->launches;
+        if (h->timing) {
+            wt_handle::Ev e{h->get_event(), h->get_event(), cat};
+            cudaEventRecord(e.a, s);
+            h->evs.push_back(e);
+            idx = (int)h->evs.size() - 1;
+        }
+    }
+    ~Scope() {
+        if (idx >= 0) cudaEventRecord(h->evs[idx].b, s);
+    }
+};
+
 struct Runner {
     wt_handle* h;
     cudaStream_t s;
+    int cat = CAT_MEM;
 
     void gemm(const TapGemm& g) {
+        Scope sc(h, cat, s);
         launch_tap_gemm_simt(g, s);
-        ++h->launches;
     }
 
     // Conv1d as tap-GEMM on channels-last rows. `reflect`: SConv1d non-causal padding rule
@@ -438,13 +481,15 @@ struct Runner {
 // encoder: SEANetEncoder.forward on a chunk (reference encoder/modules/seanet.py:143-144)
 // returns z rows [Bc*L, D] (channels-last)
 // ---------------------------------------------------------------------------------------
-float* encoder_chunk(wt_handle* h, const float* wav, int Bc, int T, int b0, cudaStream_t s) {
+// front: conv0 + 4 x (ResBlock, ELU, strided conv) on a chunk of clips; the last strided conv
+// writes its [Bc*L, D] rows into `pre` (a slice of the group-wide pre-LSTM buffer).
+void encoder_front(wt_handle* h, const float* wav, int Bc, int T, int b0, float* pre, cudaStream_t s) {
     const wt_config& c = h->cfg;
     Runner r{h, s};
     int Tc = T, C = c.n_filters;
     float* cur = h->alloc((size_t)Bc * Tc * C);
-    launch_conv0(wav, h->conv0_w, h->conv0_b, cur, Bc, T, C, s);
-    ++h->launches;
+    r.cat = CAT_ENC_CONV;
+    { Scope sc(h, CAT_ENC_CONV, s); launch_conv0(wav, h->conv0_w, h->conv0_b, cur, Bc, T, C, s); }
     h->tap("enc0", cur, Bc, Tc, C, b0, s);
     int idx = 1;
     for (int i = 0; i < 4; ++i) {
@@ -458,45 +503,51 @@ float* encoder_chunk(wt_handle* h, const float* wav, int Bc, int T, int b0, cuda
         h->tap(("enc" + std::to_string(idx)).c_str(), y, Bc, Tc, C, b0, s);
         // ELU + strided SConv1d (seanet.py:121-131)
         int Tn = (Tc + c.strides[i] - 1) / c.strides[i];
-        float* z = h->alloc((size_t)Bc * Tn * 2 * C);
+        float* z = (i == 3) ? pre : h->alloc((size_t)Bc * Tn * 2 * C);
         r.conv(h->down[i], y, z, Bc, Tc, true, PRO_ELU);
         h->tap(("enc" + std::to_string(idx + 2)).c_str(), z, Bc, Tn, 2 * C, b0, s);
         cur = z; Tc = Tn; C *= 2; idx += 3;
     }
-    // SLSTM (reference encoder/modules/lstm.py:31-39)
-    const int L = Tc, D = C;
-    const long long M = (long long)Bc * L;
+}
+
+// back: SLSTM (reference encoder/modules/lstm.py:31-39) + ELU + final k7 conv on a whole group of
+// clips at once, so that each recurrent step is one [Bg, D] x [D, 4D] contraction.
+float* encoder_back(wt_handle* h, const float* pre, int Bg, int L, int b0, cudaStream_t s) {
+    const wt_config& c = h->cfg;
+    Runner r{h, s};
+    const int D = c.dimension;
+    const long long M = (long long)Bg * L;
     float* xin = h->alloc((size_t)M * 4 * D);
     float* ybuf[4];
     for (int l = 0; l < c.lstm_layers; ++l) ybuf[l] = h->alloc((size_t)M * D);
-    float* gates = h->alloc((size_t)Bc * 4 * D);
-    float* cst = h->alloc((size_t)Bc * D);
-    const float* lin = cur;
+    float* gates = h->alloc((size_t)Bg * 4 * D);
+    float* cst = h->alloc((size_t)Bg * D);
+    const float* lin = pre;
+    r.cat = CAT_LSTM;
     for (int l = 0; l < c.lstm_layers; ++l) {
         r.linear(lin, h->lstm[l].w_ih, h->lstm[l].bias, xin, M, 4 * D, D, ACT_NONE, nullptr, nullptr);
-        WT_CUDA(cudaMemsetAsync(cst, 0, (size_t)Bc * D * sizeof(float), s));
+        WT_CUDA(cudaMemsetAsync(cst, 0, (size_t)Bg * D * sizeof(float), s));
         for (int t = 0; t < L; ++t) {
             const float* g_in;
             long long ldg;
             if (t == 0) {
                 g_in = xin; ldg = (long long)L * 4 * D;  // h_{-1} = 0
             } else {
-                r.linear(ybuf[l] + (size_t)(t - 1) * D, h->lstm[l].w_hh, nullptr, gates, Bc, 4 * D, D, ACT_NONE, nullptr,
+                r.linear(ybuf[l] + (size_t)(t - 1) * D, h->lstm[l].w_hh, nullptr, gates, Bg, 4 * D, D, ACT_NONE, nullptr,
                          xin + (size_t)t * 4 * D, L * D, 4 * D, L * 4 * D);
                 g_in = gates; ldg = 4 * D;
             }
-            launch_lstm_pointwise(g_in, cst, ybuf[l] + (size_t)t * D, Bc, D, ldg, (long long)L * D, s);
-            ++h->launches;
+            { Scope sc(h, CAT_LSTM, s); launch_lstm_pointwise(g_in, cst, ybuf[l] + (size_t)t * D, Bg, D, ldg, (long long)L * D, s); }
         }
         lin = ybuf[l];
     }
     float* lo = h->alloc((size_t)M * D);
-    launch_add(lin, cur, lo, M * D, s);
-    ++h->launches;
-    h->tap(("enc" + std::to_string(idx)).c_str(), lo, Bc, L, D, b0, s);
+    { Scope sc(h, CAT_LSTM, s); launch_add(lin, pre, lo, M * D, s); }
+    r.cat = CAT_ENC_CONV;
+    h->tap("enc13", lo, Bg, L, D, b0, s);
     float* z = h->alloc((size_t)M * D);
-    r.conv(h->enc_last, lo, z, Bc, L, true, PRO_ELU);
-    h->tap(("enc" + std::to_string(idx + 2)).c_str(), z, Bc, L, D, b0, s);
+    r.conv(h->enc_last, lo, z, Bg, L, true, PRO_ELU);
+    h->tap("enc15", z, Bg, L, D, b0, s);
     return z;
 }
 
@@ -517,51 +568,53 @@ void decoder_chunk(wt_handle* h, const float* features /*[Bc, Din, L]*/, int Bc,
     float* t2 = h->alloc((size_t)M * D);
     float* bigA = h->alloc((size_t)M * big);
     float* bigB = h->alloc((size_t)M * big);
-    auto K1 = [&]() { ++h->launches; };
     const float eps = 1e-6f;
 
-    launch_transpose_bcl_to_blc(features, xin, Bc, Din, L, s); K1();
+    { Scope sc(h, CAT_MEM, s); launch_transpose_bcl_to_blc(features, xin, Bc, Din, L, s); }
+    r.cat = CAT_DEC_CONV;
     r.conv(h->embed, xin, x, Bc, L, false, PRO_NONE);
     h->tap("dec_embed", x, Bc, L, D, b0, s);
 
     auto resnet = [&](const wt_handle::Resnet& p) {
-        launch_groupnorm(x, p.n1w, p.n1b, t1, Bc, L, D, 32, eps, 1, s); K1();
+        { Scope sc(h, CAT_MEM, s); launch_groupnorm(x, p.n1w, p.n1b, t1, Bc, L, D, 32, eps, 1, s); }
         r.conv(p.c1, t1, t2, Bc, L, false, PRO_NONE);
-        launch_groupnorm(t2, p.n2w, p.n2b, t1, Bc, L, D, 32, eps, 1, s); K1();
+        { Scope sc(h, CAT_MEM, s); launch_groupnorm(t2, p.n2w, p.n2b, t1, Bc, L, D, 32, eps, 1, s); }
         r.conv(p.c2, t1, x, Bc, L, false, PRO_NONE, ACT_NONE, x);
     };
     resnet(h->pos[0]); h->tap("dec_pos0", x, Bc, L, D, b0, s);
     resnet(h->pos[1]); h->tap("dec_pos1", x, Bc, L, D, b0, s);
     {   // AttnBlock (reference decoder/models.py:107-127)
-        launch_groupnorm(x, h->attn.nw, h->attn.nb, t1, Bc, L, D, 32, eps, 0, s); K1();
+        { Scope sc(h, CAT_MEM, s); launch_groupnorm(x, h->attn.nw, h->attn.nb, t1, Bc, L, D, 32, eps, 0, s); }
         r.linear(t1, h->attn.wqkv, h->attn.bqkv, bigA, M, 3 * D, D, ACT_NONE, nullptr, nullptr);
-        launch_attention(bigA, t2, Bc, L, D, s); K1();
+        { Scope sc(h, CAT_ATTN, s); launch_attention(bigA, t2, Bc, L, D, s); }
         r.linear(t2, h->attn.proj.w, h->attn.proj.b, x, M, D, D, ACT_NONE, nullptr, x);
         h->tap("dec_pos2", x, Bc, L, D, b0, s);
     }
     resnet(h->pos[2]); h->tap("dec_pos3", x, Bc, L, D, b0, s);
     resnet(h->pos[3]); h->tap("dec_pos4", x, Bc, L, D, b0, s);
-    launch_groupnorm(x, h->gn5w, h->gn5b, t1, Bc, L, D, 32, eps, 0, s); K1();
+    { Scope sc(h, CAT_MEM, s); launch_groupnorm(x, h->gn5w, h->gn5b, t1, Bc, L, D, 32, eps, 0, s); }
     h->tap("dec_pos5", t1, Bc, L, D, b0, s);
     // AdaLayerNorm keyed by bandwidth_id (reference decoder/modules.py:81-86)
-    launch_layernorm(t1, h->norm_scale + (size_t)bw * D, h->norm_shift + (size_t)bw * D, x, M, D, eps, s); K1();
+    { Scope sc(h, CAT_MEM, s); launch_layernorm(t1, h->norm_scale + (size_t)bw * D, h->norm_shift + (size_t)bw * D, x, M, D, eps, s); }
     h->tap("dec_norm", x, Bc, L, D, b0, s);
     for (int i = 0; i < c.num_layers; ++i) {
         // ConvNeXtBlock (reference decoder/modules.py:43-60)
         const auto& p = h->cnx[i];
-        launch_dwconv_ln(x, p.dw, p.db, p.scale + (size_t)bw * D, p.shift + (size_t)bw * D, t1, Bc, L, D, eps, s); K1();
+        r.cat = CAT_PWCONV;
+        { Scope sc(h, CAT_MEM, s); launch_dwconv_ln(x, p.dw, p.db, p.scale + (size_t)bw * D, p.shift + (size_t)bw * D, t1, Bc, L, D, eps, s); }
         r.linear(t1, p.w1, p.b1, bigA, M, Hd, D, ACT_GELU, nullptr, nullptr);
         r.linear(bigA, p.w2, p.b2, x, M, D, Hd, ACT_NONE, p.gamma, x);
         h->tap(("dec_cnx" + std::to_string(i)).c_str(), x, Bc, L, D, b0, s);
     }
-    launch_layernorm(x, h->fln_w, h->fln_b, t1, M, D, eps, s); K1();
+    { Scope sc(h, CAT_MEM, s); launch_layernorm(x, h->fln_w, h->fln_b, t1, M, D, eps, s); }
     h->tap("dec_final", t1, Bc, L, D, b0, s);
     const int N = c.n_fft, half = N / 2 + 1;
+    r.cat = CAT_HEAD;
     r.linear(t1, h->head_w, h->head_b, bigA, M, N + 2, D, ACT_NONE, nullptr, nullptr);
     h->tap("dec_headlin", bigA, Bc, L, N + 2, b0, s);
-    launch_spectral(bigA, bigB, M, half, h->Kp, s); K1();
+    { Scope sc(h, CAT_MEM, s); launch_spectral(bigA, bigB, M, half, h->Kp, s); }
     r.linear(bigB, h->basis, nullptr, bigA, M, N, h->Kp, ACT_NONE, nullptr, nullptr);
-    launch_overlap_add(bigA, h->wsq, audio, Bc, L, N, c.hop_length, s); K1();
+    { Scope sc(h, CAT_MEM, s); launch_overlap_add(bigA, h->wsq, audio, Bc, L, N, c.hop_length, s); }
 }
 
 void check_err_flag(wt_handle* h, cudaStream_t s, const char* what) {
@@ -579,23 +632,30 @@ void do_encode(wt_handle* h, const float* wav, int B, int T, float* features_out
     if (B < 0 || T <= 0) throw Error(WT_ERR_VALUE, "encode: expected wav [B, T] with T > 0");
     h->ensure_arena(workspace_bytes(h, B, T));
     const int L = frames_for(c, T), D = c.dimension;
-    for (int b0 = 0; b0 < B; b0 += ENC_CHUNK) {
-        const int Bc = std::min(ENC_CHUNK, B - b0);
+    for (int g0 = 0; g0 < B; g0 += ENC_GROUP) {
+        const int Bg = std::min(ENC_GROUP, B - g0);
         h->arena_off = 0;
-        float* z = encoder_chunk(h, wav + (size_t)b0 * T, Bc, T, b0, s);
-        const long long M = (long long)Bc * L;
+        float* pre = h->alloc((size_t)Bg * L * D);
+        const size_t mark = h->arena_off;
+        for (int b0 = 0; b0 < Bg; b0 += ENC_CHUNK) {
+            const int Bc = std::min(ENC_CHUNK, Bg - b0);
+            h->arena_off = mark;
+            encoder_front(h, wav + (size_t)(g0 + b0) * T, Bc, T, g0 + b0, pre + (size_t)b0 * L * D, s);
+        }
+        h->arena_off = mark;
+        float* z = encoder_back(h, pre, Bg, L, g0, s);
+        const long long M = (long long)Bg * L;
         if (z_out) {
-            launch_transpose_blc_to_bcl(z, z_out + (size_t)b0 * D * L, Bc, L, D, s);
-            ++h->launches;
+            Scope sc(h, CAT_MEM, s);
+            launch_transpose_blc_to_bcl(z, z_out + (size_t)g0 * D * L, Bg, L, D, s);
         }
         if (codes_out) {
-            long long* codes = reinterpret_cast<long long*>(codes_out) + (size_t)b0 * L;
-            launch_vq_simt(z, h->codebooks, h->cnorm, M, D, c.vq_bins, codes, s);
-            ++h->launches;
+            long long* codes = reinterpret_cast<long long*>(codes_out) + (size_t)g0 * L;
+            { Scope sc(h, CAT_VQ, s); launch_vq_simt(z, h->codebooks, h->cnorm, M, D, c.vq_bins, codes, s); }
             if (features_out) {
-                launch_codes_to_features(h->codebooks, codes, features_out + (size_t)b0 * D * L, 1, Bc, L, D, c.vq_bins,
+                Scope sc(h, CAT_MEM, s);
+                launch_codes_to_features(h->codebooks, codes, features_out + (size_t)g0 * D * L, 1, Bg, L, D, c.vq_bins,
                                          nullptr, s);
-                ++h->launches;
             }
         }
     }
@@ -722,9 +782,11 @@ int wt_codes_to_features(wt_handle* h, const int64_t* codes, int32_t K, int32_t 
         if (K < 1 || K > h->cfg.num_quantizers)
             throw Error(WT_ERR_INDEX, "codes_to_features: more code books than the checkpoint holds");
         cudaStream_t s = (cudaStream_t)stream;
-        launch_codes_to_features(h->codebooks, reinterpret_cast<const long long*>(codes), features_out, K, B, L,
-                                 h->cfg.dimension, h->cfg.vq_bins, h->err_flag, s);
-        ++h->launches;
+        {
+            Scope sc(h, CAT_MEM, s);
+            launch_codes_to_features(h->codebooks, reinterpret_cast<const long long*>(codes), features_out, K, B, L,
+                                     h->cfg.dimension, h->cfg.vq_bins, h->err_flag, s);
+        }
         check_err_flag(h, s, "codes_to_features");
     });
 }
@@ -742,12 +804,14 @@ int wt_vq(wt_handle* h, const float* x, int64_t N, int64_t* codes_out, float* qu
         if (!x || !codes_out) throw Error(WT_ERR_VALUE, "wt_vq: null buffer");
         cudaStream_t s = (cudaStream_t)stream;
         const wt_config& c = h->cfg;
-        launch_vq_simt(x, h->codebooks, h->cnorm, N, c.dimension, c.vq_bins, reinterpret_cast<long long*>(codes_out), s);
-        ++h->launches;
+        {
+            Scope sc(h, CAT_VQ, s);
+            launch_vq_simt(x, h->codebooks, h->cnorm, N, c.dimension, c.vq_bins, reinterpret_cast<long long*>(codes_out), s);
+        }
         if (quantized_out) {
+            Scope sc(h, CAT_MEM, s);
             launch_gather_rows(h->codebooks, reinterpret_cast<const long long*>(codes_out), quantized_out, N,
                                c.dimension, c.vq_bins, nullptr, s);
-            ++h->launches;
         }
     });
 }
@@ -808,6 +872,33 @@ int wt_tap_clear(wt_handle* h) {
 }
 
 int64_t wt_launch_count(const wt_handle* h) { return h ? h->launches : -1; }
+
+int wt_timing_enable(wt_handle* h, int32_t on) {
+    return guarded(h, [&] {
+        WT_CUDA(cudaDeviceSynchronize());
+        for (auto& e : h->evs) { h->ev_pool.push_back(e.a); h->ev_pool.push_back(e.b); }
+        h->evs.clear();
+        h->timing = on != 0;
+    });
+}
+
+int wt_timing_read(wt_handle* h, int32_t category, double* total_ms, int64_t* n_launches) {
+    return guarded(h, [&] {
+        if (category < 0 || category >= CAT_COUNT) throw Error(WT_ERR_VALUE, "wt_timing_read: unknown category");
+        WT_CUDA(cudaDeviceSynchronize());
+        double ms = 0;
+        int64_t n = 0;
+        for (auto& e : h->evs) {
+            if (e.cat != category) continue;
+            float t = 0;
+            WT_CUDA(cudaEventElapsedTime(&t, e.a, e.b));
+            ms += t;
+            ++n;
+        }
+        if (total_ms) *total_ms = ms;
+        if (n_launches) *n_launches = n;
+    });
+}
 
 int wt_set_plan(wt_handle* h, int32_t plan) {
     return guarded(h, [&] {
