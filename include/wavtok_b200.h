@@ -126,6 +126,15 @@ int64_t wt_launch_count(const wt_handle* h);
 int wt_timing_enable(wt_handle* h, int32_t on);
 int wt_timing_read(wt_handle* h, int32_t category, double* total_ms, int64_t* n_launches);
 
+/* Kernel-level test hook for the tcgen05 tap-GEMM (handle-free; allocates and frees its own scratch,
+ * synchronises). out[m, n] = epi(sum_{j<taps} sum_c A[m + j - (taps-1)/2, c] * W[n, j*Cin + c]) over the
+ * rows of A [rows, Cin] (rows outside are zero); W [N, taps*Cin]; all pointers fp32 DEVICE memory; bias /
+ * gamma [N] and res [rows, N] optional; act 0 none, 1 GELU; passes 1 or 3 (split-fp16 operand passes).
+ * out_f32 [rows, N]; out_split (optional) receives hi + lo of the split-fp16 output planes. */
+int wt_test_tap_gemm(int32_t device, const float* A, int32_t rows, int32_t Cin, int32_t taps, const float* W, int32_t N,
+                     const float* bias, const float* gamma, const float* res, int32_t act, int32_t passes,
+                     float* out_f32, float* out_split, void* stream);
+
 /* Compute plan: 0 = fp32 CUDA-core contractions everywhere (bit-conservative);
  * 1 = tcgen05 tensor-core contractions with split-fp16 operands where validated. */
 int wt_set_plan(wt_handle* h, int32_t plan);

@@ -11,6 +11,7 @@
 
 #include "../../include/wavtok_b200.h"
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace wt {
 
@@ -898,6 +899,55 @@ int wt_timing_read(wt_handle* h, int32_t category, double* total_ms, int64_t* n_
         if (total_ms) *total_ms = ms;
         if (n_launches) *n_launches = n;
     });
+}
+
+int wt_test_tap_gemm(int32_t device, const float* A, int32_t rows, int32_t Cin, int32_t taps, const float* W, int32_t N,
+                     const float* bias, const float* gamma, const float* res, int32_t act, int32_t passes,
+                     float* out_f32, float* out_split, void* stream) {
+    try {
+        WT_CUDA(cudaSetDevice(device));
+        cudaStream_t s = (cudaStream_t)stream;
+        const long long K = (long long)taps * Cin;
+        __half *a_hi, *a_lo, *w_hi, *w_lo, *o_hi = nullptr, *o_lo = nullptr;
+        WT_CUDA(cudaMalloc(&a_hi, (size_t)rows * Cin * 2));
+        WT_CUDA(cudaMalloc(&a_lo, (size_t)rows * Cin * 2));
+        WT_CUDA(cudaMalloc(&w_hi, (size_t)N * K * 2));
+        WT_CUDA(cudaMalloc(&w_lo, (size_t)N * K * 2));
+        const int ldh = (N + 7) / 8 * 8;
+        if (out_split) {
+            WT_CUDA(cudaMalloc(&o_hi, (size_t)rows * ldh * 2));
+            WT_CUDA(cudaMalloc(&o_lo, (size_t)rows * ldh * 2));
+        }
+        launch_split_f16(A, a_hi, a_lo, rows, Cin, Cin, Cin, s);
+        launch_split_f16(W, w_hi, w_lo, N, (int)K, K, K, s);
+        TcGemm g;
+        g.A_hi = a_hi; g.A_lo = a_lo; g.rowsA = rows; g.Cin = Cin; g.lda = Cin; g.taps = taps; g.center = (taps - 1) / 2;
+        g.W_hi = w_hi; g.W_lo = w_lo; g.M = rows; g.N = N; g.K = (int)K; g.passes = passes;
+        g.bias = bias; g.gamma = gamma; g.res = res; g.ldres = N; g.act = act;
+        g.out_f32 = out_f32; g.ldo = N; g.out_hi = o_hi; g.out_lo = o_lo; g.ldh = ldh;
+        launch_tap_gemm_tc(g, s);
+        WT_CUDA(cudaStreamSynchronize(s));
+        if (out_split) {
+            // reconstruct hi + lo on the host side of the test: copy planes back through a tiny kernel-free path
+            std::vector<__half> hh((size_t)rows * ldh), hl((size_t)rows * ldh);
+            WT_CUDA(cudaMemcpy(hh.data(), o_hi, hh.size() * 2, cudaMemcpyDeviceToHost));
+            WT_CUDA(cudaMemcpy(hl.data(), o_lo, hl.size() * 2, cudaMemcpyDeviceToHost));
+            std::vector<float> sum((size_t)rows * N);
+            for (long long r = 0; r < rows; ++r)
+                for (int n = 0; n < N; ++n)
+                    sum[r * N + n] = __half2float(hh[r * ldh + n]) + __half2float(hl[r * ldh + n]);
+            WT_CUDA(cudaMemcpy(out_split, sum.data(), sum.size() * 4, cudaMemcpyHostToDevice));
+        }
+        for (void* p : {(void*)a_hi, (void*)a_lo, (void*)w_hi, (void*)w_lo, (void*)o_hi, (void*)o_lo})
+            if (p) cudaFree(p);
+        return WT_OK;
+    } catch (const Error& e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return WT_ERR_RUNTIME;
+    }
 }
 
 int wt_set_plan(wt_handle* h, int32_t plan) {
