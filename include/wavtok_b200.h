@@ -136,7 +136,8 @@ int wt_test_tap_gemm(int32_t device, const float* A, int32_t rows, int32_t Cin, 
                      float* out_f32, float* out_split, void* stream);
 
 /* Compute plan: 0 = fp32 CUDA-core contractions everywhere (bit-conservative);
- * 1 = tcgen05 tensor-core contractions with split-fp16 operands where validated. */
+ * 1 = tcgen05 tensor-core contractions with split-fp16 operands, 3 passes (hi*hi + hi*lo + lo*hi);
+ * 2 = as 1, but the 24 ConvNeXt pointwise GEMMs run single-pass fp16. */
 int wt_set_plan(wt_handle* h, int32_t plan);
 
 const char* wt_last_error(void);

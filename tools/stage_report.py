@@ -19,8 +19,13 @@ from wavtokenizer_b200 import spec  # noqa: E402
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    plan = int(sys.argv[sys.argv.index("--plan") + 1]) if "--plan" in sys.argv else 0
+    argv = sys.argv[1:]
+    plan = 0
+    if "--plan" in argv:
+        i = argv.index("--plan")
+        plan = int(argv[i + 1])
+        del argv[i:i + 2]
+    args = argv
     tags = args or ["small600"]
     for tag in tags:
         cfg, sd = helpers.model(tag)

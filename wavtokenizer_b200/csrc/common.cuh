@@ -1,5 +1,6 @@
 // Shared declarations for the wavtok_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -70,17 +71,30 @@ void launch_codes_to_features(const float* codebooks, const long long* codes, fl
 void launch_transpose_bcl_to_blc(const float* in, float* out, int B, int C, int L, cudaStream_t s);
 void launch_transpose_blc_to_bcl(const float* in, float* out, int B, int L, int C, cudaStream_t s);
 
-// decoder
-void launch_groupnorm(const float* x, const float* w, const float* b, float* out, int B, int L, int C, int groups,
-                      float eps, int swish, cudaStream_t s);
-void launch_layernorm(const float* x, const float* w, const float* b, float* out, long long M, int C, float eps,
+// Row-wise output of a producer kernel: fp32 rows and/or the split-fp16 planes of the next GEMM's A operand.
+struct RowOut {
+    float* f32 = nullptr;
+    __half* hi = nullptr;
+    __half* lo = nullptr;
+};
+inline RowOut out_f32(float* p) { RowOut o; o.f32 = p; return o; }
+inline RowOut out_split(__half* hi, __half* lo, float* also_f32 = nullptr) {
+    RowOut o; o.hi = hi; o.lo = lo; o.f32 = also_f32; return o;
+}
+
+// decoder (clip b owns rows [b*Lp, b*Lp + L); Lp - L halo rows after each clip are written as zeros)
+void launch_features_to_rows(const float* in /*[B,C,L]*/, RowOut out, int B, int C, int L, int Lp, cudaStream_t s);
+void launch_groupnorm(const float* x, const float* w, const float* b, RowOut out, int B, int L, int Lp, int C,
+                      int groups, float eps, int swish, cudaStream_t s);
+void launch_layernorm(const float* x, const float* w, const float* b, RowOut out, long long M, int C, float eps,
                       cudaStream_t s);
 void launch_dwconv_ln(const float* x, const float* dw /*[C,7]*/, const float* db, const float* scale,
-                      const float* shift, float* out, int B, int L, int C, float eps, cudaStream_t s);
-void launch_attention(const float* qkv /*[B*L, 3C]*/, float* out /*[B*L, C]*/, int B, int L, int C, cudaStream_t s);
-void launch_spectral(const float* z /*[M, 2*half]*/, float* S /*[M, ldS]*/, long long M, int half, int ldS,
+                      const float* shift, RowOut out, int B, int L, int Lp, int C, float eps, cudaStream_t s);
+void launch_attention(const float* qkv /*[B*Lp, 3C]*/, RowOut out /*[B*Lp, C]*/, int B, int L, int Lp, int C,
+                      cudaStream_t s);
+void launch_spectral(const float* z /*[M, ldz]*/, int ldz, RowOut S /*[M, ldS]*/, long long M, int half, int ldS,
                      cudaStream_t s);
-void launch_overlap_add(const float* frames /*[B*L, n_fft]*/, const float* wsq /*[n_fft]*/, float* audio, int B, int L,
-                        int n_fft, int hop, cudaStream_t s);
+void launch_overlap_add(const float* frames /*[B*Lp, n_fft]*/, const float* wsq /*[n_fft]*/, float* audio, int B, int L,
+                        int Lp, int n_fft, int hop, cudaStream_t s);
 
 }  // namespace wt

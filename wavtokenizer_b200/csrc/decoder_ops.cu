@@ -1,6 +1,12 @@
 // Memory-bound decoder kernels: GroupNorm(+swish), LayerNorm / AdaLayerNorm, depthwise conv fused
 // with AdaLayerNorm, single-head attention, spectral (mag/phase -> re/im) and overlap-add.
-// All tensors are channels-last rows [B*L, C] fp32.
+//
+// Activations are channels-last rows. Clip b owns rows [b*Lp, b*Lp + L); with Lp > L the Lp - L rows
+// after each clip are the zero halo of the padded row space the tcgen05 tap-GEMM reads (gemm_tc.cu).
+// Every producer can write fp32 rows or the split-fp16 operand planes (hi = fp16(x), lo = fp16(x - hi))
+// of the next GEMM directly, so no separate conversion pass touches HBM.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace wt {
@@ -26,16 +32,25 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return t;
 }
 
+__device__ __forceinline__ void put(const RowOut& o, long long idx, float v) {
+    if (o.f32) o.f32[idx] = v;
+    if (o.hi) {
+        __half h = __float2half_rn(v);
+        o.hi[idx] = h;
+        if (o.lo) o.lo[idx] = __float2half_rn(v - __half2float(h));
+    }
+}
+
 // Normalize = GroupNorm(32, C, eps=1e-6, affine) (+ x*sigmoid(x)) (reference decoder/models.py:10-16,
 // 58-78, 107-110). One block per (clip, group): statistics span all L frames of the clip, two-pass
-// (mean, then centred variance); the clip slice (L*C*4 B) stays in L2 between passes.
+// (mean, then centred variance); the clip slice stays in L2 between passes. Halo rows are written as zeros.
 __global__ void __launch_bounds__(256) groupnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                        const float* __restrict__ bsh, float* __restrict__ out, int L,
+                                                        const float* __restrict__ bsh, RowOut out, int L, int Lp,
                                                         int C, int cpg, float eps, int swish) {
     __shared__ float red[8];
     const int b = blockIdx.y, g = blockIdx.x;
-    const float* xb = x + (long long)b * L * C + g * cpg;
-    float* ob = out + (long long)b * L * C + g * cpg;
+    const long long base = (long long)b * Lp * C + g * cpg;
+    const float* xb = x + base;
     const int n = L * cpg;
     float s = 0.f;
     for (int i = threadIdx.x; i < n; i += 256) {
@@ -51,11 +66,14 @@ __global__ void __launch_bounds__(256) groupnorm_kernel(const float* __restrict_
     }
     const float var = block_sum<8>(v, red) / (float)n;
     const float rstd = rsqrtf(var + eps);
-    for (int i = threadIdx.x; i < n; i += 256) {
+    for (int i = threadIdx.x; i < Lp * cpg; i += 256) {
         int t = i / cpg, c = i - t * cpg;
-        float y = (xb[(long long)t * C + c] - mean) * rstd * w[g * cpg + c] + bsh[g * cpg + c];
-        if (swish) y = y / (1.f + expf(-y));
-        ob[(long long)t * C + c] = y;
+        float y = 0.f;
+        if (t < L) {
+            y = (xb[(long long)t * C + c] - mean) * rstd * w[g * cpg + c] + bsh[g * cpg + c];
+            if (swish) y = y / (1.f + expf(-y));
+        }
+        put(out, base + (long long)t * C + c, y);
     }
 }
 
@@ -64,8 +82,8 @@ __global__ void __launch_bounds__(256) groupnorm_kernel(const float* __restrict_
 // nn.LayerNorm (decoder/models.py:195, 234).
 template <int PER>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                        const float* __restrict__ b, float* __restrict__ out,
-                                                        long long M, float eps) {
+                                                        const float* __restrict__ b, RowOut out, long long M,
+                                                        float eps) {
     constexpr int C = PER * 32;
     const int lane = threadIdx.x & 31;
     long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -80,11 +98,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 #pragma unroll
     for (int i = 0; i < PER; ++i) { float d = v[i] - mean; q = fmaf(d, d, q); }
     const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
-    float* orow = out + row * C;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         int c = lane + 32 * i;
-        orow[c] = (v[i] - mean) * rstd * w[c] + b[c];
+        put(out, row * C + c, (v[i] - mean) * rstd * w[c] + b[c]);
     }
 }
 
@@ -94,13 +111,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 template <int PER>
 __global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ dw,
                                                         const float* __restrict__ db, const float* __restrict__ scale,
-                                                        const float* __restrict__ shift, float* __restrict__ out,
-                                                        int B, int L, float eps) {
+                                                        const float* __restrict__ shift, RowOut out, int B, int L,
+                                                        int Lp, float eps) {
     constexpr int C = PER * 32;
     const int lane = threadIdx.x & 31;
     long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= (long long)B * L) return;
-    const int b = (int)(row / L), t = (int)(row - (long long)b * L);
+    if (row >= (long long)B * Lp) return;
+    const int b = (int)(row / Lp), t = (int)(row - (long long)b * Lp);
+    if (t >= L) {  // halo row of the padded row space
+#pragma unroll
+        for (int i = 0; i < PER; ++i) put(out, row * C + lane + 32 * i, 0.f);
+        return;
+    }
     float v[PER];
 #pragma unroll
     for (int i = 0; i < PER; ++i) v[i] = db[lane + 32 * i];
@@ -108,7 +130,7 @@ __global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict_
     for (int j = 0; j < 7; ++j) {
         int tj = t - 3 + j;
         if (tj < 0 || tj >= L) continue;
-        const float* xr = x + ((long long)b * L + tj) * C;
+        const float* xr = x + ((long long)b * Lp + tj) * C;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             int c = lane + 32 * i;
@@ -123,27 +145,32 @@ __global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict_
 #pragma unroll
     for (int i = 0; i < PER; ++i) { float d = v[i] - mean; q = fmaf(d, d, q); }
     const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
-    float* orow = out + row * C;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         int c = lane + 32 * i;
-        orow[c] = (v[i] - mean) * rstd * scale[c] + shift[c];
+        put(out, row * C + c, (v[i] - mean) * rstd * scale[c] + shift[c]);
     }
 }
 
 // AttnBlock core (reference decoder/models.py:115-123): softmax(q k^T * C^-0.5) v, one head of width C
 // over the L frames of a clip. One warp per query row, 8 queries per block; scores live in shared memory.
 template <int PER>
-__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int L,
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, RowOut out, int L, int Lp,
                                                         float scale) {
     constexpr int C = PER * 32;
     extern __shared__ float sm[];  // [8][L] scores
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const int qi = blockIdx.x * 8 + warp;
-    const float* base = qkv + (long long)b * L * 3 * C;
+    const float* base = qkv + (long long)b * Lp * 3 * C;
     float* sc = sm + warp * L;
-    if (qi >= L) return;
+    if (qi >= Lp) return;
+    const long long orow = ((long long)b * Lp + qi) * C;
+    if (qi >= L) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) put(out, orow + lane + 32 * i, 0.f);
+        return;
+    }
     float q[PER];
 #pragma unroll
     for (int i = 0; i < PER; ++i) q[i] = base[(long long)qi * 3 * C + lane + 32 * i];
@@ -176,14 +203,13 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
 #pragma unroll
         for (int i = 0; i < PER; ++i) o[i] = fmaf(p, vr[lane + 32 * i], o[i]);
     }
-    float* orow = out + ((long long)b * L + qi) * C;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) orow[lane + 32 * i] = o[i];
+    for (int i = 0; i < PER; ++i) put(out, orow + lane + 32 * i, o[i]);
 }
 
-// ISTFTHead spectral step (reference decoder/heads.py:55-65): z = [log-mag | phase] ->
+// ISTFTHead spectral step (reference decoder/heads.py:55-65): z = [log-mag | phase] (row pitch ldz) ->
 // S = [min(exp(m), 100) cos p | min(exp(m), 100) sin p], zero-filled to ldS columns (the K of the iDFT GEMM).
-__global__ void spectral_kernel(const float* __restrict__ z, float* __restrict__ S, long long M, int half, int ldS) {
+__global__ void spectral_kernel(const float* __restrict__ z, int ldz, RowOut S, long long M, int half, int ldS) {
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= M * ldS) return;
     long long m = gid / ldS;
@@ -191,19 +217,19 @@ __global__ void spectral_kernel(const float* __restrict__ z, float* __restrict__
     float v = 0.f;
     if (c < 2 * half) {
         int i = c < half ? c : c - half;
-        float mag = fminf(expf(z[m * 2 * half + i]), 100.f);
+        float mag = fminf(expf(z[m * ldz + i]), 100.f);
         float sn, cs;
-        sincosf(z[m * 2 * half + half + i], &sn, &cs);
+        sincosf(z[m * ldz + half + i], &sn, &cs);
         v = c < half ? mag * cs : mag * sn;
     }
-    S[gid] = v;
+    put(S, gid, v);
 }
 
 // ISTFT "same" overlap-add + envelope normalisation (reference decoder/spectral_ops.py:58-73).
 // frames already carry the window (folded into the iDFT basis). Each output sample sums the <= n_fft/hop
 // frames that cover it and divides by the matching sum of squared window samples.
 __global__ void overlap_add_kernel(const float* __restrict__ frames, const float* __restrict__ wsq,
-                                   float* __restrict__ audio, int L, int n_fft, int hop, int pad) {
+                                   float* __restrict__ audio, int L, int Lp, int n_fft, int hop, int pad) {
     const int b = blockIdx.y;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int len = L * hop;
@@ -216,23 +242,40 @@ __global__ void overlap_add_kernel(const float* __restrict__ frames, const float
     float acc = 0.f, env = 0.f;
     for (int t = t_lo; t <= t_hi; ++t) {
         int k = p - t * hop;
-        acc += frames[((long long)b * L + t) * n_fft + k];
+        acc += frames[((long long)b * Lp + t) * n_fft + k];
         env += wsq[k];
     }
     audio[(long long)b * len + n] = acc / env;
 }
 
+// features [B, C, L] (API layout) -> rows [B*Lp, C] (fp32 or split planes), halo rows zeroed.
+__global__ void features_to_rows_kernel(const float* __restrict__ in, RowOut out, int C, int L, int Lp) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const float* ib = in + (long long)b * C * L;
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, t = t0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && t < L) ? ib[(long long)c * L + t] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int t = t0 + i, c = c0 + threadIdx.x;
+        if (t < Lp && c < C) put(out, ((long long)b * Lp + t) * C + c, tile[threadIdx.x][i]);
+    }
+}
+
 }  // namespace
 
-void launch_groupnorm(const float* x, const float* w, const float* b, float* out, int B, int L, int C, int groups,
-                      float eps, int swish, cudaStream_t s) {
+void launch_groupnorm(const float* x, const float* w, const float* b, RowOut out, int B, int L, int Lp, int C,
+                      int groups, float eps, int swish, cudaStream_t s) {
     if (B <= 0 || L <= 0) return;
     dim3 grid(groups, B);
-    groupnorm_kernel<<<grid, 256, 0, s>>>(x, w, b, out, L, C, C / groups, eps, swish);
+    groupnorm_kernel<<<grid, 256, 0, s>>>(x, w, b, out, L, Lp, C, C / groups, eps, swish);
     WT_CUDA(cudaGetLastError());
 }
 
-void launch_layernorm(const float* x, const float* w, const float* b, float* out, long long M, int C, float eps,
+void launch_layernorm(const float* x, const float* w, const float* b, RowOut out, long long M, int C, float eps,
                       cudaStream_t s) {
     if (M <= 0) return;
     if (C != 768) throw Error(1, "layernorm: backbone dim must be 768");
@@ -241,15 +284,15 @@ void launch_layernorm(const float* x, const float* w, const float* b, float* out
 }
 
 void launch_dwconv_ln(const float* x, const float* dw, const float* db, const float* scale, const float* shift,
-                      float* out, int B, int L, int C, float eps, cudaStream_t s) {
+                      RowOut out, int B, int L, int Lp, int C, float eps, cudaStream_t s) {
     if (B <= 0 || L <= 0) return;
     if (C != 768) throw Error(1, "dwconv_ln: backbone dim must be 768");
-    long long M = (long long)B * L;
-    dwconv_ln_kernel<24><<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, dw, db, scale, shift, out, B, L, eps);
+    long long M = (long long)B * Lp;
+    dwconv_ln_kernel<24><<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, dw, db, scale, shift, out, B, L, Lp, eps);
     WT_CUDA(cudaGetLastError());
 }
 
-void launch_attention(const float* qkv, float* out, int B, int L, int C, cudaStream_t s) {
+void launch_attention(const float* qkv, RowOut out, int B, int L, int Lp, int C, cudaStream_t s) {
     if (B <= 0 || L <= 0) return;
     if (C != 768) throw Error(1, "attention: backbone dim must be 768");
     size_t smem = (size_t)8 * L * sizeof(float);
@@ -259,23 +302,30 @@ void launch_attention(const float* qkv, float* out, int B, int L, int C, cudaStr
         WT_CUDA(cudaFuncSetAttribute(attention_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = 200 * 1024;
     }
-    dim3 grid((L + 7) / 8, B);
-    attention_kernel<24><<<grid, 256, smem, s>>>(qkv, out, L, 1.0f / sqrtf((float)C));
+    dim3 grid((Lp + 7) / 8, B);
+    attention_kernel<24><<<grid, 256, smem, s>>>(qkv, out, L, Lp, 1.0f / sqrtf((float)C));
     WT_CUDA(cudaGetLastError());
 }
 
-void launch_spectral(const float* z, float* S, long long M, int half, int ldS, cudaStream_t s) {
+void launch_spectral(const float* z, int ldz, RowOut S, long long M, int half, int ldS, cudaStream_t s) {
     if (M <= 0) return;
     long long n = M * ldS;
-    spectral_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(z, S, M, half, ldS);
+    spectral_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(z, ldz, S, M, half, ldS);
     WT_CUDA(cudaGetLastError());
 }
 
-void launch_overlap_add(const float* frames, const float* wsq, float* audio, int B, int L, int n_fft, int hop,
+void launch_overlap_add(const float* frames, const float* wsq, float* audio, int B, int L, int Lp, int n_fft, int hop,
                         cudaStream_t s) {
     if (B <= 0 || L <= 0) return;
     dim3 grid((L * hop + 255) / 256, B);
-    overlap_add_kernel<<<grid, 256, 0, s>>>(frames, wsq, audio, L, n_fft, hop, (n_fft - hop) / 2);
+    overlap_add_kernel<<<grid, 256, 0, s>>>(frames, wsq, audio, L, Lp, n_fft, hop, (n_fft - hop) / 2);
+    WT_CUDA(cudaGetLastError());
+}
+
+void launch_features_to_rows(const float* in, RowOut out, int B, int C, int L, int Lp, cudaStream_t s) {
+    if (B <= 0 || L <= 0) return;
+    dim3 grid((Lp + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    features_to_rows_kernel<<<grid, block, 0, s>>>(in, out, C, L, Lp);
     WT_CUDA(cudaGetLastError());
 }
 

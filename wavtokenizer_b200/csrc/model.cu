@@ -26,7 +26,14 @@ constexpr int DEC_CHUNK = 128;  // clips per decoder pass
 struct ConvW {
     float* w = nullptr;  // [cout, k*cin], K index = tap*cin + c
     float* b = nullptr;  // [cout]
+    __half* w_hi = nullptr;  // split-fp16 planes of w for the tcgen05 path
+    __half* w_lo = nullptr;
     int cout = 0, cin = 0, k = 1, stride = 1;
+};
+
+struct HalfW {  // split-fp16 planes of a plain [N, K] weight
+    __half* hi = nullptr;
+    __half* lo = nullptr;
 };
 
 struct TapReq {
@@ -62,15 +69,17 @@ struct wt_handle {
     // decoder
     ConvW embed;
     struct Resnet { float *n1w, *n1b, *n2w, *n2b; ConvW c1, c2; } pos[4];
-    struct Attn { float *nw, *nb, *wqkv, *bqkv; ConvW proj; } attn{};
+    struct Attn { float *nw, *nb, *wqkv, *bqkv; ConvW proj; HalfW wqkv_h; } attn{};
     float *gn5w = nullptr, *gn5b = nullptr;
     float *norm_scale = nullptr, *norm_shift = nullptr;  // [E, dim]
-    struct Cnx { float *dw, *db, *scale, *shift, *w1, *b1, *w2, *b2, *gamma; };
+    struct Cnx { float *dw, *db, *scale, *shift, *w1, *b1, *w2, *b2, *gamma; HalfW w1_h, w2_h; };
     std::vector<Cnx> cnx;
     float *fln_w = nullptr, *fln_b = nullptr;
     float *head_w = nullptr, *head_b = nullptr;
     float *basis = nullptr, *wsq = nullptr;
-    int Kp = 0;  // padded K of the inverse-DFT GEMM
+    HalfW head_h, basis_h;
+    int Kp = 0;   // padded K of the inverse-DFT GEMM (multiple of 64)
+    int ldz = 0;  // row pitch of the head output (n_fft + 2 rounded up to 4 floats)
 
     // workspace arena (bump allocator, reset per call)
     char* arena = nullptr;
@@ -114,6 +123,22 @@ struct wt_handle {
         return d;
     }
 
+    HalfW upload_split(const std::vector<float>& v) {
+        std::vector<__half> hi(v.size()), lo(v.size());
+        for (size_t i = 0; i < v.size(); ++i) {
+            hi[i] = __float2half_rn(v[i]);
+            lo[i] = __float2half_rn(v[i] - __half2float(hi[i]));
+        }
+        HalfW w;
+        WT_CUDA(cudaMalloc(&w.hi, std::max<size_t>(v.size(), 1) * sizeof(__half)));
+        owned.push_back(w.hi);
+        WT_CUDA(cudaMalloc(&w.lo, std::max<size_t>(v.size(), 1) * sizeof(__half)));
+        owned.push_back(w.lo);
+        WT_CUDA(cudaMemcpy(w.hi, hi.data(), v.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        WT_CUDA(cudaMemcpy(w.lo, lo.data(), v.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        return w;
+    }
+
     void ensure_arena(size_t bytes) {
         if (bytes <= arena_cap) return;
         WT_CUDA(cudaDeviceSynchronize());
@@ -131,14 +156,24 @@ struct wt_handle {
         return p;
     }
 
-    void tap(const char* name, const float* src, int B, int T, int C, int b0, cudaStream_t s) {
+    // src rows: clip b at row b*Tp, T valid rows of C floats with row pitch ld
+    void tap(const char* name, const float* src, int B, int T, int C, int b0, cudaStream_t s, int Tp = 0, int ld = 0) {
         if (taps.empty() || b0 != 0) return;
         auto it = taps.find(name);
         if (it == taps.end()) return;
+        if (!Tp) Tp = T;
+        if (!ld) ld = C;
         it->second.B = B; it->second.T = T; it->second.C = C;
         int64_t n = (int64_t)B * T * C;
-        if (it->second.buf && n <= it->second.cap)
+        if (!it->second.buf || n > it->second.cap) return;
+        if (Tp == T && ld == C) {
             WT_CUDA(cudaMemcpyAsync(it->second.buf, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        } else {
+            for (int b = 0; b < B; ++b)
+                WT_CUDA(cudaMemcpy2DAsync(it->second.buf + (size_t)b * T * C, (size_t)C * sizeof(float),
+                                          src + (size_t)b * Tp * ld, (size_t)ld * sizeof(float),
+                                          (size_t)C * sizeof(float), T, cudaMemcpyDeviceToDevice, s));
+        }
     }
 };
 
@@ -189,7 +224,9 @@ ConvW load_wn_conv(wt_handle* h, const Table& t, const std::string& p, int cout,
     auto w = fold_weight_norm(g, v, cout, cin, k);
     ConvW c;
     c.cout = cout; c.cin = cin; c.k = k; c.stride = stride;
-    c.w = h->upload(relayout_conv(w.data(), cout, cin, k));
+    auto rl = relayout_conv(w.data(), cout, cin, k);
+    c.w = h->upload(rl);
+    if ((k * cin) % 64 == 0 && cin % 64 == 0) { HalfW hw = h->upload_split(rl); c.w_hi = hw.hi; c.w_lo = hw.lo; }
     c.b = h->upload(std::vector<float>(b, b + cout));
     return c;
 }
@@ -199,7 +236,9 @@ ConvW load_conv(wt_handle* h, const Table& t, const std::string& p, int cout, in
     const float* b = t.get(p + "bias", cout);
     ConvW c;
     c.cout = cout; c.cin = cin; c.k = k; c.stride = 1;
-    c.w = h->upload(relayout_conv(w, cout, cin, k));
+    auto rl = relayout_conv(w, cout, cin, k);
+    c.w = h->upload(rl);
+    if (cin % 64 == 0) { HalfW hw = h->upload_split(rl); c.w_hi = hw.hi; c.w_lo = hw.lo; }
     c.b = h->upload(std::vector<float>(b, b + cout));
     return c;
 }
@@ -292,6 +331,7 @@ void prepare(wt_handle* h, const Table& t) {
             ++o;
         }
         h->attn.wqkv = h->upload(w);
+        h->attn.wqkv_h = h->upload_split(w);
         h->attn.bqkv = h->upload(b);
         h->attn.proj = load_conv(h, t, p + "proj_out.", D, D, 1);
     }
@@ -308,6 +348,8 @@ void prepare(wt_handle* h, const Table& t) {
         x.scale = load_vec(h, t, p + "norm.scale.weight", (int64_t)NE * D);
         x.shift = load_vec(h, t, p + "norm.shift.weight", (int64_t)NE * D);
         x.w1 = load_vec(h, t, p + "pwconv1.weight", (int64_t)H * D);
+        { const float* wp = t.get(p + "pwconv1.weight", (int64_t)H * D); x.w1_h = h->upload_split(std::vector<float>(wp, wp + (size_t)H * D)); }
+        { const float* wp = t.get(p + "pwconv2.weight", (int64_t)D * H); x.w2_h = h->upload_split(std::vector<float>(wp, wp + (size_t)D * H)); }
         x.b1 = load_vec(h, t, p + "pwconv1.bias", H);
         x.w2 = load_vec(h, t, p + "pwconv2.weight", (int64_t)D * H);
         x.b2 = load_vec(h, t, p + "pwconv2.bias", D);
@@ -320,9 +362,11 @@ void prepare(wt_handle* h, const Table& t) {
     //      decoder/spectral_ops.py:56-57: irfft(norm="backward") * window) ----
     const int N = c.n_fft, half = N / 2 + 1;
     h->head_w = load_vec(h, t, "head.out.weight", (int64_t)(N + 2) * D);
+    { const float* wp = t.get("head.out.weight", (int64_t)(N + 2) * D); h->head_h = h->upload_split(std::vector<float>(wp, wp + (size_t)(N + 2) * D)); }
+    h->ldz = (int)align_up(N + 2, 4);
     h->head_b = load_vec(h, t, "head.out.bias", N + 2);
     const float* win = t.get("head.istft.window", N);
-    h->Kp = (int)align_up(2 * half, 16);
+    h->Kp = (int)align_up(2 * half, 64);
     std::vector<float> basis((size_t)N * h->Kp, 0.f), wsq(N);
     const double two_pi = 6.283185307179586476925286766559;
     for (int n = 0; n < N; ++n) {
@@ -336,6 +380,7 @@ void prepare(wt_handle* h, const Table& t) {
         }
     }
     h->basis = h->upload(basis);
+    h->basis_h = h->upload_split(basis);
     h->wsq = h->upload(wsq);
     WT_CUDA(cudaMalloc(&h->err_flag, sizeof(int)));
     WT_CUDA(cudaMemset(h->err_flag, 0, sizeof(int)));
@@ -382,13 +427,16 @@ size_t enc_back_floats(const wt_config& c, int Bg, int L) {
 }
 
 size_t dec_chunk_floats(const wt_config& c, int Bc, int L, int Kp) {
+    // covers both plans (the tcgen05 plan adds 3 halo rows per clip and the split-fp16 operand planes)
     size_t tot = 0;
     auto a = [&](size_t n) { tot += align_up(n * sizeof(float), 256) / sizeof(float); };
-    const size_t M = (size_t)Bc * L;
-    size_t big = std::max<size_t>(std::max<size_t>(3 * c.dim, c.intermediate_dim), std::max<size_t>(c.n_fft + 2, Kp));
-    a(M * c.dimension);
-    a(M * c.dim); a(M * c.dim); a(M * c.dim);
-    a(M * big); a(M * big);
+    const size_t R = (size_t)Bc * (L + 3);
+    const size_t ldz = align_up(c.n_fft + 2, 4);
+    size_t big = std::max<size_t>(std::max<size_t>(3 * c.dim, c.intermediate_dim), std::max<size_t>(ldz, Kp));
+    a(R * c.dimension);                          // xin (fp32 or both fp16 planes)
+    a(R * c.dim); a(R * c.dim); a(R * c.dim);    // x, t1/t2, a planes
+    a(R * big); a(R * big);                      // qkv / z / frames ; S or GELU planes
+    a(R * Kp);                                   // S planes (tcgen05 plan)
     return tot;
 }
 
@@ -556,13 +604,13 @@ float* encoder_back(wt_handle* h, const float* pre, int Bg, int L, int b0, cudaS
 // decoder: VocosBackbone + ISTFTHead on a chunk (reference decoder/models.py:223-235,
 // decoder/heads.py:42-67)
 // ---------------------------------------------------------------------------------------
-void decoder_chunk(wt_handle* h, const float* features /*[Bc, Din, L]*/, int Bc, int L, int bw, float* audio, int b0,
-                   cudaStream_t s) {
+void decoder_chunk_simt(wt_handle* h, const float* features /*[Bc, Din, L]*/, int Bc, int L, int bw, float* audio,
+                        int b0, cudaStream_t s) {
     const wt_config& c = h->cfg;
     Runner r{h, s};
     const int D = c.dim, Hd = c.intermediate_dim, Din = c.dimension;
     const long long M = (long long)Bc * L;
-    const size_t big = std::max<size_t>(std::max<size_t>(3 * D, Hd), std::max<size_t>(c.n_fft + 2, h->Kp));
+    const size_t big = std::max<size_t>(std::max<size_t>(3 * D, Hd), std::max<size_t>(h->ldz, h->Kp));
     float* xin = h->alloc((size_t)M * Din);
     float* x = h->alloc((size_t)M * D);
     float* t1 = h->alloc((size_t)M * D);
@@ -577,45 +625,138 @@ void decoder_chunk(wt_handle* h, const float* features /*[Bc, Din, L]*/, int Bc,
     h->tap("dec_embed", x, Bc, L, D, b0, s);
 
     auto resnet = [&](const wt_handle::Resnet& p) {
-        { Scope sc(h, CAT_MEM, s); launch_groupnorm(x, p.n1w, p.n1b, t1, Bc, L, D, 32, eps, 1, s); }
+        { Scope sc(h, CAT_MEM, s); launch_groupnorm(x, p.n1w, p.n1b, out_f32(t1), Bc, L, L, D, 32, eps, 1, s); }
         r.conv(p.c1, t1, t2, Bc, L, false, PRO_NONE);
-        { Scope sc(h, CAT_MEM, s); launch_groupnorm(t2, p.n2w, p.n2b, t1, Bc, L, D, 32, eps, 1, s); }
+        { Scope sc(h, CAT_MEM, s); launch_groupnorm(t2, p.n2w, p.n2b, out_f32(t1), Bc, L, L, D, 32, eps, 1, s); }
         r.conv(p.c2, t1, x, Bc, L, false, PRO_NONE, ACT_NONE, x);
     };
     resnet(h->pos[0]); h->tap("dec_pos0", x, Bc, L, D, b0, s);
     resnet(h->pos[1]); h->tap("dec_pos1", x, Bc, L, D, b0, s);
     {   // AttnBlock (reference decoder/models.py:107-127)
-        { Scope sc(h, CAT_MEM, s); launch_groupnorm(x, h->attn.nw, h->attn.nb, t1, Bc, L, D, 32, eps, 0, s); }
+        { Scope sc(h, CAT_MEM, s); launch_groupnorm(x, h->attn.nw, h->attn.nb, out_f32(t1), Bc, L, L, D, 32, eps, 0, s); }
         r.linear(t1, h->attn.wqkv, h->attn.bqkv, bigA, M, 3 * D, D, ACT_NONE, nullptr, nullptr);
-        { Scope sc(h, CAT_ATTN, s); launch_attention(bigA, t2, Bc, L, D, s); }
+        { Scope sc(h, CAT_ATTN, s); launch_attention(bigA, out_f32(t2), Bc, L, L, D, s); }
         r.linear(t2, h->attn.proj.w, h->attn.proj.b, x, M, D, D, ACT_NONE, nullptr, x);
         h->tap("dec_pos2", x, Bc, L, D, b0, s);
     }
     resnet(h->pos[2]); h->tap("dec_pos3", x, Bc, L, D, b0, s);
     resnet(h->pos[3]); h->tap("dec_pos4", x, Bc, L, D, b0, s);
-    { Scope sc(h, CAT_MEM, s); launch_groupnorm(x, h->gn5w, h->gn5b, t1, Bc, L, D, 32, eps, 0, s); }
+    { Scope sc(h, CAT_MEM, s); launch_groupnorm(x, h->gn5w, h->gn5b, out_f32(t1), Bc, L, L, D, 32, eps, 0, s); }
     h->tap("dec_pos5", t1, Bc, L, D, b0, s);
     // AdaLayerNorm keyed by bandwidth_id (reference decoder/modules.py:81-86)
-    { Scope sc(h, CAT_MEM, s); launch_layernorm(t1, h->norm_scale + (size_t)bw * D, h->norm_shift + (size_t)bw * D, x, M, D, eps, s); }
+    { Scope sc(h, CAT_MEM, s); launch_layernorm(t1, h->norm_scale + (size_t)bw * D, h->norm_shift + (size_t)bw * D, out_f32(x), M, D, eps, s); }
     h->tap("dec_norm", x, Bc, L, D, b0, s);
     for (int i = 0; i < c.num_layers; ++i) {
         // ConvNeXtBlock (reference decoder/modules.py:43-60)
         const auto& p = h->cnx[i];
         r.cat = CAT_PWCONV;
-        { Scope sc(h, CAT_MEM, s); launch_dwconv_ln(x, p.dw, p.db, p.scale + (size_t)bw * D, p.shift + (size_t)bw * D, t1, Bc, L, D, eps, s); }
+        { Scope sc(h, CAT_MEM, s); launch_dwconv_ln(x, p.dw, p.db, p.scale + (size_t)bw * D, p.shift + (size_t)bw * D, out_f32(t1), Bc, L, L, D, eps, s); }
         r.linear(t1, p.w1, p.b1, bigA, M, Hd, D, ACT_GELU, nullptr, nullptr);
         r.linear(bigA, p.w2, p.b2, x, M, D, Hd, ACT_NONE, p.gamma, x);
         h->tap(("dec_cnx" + std::to_string(i)).c_str(), x, Bc, L, D, b0, s);
     }
-    { Scope sc(h, CAT_MEM, s); launch_layernorm(x, h->fln_w, h->fln_b, t1, M, D, eps, s); }
+    { Scope sc(h, CAT_MEM, s); launch_layernorm(x, h->fln_w, h->fln_b, out_f32(t1), M, D, eps, s); }
     h->tap("dec_final", t1, Bc, L, D, b0, s);
     const int N = c.n_fft, half = N / 2 + 1;
     r.cat = CAT_HEAD;
-    r.linear(t1, h->head_w, h->head_b, bigA, M, N + 2, D, ACT_NONE, nullptr, nullptr);
-    h->tap("dec_headlin", bigA, Bc, L, N + 2, b0, s);
-    { Scope sc(h, CAT_MEM, s); launch_spectral(bigA, bigB, M, half, h->Kp, s); }
+    r.linear(t1, h->head_w, h->head_b, bigA, M, N + 2, D, ACT_NONE, nullptr, nullptr, 0, h->ldz);
+    h->tap("dec_headlin", bigA, Bc, L, N + 2, b0, s, L, h->ldz);
+    { Scope sc(h, CAT_MEM, s); launch_spectral(bigA, h->ldz, out_f32(bigB), M, half, h->Kp, s); }
     r.linear(bigB, h->basis, nullptr, bigA, M, N, h->Kp, ACT_NONE, nullptr, nullptr);
-    { Scope sc(h, CAT_MEM, s); launch_overlap_add(bigA, h->wsq, audio, Bc, L, N, c.hop_length, s); }
+    { Scope sc(h, CAT_MEM, s); launch_overlap_add(bigA, h->wsq, audio, Bc, L, L, N, c.hop_length, s); }
+}
+
+// tcgen05 plan: same dataflow in the padded row space (3 zero rows after each clip), every contraction on
+// the tensor cores with split-fp16 operands, every A operand written as hi/lo planes by its producer.
+void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int Bc, int L, int bw, float* audio,
+                      int b0, cudaStream_t s) {
+    const wt_config& c = h->cfg;
+    Runner r{h, s};
+    const int D = c.dim, Hd = c.intermediate_dim, Din = c.dimension;
+    const int Lp = L + 3;
+    const long long R = (long long)Bc * Lp;
+    const int pw_passes = h->plan >= 2 ? 1 : 3;  // plan 2: single-pass fp16 for the 24 ConvNeXt GEMMs
+    const size_t big = std::max<size_t>(std::max<size_t>(3 * D, Hd), std::max<size_t>(h->ldz, h->Kp));
+    auto halves = [&](size_t n) { return reinterpret_cast<__half*>(h->alloc((n + 1) / 2)); };
+    __half* xin_hi = halves((size_t)R * Din);
+    __half* xin_lo = halves((size_t)R * Din);
+    float* x = h->alloc((size_t)R * D);
+    float* t2 = h->alloc((size_t)R * D);
+    __half* a_hi = halves((size_t)R * D);
+    __half* a_lo = halves((size_t)R * D);
+    float* bigA = h->alloc((size_t)R * big);
+    __half* g_hi = halves((size_t)R * Hd);
+    __half* g_lo = halves((size_t)R * Hd);
+    __half* S_hi = halves((size_t)R * h->Kp);
+    __half* S_lo = halves((size_t)R * h->Kp);
+    const float eps = 1e-6f;
+
+    auto gemm = [&](const __half* ahi, const __half* alo, int Cin, int taps, const __half* whi, const __half* wlo, int N,
+                    int passes, const float* bias, int act, const float* gamma, const float* res, float* of32, int ldo,
+                    __half* ohi, __half* olo, int ldh) {
+        TcGemm g;
+        g.A_hi = ahi; g.A_lo = alo; g.rowsA = R; g.Cin = Cin; g.lda = Cin; g.taps = taps; g.center = (taps - 1) / 2;
+        g.W_hi = whi; g.W_lo = wlo; g.M = (int)R; g.N = N; g.K = taps * Cin; g.passes = passes;
+        g.bias = bias; g.act = act; g.gamma = gamma; g.res = res; g.ldres = ldo;
+        g.out_f32 = of32; g.ldo = ldo; g.out_hi = ohi; g.out_lo = olo; g.ldh = ldh;
+        Scope sc(h, r.cat, s);
+        launch_tap_gemm_tc(g, s);
+    };
+
+    { Scope sc(h, CAT_MEM, s); launch_features_to_rows(features, out_split(xin_hi, xin_lo), Bc, Din, L, Lp, s); }
+    r.cat = CAT_DEC_CONV;
+    gemm(xin_hi, xin_lo, Din, 7, h->embed.w_hi, h->embed.w_lo, D, 3, h->embed.b, ACT_NONE, nullptr, nullptr, x, D,
+         nullptr, nullptr, 0);
+    h->tap("dec_embed", x, Bc, L, D, b0, s, Lp);
+
+    auto resnet = [&](const wt_handle::Resnet& p) {
+        { Scope sc(h, CAT_MEM, s); launch_groupnorm(x, p.n1w, p.n1b, out_split(a_hi, a_lo), Bc, L, Lp, D, 32, eps, 1, s); }
+        gemm(a_hi, a_lo, D, 3, p.c1.w_hi, p.c1.w_lo, D, 3, p.c1.b, ACT_NONE, nullptr, nullptr, t2, D, nullptr, nullptr, 0);
+        { Scope sc(h, CAT_MEM, s); launch_groupnorm(t2, p.n2w, p.n2b, out_split(a_hi, a_lo), Bc, L, Lp, D, 32, eps, 1, s); }
+        gemm(a_hi, a_lo, D, 3, p.c2.w_hi, p.c2.w_lo, D, 3, p.c2.b, ACT_NONE, nullptr, x, x, D, nullptr, nullptr, 0);
+    };
+    resnet(h->pos[0]); h->tap("dec_pos0", x, Bc, L, D, b0, s, Lp);
+    resnet(h->pos[1]); h->tap("dec_pos1", x, Bc, L, D, b0, s, Lp);
+    {
+        { Scope sc(h, CAT_MEM, s); launch_groupnorm(x, h->attn.nw, h->attn.nb, out_split(a_hi, a_lo), Bc, L, Lp, D, 32, eps, 0, s); }
+        gemm(a_hi, a_lo, D, 1, h->attn.wqkv_h.hi, h->attn.wqkv_h.lo, 3 * D, 3, h->attn.bqkv, ACT_NONE, nullptr, nullptr,
+             bigA, 3 * D, nullptr, nullptr, 0);
+        { Scope sc(h, CAT_ATTN, s); launch_attention(bigA, out_split(a_hi, a_lo), Bc, L, Lp, D, s); }
+        gemm(a_hi, a_lo, D, 1, h->attn.proj.w_hi, h->attn.proj.w_lo, D, 3, h->attn.proj.b, ACT_NONE, nullptr, x, x, D,
+             nullptr, nullptr, 0);
+        h->tap("dec_pos2", x, Bc, L, D, b0, s, Lp);
+    }
+    resnet(h->pos[2]); h->tap("dec_pos3", x, Bc, L, D, b0, s, Lp);
+    resnet(h->pos[3]); h->tap("dec_pos4", x, Bc, L, D, b0, s, Lp);
+    { Scope sc(h, CAT_MEM, s); launch_groupnorm(x, h->gn5w, h->gn5b, out_f32(t2), Bc, L, Lp, D, 32, eps, 0, s); }
+    h->tap("dec_pos5", t2, Bc, L, D, b0, s, Lp);
+    { Scope sc(h, CAT_MEM, s); launch_layernorm(t2, h->norm_scale + (size_t)bw * D, h->norm_shift + (size_t)bw * D, out_f32(x), R, D, eps, s); }
+    h->tap("dec_norm", x, Bc, L, D, b0, s, Lp);
+    r.cat = CAT_PWCONV;
+    for (int i = 0; i < c.num_layers; ++i) {
+        const auto& p = h->cnx[i];
+        { Scope sc(h, CAT_MEM, s); launch_dwconv_ln(x, p.dw, p.db, p.scale + (size_t)bw * D, p.shift + (size_t)bw * D, out_split(a_hi, a_lo), Bc, L, Lp, D, eps, s); }
+        gemm(a_hi, a_lo, D, 1, p.w1_h.hi, p.w1_h.lo, Hd, pw_passes, p.b1, ACT_GELU, nullptr, nullptr, nullptr, 0,
+             g_hi, pw_passes == 3 ? g_lo : nullptr, Hd);
+        gemm(g_hi, g_lo, Hd, 1, p.w2_h.hi, p.w2_h.lo, D, pw_passes, p.b2, ACT_NONE, p.gamma, x, x, D, nullptr, nullptr, 0);
+        h->tap(("dec_cnx" + std::to_string(i)).c_str(), x, Bc, L, D, b0, s, Lp);
+    }
+    { Scope sc(h, CAT_MEM, s); launch_layernorm(x, h->fln_w, h->fln_b, out_split(a_hi, a_lo, t2), R, D, eps, s); }
+    h->tap("dec_final", t2, Bc, L, D, b0, s, Lp);
+    const int N = c.n_fft, half = N / 2 + 1;
+    r.cat = CAT_HEAD;
+    gemm(a_hi, a_lo, D, 1, h->head_h.hi, h->head_h.lo, N + 2, 3, h->head_b, ACT_NONE, nullptr, nullptr, bigA, h->ldz,
+         nullptr, nullptr, 0);
+    h->tap("dec_headlin", bigA, Bc, L, N + 2, b0, s, Lp, h->ldz);
+    { Scope sc(h, CAT_MEM, s); launch_spectral(bigA, h->ldz, out_split(S_hi, S_lo), R, half, h->Kp, s); }
+    gemm(S_hi, S_lo, h->Kp, 1, h->basis_h.hi, h->basis_h.lo, N, 3, nullptr, ACT_NONE, nullptr, nullptr, bigA, N, nullptr,
+         nullptr, 0);
+    { Scope sc(h, CAT_MEM, s); launch_overlap_add(bigA, h->wsq, audio, Bc, L, Lp, N, c.hop_length, s); }
+}
+
+void decoder_chunk(wt_handle* h, const float* features, int Bc, int L, int bw, float* audio, int b0, cudaStream_t s) {
+    if (h->plan >= 1) decoder_chunk_tc(h, features, Bc, L, bw, audio, b0, s);
+    else decoder_chunk_simt(h, features, Bc, L, bw, audio, b0, s);
 }
 
 void check_err_flag(wt_handle* h, cudaStream_t s, const char* what) {
@@ -952,7 +1093,7 @@ int wt_test_tap_gemm(int32_t device, const float* A, int32_t rows, int32_t Cin, 
 
 int wt_set_plan(wt_handle* h, int32_t plan) {
     return guarded(h, [&] {
-        if (plan != 0) throw Error(WT_ERR_VALUE, "unknown compute plan");
+        if (plan < 0 || plan > 2) throw Error(WT_ERR_VALUE, "unknown compute plan");
         h->plan = plan;
     });
 }
