@@ -57,6 +57,11 @@ void launch_conv0(const float* wav, const float* w /*[C,7]*/, const float* bias,
 void launch_lstm_pointwise(const float* gates /*row b*ldg, 4H wide*/, float* c /*[B,H]*/, float* y /*row b*ldy*/,
                            int B, int H, long long ldg, long long ldy, cudaStream_t s);
 void launch_add(const float* a, const float* b, float* out, long long n, cudaStream_t s);
+// tcgen05 encoder helpers (padded, split-fp16 layouts; see model.cu encoder_front_tc)
+void launch_conv0_planes(const float* wav, const float* w, const float* bias, __half* raw_hi, __half* raw_lo,
+                         __half* elu_hi, __half* elu_lo, int B, int T, int C, cudaStream_t s);
+void launch_lstm_skip_elu_pad(const float* y, const float* x, float* out_f32, __half* elu_hi, __half* elu_lo, int B,
+                              int L, int D, cudaStream_t s);
 
 // vq
 void launch_vq_simt(const float* x, const float* codebook, const float* cnorm, long long N, int D, int bins,

@@ -1,5 +1,7 @@
 // Encoder-side kernels that are not tap-GEMMs: the 1->C first convolution, the LSTM cell
 // pointwise update and layout transposes.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace wt {
@@ -45,6 +47,97 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ wa
         }
         o[c4] = make_float4(r[0], r[1], r[2], r[3]);
     }
+}
+
+__device__ __forceinline__ void split_store8(__half* hi, __half* lo, long long off, const float (&v)[8]) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
+        __half l0 = __float2half_rn(v[2 * i] - __half2float(h0)), l1 = __float2half_rn(v[2 * i + 1] - __half2float(h1));
+        h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// conv0 for the tcgen05 encoder: same arithmetic as conv0_kernel, but one thread per PADDED position of the
+// next layer's input layout (clip pitch T + 2, data at offset 1, reflect halo of 1 on both sides), writing
+// the split-fp16 planes of x (shortcut operand) and of ELU(x) (k3-conv operand).
+template <int C>
+__global__ void __launch_bounds__(256) conv0_planes_kernel(const float* __restrict__ wav, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, __half* __restrict__ raw_hi,
+                                                           __half* __restrict__ raw_lo, __half* __restrict__ elu_hi,
+                                                           __half* __restrict__ elu_lo, int B, int T) {
+    __shared__ float ws[C * 7];
+    __shared__ float bs[C];
+    for (int i = threadIdx.x; i < C * 7; i += blockDim.x) ws[i] = w[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) bs[i] = bias[i];
+    __syncthreads();
+    const int P = T + 2;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * P) return;
+    int b = (int)(gid / P);
+    int p = (int)(gid - (long long)b * P);
+    int t = p - 1;
+    if (t < 0) t = -t;
+    if (t >= T) t = 2 * (T - 1) - t;
+    const float* x = wav + (long long)b * T;
+    float xv[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        int ti = t - 3 + j;
+        if (ti < 0) ti = -ti;
+        if (ti >= T) ti = 2 * (T - 1) - ti;
+        xv[j] = x[ti];
+    }
+#pragma unroll
+    for (int c8 = 0; c8 < C / 8; ++c8) {
+        float r[8], e[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            int c = c8 * 8 + u;
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) acc = fmaf(ws[c * 7 + j], xv[j], acc);
+            r[u] = acc + bs[c];
+            e[u] = r[u] > 0.f ? r[u] : expm1f(r[u]);
+        }
+        split_store8(raw_hi, raw_lo, gid * C + c8 * 8, r);
+        split_store8(elu_hi, elu_lo, gid * C + c8 * 8, e);
+    }
+}
+
+// SLSTM skip connection y + x (reference encoder/modules/lstm.py:38) fused with the ELU in front of the last
+// encoder conv: writes fp32 rows [B*L, D] (tap) and the split planes of ELU(y + x) in the reflect-padded layout
+// of the k7 conv (clip pitch L + 6, data at offset 3).
+__global__ void lstm_skip_elu_pad_kernel(const float* __restrict__ y, const float* __restrict__ x,
+                                         float* __restrict__ out_f32, __half* __restrict__ elu_hi,
+                                         __half* __restrict__ elu_lo, int B, int L, int D) {
+    const int P = L + 6;
+    const int d8 = D / 8;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * P * d8) return;
+    int c8 = (int)(gid % d8);
+    long long row = gid / d8;
+    int b = (int)(row / P), p = (int)(row - (long long)b * P);
+    int t = p - 3;
+    const bool interior = t >= 0 && t < L;
+    if (t < 0) t = -t;
+    if (t >= L) t = 2 * (L - 1) - t;
+    const long long src = ((long long)b * L + t) * D + c8 * 8;
+    float v[8], e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        v[i] = y[src + i] + x[src + i];
+        e[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
+    }
+    if (interior && out_f32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out_f32[src + i] = v[i];
+    }
+    split_store8(elu_hi, elu_lo, row * D + c8 * 8, e);
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -99,6 +192,22 @@ void launch_conv0(const float* wav, const float* w, const float* bias, float* ou
     long long n = (long long)B * T;
     int Trefl = T > 4 ? T : 4;  // reflect needs length > pad (3): zero-extend short signals (conv.py:86-94)
     conv0_kernel<32><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wav, w, bias, out, B, T, Trefl);
+    WT_CUDA(cudaGetLastError());
+}
+
+void launch_conv0_planes(const float* wav, const float* w, const float* bias, __half* raw_hi, __half* raw_lo,
+                         __half* elu_hi, __half* elu_lo, int B, int T, int C, cudaStream_t s) {
+    if (C != 32) throw Error(1, "conv0: n_filters must be 32");
+    if (T < 4) throw Error(4, "conv0_planes: clip too short for the tcgen05 encoder layout");
+    long long n = (long long)B * (T + 2);
+    conv0_planes_kernel<32><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wav, w, bias, raw_hi, raw_lo, elu_hi, elu_lo, B, T);
+    WT_CUDA(cudaGetLastError());
+}
+
+void launch_lstm_skip_elu_pad(const float* y, const float* x, float* out_f32, __half* elu_hi, __half* elu_lo, int B,
+                              int L, int D, cudaStream_t s) {
+    long long n = (long long)B * (L + 6) * (D / 8);
+    lstm_skip_elu_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y, x, out_f32, elu_hi, elu_lo, B, L, D);
     WT_CUDA(cudaGetLastError());
 }
 

@@ -1,18 +1,21 @@
-// tcgen05 tap-GEMM for sm_100a (plan 1): the tensor-core contraction behind every Conv1d / Linear
-// of the decoder (reference decoder/models.py:58-127,177; decoder/modules.py:43-60; decoder/heads.py:53),
-// the LSTM input projection and the final encoder conv.
+// tcgen05 GEMM for sm_100a: the tensor-core contraction behind every Conv1d / Linear of the path
+// (reference encoder/modules/conv.py:195-211, encoder/modules/seanet.py:45-63,105-141,
+// encoder/modules/lstm.py:20, decoder/models.py:58-127,177, decoder/modules.py:43-60, decoder/heads.py:53).
 //
-//   out[m, n] = epi( sum_{j<taps} sum_{c<Cin} A[m + j - center, c] * W[n, j*Cin + c] )
+//   out[m, n] = epi( sum_seg sum_kb A_seg[row(m, kb), cols(kb)] . W[n, kb*64 : kb*64+64] )
 //
 // * Operands are fp16 "split" planes: x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi) (~22 mantissa
 //   bits). PASSES = 3 issues hi*hi + hi*lo + lo*hi per k-step (fp32 accumulate in TMEM), which keeps the
 //   path inside the parity bars of BASELINE.json; PASSES = 1 uses the hi planes only.
-// * A rows live in a "padded row space": clip b owns rows [b*Lp, b*Lp + L) followed by Lp - L zero rows, so
-//   a k-tap Conv1d is k row-shifted TMA loads of the same 2-D tensor (out-of-range rows are zero-filled by
-//   TMA); no im2col and no per-tap index arithmetic in the mainloop.
+// * A operands are TMA tensor maps over channels-last activations. Two addressing modes (gemm_tc.cuh):
+//   "tap" mode (a k-tap stride-1 conv is k row-shifted loads of the same 2-D tensor; rows outside the
+//   tensor are zero-filled by TMA) and "window" mode (rows of the tensor map OVERLAP: row stride =
+//   conv_stride*C, row length = k*C, i.e. the im2col matrix of a strided Conv1d without materialising it).
+//   Up to two segments accumulate into one tile (ResBlock: conv1x1(ELU(h)) + shortcut1x1(x)).
 // * One CTA per SM, persistent over output tiles (128 x BN). Warp 0 = TMA producer, warp 1 = MMA issuer
 //   (single thread, tcgen05.mma cta_group::1 kind::f16) + TMEM allocator, warps 2..5 = epilogue
-//   (tcgen05.ld 32x32b -> bias / GELU / layer-scale / residual -> fp32 and/or split-fp16 stores).
+//   (tcgen05.ld 32x32b -> bias / GELU / layer-scale / residual / ELU / LSTM cell -> fp32 and/or
+//   split-fp16 stores, optionally re-mapped into the reflect-padded layout of the consumer).
 //   Two TMEM accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -97,7 +100,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -109,8 +112,82 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+__device__ __forceinline__ float sigmoid1(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    __half h0 = __float2half_rn(a), h1 = __float2half_rn(b);
+    __half l0 = __float2half_rn(a - __half2float(h0));
+    __half l1 = __float2half_rn(b - __half2float(h1));
+    hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+}
+
+// Store CW consecutive values of one row as split planes (16-byte vector stores).
+template <int CW, bool ELU>
+__device__ __forceinline__ void store_planes(__half* hi_p, __half* lo_p, long long off, const float (&v)[CW]) {
+    uint32_t hi[CW / 2], lo[CW / 2];
+#pragma unroll
+    for (int i = 0; i < CW / 2; ++i) {
+        float a = v[2 * i], b = v[2 * i + 1];
+        if (ELU) { a = elu1(a); b = elu1(b); }
+        split2(a, b, hi[i], lo[i]);
+    }
+    uint4* oh = reinterpret_cast<uint4*>(hi_p + off);
+#pragma unroll
+    for (int i = 0; i < CW / 8; ++i) oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+    if (lo_p) {
+        uint4* ol = reinterpret_cast<uint4*>(lo_p + off);
+#pragma unroll
+        for (int i = 0; i < CW / 8; ++i) ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+    }
+}
+
+template <int CW>
+__device__ __forceinline__ void store_row(const TcGemm& g, long long row, int nb, const float (&v)[CW], bool full) {
+    if (full) {
+        if (g.out_f32) {
+            float* o = g.out_f32 + row * g.ldo + nb;
+#pragma unroll
+            for (int i = 0; i < CW; i += 4)
+                *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+        if (g.out_hi) store_planes<CW, false>(g.out_hi, g.out_lo, row * g.ldh + nb, v);
+        if (g.elu_hi) store_planes<CW, true>(g.elu_hi, g.elu_lo, row * g.ldh2 + nb, v);
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < CW; ++i) {
+            const int n = nb + i;
+            if (n >= g.N) break;
+            float x = 0.f;
+#pragma unroll
+            for (int k = 0; k < CW; ++k) x = (k == i) ? v[k] : x;  // keeps v[] in registers
+            if (g.out_f32) g.out_f32[row * g.ldo + n] = x;
+            if (g.out_hi) {
+                __half h = __float2half_rn(x);
+                g.out_hi[row * g.ldh + n] = h;
+                if (g.out_lo) g.out_lo[row * g.ldh + n] = __float2half_rn(x - __half2float(h));
+            }
+            if (g.elu_hi) {
+                float e = elu1(x);
+                __half h = __float2half_rn(e);
+                g.elu_hi[row * g.ldh2 + n] = h;
+                if (g.elu_lo) g.elu_lo[row * g.ldh2 + n] = __float2half_rn(e - __half2float(h));
+            }
+        }
+    }
+}
 
 template <int BN, int PASSES>
 struct Cfg {
@@ -120,15 +197,20 @@ struct Cfg {
     static constexpr int STAGE = PLANES * (A_PLANE + B_PLANE);
     static constexpr int STAGES = (200 * 1024) / STAGE > 8 ? 8 : (200 * 1024) / STAGE;
     static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages; 256 or 512 (power of two)
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages (power of two >= 32)
+    static constexpr int CW = BN < 32 ? BN : 32;                 // epilogue chunk width
+};
+
+struct Maps {
+    CUtensorMap a[2][2];  // [segment][plane]
+    CUtensorMap w[2];     // [plane]
 };
 
 template <int BN, int PASSES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
-                   const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
-                   const TcGemm g) {
+tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     using C = Cfg<BN, PASSES>;
+    constexpr int CW = C::CW;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + C::STAGES * C::STAGE;
@@ -138,15 +220,14 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_con
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
-    uint32_t* tmem_slot_ptr =
-        reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (g.M + BM - 1) / BM;
     const int n_tiles = (g.N + BN - 1) / BN;
     const int total_tiles = m_tiles * n_tiles;
-    const int kb_per_tap = g.Cin / BK;
-    const int num_kb = g.taps * kb_per_tap;
+    const int nkb0 = g.seg[0].num_kb;
+    const int num_kb = nkb0 + (g.nseg > 1 ? g.seg[1].num_kb : 0);
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -179,16 +260,20 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_con
                 const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
                 const int m0 = mt * BM, n0 = nt * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    const int tap = kb / kb_per_tap;
-                    const int c0 = (kb - tap * kb_per_tap) * BK;
+                    const int si = kb < nkb0 ? 0 : 1;
+                    const int kl = si ? kb - nkb0 : kb;
+                    const int kpt = g.seg[si].kb_per_tap;
+                    const int tap = kl / kpt;
+                    const int c0 = (kl - tap * kpt) * BK;
+                    const int r0 = m0 + g.seg[si].shift0 + tap;
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * C::STAGE;
                     mbar_expect_tx(full_bar(stage), C::STAGE);
-                    tma_load_2d(sa, &mapA_hi, c0, m0 + tap - g.center, full_bar(stage));
-                    if (PASSES == 3) tma_load_2d(sa + C::A_PLANE, &mapA_lo, c0, m0 + tap - g.center, full_bar(stage));
+                    tma_load_2d(sa, &maps.a[si][0], c0, r0, full_bar(stage));
+                    if (PASSES == 3) tma_load_2d(sa + C::A_PLANE, &maps.a[si][1], c0, r0, full_bar(stage));
                     const uint32_t sb = sa + C::PLANES * C::A_PLANE;
-                    tma_load_2d(sb, &mapW_hi, kb * BK, n0, full_bar(stage));
-                    if (PASSES == 3) tma_load_2d(sb + C::B_PLANE, &mapW_lo, kb * BK, n0, full_bar(stage));
+                    tma_load_2d(sb, &maps.w[0], kb * BK, n0, full_bar(stage));
+                    if (PASSES == 3) tma_load_2d(sb + C::B_PLANE, &maps.w[1], kb * BK, n0, full_bar(stage));
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -241,86 +326,108 @@ tap_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_con
             const int n0 = nt * BN;
             mbar_wait(tfull_bar(acc), acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const bool row_ok = m < g.M;
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            bool row_ok = m < g.M;
+            // destination rows (identity, or re-mapped into the consumer's reflect-padded layout)
+            long long dst = m, mir_l = -1, mir_r = -1;
+            if (g.map.Pin) {
+                const int b = m / g.map.Pin, t = m - b * g.map.Pin;
+                row_ok = row_ok && t < g.map.Tvalid;
+                const long long base = (long long)b * g.map.Pout + g.map.off;
+                dst = base + t;
+                if (t >= 1 && t <= g.map.hl) mir_l = base - t;
+                if (t <= g.map.Tvalid - 2 && t >= g.map.Tvalid - 1 - g.map.hr)
+                    mir_r = base + 2 * (g.map.Tvalid - 1) - t;
+            }
+            if (BN == 128 && g.act == TC_ACT_LSTM) {
+                // LSTM cell (reference encoder/modules/lstm.py:20; gates i, f, g, o). Tile columns hold
+                // [i | f | g | o] x 32 hidden units; the thread owns one batch row.
+                const int u0 = nt * 32;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                __syncwarp();  // tcgen05.ld is .sync.aligned: re-converge after the predicated stores below
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-                const int nb = n0 + c * 32;
-                if (!row_ok || nb >= g.N) continue;
-                float v[32];
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t ri[16], rf[16], rg[16], ro[16];
+                    __syncwarp();
+                    tmem_ld(tbase + 0 + hf * 16, ri);
+                    tmem_ld(tbase + 32 + hf * 16, rf);
+                    tmem_ld(tbase + 64 + hf * 16, rg);
+                    tmem_ld(tbase + 96 + hf * 16, ro);
+                    if (!row_ok) continue;
+                    const float* xr = g.res + (long long)m * g.ldres + n0 + hf * 16;
+                    float* cr = g.cell + (long long)m * g.hidden + u0 + hf * 16;
+                    float hv[16];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                const bool full = nb + 32 <= g.N;
-                if (full) {
-                    if (g.bias) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            float4 b = *reinterpret_cast<const float4*>(g.bias + nb + i);
-                            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-                        }
+                    for (int i = 0; i < 16; ++i) {
+                        const float ig = sigmoid1(__uint_as_float(ri[i]) + xr[i]);
+                        const float fg = sigmoid1(__uint_as_float(rf[i]) + xr[32 + i]);
+                        const float gg = tanhf(__uint_as_float(rg[i]) + xr[64 + i]);
+                        const float og = sigmoid1(__uint_as_float(ro[i]) + xr[96 + i]);
+                        const float cn = fg * cr[i] + ig * gg;
+                        cr[i] = cn;
+                        hv[i] = og * tanhf(cn);
                     }
-                    if (g.act == ACT_GELU) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-                    }
-                    if (g.gamma) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            float4 b = *reinterpret_cast<const float4*>(g.gamma + nb + i);
-                            v[i] *= b.x; v[i + 1] *= b.y; v[i + 2] *= b.z; v[i + 3] *= b.w;
-                        }
-                    }
-                    if (g.res) {
-                        const float* rr = g.res + (long long)m * g.ldres + nb;
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            float4 b = *reinterpret_cast<const float4*>(rr + i);
-                            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-                        }
-                    }
+                    const int nb = u0 + hf * 16;
                     if (g.out_f32) {
                         float* o = g.out_f32 + (long long)m * g.ldo + nb;
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4*>(o + i) = make_float4(hv[i], hv[i + 1], hv[i + 2], hv[i + 3]);
                     }
-                    if (g.out_hi) {
-                        uint32_t hi[16], lo[16];
+                    if (g.out_hi) store_planes<16, false>(g.out_hi, g.out_lo, (long long)m * g.ldh + nb, hv);
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BN / CW; ++c) {
+                    uint32_t r[CW];
+                    __syncwarp();  // tcgen05.ld is .sync.aligned: re-converge after the predicated stores below
+                    tmem_ld(tbase + (uint32_t)(c * CW), r);
+                    const int nb = n0 + c * CW;
+                    if (!row_ok || nb >= g.N) continue;
+                    float v[CW];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
-                            __half l0 = __float2half_rn(v[2 * i] - __half2float(h0));
-                            __half l1 = __float2half_rn(v[2 * i + 1] - __half2float(h1));
-                            hi[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                            lo[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                    for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
+                    const bool full = nb + CW <= g.N;
+                    if (full) {
+                        if (g.bias) {
+#pragma unroll
+                            for (int i = 0; i < CW; i += 4) {
+                                float4 b = *reinterpret_cast<const float4*>(g.bias + nb + i);
+                                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                            }
                         }
-                        uint4* oh = reinterpret_cast<uint4*>(g.out_hi + (long long)m * g.ldh + nb);
+                        if (g.act == TC_ACT_GELU) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-                        if (g.out_lo) {
-                            uint4* ol = reinterpret_cast<uint4*>(g.out_lo + (long long)m * g.ldh + nb);
+                            for (int i = 0; i < CW; ++i) v[i] = gelu_erf(v[i]);
+                        }
+                        if (g.gamma) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                            for (int i = 0; i < CW; i += 4) {
+                                float4 b = *reinterpret_cast<const float4*>(g.gamma + nb + i);
+                                v[i] *= b.x; v[i + 1] *= b.y; v[i + 2] *= b.z; v[i + 3] *= b.w;
+                            }
+                        }
+                        if (g.res) {
+                            const float* rr = g.res + (long long)m * g.ldres + nb;
+#pragma unroll
+                            for (int i = 0; i < CW; i += 4) {
+                                float4 b = *reinterpret_cast<const float4*>(rr + i);
+                                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < CW; ++i) {
+                            const int n = nb + i;
+                            if (n < g.N) {
+                                if (g.bias) v[i] += g.bias[n];
+                                if (g.act == TC_ACT_GELU) v[i] = gelu_erf(v[i]);
+                                if (g.gamma) v[i] *= g.gamma[n];
+                                if (g.res) v[i] += g.res[(long long)m * g.ldres + n];
+                            }
                         }
                     }
-                } else {
-                    for (int i = 0; i < 32 && nb + i < g.N; ++i) {
-                        float x = v[i];
-                        const int n = nb + i;
-                        if (g.bias) x += g.bias[n];
-                        if (g.act == ACT_GELU) x = gelu_erf(x);
-                        if (g.gamma) x *= g.gamma[n];
-                        if (g.res) x += g.res[(long long)m * g.ldres + n];
-                        if (g.out_f32) g.out_f32[(long long)m * g.ldo + n] = x;
-                        if (g.out_hi) {
-                            __half h = __float2half_rn(x);
-                            g.out_hi[(long long)m * g.ldh + n] = h;
-                            if (g.out_lo) g.out_lo[(long long)m * g.ldh + n] = __float2half_rn(x - __half2float(h));
-                        }
-                    }
+                    store_row<CW>(g, dst, nb, v, full);
+                    if (mir_l >= 0) store_row<CW>(g, mir_l, nb, v, full);
+                    if (mir_r >= 0) store_row<CW>(g, mir_r, nb, v, full);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -358,17 +465,22 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D fp16 row-major [rows, cols] (row pitch ld elements) -> tensor map with a [box_rows, 64] box, 128 B swizzle.
-CUtensorMap make_map(const __half* base, long long rows, long long cols, long long ld, int box_rows) {
+// 2-D fp16 tensor: `rows` rows of `inner` elements, row r starting r*stride elements after the base
+// (stride < inner: overlapping rows) -> tensor map with a [box_rows, 64] box and 128 B swizzle.
+CUtensorMap make_map(const __half* base, long long rows, long long inner, long long stride, int box_rows) {
     CUtensorMap m;
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__half)};
+    if (rows < 1) rows = 1;
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)stride * sizeof(__half)};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box,
                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) throw Error(4, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    if (r != CUDA_SUCCESS)
+        throw Error(4, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r) + " (rows " +
+                           std::to_string(rows) + ", inner " + std::to_string(inner) + ", stride " +
+                           std::to_string(stride) + ")");
     return m;
 }
 
@@ -391,14 +503,29 @@ void launch_cfg(const TcGemm& g, cudaStream_t s) {
                                      C::SMEM));
         attr = true;
     }
-    CUtensorMap a_hi = make_map(g.A_hi, g.rowsA, g.Cin, g.lda, BM);
-    CUtensorMap a_lo = make_map(PASSES == 3 ? g.A_lo : g.A_hi, g.rowsA, g.Cin, g.lda, BM);
-    CUtensorMap w_hi = make_map(g.W_hi, g.N, g.K, g.K, BN);
-    CUtensorMap w_lo = make_map(PASSES == 3 ? g.W_lo : g.W_hi, g.N, g.K, g.K, BN);
+    Maps maps;
+    for (int si = 0; si < 2; ++si) {
+        const TcSeg& sg = g.seg[si < g.nseg ? si : 0];
+        maps.a[si][0] = make_map(sg.hi, sg.rows, sg.inner, sg.stride, BM);
+        maps.a[si][1] = make_map(PASSES == 3 ? sg.lo : sg.hi, sg.rows, sg.inner, sg.stride, BM);
+    }
+    maps.w[0] = make_map(g.W_hi, g.N, g.K, g.K, BN);
+    maps.w[1] = make_map(PASSES == 3 ? g.W_lo : g.W_hi, g.N, g.K, g.K, BN);
     const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    tap_gemm_tc_kernel<BN, PASSES><<<grid, NUM_THREADS, C::SMEM, s>>>(a_hi, a_lo, w_hi, w_lo, g);
+    tap_gemm_tc_kernel<BN, PASSES><<<grid, NUM_THREADS, C::SMEM, s>>>(maps, g);
     WT_CUDA(cudaGetLastError());
+}
+
+template <int PASSES>
+void launch_bn(const TcGemm& g, cudaStream_t s) {
+    if (g.act == TC_ACT_LSTM) return launch_cfg<128, PASSES>(g, s);
+    if (g.N <= 16) return launch_cfg<16, PASSES>(g, s);
+    if (g.N <= 32) return launch_cfg<32, PASSES>(g, s);
+    if (g.N <= 64) return launch_cfg<64, PASSES>(g, s);
+    if (g.N <= 128) return launch_cfg<128, PASSES>(g, s);
+    const bool wide = g.N % 256 == 0 || g.N > 1024;
+    if (wide) launch_cfg<256, PASSES>(g, s); else launch_cfg<128, PASSES>(g, s);
 }
 
 // fp32 -> split fp16 planes (weights at load time; activations whose producer is not fused yet)
@@ -422,17 +549,22 @@ __global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict
 
 void launch_tap_gemm_tc(const TcGemm& g, cudaStream_t s) {
     if (g.M <= 0 || g.N <= 0) return;
-    if (g.Cin % BK != 0 || g.K != g.taps * g.Cin) throw Error(4, "tap_gemm_tc: Cin must be a multiple of 64");
-    if (g.lda % 8 != 0) throw Error(4, "tap_gemm_tc: lda must be a multiple of 8 (16-byte TMA pitch)");
-    if ((g.out_f32 && g.ldo % 4) || (g.res && g.ldres % 4) || (g.out_hi && g.ldh % 8))
-        throw Error(4, "tap_gemm_tc: output pitches must keep 16-byte alignment");
-    if (g.passes != 1 && g.passes != 3) throw Error(4, "tap_gemm_tc: passes must be 1 or 3");
-    const bool wide = g.N % 256 == 0 || g.N > 1024;
-    if (g.passes == 3) {
-        if (wide) launch_cfg<256, 3>(g, s); else launch_cfg<128, 3>(g, s);
-    } else {
-        if (wide) launch_cfg<256, 1>(g, s); else launch_cfg<128, 1>(g, s);
+    int kbs = 0;
+    for (int si = 0; si < g.nseg; ++si) {
+        const TcSeg& sg = g.seg[si];
+        if (sg.stride % 8 != 0) throw Error(4, "gemm_tc: A row stride must be a multiple of 8 (16-byte TMA pitch)");
+        if (sg.num_kb < 1 || sg.kb_per_tap < 1) throw Error(4, "gemm_tc: empty A segment");
+        if ((reinterpret_cast<uintptr_t>(sg.hi) & 15) || (reinterpret_cast<uintptr_t>(sg.lo) & 15))
+            throw Error(4, "gemm_tc: A planes must be 16-byte aligned");
+        kbs += sg.num_kb;
     }
+    if (g.nseg < 1 || g.nseg > 2 || g.K != kbs * BK) throw Error(4, "gemm_tc: K must equal 64 * total k-blocks");
+    if ((g.out_f32 && g.ldo % 4) || (g.res && g.ldres % 4) || (g.out_hi && g.ldh % 8) || (g.elu_hi && g.ldh2 % 8))
+        throw Error(4, "gemm_tc: output pitches must keep 16-byte alignment");
+    if (g.passes != 1 && g.passes != 3) throw Error(4, "gemm_tc: passes must be 1 or 3");
+    if (g.act == TC_ACT_LSTM && (g.N % 128 || !g.cell || !g.res || g.map.Pin))
+        throw Error(4, "gemm_tc: LSTM epilogue needs N % 128 == 0, a cell state and the input projection");
+    if (g.passes == 3) launch_bn<3>(g, s); else launch_bn<1>(g, s);
 }
 
 void launch_split_f16(const float* x, __half* hi, __half* lo, long long rows, int cols, long long ld_in,

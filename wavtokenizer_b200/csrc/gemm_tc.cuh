@@ -1,37 +1,84 @@
-// tcgen05 tap-GEMM launch descriptor (see gemm_tc.cu).
+// tcgen05 GEMM launch descriptor (see gemm_tc.cu).
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace wt {
 
+// One A-operand segment: a 2-D fp16 tensor (split planes hi/lo) whose row r starts `stride` elements
+// after row r-1 and exposes `inner` contiguous elements. stride < inner gives OVERLAPPING rows: the
+// im2col matrix of a Conv1d over channels-last data without materialising it (row stride = conv stride
+// * channels, inner = kernel * channels). Columns past `inner` and rows outside [0, rows) read as zero
+// (TMA out-of-bounds fill). The segment contributes num_kb k-blocks of 64; k-block kb loads columns
+// (kb % kb_per_tap) * 64 of row  m + shift0 + kb / kb_per_tap  ("tap" mode: kb_per_tap = Cin / 64;
+// "window" mode: kb_per_tap = num_kb).
+struct TcSeg {
+    const __half* hi = nullptr;
+    const __half* lo = nullptr;
+    long long rows = 0;
+    long long inner = 0;
+    long long stride = 0;
+    int num_kb = 0;
+    int kb_per_tap = 1;
+    int shift0 = 0;
+};
+
+// Output row remap: GEMM row m = b*Pin + t (valid iff t < Tvalid) is stored at row b*Pout + off + t, and
+// mirrored into the reflect halo rows [off - hl, off) and [off + Tvalid, off + Tvalid + hr) of the padded
+// layout its consumer reads (reference encoder/modules/conv.py:79-96 reflect padding). Pin == 0: identity.
+struct RowMap {
+    int Pin = 0, Tvalid = 0, Pout = 0, off = 0, hl = 0, hr = 0;
+};
+
+enum : int { TC_ACT_NONE = 0, TC_ACT_GELU = 1, TC_ACT_LSTM = 2 };
+
 struct TcGemm {
-    // A: split-fp16 planes [rowsA, Cin] (row pitch lda elements) in padded row space
-    const __half* A_hi = nullptr;
-    const __half* A_lo = nullptr;
-    long long rowsA = 0;
-    int Cin = 0, lda = 0;
-    int taps = 1, center = 0;  // out row m reads A rows m + j - center, j < taps (rows outside [0, rowsA) are zero)
-    // W: split-fp16 planes [N, K], K = taps*Cin, K index = tap*Cin + c
+    TcSeg seg[2];
+    int nseg = 1;
+    // W: split-fp16 planes [N, K], K = 64 * (seg[0].num_kb + seg[1].num_kb)
     const __half* W_hi = nullptr;
     const __half* W_lo = nullptr;
     int M = 0, N = 0, K = 0;
     int passes = 3;  // 3: hi*hi + hi*lo + lo*hi; 1: hi*hi only
-    // epilogue: v = acc + bias; act; v *= gamma; v += res; store fp32 and/or split fp16
+    // epilogue: v = acc + bias; act; v *= gamma; v += res[m]; stores of v and/or ELU(v)
     const float* bias = nullptr;
     const float* gamma = nullptr;
-    const float* res = nullptr;
+    const float* res = nullptr;  // indexed by the GEMM row m (no remap)
     int ldres = 0;
-    int act = 0;
-    float* out_f32 = nullptr;
+    int act = TC_ACT_NONE;
+    RowMap map;
+    float* out_f32 = nullptr;  // v
     int ldo = 0;
-    __half* out_hi = nullptr;
+    __half* out_hi = nullptr;  // split planes of v
     __half* out_lo = nullptr;
     int ldh = 0;
+    __half* elu_hi = nullptr;  // split planes of ELU(v)
+    __half* elu_lo = nullptr;
+    int ldh2 = 0;
+    // TC_ACT_LSTM (see gemm_tc.cu): columns are [i | f | g | o] blocks of 32 units per 128-wide tile
+    float* cell = nullptr;     // [M, H] cell state, updated in place
+    int hidden = 0;
 };
 
 void launch_tap_gemm_tc(const TcGemm& g, cudaStream_t s);
 void launch_split_f16(const float* x, __half* hi, __half* lo, long long rows, int cols, long long ld_in,
                       long long ld_out, cudaStream_t s);
+
+// Convenience: a dense / tap-mode segment over rows [rows, Cin] with pitch lda.
+inline TcSeg tc_taps(const __half* hi, const __half* lo, long long rows, int Cin, int lda, int taps, int center) {
+    TcSeg s;
+    s.hi = hi; s.lo = lo; s.rows = rows; s.inner = Cin; s.stride = lda;
+    s.kb_per_tap = Cin / 64; s.num_kb = taps * s.kb_per_tap; s.shift0 = -center;
+    return s;
+}
+// Window-mode segment: row r = elements [r*stride, r*stride + inner) of a flat buffer holding total_elems.
+inline TcSeg tc_window(const __half* hi, const __half* lo, long long total_elems, long long inner, long long stride,
+                       int shift0 = 0) {
+    TcSeg s;
+    s.hi = hi; s.lo = lo; s.inner = inner; s.stride = stride;
+    s.rows = total_elems >= inner ? (total_elems - inner) / stride + 1 : 0;
+    s.num_kb = (int)((inner + 63) / 64); s.kb_per_tap = s.num_kb; s.shift0 = shift0;
+    return s;
+}
 
 }  // namespace wt

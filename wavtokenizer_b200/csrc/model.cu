@@ -29,6 +29,7 @@ struct ConvW {
     __half* w_hi = nullptr;  // split-fp16 planes of w for the tcgen05 path
     __half* w_lo = nullptr;
     int cout = 0, cin = 0, k = 1, stride = 1;
+    std::vector<float> hw, hb;  // host copies (relayouted weight, bias) for composing fused weights
 };
 
 struct HalfW {  // split-fp16 planes of a plain [N, K] weight
@@ -63,6 +64,11 @@ struct wt_handle {
     ConvW down[4];
     struct Lstm { float *w_ih = nullptr, *w_hh = nullptr, *bias = nullptr; } lstm[4];
     ConvW enc_last;
+    // tcgen05 encoder weights: k3 conv padded to K % 64 == 0; conv1x1 and shortcut fused along K
+    struct RbTc { HalfW w1; int Kp1 = 0; HalfW w2; int kb0 = 0, kb1 = 0; float* bias2 = nullptr; } rb_tc[4];
+    // LSTM weights with gate rows permuted so that each 128-wide tile holds [i | f | g | o] x 32 hidden units
+    struct LstmTc { HalfW w_ih, w_hh; float* bias = nullptr; } lstm_tc[4];
+    float* zero_rows = nullptr;  // zero planes standing in for h_{-1}
     // vq
     float* codebooks = nullptr;  // [num_quantizers * bins, D]
     float* cnorm = nullptr;      // [bins] of codebook 0
@@ -226,8 +232,10 @@ ConvW load_wn_conv(wt_handle* h, const Table& t, const std::string& p, int cout,
     c.cout = cout; c.cin = cin; c.k = k; c.stride = stride;
     auto rl = relayout_conv(w.data(), cout, cin, k);
     c.w = h->upload(rl);
-    if ((k * cin) % 64 == 0 && cin % 64 == 0) { HalfW hw = h->upload_split(rl); c.w_hi = hw.hi; c.w_lo = hw.lo; }
+    if ((k * cin) % 64 == 0) { HalfW hw = h->upload_split(rl); c.w_hi = hw.hi; c.w_lo = hw.lo; }
     c.b = h->upload(std::vector<float>(b, b + cout));
+    c.hw = rl;
+    c.hb.assign(b, b + cout);
     return c;
 }
 
@@ -285,6 +293,55 @@ void prepare(wt_handle* h, const Table& t) {
         h->lstm[l].bias = h->upload(bias);
     }
     h->enc_last = load_wn_conv(h, t, E + std::to_string(idx + 2) + ".", c.dimension, ch, 7, 1);
+    {   // tcgen05 encoder weight forms
+        int C = c.n_filters;
+        for (int i = 0; i < 4; ++i) {
+            auto& rt = h->rb_tc[i];
+            const ConvW& c1 = h->rb[i].c1;
+            const ConvW& c2 = h->rb[i].c2;
+            const ConvW& sc = h->rb[i].sc;
+            const int K1 = 3 * C;
+            rt.Kp1 = (int)align_up(K1, 64);
+            std::vector<float> w1((size_t)(C / 2) * rt.Kp1, 0.f);
+            for (int n = 0; n < C / 2; ++n)
+                for (int k = 0; k < K1; ++k) w1[(size_t)n * rt.Kp1 + k] = c1.hw[(size_t)n * K1 + k];
+            rt.w1 = h->upload_split(w1);
+            rt.kb0 = (C / 2 + 63) / 64;
+            rt.kb1 = (C + 63) / 64;
+            const int K2 = 64 * (rt.kb0 + rt.kb1);
+            std::vector<float> w2((size_t)C * K2, 0.f), b2(C);
+            for (int n = 0; n < C; ++n) {
+                for (int k = 0; k < C / 2; ++k) w2[(size_t)n * K2 + k] = c2.hw[(size_t)n * (C / 2) + k];
+                for (int k = 0; k < C; ++k) w2[(size_t)n * K2 + 64 * rt.kb0 + k] = sc.hw[(size_t)n * C + k];
+                b2[n] = c2.hb[n] + sc.hb[n];
+            }
+            rt.w2 = h->upload_split(w2);
+            rt.bias2 = h->upload(b2);
+            C *= 2;
+        }
+        const int D = c.dimension;
+        if (D % 32 == 0) {
+            for (int l = 0; l < c.lstm_layers; ++l) {
+                std::string p = E + std::to_string(idx) + ".lstm.";
+                std::string sfx = "_l" + std::to_string(l);
+                const float* wi = t.get(p + "weight_ih" + sfx, (int64_t)4 * D * D);
+                const float* wh = t.get(p + "weight_hh" + sfx, (int64_t)4 * D * D);
+                const float* bi = t.get(p + "bias_ih" + sfx, 4 * D);
+                const float* bh = t.get(p + "bias_hh" + sfx, 4 * D);
+                std::vector<float> pwi((size_t)4 * D * D), pwh((size_t)4 * D * D), pb((size_t)4 * D);
+                for (int np = 0; np < 4 * D; ++np) {
+                    const int nt = np / 128, gate = (np % 128) / 32, j = np % 32;
+                    const int src = gate * D + nt * 32 + j;
+                    std::memcpy(&pwi[(size_t)np * D], wi + (size_t)src * D, D * sizeof(float));
+                    std::memcpy(&pwh[(size_t)np * D], wh + (size_t)src * D, D * sizeof(float));
+                    pb[np] = bi[src] + bh[src];
+                }
+                h->lstm_tc[l].w_ih = h->upload_split(pwi);
+                h->lstm_tc[l].w_hh = h->upload_split(pwh);
+                h->lstm_tc[l].bias = h->upload(pb);
+            }
+        }
+    }
 
     // ---- codebooks (reference encoder/quantization/core_vq.py:126-133) ----
     {
@@ -384,6 +441,14 @@ void prepare(wt_handle* h, const Table& t) {
     h->wsq = h->upload(wsq);
     WT_CUDA(cudaMalloc(&h->err_flag, sizeof(int)));
     WT_CUDA(cudaMemset(h->err_flag, 0, sizeof(int)));
+    {
+        void* z = nullptr;
+        const size_t bytes = (size_t)ENC_GROUP * c.dimension * sizeof(__half);
+        WT_CUDA(cudaMalloc(&z, bytes));
+        WT_CUDA(cudaMemset(z, 0, bytes));
+        h->owned.push_back(z);
+        h->zero_rows = reinterpret_cast<float*>(z);
+    }
     WT_CUDA(cudaMallocHost(&h->err_host, sizeof(int)));
 }
 
@@ -412,6 +477,23 @@ size_t enc_front_floats(const wt_config& c, int Bc, int T) {
     return tot;
 }
 
+// tcgen05 encoder front: planes of x / ELU(x) (pitch T+2), ELU(h1) (pitch T+2), ELU(y) (pitch (T'+1)*s)
+size_t enc_front_tc_floats(const wt_config& c, int Bc, int T) {
+    size_t tot = 0;
+    size_t Tc = T, C = c.n_filters;
+    auto a = [&](size_t halves) { tot += align_up(((halves + 1) / 2) * sizeof(float), 256) / sizeof(float); };
+    for (int i = 0; i < 4; ++i) {
+        const size_t s_ = c.strides[i], Tn = (Tc + s_ - 1) / s_;
+        for (int k = 0; k < 4; ++k) a((size_t)Bc * (Tc + 2) * C);
+        for (int k = 0; k < 2; ++k) a((size_t)Bc * (Tc + 2) * (C / 2));
+        for (int k = 0; k < 2; ++k) a((size_t)Bc * (Tn + 1) * s_ * C);
+        tot += align_up((size_t)Bc * (Tc + 2) * C * sizeof(float), 256) / sizeof(float);  // optional fp32 tap copies
+        tot += align_up((size_t)Bc * (Tn + 2) * 2 * C * sizeof(float), 256) / sizeof(float);
+        Tc = Tn; C *= 2;
+    }
+    return tot;
+}
+
 size_t enc_back_floats(const wt_config& c, int Bg, int L) {
     size_t tot = 0;
     auto a = [&](size_t n) { tot += align_up(n * sizeof(float), 256) / sizeof(float); };
@@ -423,6 +505,9 @@ size_t enc_back_floats(const wt_config& c, int Bg, int L) {
     a((size_t)Bg * D);                                 // c
     a(M * D);                                          // lstm + skip
     a(M * D);                                          // z
+    a(M * D);                                          // split planes of the pre-LSTM rows (tcgen05 plan)
+    for (int l = 0; l < c.lstm_layers; ++l) a(M * D);  // split planes of y_l
+    a((size_t)Bg * (L + 6) * D);                       // ELU(lstm + skip) planes, reflect-padded
     return tot;
 }
 
@@ -444,7 +529,8 @@ size_t workspace_bytes(const wt_handle* h, int B, int T) {
     const wt_config& c = h->cfg;
     int L = frames_for(c, T);
     size_t e = enc_back_floats(c, std::min(B, ENC_GROUP), L) +
-               std::max(enc_front_floats(c, std::min(B, ENC_CHUNK), T), (size_t)0);
+               std::max(enc_front_floats(c, std::min(B, ENC_CHUNK), T),
+                        enc_front_tc_floats(c, std::min(B, ENC_CHUNK), T));
     size_t d = dec_chunk_floats(c, std::min(B, DEC_CHUNK), L, h->Kp);
     return std::max(e, d) * sizeof(float) + 4096;
 }
@@ -601,6 +687,181 @@ float* encoder_back(wt_handle* h, const float* pre, int Bg, int L, int b0, cudaS
 }
 
 // ---------------------------------------------------------------------------------------
+// tcgen05 encoder. Every conv is a GEMM over a TMA tensor map of the channels-last activation:
+//   * stride-1 k-tap conv and strided conv (k = 2s): "window" map with OVERLAPPING rows
+//     (row stride = s*C elements, row length = k*C) over the reflect-padded clip slots;
+//   * ResBlock tail: conv1x1(ELU(h1)) + shortcut1x1(x) as two A segments into one accumulator.
+// Producers (conv0 kernel / GEMM epilogues) write the split-fp16 planes the consumer reads, already
+// ELU-activated and re-mapped into the consumer's padded layout including its reflect halo rows.
+// Layouts (rows per clip): RB input  P = T+2, data at 1, halo 1/1;  strided-conv input P = (T'+1)*s,
+// data at left = s - s/2, halo left / (s/2 + extra)  (reference encoder/modules/conv.py:54-61,195-211).
+// ---------------------------------------------------------------------------------------
+bool encoder_tc_supported(const wt_config& c, int T) {
+    long long Tc = T;
+    for (int i = 0; i < 4; ++i) {
+        const int s_ = c.strides[i];
+        const long long Tn = (Tc + s_ - 1) / s_;
+        const long long hr = s_ / 2 + (Tn * s_ - Tc);
+        if (Tc < 4 || Tc <= hr + 1 || Tc <= s_) return false;  // reflect halo must stay inside the clip
+        Tc = Tn;
+    }
+    return Tc >= 4 && c.dimension == 512 && c.n_filters == 32;
+}
+
+void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, float* pre, __half* pre_hi,
+                      __half* pre_lo, cudaStream_t s) {
+    const wt_config& c = h->cfg;
+    auto halves = [&](size_t n) { return reinterpret_cast<__half*>(h->alloc((n + 1) / 2)); };
+    auto run = [&](TcGemm& g) {
+        Scope sc(h, CAT_ENC_CONV, s);
+        launch_tap_gemm_tc(g, s);
+    };
+    auto want = [&](const std::string& name) { return b0 == 0 && h->taps.count(name) > 0; };
+    int Tc = T, C = c.n_filters;
+    // X planes of level 0 come from the conv0 kernel
+    size_t nX = (size_t)Bc * (Tc + 2) * C;
+    __half *xr_hi = halves(nX), *xr_lo = halves(nX), *xe_hi = halves(nX), *xe_lo = halves(nX);
+    {
+        Scope sc(h, CAT_ENC_CONV, s);
+        launch_conv0_planes(wav, h->conv0_w, h->conv0_b, xr_hi, xr_lo, xe_hi, xe_lo, Bc, T, C, s);
+    }
+    int idx = 1;
+    for (int i = 0; i < 4; ++i) {
+        const int s_ = c.strides[i];
+        const int Tn = (Tc + s_ - 1) / s_;
+        const int P = Tc + 2;
+        const long long rowsX = (long long)Bc * P;
+        const auto& rt = h->rb_tc[i];
+        // ---- G1: h1 = conv_k3(ELU(x)) -> ELU(h1) planes, same row space ----
+        const size_t nH = (size_t)rowsX * (C / 2);
+        __half *he_hi = halves(nH), *he_lo = halves(nH);
+        {
+            TcGemm g;
+            g.seg[0] = tc_window(xe_hi, xe_lo, rowsX * C, 3 * C, C);
+            g.W_hi = rt.w1.hi; g.W_lo = rt.w1.lo; g.M = (int)rowsX; g.N = C / 2; g.K = rt.Kp1; g.passes = 3;
+            g.bias = h->rb[i].c1.b;
+            g.elu_hi = he_hi; g.elu_lo = he_lo; g.ldh2 = C / 2;
+            run(g);
+        }
+        // ---- G2: y = conv1x1(ELU(h1)) + shortcut(x) -> ELU(y) planes in the strided conv's padded layout ----
+        const int right = s_ / 2, left = s_ - right, extra = Tn * s_ - Tc;
+        const int Py = (Tn + 1) * s_;
+        const size_t nY = (size_t)Bc * Py * C;
+        __half *ye_hi = halves(nY), *ye_lo = halves(nY);
+        float* y_tap = want("enc" + std::to_string(idx)) ? h->alloc(nY) : nullptr;
+        {
+            TcGemm g;
+            g.nseg = 2;
+            g.seg[0] = tc_window(he_hi, he_lo, rowsX * (C / 2), C / 2, C / 2);
+            g.seg[1] = tc_window(xr_hi, xr_lo, rowsX * C, C, C, /*shift0=*/1);
+            g.W_hi = rt.w2.hi; g.W_lo = rt.w2.lo; g.M = (int)rowsX; g.N = C; g.K = 64 * (rt.kb0 + rt.kb1); g.passes = 3;
+            g.bias = rt.bias2;
+            g.map.Pin = P; g.map.Tvalid = Tc; g.map.Pout = Py; g.map.off = left; g.map.hl = left; g.map.hr = right + extra;
+            g.elu_hi = ye_hi; g.elu_lo = ye_lo; g.ldh2 = C;
+            g.out_f32 = y_tap; g.ldo = C;
+            run(g);
+        }
+        if (y_tap) h->tap(("enc" + std::to_string(idx)).c_str(), y_tap + (size_t)left * C, Bc, Tc, C, b0, s, Py);
+        // ---- G3: z = strided conv(ELU(y)) -> next level's planes (x and ELU(x)), or the pre-LSTM rows ----
+        const int Q = Tn + 1;
+        const int C2 = 2 * C;
+        TcGemm g;
+        g.seg[0] = tc_window(ye_hi, ye_lo, (long long)nY, 2 * s_ * C, (long long)s_ * C);
+        g.W_hi = h->down[i].w_hi; g.W_lo = h->down[i].w_lo; g.M = Bc * Q; g.N = C2; g.K = 2 * s_ * C; g.passes = 3;
+        g.bias = h->down[i].b;
+        g.map.Pin = Q; g.map.Tvalid = Tn;
+        float* z_tap = nullptr;
+        if (i < 3) {
+            const size_t nX2 = (size_t)Bc * (Tn + 2) * C2;
+            xr_hi = halves(nX2); xr_lo = halves(nX2); xe_hi = halves(nX2); xe_lo = halves(nX2);
+            g.map.Pout = Tn + 2; g.map.off = 1; g.map.hl = 1; g.map.hr = 1;
+            g.out_hi = xr_hi; g.out_lo = xr_lo; g.ldh = C2;
+            g.elu_hi = xe_hi; g.elu_lo = xe_lo; g.ldh2 = C2;
+            if (want("enc" + std::to_string(idx + 2))) { z_tap = h->alloc(nX2); g.out_f32 = z_tap; g.ldo = C2; }
+        } else {
+            g.map.Pout = Tn; g.map.off = 0; g.map.hl = 0; g.map.hr = 0;
+            g.out_f32 = pre; g.ldo = C2;
+            g.out_hi = pre_hi; g.out_lo = pre_lo; g.ldh = C2;
+        }
+        run(g);
+        if (i < 3) {
+            if (z_tap) h->tap(("enc" + std::to_string(idx + 2)).c_str(), z_tap + (size_t)C2, Bc, Tn, C2, b0, s, Tn + 2);
+        } else {
+            h->tap(("enc" + std::to_string(idx + 2)).c_str(), pre, Bc, Tn, C2, b0, s);
+        }
+        Tc = Tn; C = C2; idx += 3;
+    }
+}
+
+// SLSTM + ELU + final k7 conv on the tensor cores: hoisted input projections, one GEMM launch per time
+// step whose epilogue is the LSTM cell (gates never leave the SM), final conv over the reflect-padded rows.
+float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, const __half* pre_lo, int Bg, int L,
+                       int b0, cudaStream_t s) {
+    const wt_config& c = h->cfg;
+    const int D = c.dimension;
+    const long long M = (long long)Bg * L;
+    auto halves = [&](size_t n) { return reinterpret_cast<__half*>(h->alloc((n + 1) / 2)); };
+    float* xin = h->alloc((size_t)M * 4 * D);
+    float* cst = h->alloc((size_t)Bg * D);
+    float* ybuf[4];
+    __half *yh_hi[4], *yh_lo[4];
+    for (int l = 0; l < c.lstm_layers; ++l) {
+        ybuf[l] = h->alloc((size_t)M * D);
+        yh_hi[l] = halves((size_t)M * D);
+        yh_lo[l] = halves((size_t)M * D);
+    }
+    const __half *lin_hi = pre_hi, *lin_lo = pre_lo;
+    const __half* zero = reinterpret_cast<const __half*>(h->zero_rows);
+    for (int l = 0; l < c.lstm_layers; ++l) {
+        const auto& w = h->lstm_tc[l];
+        {   // xin = W_ih x + b_ih + b_hh for all L steps at once (gate rows permuted like the recurrent tile)
+            TcGemm g;
+            g.seg[0] = tc_taps(lin_hi, lin_lo, M, D, D, 1, 0);
+            g.W_hi = w.w_ih.hi; g.W_lo = w.w_ih.lo; g.M = (int)M; g.N = 4 * D; g.K = D; g.passes = 3;
+            g.bias = w.bias; g.out_f32 = xin; g.ldo = 4 * D;
+            Scope sc(h, CAT_LSTM, s);
+            launch_tap_gemm_tc(g, s);
+        }
+        WT_CUDA(cudaMemsetAsync(cst, 0, (size_t)Bg * D * sizeof(float), s));
+        for (int t = 0; t < L; ++t) {
+            TcGemm g;
+            if (t == 0) g.seg[0] = tc_taps(zero, zero, Bg, D, D, 1, 0);  // h_{-1} = 0
+            else g.seg[0] = tc_taps(yh_hi[l] + (size_t)(t - 1) * D, yh_lo[l] + (size_t)(t - 1) * D, Bg, D, L * D, 1, 0);
+            g.W_hi = w.w_hh.hi; g.W_lo = w.w_hh.lo; g.M = Bg; g.N = 4 * D; g.K = D; g.passes = 3;
+            g.act = TC_ACT_LSTM; g.res = xin + (size_t)t * 4 * D; g.ldres = L * 4 * D; g.cell = cst; g.hidden = D;
+            g.out_f32 = ybuf[l] + (size_t)t * D; g.ldo = L * D;
+            g.out_hi = yh_hi[l] + (size_t)t * D; g.out_lo = yh_lo[l] + (size_t)t * D; g.ldh = L * D;
+            Scope sc(h, CAT_LSTM, s);
+            launch_tap_gemm_tc(g, s);
+        }
+        lin_hi = yh_hi[l]; lin_lo = yh_lo[l];
+    }
+    const float* ylast = c.lstm_layers ? ybuf[c.lstm_layers - 1] : pre;
+    float* lo = h->alloc((size_t)M * D);
+    const size_t nE = (size_t)Bg * (L + 6) * D;
+    __half *e_hi = halves(nE), *e_lo = halves(nE);
+    {
+        Scope sc(h, CAT_LSTM, s);
+        if (c.lstm_layers) launch_lstm_skip_elu_pad(ylast, pre, lo, e_hi, e_lo, Bg, L, D, s);
+        else launch_lstm_skip_elu_pad(pre, h->zero_rows /*unused*/, lo, e_hi, e_lo, Bg, L, D, s);
+    }
+    h->tap("enc13", lo, Bg, L, D, b0, s);
+    float* z = h->alloc((size_t)M * D);
+    {
+        TcGemm g;
+        g.seg[0] = tc_window(e_hi, e_lo, (long long)nE, 7 * D, D);
+        g.W_hi = h->enc_last.w_hi; g.W_lo = h->enc_last.w_lo; g.M = Bg * (L + 6); g.N = D; g.K = 7 * D; g.passes = 3;
+        g.bias = h->enc_last.b;
+        g.map.Pin = L + 6; g.map.Tvalid = L; g.map.Pout = L; g.map.off = 0;
+        g.out_f32 = z; g.ldo = D;
+        Scope sc(h, CAT_ENC_CONV, s);
+        launch_tap_gemm_tc(g, s);
+    }
+    h->tap("enc15", z, Bg, L, D, b0, s);
+    return z;
+}
+
+// ---------------------------------------------------------------------------------------
 // decoder: VocosBackbone + ISTFTHead on a chunk (reference decoder/models.py:223-235,
 // decoder/heads.py:42-67)
 // ---------------------------------------------------------------------------------------
@@ -695,7 +956,7 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
                     int passes, const float* bias, int act, const float* gamma, const float* res, float* of32, int ldo,
                     __half* ohi, __half* olo, int ldh) {
         TcGemm g;
-        g.A_hi = ahi; g.A_lo = alo; g.rowsA = R; g.Cin = Cin; g.lda = Cin; g.taps = taps; g.center = (taps - 1) / 2;
+        g.seg[0] = tc_taps(ahi, alo, R, Cin, Cin, taps, (taps - 1) / 2);
         g.W_hi = whi; g.W_lo = wlo; g.M = (int)R; g.N = N; g.K = taps * Cin; g.passes = passes;
         g.bias = bias; g.act = act; g.gamma = gamma; g.res = res; g.ldres = ldo;
         g.out_f32 = of32; g.ldo = ldo; g.out_hi = ohi; g.out_lo = olo; g.ldh = ldh;
@@ -777,15 +1038,20 @@ void do_encode(wt_handle* h, const float* wav, int B, int T, float* features_out
     for (int g0 = 0; g0 < B; g0 += ENC_GROUP) {
         const int Bg = std::min(ENC_GROUP, B - g0);
         h->arena_off = 0;
+        const bool tc = h->plan >= 1 && encoder_tc_supported(c, T) && c.lstm_layers >= 1;
         float* pre = h->alloc((size_t)Bg * L * D);
+        __half* pre_hi = reinterpret_cast<__half*>(h->alloc((size_t)Bg * L * D / 2));
+        __half* pre_lo = reinterpret_cast<__half*>(h->alloc((size_t)Bg * L * D / 2));
         const size_t mark = h->arena_off;
         for (int b0 = 0; b0 < Bg; b0 += ENC_CHUNK) {
             const int Bc = std::min(ENC_CHUNK, Bg - b0);
             h->arena_off = mark;
-            encoder_front(h, wav + (size_t)(g0 + b0) * T, Bc, T, g0 + b0, pre + (size_t)b0 * L * D, s);
+            const size_t ro = (size_t)b0 * L * D;
+            if (tc) encoder_front_tc(h, wav + (size_t)(g0 + b0) * T, Bc, T, g0 + b0, pre + ro, pre_hi + ro, pre_lo + ro, s);
+            else encoder_front(h, wav + (size_t)(g0 + b0) * T, Bc, T, g0 + b0, pre + ro, s);
         }
         h->arena_off = mark;
-        float* z = encoder_back(h, pre, Bg, L, g0, s);
+        float* z = tc ? encoder_back_tc(h, pre, pre_hi, pre_lo, Bg, L, g0, s) : encoder_back(h, pre, Bg, L, g0, s);
         const long long M = (long long)Bg * L;
         if (z_out) {
             Scope sc(h, CAT_MEM, s);
@@ -1062,7 +1328,7 @@ int wt_test_tap_gemm(int32_t device, const float* A, int32_t rows, int32_t Cin, 
         launch_split_f16(A, a_hi, a_lo, rows, Cin, Cin, Cin, s);
         launch_split_f16(W, w_hi, w_lo, N, (int)K, K, K, s);
         TcGemm g;
-        g.A_hi = a_hi; g.A_lo = a_lo; g.rowsA = rows; g.Cin = Cin; g.lda = Cin; g.taps = taps; g.center = (taps - 1) / 2;
+        g.seg[0] = tc_taps(a_hi, a_lo, rows, Cin, Cin, taps, (taps - 1) / 2);
         g.W_hi = w_hi; g.W_lo = w_lo; g.M = rows; g.N = N; g.K = (int)K; g.passes = passes;
         g.bias = bias; g.gamma = gamma; g.res = res; g.ldres = N; g.act = act;
         g.out_f32 = out_f32; g.ldo = N; g.out_hi = o_hi; g.out_lo = o_lo; g.ldh = ldh;
