@@ -135,6 +135,11 @@ int wt_test_tap_gemm(int32_t device, const float* A, int32_t rows, int32_t Cin, 
                      const float* bias, const float* gamma, const float* res, int32_t act, int32_t passes,
                      float* out_f32, float* out_split, void* stream);
 
+/* Performance debugging: when dev_buf != NULL every subsequent tcgen05 GEMM launch writes per-CTA clock64
+ * stamps (64 int64 slots per CTA: 0 prologue done, 1..16 producer issued k-block, 17..32 k-block landed,
+ * 40 first accumulator ready, 41 first epilogue done, 42 all roles finished). NULL switches it off. */
+int wt_debug_timeline(long long* dev_buf);
+
 /* Compute plan: 0 = fp32 CUDA-core contractions everywhere (bit-conservative);
  * 1 = tcgen05 tensor-core contractions with split-fp16 operands, 3 passes (hi*hi + hi*lo + lo*hi);
  * 2 = as 1, but the 24 ConvNeXt pointwise GEMMs run single-pass fp16. */

@@ -17,21 +17,26 @@ from wavtokenizer_b200 import _native, spec
 
 pytestmark = pytest.mark.gpu
 
-PLANS = [0]
+PLANS = [0, 1, 2]  # 0: fp32 CUDA cores; 1: tcgen05 3-pass split-fp16; 2: as 1 with single-pass ConvNeXt GEMMs
 SKIP_TAPS = {"enc2", "enc5", "enc8", "enc11", "enc14"}  # ELU outputs: fused into the next conv's loader
 SNR_BAR_DB = 60.0          # north_star waveform / feature tolerance
-FP32_STAGE_BAR_DB = 100.0  # plan 0 computes in fp32: every stage must agree far beyond the bar
+# per-stage bars: plan 0 computes in fp32 (far beyond the bar); the tcgen05 plans carry ~20-22 operand bits
+STAGE_BAR_DB = {0: 100.0, 1: 85.0, 2: 70.0}
+AUDIO_BAR_DB = {0: 100.0, 1: 70.0, 2: 70.0}
 
 
 def codebook(sd):
     return sd[spec.CODEBOOK_PREFIX + "0._codebook.embed"]
 
 
-@pytest.fixture(scope="module", params=helpers.TAGS)
+@pytest.fixture(scope="module", params=[(t, p) for t in helpers.TAGS for p in PLANS],
+                ids=lambda tp: f"{tp[0]}-plan{tp[1]}")
 def setup(request):
-    tag = request.param
+    tag, plan = request.param
     cfg, sd = helpers.model(tag)
-    return tag, cfg, sd, helpers.golden(tag), native_model(tag)
+    m = native_model(tag, plan)
+    m.test_plan = plan
+    return tag, cfg, sd, helpers.golden(tag), m
 
 
 def test_loaded_native_library():
@@ -44,7 +49,9 @@ def test_loaded_native_library():
 
 def test_every_stage_matches_reference_taps(setup):
     tag, cfg, sd, g, m = setup
-    names = [str(n) for n in g["tap_names"] if str(n) not in SKIP_TAPS]
+    plan = m.test_plan
+    skip = SKIP_TAPS | ({"enc0"} if plan else set())  # tcgen05 encoder: conv0 writes operand planes only
+    names = [str(n) for n in g["tap_names"] if str(n) not in skip]
     taps = Taps(m, names)
     wav = spec.synthetic_audio(2, int(g["e2e_T"]), seed=11).cuda()
     bw = torch.tensor([2]).cuda()
@@ -61,10 +68,10 @@ def test_every_stage_matches_reference_taps(setup):
         snr = helpers.snr_db(torch.from_numpy(g["tap_" + n]), golden_sub(t))
         if snr < worst[1]:
             worst = (n, snr)
-    assert worst[1] >= FP32_STAGE_BAR_DB, worst
+    assert worst[1] >= STAGE_BAR_DB[plan], worst
     z = taps.get("enc15")
     taps.close()
-    assert helpers.snr_db(torch.from_numpy(g["e2e_z"]), z) >= FP32_STAGE_BAR_DB
+    assert helpers.snr_db(torch.from_numpy(g["e2e_z"]), z) >= STAGE_BAR_DB[plan]
     rep = O.vq_tie_report(z.permute(0, 2, 1).reshape(-1, cfg.dimension), codebook(sd), codes.cpu(), ref_codes)
     assert rep["hard_mismatches"] == 0, rep
     assert rep["match_pct"] >= 98.0, rep
@@ -72,7 +79,7 @@ def test_every_stage_matches_reference_taps(setup):
     assert codes.shape == (1, 2, cfg.frames_for(int(g["e2e_T"]))) and codes.dtype == torch.int64
     assert torch.equal(feats.cpu(), O.codes_to_features(sd, cfg, codes.cpu()))
     assert audio.shape == g["e2e_audio"].shape
-    assert helpers.snr_db(torch.from_numpy(g["e2e_audio"]), audio.cpu()) >= max(SNR_BAR_DB, FP32_STAGE_BAR_DB)
+    assert helpers.snr_db(torch.from_numpy(g["e2e_audio"]), audio.cpu()) >= max(SNR_BAR_DB, AUDIO_BAR_DB[plan])
 
 
 def test_three_second_clip(setup):
@@ -148,7 +155,7 @@ def test_batch_independence_and_chunking(setup):
         f1, c1 = m.encode_infer(wav[i:i + 1], bandwidth_id=bw)
         assert torch.equal(c1[0, 0], c_all[0, i])
         a1 = m.decode(f1, bandwidth_id=bw)
-        assert helpers.snr_db(a1, a_all[i:i + 1]) >= 100
+        assert helpers.snr_db(a1, a_all[i:i + 1]) >= 100  # same kernels, different tile positions
 
 
 def test_encoder_module_entry(setup):
@@ -156,7 +163,7 @@ def test_encoder_module_entry(setup):
     tag, cfg, sd, g, m = setup
     wav = spec.synthetic_audio(2, int(g["e2e_T"]), seed=11).cuda()
     z = m.feature_extractor.encodec.encoder(wav.unsqueeze(1))
-    assert helpers.snr_db(torch.from_numpy(g["e2e_z"]), z.cpu()) >= FP32_STAGE_BAR_DB
+    assert helpers.snr_db(torch.from_numpy(g["e2e_z"]), z.cpu()) >= STAGE_BAR_DB[m.test_plan]
 
 
 def test_vq_matches_oracle_on_calibration_like_frames():
@@ -223,12 +230,13 @@ def test_host_buffer_entry_point(setup):
     assert torch.equal(codes_h, c.cpu()) and torch.equal(audio_h, a.cpu())
 
 
-def test_full_size_properties():
+@pytest.mark.parametrize("plan", [0, 2])
+def test_full_size_properties(plan):
     """BASELINE.json configs[1] size (small-320, 256 x 3 s): size-independent properties — features are
     exact codebook rows of the codes, decoding is deterministic and batch-order equivariant, and a
     sampled subset of clips matches the oracle."""
     cfg, sd = helpers.model("small320")
-    m = native_model("small320")
+    m = native_model("small320", plan)
     B = 256
     wav = spec.synthetic_audio(B, 72000, seed=77).cuda()
     bw = torch.tensor([0]).cuda()
@@ -241,7 +249,7 @@ def test_full_size_properties():
     f2, c2 = m.encode_infer(wav[perm], bandwidth_id=bw)
     assert torch.equal(c2[0], codes[0][perm])
     a2 = m.decode(f2, bandwidth_id=bw)
-    assert helpers.snr_db(audio[perm], a2) >= 100
+    assert helpers.snr_db(audio[perm], a2) >= 90
     idx = [0, 100, 255]
     with torch.inference_mode():
         z = O.seanet_encoder(sd, cfg, wav[idx].cpu().unsqueeze(1), library_lstm=True)

@@ -72,6 +72,10 @@ void launch_gather_rows(const float* codebook, const long long* codes, float* ou
 void launch_codes_to_features(const float* codebooks, const long long* codes, float* out, int K, int B, int L, int D,
                               int bins, int* err_flag, cudaStream_t s);
 
+// tcgen05 VQ helpers
+void launch_center_split(const float* x, const float* mu, __half* hi, __half* lo, long long N, int D, cudaStream_t s);
+void launch_best_to_codes(const unsigned long long* best, long long* codes, long long N, cudaStream_t s);
+
 // layout
 void launch_transpose_bcl_to_blc(const float* in, float* out, int B, int C, int L, cudaStream_t s);
 void launch_transpose_blc_to_bcl(const float* in, float* out, int B, int L, int C, cudaStream_t s);
@@ -97,6 +101,11 @@ void launch_dwconv_ln(const float* x, const float* dw /*[C,7]*/, const float* db
                       const float* shift, RowOut out, int B, int L, int Lp, int C, float eps, cudaStream_t s);
 void launch_attention(const float* qkv /*[B*Lp, 3C]*/, RowOut out /*[B*Lp, C]*/, int B, int L, int Lp, int C,
                       cudaStream_t s);
+// tensor-core attention helpers (scores and P.V run as batched tcgen05 GEMMs)
+void launch_softmax_planes(const float* S, int ldS, __half* p_hi, __half* p_lo, int Lpad, int B, int L, int Lp,
+                           float scale, cudaStream_t s);
+void launch_vt_planes(const __half* q_hi, const __half* q_lo, __half* vt_hi, __half* vt_lo, int B, int L, int Lp, int C,
+                      int Lpad, cudaStream_t s);
 void launch_spectral(const float* z /*[M, ldz]*/, int ldz, RowOut S /*[M, ldS]*/, long long M, int half, int ldS,
                      cudaStream_t s);
 void launch_overlap_add(const float* frames /*[B*Lp, n_fft]*/, const float* wsq /*[n_fft]*/, float* audio, int B, int L,

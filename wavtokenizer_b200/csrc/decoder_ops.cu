@@ -265,7 +265,85 @@ __global__ void features_to_rows_kernel(const float* __restrict__ in, RowOut out
     }
 }
 
+// softmax(q k^T * C^-0.5) rows for the tensor-core attention (reference decoder/models.py:117-120):
+// S [B*Lp, ldS] fp32 raw scores -> split-fp16 planes of the probabilities [B*Lp, Lpad], zero for keys >= L
+// (they are the K dimension of the P.V GEMM) and for halo query rows. One warp per query row.
+__global__ void __launch_bounds__(256) softmax_planes_kernel(const float* __restrict__ S, int ldS,
+                                                             __half* __restrict__ p_hi, __half* __restrict__ p_lo,
+                                                             int Lpad, int B, int L, int Lp, float scale) {
+    const int lane = threadIdx.x & 31;
+    long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= (long long)B * Lp) return;
+    const int i = (int)(row % Lp);
+    __half* oh = p_hi + row * Lpad;
+    __half* ol = p_lo + row * Lpad;
+    if (i >= L) {
+        for (int j = lane; j < Lpad; j += 32) { oh[j] = __float2half_rn(0.f); ol[j] = __float2half_rn(0.f); }
+        return;
+    }
+    const float* sr = S + row * ldS;
+    float mx = -INFINITY;
+    for (int j = lane; j < L; j += 32) mx = fmaxf(mx, sr[j] * scale);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float den = 0.f;
+    for (int j = lane; j < L; j += 32) den += expf(sr[j] * scale - mx);
+    den = warp_sum(den);
+    const float inv = 1.f / den;
+    for (int j = lane; j < Lpad; j += 32) {
+        float p = j < L ? expf(sr[j] * scale - mx) * inv : 0.f;
+        __half h = __float2half_rn(p);
+        oh[j] = h;
+        ol[j] = __float2half_rn(p - __half2float(h));
+    }
+}
+
+// V^T planes for the P.V GEMM: qkv planes [B*Lp, 3C] (v = columns 2C..3C) -> vT [B*C, Lpad], zero for keys >= L.
+__global__ void vt_planes_kernel(const __half* __restrict__ q_hi, const __half* __restrict__ q_lo,
+                                 __half* __restrict__ vt_hi, __half* __restrict__ vt_lo, int L, int Lp, int C,
+                                 int Lpad) {
+    __shared__ __half th[32][34], tl[32][34];
+    const int b = blockIdx.z;
+    const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int j = j0 + r, c = c0 + threadIdx.x;
+        __half h = __float2half_rn(0.f), l = h;
+        if (j < L) {
+            const long long src = ((long long)b * Lp + j) * 3 * C + 2 * C + c;
+            h = q_hi[src];
+            l = q_lo[src];
+        }
+        th[r][threadIdx.x] = h;
+        tl[r][threadIdx.x] = l;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r, j = j0 + threadIdx.x;
+        if (j < Lpad) {
+            const long long dst = ((long long)b * C + c) * Lpad + j;
+            vt_hi[dst] = th[threadIdx.x][r];
+            vt_lo[dst] = tl[threadIdx.x][r];
+        }
+    }
+}
+
 }  // namespace
+
+void launch_softmax_planes(const float* S, int ldS, __half* p_hi, __half* p_lo, int Lpad, int B, int L, int Lp,
+                           float scale, cudaStream_t s) {
+    if (B <= 0 || L <= 0) return;
+    long long rows = (long long)B * Lp;
+    softmax_planes_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(S, ldS, p_hi, p_lo, Lpad, B, L, Lp, scale);
+    WT_CUDA(cudaGetLastError());
+}
+
+void launch_vt_planes(const __half* q_hi, const __half* q_lo, __half* vt_hi, __half* vt_lo, int B, int L, int Lp, int C,
+                      int Lpad, cudaStream_t s) {
+    if (B <= 0 || L <= 0) return;
+    dim3 grid((Lpad + 31) / 32, C / 32, B), block(32, 8);
+    vt_planes_kernel<<<grid, block, 0, s>>>(q_hi, q_lo, vt_hi, vt_lo, L, Lp, C, Lpad);
+    WT_CUDA(cudaGetLastError());
+}
 
 void launch_groupnorm(const float* x, const float* w, const float* b, RowOut out, int B, int L, int Lp, int C,
                       int groups, float eps, int swish, cudaStream_t s) {

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) conv0_planes_kernel(const float* __restri
     }
 }
 
-// SLSTM skip connection y + x (reference encoder/modules/lstm.py:38) fused with the ELU in front of the last
+// SLSTM skip connection y + x (reference encoder/modules/lstm.py:38; y and x in time-major rows) fused with the ELU in front of the last
 // encoder conv: writes fp32 rows [B*L, D] (tap) and the split planes of ELU(y + x) in the reflect-padded layout
 // of the k7 conv (clip pitch L + 6, data at offset 3).
 __global__ void lstm_skip_elu_pad_kernel(const float* __restrict__ y, const float* __restrict__ x,
@@ -126,7 +126,8 @@ __global__ void lstm_skip_elu_pad_kernel(const float* __restrict__ y, const floa
     const bool interior = t >= 0 && t < L;
     if (t < 0) t = -t;
     if (t >= L) t = 2 * (L - 1) - t;
-    const long long src = ((long long)b * L + t) * D + c8 * 8;
+    const long long src = ((long long)t * B + b) * D + c8 * 8;   // y, x: time-major rows [t*B + b]
+    const long long dst = ((long long)b * L + t) * D + c8 * 8;   // fp32 copy: batch-major rows
     float v[8], e[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -135,7 +136,7 @@ __global__ void lstm_skip_elu_pad_kernel(const float* __restrict__ y, const floa
     }
     if (interior && out_f32) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) out_f32[src + i] = v[i];
+        for (int i = 0; i < 8; ++i) out_f32[dst + i] = v[i];
     }
     split_store8(elu_hi, elu_lo, row * D + c8 * 8, e);
 }

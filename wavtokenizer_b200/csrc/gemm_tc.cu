@@ -20,6 +20,9 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
@@ -30,7 +33,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // fp16 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NEPI = 16;                       // epilogue warps: 4 per TMEM lane quarter, splitting the columns
+constexpr int NUM_THREADS = 64 + NEPI * 32;    // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue
 constexpr uint32_t SPIN_LIMIT = 1u << 28;  // a wedged pipeline traps instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -122,7 +126,27 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Exact-erf GELU (reference decoder/modules.py:35, nn.GELU()). erf through the branch-free rational form of
+// Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, below the 2^-22 resolution of the split-fp16 operands the
+// result is stored in): two MUFU ops and ~12 FMAs per element instead of erff's divergent ~40-instruction paths.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.f - p * t * __expf(-z * z);
+    return 0.5f * x * (1.f + copysignf(e, x));
+}
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
 __device__ __forceinline__ float sigmoid1(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -163,7 +187,16 @@ __device__ __forceinline__ void store_row(const TcGemm& g, long long row, int nb
             for (int i = 0; i < CW; i += 4)
                 *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
-        if (g.out_hi) store_planes<CW, false>(g.out_hi, g.out_lo, row * g.ldh + nb, v);
+        if (g.out_hi) {
+            if (g.plane_shift) {
+                float w[CW];
+#pragma unroll
+                for (int i = 0; i < CW; ++i) w[i] = v[i] - g.plane_shift[nb + i];
+                store_planes<CW, false>(g.out_hi, g.out_lo, row * g.ldh + nb, w);
+            } else {
+                store_planes<CW, false>(g.out_hi, g.out_lo, row * g.ldh + nb, v);
+            }
+        }
         if (g.elu_hi) store_planes<CW, true>(g.elu_hi, g.elu_lo, row * g.ldh2 + nb, v);
     } else {
 #pragma unroll 1
@@ -175,6 +208,7 @@ __device__ __forceinline__ void store_row(const TcGemm& g, long long row, int nb
             for (int k = 0; k < CW; ++k) x = (k == i) ? v[k] : x;  // keeps v[] in registers
             if (g.out_f32) g.out_f32[row * g.ldo + n] = x;
             if (g.out_hi) {
+                if (g.plane_shift) x -= g.plane_shift[n];
                 __half h = __float2half_rn(x);
                 g.out_hi[row * g.ldh + n] = h;
                 if (g.out_lo) g.out_lo[row * g.ldh + n] = __float2half_rn(x - __half2float(h));
@@ -198,7 +232,9 @@ struct Cfg {
     static constexpr int STAGES = (200 * 1024) / STAGE > 8 ? 8 : (200 * 1024) / STAGE;
     static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages (power of two >= 32)
-    static constexpr int CW = BN < 32 ? BN : 32;                 // epilogue chunk width
+    static constexpr int G = NEPI / 4;                           // epilogue warps per TMEM lane quarter
+    static constexpr int CW = BN / G >= 16 ? 16 : 8;             // epilogue chunk width (columns per tcgen05.ld)
+    static constexpr int EPI_SMEM = 0;
 };
 
 struct Maps {
@@ -223,9 +259,13 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long* dbg = g.dbg ? g.dbg + (long long)blockIdx.x * 64 : nullptr;
+    const long long t_begin = dbg ? clock64() : 0;
+    auto stamp = [&](int slot) { if (dbg && slot < 64) dbg[slot] = clock64() - t_begin; };
     const int m_tiles = (g.M + BM - 1) / BM;
     const int n_tiles = (g.N + BN - 1) / BN;
-    const int total_tiles = m_tiles * n_tiles;
+    const int per_batch = m_tiles * n_tiles;
+    const int total_tiles = per_batch * g.batch;
     const int nkb0 = g.seg[0].num_kb;
     const int num_kb = nkb0 + (g.nseg > 1 ? g.seg[1].num_kb : 0);
 
@@ -236,7 +276,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+            mbar_init(tempty_bar(s), NEPI);  // one arrive per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -250,23 +290,25 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
+    if (threadIdx.x == 0) stamp(0);  // prologue done
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
-                const int m0 = mt * BM, n0 = nt * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    const int si = kb < nkb0 ? 0 : 1;
-                    const int kl = si ? kb - nkb0 : kb;
-                    const int kpt = g.seg[si].kb_per_tap;
-                    const int tap = kl / kpt;
-                    const int c0 = (kl - tap * kpt) * BK;
-                    const int r0 = m0 + g.seg[si].shift0 + tap;
-                    mbar_wait(empty_bar(stage), phase ^ 1);
+        // ===================== TMA producer (whole warp loops; lane 0 issues) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int bz = tile / per_batch, rem = tile - bz * per_batch;
+            const int mt = rem / n_tiles, nt = rem - mt * n_tiles;
+            const int m0 = mt * BM + (int)(bz * g.a_brows), n0 = nt * BN + (int)(bz * g.w_brows);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int si = kb < nkb0 ? 0 : 1;
+                const int kl = si ? kb - nkb0 : kb;
+                const int kpt = g.seg[si].kb_per_tap;
+                const int tap = kl / kpt;
+                const int c0 = (kl - tap * kpt) * BK;
+                const int r0 = m0 + g.seg[si].shift0 + tap;
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                if (lane == 0) {
                     const uint32_t sa = smem_base + stage * C::STAGE;
                     mbar_expect_tx(full_bar(stage), C::STAGE);
                     tma_load_2d(sa, &maps.a[si][0], c0, r0, full_bar(stage));
@@ -274,25 +316,28 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                     const uint32_t sb = sa + C::PLANES * C::A_PLANE;
                     tma_load_2d(sb, &maps.w[0], kb * BK, n0, full_bar(stage));
                     if (PASSES == 3) tma_load_2d(sb + C::B_PLANE, &maps.w[1], kb * BK, n0, full_bar(stage));
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (tile == (int)blockIdx.x) stamp(1 + kb);  // slots 1..16: producer issued k-block kb (first tile)
                 }
+                __syncwarp();
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        // ===================== MMA issuer (whole warp loops; lane 0 issues) =====================
+        constexpr uint32_t idesc = umma_idesc_f16(BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(full_bar(stage), phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(full_bar(stage), phase);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    if (tile == (int)blockIdx.x) stamp(17 + kb);  // slots 17..32: data of k-block kb landed
                     const uint32_t sa = smem_base + stage * C::STAGE;
                     const uint32_t sb = sa + C::PLANES * C::A_PLANE;
 #pragma unroll
@@ -309,74 +354,113 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                         }
                     }
                     umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (kb == num_kb - 1) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
                 }
-                umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
-        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        const int q = warp & 3;        // TMEM lane quarter this warp may read (hardware: warp id % 4)
+        const int cg = (warp - 2) >> 2;  // which share of the tile's columns this warp handles
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
-            const int m = mt * BM + q * 32 + lane;
+            const int bz = tile / per_batch, rem = tile - bz * per_batch;
+            const int mt = rem / n_tiles, nt = rem - mt * n_tiles;
+            const int m_local = mt * BM + q * 32 + lane;
+            const int m = m_local + (int)(bz * g.o_brows);
             const int n0 = nt * BN;
             mbar_wait(tfull_bar(acc), acc_phase);
+            if (tile == (int)blockIdx.x && threadIdx.x == 64) stamp(40);  // accumulator of the first tile ready
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-            bool row_ok = m < g.M;
+            bool row_ok = m_local < g.M;
             // destination rows (identity, or re-mapped into the consumer's reflect-padded layout)
             long long dst = m, mir_l = -1, mir_r = -1;
             if (g.map.Pin) {
                 const int b = m / g.map.Pin, t = m - b * g.map.Pin;
                 row_ok = row_ok && t < g.map.Tvalid;
-                const long long base = (long long)b * g.map.Pout + g.map.off;
-                dst = base + t;
-                if (t >= 1 && t <= g.map.hl) mir_l = base - t;
+                const long long sb = g.map.sb ? g.map.sb : g.map.Pout, st = g.map.st ? g.map.st : 1;
+                const long long base = (long long)b * sb + (long long)g.map.off * st;
+                dst = base + t * st;
+                if (t >= 1 && t <= g.map.hl) mir_l = base - t * st;
                 if (t <= g.map.Tvalid - 2 && t >= g.map.Tvalid - 1 - g.map.hr)
-                    mir_r = base + 2 * (g.map.Tvalid - 1) - t;
+                    mir_r = base + (2 * (g.map.Tvalid - 1) - t) * st;
             }
             if (BN == 128 && g.act == TC_ACT_LSTM) {
                 // LSTM cell (reference encoder/modules/lstm.py:20; gates i, f, g, o). Tile columns hold
                 // [i | f | g | o] x 32 hidden units; the thread owns one batch row.
-                const int u0 = nt * 32;
-#pragma unroll 1
-                for (int hf = 0; hf < 2; ++hf) {
-                    uint32_t ri[16], rf[16], rg[16], ro[16];
+                const int u0 = nt * 32 + cg * 8;  // this warp's 8 hidden units (4 warps per lane quarter)
+                {
+                    uint32_t ri[8], rf[8], rg[8], ro[8];
                     __syncwarp();
-                    tmem_ld(tbase + 0 + hf * 16, ri);
-                    tmem_ld(tbase + 32 + hf * 16, rf);
-                    tmem_ld(tbase + 64 + hf * 16, rg);
-                    tmem_ld(tbase + 96 + hf * 16, ro);
-                    if (!row_ok) continue;
-                    const float* xr = g.res + (long long)m * g.ldres + n0 + hf * 16;
-                    float* cr = g.cell + (long long)m * g.hidden + u0 + hf * 16;
-                    float hv[16];
+                    tmem_ld(tbase + 0 + cg * 8, ri);
+                    tmem_ld(tbase + 32 + cg * 8, rf);
+                    tmem_ld(tbase + 64 + cg * 8, rg);
+                    tmem_ld(tbase + 96 + cg * 8, ro);
+                    if (row_ok) {
+                        const float* xr = g.res + (long long)m * g.ldres + n0 + cg * 8;
+                        float* cr = g.cell + (long long)m * g.hidden + u0;
+                        float xi[8], xf[8], xg[8], xo[8], cv[8];
+                        *reinterpret_cast<float4*>(xi) = *reinterpret_cast<const float4*>(xr);
+                        *reinterpret_cast<float4*>(xi + 4) = *reinterpret_cast<const float4*>(xr + 4);
+                        *reinterpret_cast<float4*>(xf) = *reinterpret_cast<const float4*>(xr + 32);
+                        *reinterpret_cast<float4*>(xf + 4) = *reinterpret_cast<const float4*>(xr + 36);
+                        *reinterpret_cast<float4*>(xg) = *reinterpret_cast<const float4*>(xr + 64);
+                        *reinterpret_cast<float4*>(xg + 4) = *reinterpret_cast<const float4*>(xr + 68);
+                        *reinterpret_cast<float4*>(xo) = *reinterpret_cast<const float4*>(xr + 96);
+                        *reinterpret_cast<float4*>(xo + 4) = *reinterpret_cast<const float4*>(xr + 100);
+                        *reinterpret_cast<float4*>(cv) = *reinterpret_cast<const float4*>(cr);
+                        *reinterpret_cast<float4*>(cv + 4) = *reinterpret_cast<const float4*>(cr + 4);
+                        float hv[8];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float ig = sigmoid1(__uint_as_float(ri[i]) + xr[i]);
-                        const float fg = sigmoid1(__uint_as_float(rf[i]) + xr[32 + i]);
-                        const float gg = tanhf(__uint_as_float(rg[i]) + xr[64 + i]);
-                        const float og = sigmoid1(__uint_as_float(ro[i]) + xr[96 + i]);
-                        const float cn = fg * cr[i] + ig * gg;
-                        cr[i] = cn;
-                        hv[i] = og * tanhf(cn);
+                        for (int i = 0; i < 8; ++i) {
+                            const float ig = sigmoid1(__uint_as_float(ri[i]) + xi[i]);
+                            const float fg = sigmoid1(__uint_as_float(rf[i]) + xf[i]);
+                            const float gg = tanhf(__uint_as_float(rg[i]) + xg[i]);
+                            const float og = sigmoid1(__uint_as_float(ro[i]) + xo[i]);
+                            cv[i] = fg * cv[i] + ig * gg;
+                            hv[i] = og * tanhf(cv[i]);
+                        }
+                        *reinterpret_cast<float4*>(cr) = *reinterpret_cast<float4*>(cv);
+                        *reinterpret_cast<float4*>(cr + 4) = *reinterpret_cast<float4*>(cv + 4);
+                        if (g.out_f32) {
+                            float* o = g.out_f32 + (long long)m * g.ldo + u0;
+                            *reinterpret_cast<float4*>(o) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                            *reinterpret_cast<float4*>(o + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                        }
+                        if (g.out_hi) store_planes<8, false>(g.out_hi, g.out_lo, (long long)m * g.ldh + u0, hv);
                     }
-                    const int nb = u0 + hf * 16;
-                    if (g.out_f32) {
-                        float* o = g.out_f32 + (long long)m * g.ldo + nb;
+                }
+            } else if (g.act == TC_ACT_ARGMIN) {
+                // nearest code (reference encoder/quantization/core_vq.py:175-183): argmin_n ||x - c_n||^2 =
+                // argmin_n (||c_n||^2 - 2 x.c_n); operands are centred on the codebook mean (distance-invariant),
+                // first index wins ties (packed (distance, index) keys under a 64-bit atomicMin).
+                float bd = INFINITY;
+                int bi = 0;
+#pragma unroll 1
+                for (int c = cg; c < BN / CW; c += C::G) {
+                    uint32_t r[CW];
+                    __syncwarp();
+                    tmem_ld(tbase + (uint32_t)(c * CW), r);
+                    const int nb = n0 + c * CW;
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<float4*>(o + i) = make_float4(hv[i], hv[i + 1], hv[i + 2], hv[i + 3]);
+                    for (int i = 0; i < CW; ++i) {
+                        const float d = fmaf(-2.f, __uint_as_float(r[i]), g.bias[nb + i]);
+                        if (d < bd) { bd = d; bi = nb + i; }
                     }
-                    if (g.out_hi) store_planes<16, false>(g.out_hi, g.out_lo, (long long)m * g.ldh + nb, hv);
+                }
+                if (row_ok) {
+                    uint32_t u = __float_as_uint(bd);
+                    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // order-preserving float -> uint
+                    atomicMin(g.best + m, ((unsigned long long)u << 32) | (unsigned)bi);
                 }
             } else {
 #pragma unroll 1
-                for (int c = 0; c < BN / CW; ++c) {
+                for (int c = cg; c < BN / CW; c += C::G) {
                     uint32_t r[CW];
                     __syncwarp();  // tcgen05.ld is .sync.aligned: re-converge after the predicated stores below
                     tmem_ld(tbase + (uint32_t)(c * CW), r);
@@ -432,6 +516,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
+            if (tile == (int)blockIdx.x && threadIdx.x == 64) stamp(41);  // epilogue of the first tile done
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -439,6 +524,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) stamp(42);  // all roles finished
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"((uint32_t)C::TMEM_COLS)
@@ -467,9 +553,39 @@ EncodeTiledFn encode_fn() {
 
 // 2-D fp16 tensor: `rows` rows of `inner` elements, row r starting r*stride elements after the base
 // (stride < inner: overlapping rows) -> tensor map with a [box_rows, 64] box and 128 B swizzle.
-CUtensorMap make_map(const __half* base, long long rows, long long inner, long long stride, int box_rows) {
-    CUtensorMap m;
+// Descriptors are cached: the workspace arena hands out the same addresses call after call, and encoding
+// one costs ~10 us of host time (six per launch would leave the GPU idle between the ~700 launches of a step).
+struct MapKey {
+    const void* base; long long rows, inner, stride; int box;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && rows == o.rows && inner == o.inner && stride == o.stride && box == o.box;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.base);
+        auto mix = [&](size_t v) { h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
+        mix((size_t)k.rows); mix((size_t)k.inner); mix((size_t)k.stride); mix((size_t)k.box);
+        return h;
+    }
+};
+
+CUtensorMap encode_map(const __half* base, long long rows, long long inner, long long stride, int box_rows);
+
+const CUtensorMap& make_map(const __half* base, long long rows, long long inner, long long stride, int box_rows) {
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    static std::mutex mu;
     if (rows < 1) rows = 1;
+    std::lock_guard<std::mutex> lock(mu);
+    MapKey key{base, rows, inner, stride, box_rows};
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    if (cache.size() > (1u << 16)) cache.clear();
+    return cache.emplace(key, encode_map(base, rows, inner, stride, box_rows)).first->second;
+}
+
+CUtensorMap encode_map(const __half* base, long long rows, long long inner, long long stride, int box_rows) {
+    CUtensorMap m;
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)stride * sizeof(__half)};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
@@ -509,9 +625,10 @@ void launch_cfg(const TcGemm& g, cudaStream_t s) {
         maps.a[si][0] = make_map(sg.hi, sg.rows, sg.inner, sg.stride, BM);
         maps.a[si][1] = make_map(PASSES == 3 ? sg.lo : sg.hi, sg.rows, sg.inner, sg.stride, BM);
     }
-    maps.w[0] = make_map(g.W_hi, g.N, g.K, g.K, BN);
-    maps.w[1] = make_map(PASSES == 3 ? g.W_lo : g.W_hi, g.N, g.K, g.K, BN);
-    const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+    const long long ldw = g.ldw ? g.ldw : g.K, w_rows = g.w_rows ? g.w_rows : g.N;
+    maps.w[0] = make_map(g.W_hi, w_rows, g.K, ldw, BN);
+    maps.w[1] = make_map(PASSES == 3 ? g.W_lo : g.W_hi, w_rows, g.K, ldw, BN);
+    const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.batch;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     tap_gemm_tc_kernel<BN, PASSES><<<grid, NUM_THREADS, C::SMEM, s>>>(maps, g);
     WT_CUDA(cudaGetLastError());
@@ -547,7 +664,12 @@ __global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict
 
 }  // namespace
 
-void launch_tap_gemm_tc(const TcGemm& g, cudaStream_t s) {
+static long long* g_debug_timeline = nullptr;
+void set_debug_timeline(long long* dev_buf) { g_debug_timeline = dev_buf; }
+
+void launch_tap_gemm_tc(const TcGemm& g_in, cudaStream_t s) {
+    TcGemm g = g_in;
+    if (!g.dbg) g.dbg = g_debug_timeline;
     if (g.M <= 0 || g.N <= 0) return;
     int kbs = 0;
     for (int si = 0; si < g.nseg; ++si) {
@@ -564,6 +686,9 @@ void launch_tap_gemm_tc(const TcGemm& g, cudaStream_t s) {
     if (g.passes != 1 && g.passes != 3) throw Error(4, "gemm_tc: passes must be 1 or 3");
     if (g.act == TC_ACT_LSTM && (g.N % 128 || !g.cell || !g.res || g.map.Pin))
         throw Error(4, "gemm_tc: LSTM epilogue needs N % 128 == 0, a cell state and the input projection");
+    if (g.act == TC_ACT_ARGMIN && (g.N % 256 || !g.best || !g.bias || g.map.Pin))
+        throw Error(4, "gemm_tc: argmin epilogue needs N % 256 == 0, ||c||^2 and the packed best[] buffer");
+    if (g.batch < 1 || (g.ldw && g.ldw % 8)) throw Error(4, "gemm_tc: bad batch / W pitch");
     if (g.passes == 3) launch_bn<3>(g, s); else launch_bn<1>(g, s);
 }
 

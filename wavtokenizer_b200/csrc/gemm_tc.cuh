@@ -26,11 +26,14 @@ struct TcSeg {
 // Output row remap: GEMM row m = b*Pin + t (valid iff t < Tvalid) is stored at row b*Pout + off + t, and
 // mirrored into the reflect halo rows [off - hl, off) and [off + Tvalid, off + Tvalid + hr) of the padded
 // layout its consumer reads (reference encoder/modules/conv.py:79-96 reflect padding). Pin == 0: identity.
+// Destination row = b*sb + (off + t)*st with sb = Pout, st = 1 by default (batch-major); sb = 1, st = #clips
+// gives the time-major rows [t*B + b] the LSTM steps read as one contiguous [B, D] block per time step.
 struct RowMap {
     int Pin = 0, Tvalid = 0, Pout = 0, off = 0, hl = 0, hr = 0;
+    int sb = 0, st = 0;
 };
 
-enum : int { TC_ACT_NONE = 0, TC_ACT_GELU = 1, TC_ACT_LSTM = 2 };
+enum : int { TC_ACT_NONE = 0, TC_ACT_GELU = 1, TC_ACT_LSTM = 2, TC_ACT_ARGMIN = 3 };
 
 struct TcGemm {
     TcSeg seg[2];
@@ -39,7 +42,13 @@ struct TcGemm {
     const __half* W_hi = nullptr;
     const __half* W_lo = nullptr;
     int M = 0, N = 0, K = 0;
+    long long ldw = 0;     // row pitch of W in elements (0: K)
+    long long w_rows = 0;  // rows of the W tensor (0: N)
     int passes = 3;  // 3: hi*hi + hi*lo + lo*hi; 1: hi*hi only
+    // batched mode (attention): `batch` independent problems of M x N x K; problem z reads A rows shifted by
+    // z*a_brows, W rows shifted by z*w_brows and writes rows shifted by z*o_brows
+    int batch = 1;
+    long long a_brows = 0, w_brows = 0, o_brows = 0;
     // epilogue: v = acc + bias; act; v *= gamma; v += res[m]; stores of v and/or ELU(v)
     const float* bias = nullptr;
     const float* gamma = nullptr;
@@ -58,7 +67,15 @@ struct TcGemm {
     // TC_ACT_LSTM (see gemm_tc.cu): columns are [i | f | g | o] blocks of 32 units per 128-wide tile
     float* cell = nullptr;     // [M, H] cell state, updated in place
     int hidden = 0;
+    // split planes receive v - plane_shift[n] (the VQ reads frames centred on the codebook mean)
+    const float* plane_shift = nullptr;
+    // TC_ACT_ARGMIN: per row argmin_n (bias[n] - 2*acc[m, n]) merged across tiles with a packed atomicMin
+    unsigned long long* best = nullptr;
+    // optional per-CTA timeline (clock64 stamps, 64 slots per CTA) for performance debugging
+    long long* dbg = nullptr;
 };
+
+void set_debug_timeline(long long* dev_buf);
 
 void launch_tap_gemm_tc(const TcGemm& g, cudaStream_t s);
 void launch_split_f16(const float* x, __half* hi, __half* lo, long long rows, int cols, long long ld_in,

@@ -72,6 +72,10 @@ struct wt_handle {
     // vq
     float* codebooks = nullptr;  // [num_quantizers * bins, D]
     float* cnorm = nullptr;      // [bins] of codebook 0
+    // tcgen05 VQ: codebook 0 centred on its mean (distances unchanged, far better conditioned)
+    float* cb_mean = nullptr;    // [D]
+    HalfW cb_c;                  // split planes of (C - mean) [bins, D]
+    float* cnorm_c = nullptr;    // ||C - mean||^2 [bins]
     // decoder
     ConvW embed;
     struct Resnet { float *n1w, *n1b, *n2w, *n2b; ConvW c1, c2; } pos[4];
@@ -360,6 +364,24 @@ void prepare(wt_handle* h, const Table& t) {
             cn[j] = (float)s;
         }
         h->cnorm = h->upload(cn);
+        const int D0 = c.dimension;
+        std::vector<double> mu(D0, 0.0);
+        for (int j = 0; j < c.vq_bins; ++j)
+            for (int d = 0; d < D0; ++d) mu[d] += all[(size_t)j * D0 + d];
+        std::vector<float> muf(D0), cc((size_t)c.vq_bins * D0), cnc(c.vq_bins);
+        for (int d = 0; d < D0; ++d) muf[d] = (float)(mu[d] / c.vq_bins);
+        for (int j = 0; j < c.vq_bins; ++j) {
+            double s2 = 0;
+            for (int d = 0; d < D0; ++d) {
+                float v = all[(size_t)j * D0 + d] - muf[d];
+                cc[(size_t)j * D0 + d] = v;
+                s2 += (double)v * v;
+            }
+            cnc[j] = (float)s2;
+        }
+        h->cb_mean = h->upload(muf);
+        h->cb_c = h->upload_split(cc);
+        h->cnorm_c = h->upload(cnc);
     }
 
     // ---- backbone (reference decoder/models.py:166-216) ----
@@ -508,6 +530,8 @@ size_t enc_back_floats(const wt_config& c, int Bg, int L) {
     a(M * D);                                          // split planes of the pre-LSTM rows (tcgen05 plan)
     for (int l = 0; l < c.lstm_layers; ++l) a(M * D);  // split planes of y_l
     a((size_t)Bg * (L + 6) * D);                       // ELU(lstm + skip) planes, reflect-padded
+    a(M * D);                                          // centred z planes for the tcgen05 VQ
+    a(M * 2);                                          // packed (distance, index) keys
     return tot;
 }
 
@@ -522,6 +546,9 @@ size_t dec_chunk_floats(const wt_config& c, int Bc, int L, int Kp) {
     a(R * c.dim); a(R * c.dim); a(R * c.dim);    // x, t1/t2, a planes
     a(R * big); a(R * big);                      // qkv / z / frames ; S or GELU planes
     a(R * Kp);                                   // S planes (tcgen05 plan)
+    const size_t Lpad = align_up(L, 64);
+    a(R * Lpad); a(R * Lpad);                    // attention scores (fp32) and probability planes
+    a((size_t)Bc * c.dim * Lpad);                // V^T planes
     return tot;
 }
 
@@ -686,6 +713,21 @@ float* encoder_back(wt_handle* h, const float* pre, int Bg, int L, int b0, cudaS
     return z;
 }
 
+// Nearest-code search on the tensor cores: (x - mu).(c - mu) with 3-pass split-fp16 operands, argmin of
+// ||c - mu||^2 - 2 x.c fused into the GEMM epilogue (reference encoder/quantization/core_vq.py:175-183).
+// zc planes [M, D] hold the centred frames; `keys` is an [M] u64 scratch.
+void vq_tc(wt_handle* h, const __half* zc_hi, const __half* zc_lo, long long M, unsigned long long* keys,
+           long long* codes, cudaStream_t s) {
+    const wt_config& c = h->cfg;
+    WT_CUDA(cudaMemsetAsync(keys, 0xFF, (size_t)M * sizeof(unsigned long long), s));
+    TcGemm g;
+    g.seg[0] = tc_taps(zc_hi, zc_lo, M, c.dimension, c.dimension, 1, 0);
+    g.W_hi = h->cb_c.hi; g.W_lo = h->cb_c.lo; g.M = (int)M; g.N = c.vq_bins; g.K = c.dimension; g.passes = 3;
+    g.act = TC_ACT_ARGMIN; g.bias = h->cnorm_c; g.best = keys;
+    { Scope sc(h, CAT_VQ, s); launch_tap_gemm_tc(g, s); }
+    { Scope sc(h, CAT_VQ, s); launch_best_to_codes(keys, codes, M, s); }
+}
+
 // ---------------------------------------------------------------------------------------
 // tcgen05 encoder. Every conv is a GEMM over a TMA tensor map of the channels-last activation:
 //   * stride-1 k-tap conv and strided conv (k = 2s): "window" map with OVERLAPPING rows
@@ -708,7 +750,8 @@ bool encoder_tc_supported(const wt_config& c, int T) {
     return Tc >= 4 && c.dimension == 512 && c.n_filters == 32;
 }
 
-void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, float* pre, __half* pre_hi,
+// `pre*` point at the group's time-major pre-LSTM rows [t*Bg + b] already offset to this chunk's first clip.
+void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, int Bg, float* pre, __half* pre_hi,
                       __half* pre_lo, cudaStream_t s) {
     const wt_config& c = h->cfg;
     auto halves = [&](size_t n) { return reinterpret_cast<__half*>(h->alloc((n + 1) / 2)); };
@@ -780,14 +823,21 @@ void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, flo
             if (want("enc" + std::to_string(idx + 2))) { z_tap = h->alloc(nX2); g.out_f32 = z_tap; g.ldo = C2; }
         } else {
             g.map.Pout = Tn; g.map.off = 0; g.map.hl = 0; g.map.hr = 0;
+            g.map.sb = 1; g.map.st = Bg;  // time-major rows for the LSTM
             g.out_f32 = pre; g.ldo = C2;
             g.out_hi = pre_hi; g.out_lo = pre_lo; g.ldh = C2;
         }
         run(g);
         if (i < 3) {
             if (z_tap) h->tap(("enc" + std::to_string(idx + 2)).c_str(), z_tap + (size_t)C2, Bc, Tn, C2, b0, s, Tn + 2);
-        } else {
-            h->tap(("enc" + std::to_string(idx + 2)).c_str(), pre, Bc, Tn, C2, b0, s);
+        } else if (want("enc" + std::to_string(idx + 2))) {
+            auto& tr = h->taps["enc" + std::to_string(idx + 2)];
+            tr.B = Bc; tr.T = Tn; tr.C = C2;
+            if (tr.buf && (int64_t)Bc * Tn * C2 <= tr.cap)
+                for (int b = 0; b < Bc; ++b)  // gather clip b out of the time-major rows
+                    WT_CUDA(cudaMemcpy2DAsync(tr.buf + (size_t)b * Tn * C2, (size_t)C2 * sizeof(float),
+                                              pre + (size_t)b * C2, (size_t)Bg * C2 * sizeof(float),
+                                              (size_t)C2 * sizeof(float), Tn, cudaMemcpyDeviceToDevice, s));
         }
         Tc = Tn; C = C2; idx += 3;
     }
@@ -796,7 +846,7 @@ void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, flo
 // SLSTM + ELU + final k7 conv on the tensor cores: hoisted input projections, one GEMM launch per time
 // step whose epilogue is the LSTM cell (gates never leave the SM), final conv over the reflect-padded rows.
 float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, const __half* pre_lo, int Bg, int L,
-                       int b0, cudaStream_t s) {
+                       int b0, __half** zc_hi_out, __half** zc_lo_out, cudaStream_t s) {
     const wt_config& c = h->cfg;
     const int D = c.dimension;
     const long long M = (long long)Bg * L;
@@ -812,6 +862,8 @@ float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, con
     }
     const __half *lin_hi = pre_hi, *lin_lo = pre_lo;
     const __half* zero = reinterpret_cast<const __half*>(h->zero_rows);
+    // all LSTM tensors are time-major: row t*Bg + b. Step t reads rows [(t-1)*Bg, t*Bg) of the hidden-state
+    // planes through ONE tensor map (row shift (t-1)*Bg), so no descriptor is built inside the time loop.
     for (int l = 0; l < c.lstm_layers; ++l) {
         const auto& w = h->lstm_tc[l];
         {   // xin = W_ih x + b_ih + b_hh for all L steps at once (gate rows permuted like the recurrent tile)
@@ -825,12 +877,16 @@ float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, con
         WT_CUDA(cudaMemsetAsync(cst, 0, (size_t)Bg * D * sizeof(float), s));
         for (int t = 0; t < L; ++t) {
             TcGemm g;
-            if (t == 0) g.seg[0] = tc_taps(zero, zero, Bg, D, D, 1, 0);  // h_{-1} = 0
-            else g.seg[0] = tc_taps(yh_hi[l] + (size_t)(t - 1) * D, yh_lo[l] + (size_t)(t - 1) * D, Bg, D, L * D, 1, 0);
+            if (t == 0) {
+                g.seg[0] = tc_taps(zero, zero, Bg, D, D, 1, 0);  // h_{-1} = 0
+            } else {
+                g.seg[0] = tc_taps(yh_hi[l], yh_lo[l], M, D, D, 1, 0);
+                g.seg[0].shift0 = (t - 1) * Bg;
+            }
             g.W_hi = w.w_hh.hi; g.W_lo = w.w_hh.lo; g.M = Bg; g.N = 4 * D; g.K = D; g.passes = 3;
-            g.act = TC_ACT_LSTM; g.res = xin + (size_t)t * 4 * D; g.ldres = L * 4 * D; g.cell = cst; g.hidden = D;
-            g.out_f32 = ybuf[l] + (size_t)t * D; g.ldo = L * D;
-            g.out_hi = yh_hi[l] + (size_t)t * D; g.out_lo = yh_lo[l] + (size_t)t * D; g.ldh = L * D;
+            g.act = TC_ACT_LSTM; g.res = xin + (size_t)t * Bg * 4 * D; g.ldres = 4 * D; g.cell = cst; g.hidden = D;
+            g.out_f32 = ybuf[l] + (size_t)t * Bg * D; g.ldo = D;
+            g.out_hi = yh_hi[l] + (size_t)t * Bg * D; g.out_lo = yh_lo[l] + (size_t)t * Bg * D; g.ldh = D;
             Scope sc(h, CAT_LSTM, s);
             launch_tap_gemm_tc(g, s);
         }
@@ -847,6 +903,8 @@ float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, con
     }
     h->tap("enc13", lo, Bg, L, D, b0, s);
     float* z = h->alloc((size_t)M * D);
+    __half *zc_hi = halves((size_t)M * D), *zc_lo = halves((size_t)M * D);
+    *zc_hi_out = zc_hi; *zc_lo_out = zc_lo;
     {
         TcGemm g;
         g.seg[0] = tc_window(e_hi, e_lo, (long long)nE, 7 * D, D);
@@ -854,6 +912,7 @@ float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, con
         g.bias = h->enc_last.b;
         g.map.Pin = L + 6; g.map.Tvalid = L; g.map.Pout = L; g.map.off = 0;
         g.out_f32 = z; g.ldo = D;
+        g.out_hi = zc_hi; g.out_lo = zc_lo; g.ldh = D; g.plane_shift = h->cb_mean;  // centred frames for the VQ
         Scope sc(h, CAT_ENC_CONV, s);
         launch_tap_gemm_tc(g, s);
     }
@@ -946,8 +1005,9 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
     __half* a_hi = halves((size_t)R * D);
     __half* a_lo = halves((size_t)R * D);
     float* bigA = h->alloc((size_t)R * big);
-    __half* g_hi = halves((size_t)R * Hd);
-    __half* g_lo = halves((size_t)R * Hd);
+    const size_t gw = std::max(Hd, 3 * D);  // GELU planes, also the q|k|v planes of the attention block
+    __half* g_hi = halves((size_t)R * gw);
+    __half* g_lo = halves((size_t)R * gw);
     __half* S_hi = halves((size_t)R * h->Kp);
     __half* S_lo = halves((size_t)R * h->Kp);
     const float eps = 1e-6f;
@@ -978,11 +1038,39 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
     };
     resnet(h->pos[0]); h->tap("dec_pos0", x, Bc, L, D, b0, s, Lp);
     resnet(h->pos[1]); h->tap("dec_pos1", x, Bc, L, D, b0, s, Lp);
-    {
+    {   // AttnBlock on the tensor cores: QKV GEMM -> batched q.k^T -> softmax -> batched P.V -> proj (+x)
+        const int Lpad = (int)align_up(L, 64);
+        float* S = h->alloc((size_t)R * Lpad);
+        __half *p_hi = halves((size_t)R * Lpad), *p_lo = halves((size_t)R * Lpad);
+        __half *vt_hi = halves((size_t)Bc * D * Lpad), *vt_lo = halves((size_t)Bc * D * Lpad);
+        __half *qkv_hi = g_hi, *qkv_lo = g_lo;  // [R, 3D] planes (the GELU buffer is free here)
         { Scope sc(h, CAT_MEM, s); launch_groupnorm(x, h->attn.nw, h->attn.nb, out_split(a_hi, a_lo), Bc, L, Lp, D, 32, eps, 0, s); }
         gemm(a_hi, a_lo, D, 1, h->attn.wqkv_h.hi, h->attn.wqkv_h.lo, 3 * D, 3, h->attn.bqkv, ACT_NONE, nullptr, nullptr,
-             bigA, 3 * D, nullptr, nullptr, 0);
-        { Scope sc(h, CAT_ATTN, s); launch_attention(bigA, out_split(a_hi, a_lo), Bc, L, Lp, D, s); }
+             nullptr, 0, qkv_hi, qkv_lo, 3 * D);
+        r.cat = CAT_ATTN;
+        {   // scores[b, i, j] = q_i . k_j for the L frames of clip b
+            TcGemm g;
+            g.seg[0] = tc_taps(qkv_hi, qkv_lo, R, D, 3 * D, 1, 0);
+            g.W_hi = qkv_hi + D; g.W_lo = qkv_lo + D; g.ldw = 3 * D; g.w_rows = R;
+            g.M = L; g.N = Lpad; g.K = D; g.passes = 3;
+            g.batch = Bc; g.a_brows = Lp; g.w_brows = Lp; g.o_brows = Lp;
+            g.out_f32 = S; g.ldo = Lpad;
+            Scope sc(h, CAT_ATTN, s);
+            launch_tap_gemm_tc(g, s);
+        }
+        { Scope sc(h, CAT_ATTN, s); launch_softmax_planes(S, Lpad, p_hi, p_lo, Lpad, Bc, L, Lp, 1.0f / sqrtf((float)D), s); }
+        { Scope sc(h, CAT_ATTN, s); launch_vt_planes(qkv_hi, qkv_lo, vt_hi, vt_lo, Bc, L, Lp, D, Lpad, s); }
+        {   // out[b, i, :] = sum_j P[b, i, j] v_j
+            TcGemm g;
+            g.seg[0] = tc_taps(p_hi, p_lo, R, Lpad, Lpad, 1, 0);
+            g.W_hi = vt_hi; g.W_lo = vt_lo; g.ldw = Lpad; g.w_rows = (long long)Bc * D;
+            g.M = L; g.N = D; g.K = Lpad; g.passes = 3;
+            g.batch = Bc; g.a_brows = Lp; g.w_brows = D; g.o_brows = Lp;
+            g.out_hi = a_hi; g.out_lo = a_lo; g.ldh = D;
+            Scope sc(h, CAT_ATTN, s);
+            launch_tap_gemm_tc(g, s);
+        }
+        r.cat = CAT_DEC_CONV;
         gemm(a_hi, a_lo, D, 1, h->attn.proj.w_hi, h->attn.proj.w_lo, D, 3, h->attn.proj.b, ACT_NONE, nullptr, x, x, D,
              nullptr, nullptr, 0);
         h->tap("dec_pos2", x, Bc, L, D, b0, s, Lp);
@@ -1047,11 +1135,14 @@ void do_encode(wt_handle* h, const float* wav, int B, int T, float* features_out
             const int Bc = std::min(ENC_CHUNK, Bg - b0);
             h->arena_off = mark;
             const size_t ro = (size_t)b0 * L * D;
-            if (tc) encoder_front_tc(h, wav + (size_t)(g0 + b0) * T, Bc, T, g0 + b0, pre + ro, pre_hi + ro, pre_lo + ro, s);
+            const size_t to = (size_t)b0 * D;  // time-major: clip b0 starts at row b0 of every time step
+            if (tc) encoder_front_tc(h, wav + (size_t)(g0 + b0) * T, Bc, T, g0 + b0, Bg, pre + to, pre_hi + to, pre_lo + to, s);
             else encoder_front(h, wav + (size_t)(g0 + b0) * T, Bc, T, g0 + b0, pre + ro, s);
         }
         h->arena_off = mark;
-        float* z = tc ? encoder_back_tc(h, pre, pre_hi, pre_lo, Bg, L, g0, s) : encoder_back(h, pre, Bg, L, g0, s);
+        __half *zc_hi = nullptr, *zc_lo = nullptr;
+        float* z = tc ? encoder_back_tc(h, pre, pre_hi, pre_lo, Bg, L, g0, &zc_hi, &zc_lo, s)
+                      : encoder_back(h, pre, Bg, L, g0, s);
         const long long M = (long long)Bg * L;
         if (z_out) {
             Scope sc(h, CAT_MEM, s);
@@ -1059,7 +1150,13 @@ void do_encode(wt_handle* h, const float* wav, int B, int T, float* features_out
         }
         if (codes_out) {
             long long* codes = reinterpret_cast<long long*>(codes_out) + (size_t)g0 * L;
-            { Scope sc(h, CAT_VQ, s); launch_vq_simt(z, h->codebooks, h->cnorm, M, D, c.vq_bins, codes, s); }
+            if (tc) {
+                unsigned long long* keys = reinterpret_cast<unsigned long long*>(h->alloc((size_t)M * 2));
+                vq_tc(h, zc_hi, zc_lo, M, keys, codes, s);
+            } else {
+                Scope sc(h, CAT_VQ, s);
+                launch_vq_simt(z, h->codebooks, h->cnorm, M, D, c.vq_bins, codes, s);
+            }
             if (features_out) {
                 Scope sc(h, CAT_MEM, s);
                 launch_codes_to_features(h->codebooks, codes, features_out + (size_t)g0 * D * L, 1, Bg, L, D, c.vq_bins,
@@ -1212,7 +1309,20 @@ int wt_vq(wt_handle* h, const float* x, int64_t N, int64_t* codes_out, float* qu
         if (!x || !codes_out) throw Error(WT_ERR_VALUE, "wt_vq: null buffer");
         cudaStream_t s = (cudaStream_t)stream;
         const wt_config& c = h->cfg;
-        {
+        if (h->plan >= 1) {
+            const long long CH = 1 << 18;  // frames per pass: 0.5 GB of centred operand planes
+            const int D = c.dimension;
+            h->ensure_arena((size_t)std::min<long long>(N, CH) * (D * 4 + 16) + 4096);
+            for (long long n0 = 0; n0 < N; n0 += CH) {
+                const long long n = std::min(CH, N - n0);
+                h->arena_off = 0;
+                __half* hi = reinterpret_cast<__half*>(h->alloc((size_t)n * D / 2));
+                __half* lo = reinterpret_cast<__half*>(h->alloc((size_t)n * D / 2));
+                unsigned long long* keys = reinterpret_cast<unsigned long long*>(h->alloc((size_t)n * 2));
+                { Scope sc(h, CAT_VQ, s); launch_center_split(x + (size_t)n0 * D, h->cb_mean, hi, lo, n, D, s); }
+                vq_tc(h, hi, lo, n, keys, reinterpret_cast<long long*>(codes_out) + n0, s);
+            }
+        } else {
             Scope sc(h, CAT_VQ, s);
             launch_vq_simt(x, h->codebooks, h->cnorm, N, c.dimension, c.vq_bins, reinterpret_cast<long long*>(codes_out), s);
         }
@@ -1355,6 +1465,11 @@ int wt_test_tap_gemm(int32_t device, const float* A, int32_t rows, int32_t Cin, 
         g_last_error = e.what();
         return WT_ERR_RUNTIME;
     }
+}
+
+int wt_debug_timeline(long long* dev_buf) {
+    set_debug_timeline(dev_buf);
+    return WT_OK;
 }
 
 int wt_set_plan(wt_handle* h, int32_t plan) {

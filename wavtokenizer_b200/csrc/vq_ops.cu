@@ -1,6 +1,8 @@
 // Vector quantiser kernels (plan 0, fp32 CUDA cores) and codebook gathers.
 // Replaces EuclideanCodebook.quantize / dequantize (reference encoder/quantization/core_vq.py:175-190)
 // and WavTokenizer.codes_to_features (decoder/pretrained.py:209-239).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace wt {
@@ -187,7 +189,41 @@ __global__ void __launch_bounds__(256) codes_to_features_kernel(const float* __r
     }
 }
 
+// frames [N, D] fp32 -> split-fp16 planes of (x - mu): the tcgen05 VQ reads frames centred on the codebook mean
+__global__ void center_split_kernel(const float* __restrict__ x, const float* __restrict__ mu, __half* __restrict__ hi,
+                                    __half* __restrict__ lo, long long n2, int D) {
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n2) return;
+    const int c = (int)((gid * 2) % D);
+    const float2 v = *reinterpret_cast<const float2*>(x + gid * 2);
+    const float a = v.x - mu[c], b = v.y - mu[c + 1];
+    const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+    *reinterpret_cast<__half2*>(hi + gid * 2) = __halves2half2(ha, hb);
+    *reinterpret_cast<__half2*>(lo + gid * 2) =
+        __halves2half2(__float2half_rn(a - __half2float(ha)), __float2half_rn(b - __half2float(hb)));
+}
+
+// packed (distance, index) keys of the argmin epilogue -> int64 codes
+__global__ void best_to_codes_kernel(const unsigned long long* __restrict__ best, long long* __restrict__ codes,
+                                     long long n) {
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n) codes[gid] = (long long)(best[gid] & 0xFFFFFFFFull);
+}
+
 }  // namespace
+
+void launch_center_split(const float* x, const float* mu, __half* hi, __half* lo, long long N, int D, cudaStream_t s) {
+    if (N <= 0) return;
+    long long n2 = N * D / 2;
+    center_split_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, s>>>(x, mu, hi, lo, n2, D);
+    WT_CUDA(cudaGetLastError());
+}
+
+void launch_best_to_codes(const unsigned long long* best, long long* codes, long long N, cudaStream_t s) {
+    if (N <= 0) return;
+    best_to_codes_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(best, codes, N);
+    WT_CUDA(cudaGetLastError());
+}
 
 void launch_vq_simt(const float* x, const float* codebook, const float* cnorm, long long N, int D, int bins,
                     long long* codes, cudaStream_t s) {
