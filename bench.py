@@ -295,7 +295,8 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
             cpu = {k: cpu_r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "vs_baseline": None, "dtype": "f32" if args.plan == 0 else "split-f16x2 operands, f32 accumulate",
+                "data": "synthetic",
                 "config": {"workload": WORKLOAD, "clips_per_gpu": B, "samples_per_clip": T, "frames_per_clip": L,
                            "plan": args.plan, "l2": "256 MiB flush between timed iterations; activations per step "
                            "(> 10 GB) exceed the 126 MB L2", "sharding": f"by clip, {world} rank(s), all-gather of codes"},
@@ -313,7 +314,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--plan", type=int, default=int(os.environ.get("WT_PLAN", "0")))
+    ap.add_argument("--plan", type=int, default=int(os.environ.get("WT_PLAN", "2")))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

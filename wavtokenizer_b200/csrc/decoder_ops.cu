@@ -41,114 +41,190 @@ __device__ __forceinline__ void put(const RowOut& o, long long idx, float v) {
     }
 }
 
-// Normalize = GroupNorm(32, C, eps=1e-6, affine) (+ x*sigmoid(x)) (reference decoder/models.py:10-16,
-// 58-78, 107-110). One block per (clip, group): statistics span all L frames of the clip, two-pass
-// (mean, then centred variance); the clip slice stays in L2 between passes. Halo rows are written as zeros.
-__global__ void __launch_bounds__(256) groupnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                        const float* __restrict__ bsh, RowOut out, int L, int Lp,
-                                                        int C, int cpg, float eps, int swish) {
-    __shared__ float red[8];
-    const int b = blockIdx.y, g = blockIdx.x;
-    const long long base = (long long)b * Lp * C + g * cpg;
-    const float* xb = x + base;
-    const int n = L * cpg;
-    float s = 0.f;
-    for (int i = threadIdx.x; i < n; i += 256) {
-        int t = i / cpg, c = i - t * cpg;
-        s += xb[(long long)t * C + c];
+// 8 consecutive channels of one row -> fp32 and/or split planes (16-byte stores).
+__device__ __forceinline__ void put8(const RowOut& o, long long idx, const float (&v)[8]) {
+    if (o.f32) {
+        *reinterpret_cast<float4*>(o.f32 + idx) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(o.f32 + idx + 4) = make_float4(v[4], v[5], v[6], v[7]);
     }
-    const float mean = block_sum<8>(s, red) / (float)n;
-    float v = 0.f;
-    for (int i = threadIdx.x; i < n; i += 256) {
-        int t = i / cpg, c = i - t * cpg;
-        float d = xb[(long long)t * C + c] - mean;
-        v = fmaf(d, d, v);
-    }
-    const float var = block_sum<8>(v, red) / (float)n;
-    const float rstd = rsqrtf(var + eps);
-    for (int i = threadIdx.x; i < Lp * cpg; i += 256) {
-        int t = i / cpg, c = i - t * cpg;
-        float y = 0.f;
-        if (t < L) {
-            y = (xb[(long long)t * C + c] - mean) * rstd * w[g * cpg + c] + bsh[g * cpg + c];
-            if (swish) y = y / (1.f + expf(-y));
+    if (o.hi) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
+            __half l0 = __float2half_rn(v[2 * i] - __half2float(h0)), l1 = __float2half_rn(v[2 * i + 1] - __half2float(h1));
+            h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
         }
-        put(out, base + (long long)t * C + c, y);
+        *reinterpret_cast<uint4*>(o.hi + idx) = make_uint4(h[0], h[1], h[2], h[3]);
+        if (o.lo) *reinterpret_cast<uint4*>(o.lo + idx) = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
-// layer_norm over C (eps 1e-6) then * w + b, one warp per row. With w = scale[id], b = shift[id] this is
-// AdaLayerNorm (reference decoder/modules.py:81-86); with the affine parameters it is the final
-// nn.LayerNorm (decoder/models.py:195, 234).
-template <int PER>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                        const float* __restrict__ b, RowOut out, long long M,
-                                                        float eps) {
-    constexpr int C = PER * 32;
-    const int lane = threadIdx.x & 31;
-    long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= M) return;
-    const float* xr = x + row * C;
-    float v[PER];
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// Normalize = GroupNorm(32, C, eps=1e-6, affine) (+ x*sigmoid(x)) (reference decoder/models.py:10-16,
+// 58-78, 107-110). Statistics span all L frames of a clip. One block per (clip, slab of 8 groups = 192
+// channels): 48 lanes x float4 read whole 768-byte row slabs coalesced, 5 row phases; pass 1 accumulates
+// sum / sum-of-squares (combined in fp64), pass 2 re-reads the slab (L2-resident), normalises and stores
+// fp32 rows or split-fp16 planes with 8-byte vectors. Halo rows of the padded row space are written as zeros.
+constexpr int GN_LANES = 48, GN_PH = 5, GN_THREADS = GN_LANES * GN_PH;
+__global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ bsh, RowOut out, int L, int Lp,
+                                                               int C, float eps, int swish) {
+    __shared__ float ps[GN_THREADS], pq[GN_THREADS];
+    __shared__ float s_mean[8], s_rstd[8];
+    const int b = blockIdx.y, slab = blockIdx.x;
+    const int lane = threadIdx.x % GN_LANES, ph = threadIdx.x / GN_LANES;
+    const int c = slab * 192 + lane * 4;
+    const long long base = (long long)b * Lp * C + c;
+    float s = 0.f, q = 0.f;
+    for (int t = ph; t < L; t += GN_PH) {
+        const float4 v = *reinterpret_cast<const float4*>(x + base + (long long)t * C);
+        s += (v.x + v.y) + (v.z + v.w);
+        q = fmaf(v.x, v.x, q); q = fmaf(v.y, v.y, q); q = fmaf(v.z, v.z, q); q = fmaf(v.w, v.w, q);
+    }
+    ps[threadIdx.x] = s;
+    pq[threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.x < 8) {  // group g of the slab = lanes 6g..6g+5 in every phase
+        double ds = 0, dq = 0;
+        for (int p = 0; p < GN_PH; ++p)
+            for (int l = 0; l < 6; ++l) {
+                ds += ps[p * GN_LANES + threadIdx.x * 6 + l];
+                dq += pq[p * GN_LANES + threadIdx.x * 6 + l];
+            }
+        const double n = (double)L * 24.0;
+        const double mean = ds / n;
+        double var = dq / n - mean * mean;
+        if (var < 0) var = 0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const float mean = s_mean[lane / 6], rstd = s_rstd[lane / 6];
+    const float4 wv = *reinterpret_cast<const float4*>(w + c), bv = *reinterpret_cast<const float4*>(bsh + c);
+    for (int t = ph; t < Lp; t += GN_PH) {
+        float y[4] = {0.f, 0.f, 0.f, 0.f};
+        if (t < L) {
+            const float4 v = *reinterpret_cast<const float4*>(x + base + (long long)t * C);
+            y[0] = (v.x - mean) * rstd * wv.x + bv.x;
+            y[1] = (v.y - mean) * rstd * wv.y + bv.y;
+            y[2] = (v.z - mean) * rstd * wv.z + bv.z;
+            y[3] = (v.w - mean) * rstd * wv.w + bv.w;
+            if (swish) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) y[i] = y[i] / (1.f + expf(-y[i]));
+            }
+        }
+        const long long idx = base + (long long)t * C;
+        if (out.f32) *reinterpret_cast<float4*>(out.f32 + idx) = make_float4(y[0], y[1], y[2], y[3]);
+        if (out.hi) {
+            uint32_t h[2], l[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                __half h0 = __float2half_rn(y[2 * i]), h1 = __float2half_rn(y[2 * i + 1]);
+                __half l0 = __float2half_rn(y[2 * i] - __half2float(h0)), l1 = __float2half_rn(y[2 * i + 1] - __half2float(h1));
+                h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            }
+            *reinterpret_cast<uint2*>(out.hi + idx) = make_uint2(h[0], h[1]);
+            if (out.lo) *reinterpret_cast<uint2*>(out.lo + idx) = make_uint2(l[0], l[1]);
+        }
+    }
+}
+
+// layer_norm over C = 768 (eps 1e-6) then * w + b, one warp per row; lane owns 3 x 8 consecutive channels
+// (c = seg*256 + lane*8 + k) so that loads are 32-byte and stores 16-byte vectors. With w = scale[id],
+// b = shift[id] this is AdaLayerNorm (reference decoder/modules.py:81-86); with the affine parameters it is
+// the final nn.LayerNorm (decoder/models.py:195, 234).
+__device__ __forceinline__ void ln_finish(float (&v)[3][8], const float* __restrict__ w, const float* __restrict__ b,
+                                          const RowOut& out, long long row, int lane, float eps) {
+    constexpr int C = 768;
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { v[i] = xr[lane + 32 * i]; s += v[i]; }
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += v[g][k];
     const float mean = warp_sum(s) / (float)C;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { float d = v[i] - mean; q = fmaf(d, d, q); }
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float d = v[g][k] - mean; q = fmaf(d, d, q); }
     const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        int c = lane + 32 * i;
-        put(out, row * C + c, (v[i] - mean) * rstd * w[c] + b[c]);
+    for (int g = 0; g < 3; ++g) {
+        const int c = g * 256 + lane * 8;
+        float wv[8], bv[8], y[8];
+        load8(w + c, wv);
+        load8(b + c, bv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = (v[g][k] - mean) * rstd * wv[k] + bv[k];
+        put8(out, row * C + c, y);
     }
 }
 
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, RowOut out, long long M,
+                                                        float eps) {
+    const int lane = threadIdx.x & 31;
+    long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    float v[3][8];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) load8(x + row * 768 + g * 256 + lane * 8, v[g]);
+    ln_finish(v, w, b, out, row, lane, eps);
+}
+
 // ConvNeXt front half: depthwise Conv1d(k=7, pad 3 zeros, groups=C) -> AdaLayerNorm
-// (reference decoder/modules.py:30-33, 49-53). One warp per frame; the seven neighbouring rows are
-// L1/L2 hits, so HBM traffic is one read + one write of the activation.
-template <int PER>
+// (reference decoder/modules.py:30-33, 49-53). One warp per frame; the depthwise weights sit transposed in
+// shared memory ([tap][channel]); the seven neighbouring rows are L1/L2 hits, so HBM traffic is one read and
+// one write of the activation.
+constexpr int DW_ROWS = 32;  // frames per block (8 warps x 4 frames)
 __global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ dw,
                                                         const float* __restrict__ db, const float* __restrict__ scale,
                                                         const float* __restrict__ shift, RowOut out, int B, int L,
                                                         int Lp, float eps) {
-    constexpr int C = PER * 32;
-    const int lane = threadIdx.x & 31;
-    long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= (long long)B * Lp) return;
-    const int b = (int)(row / Lp), t = (int)(row - (long long)b * Lp);
-    if (t >= L) {  // halo row of the padded row space
-#pragma unroll
-        for (int i = 0; i < PER; ++i) put(out, row * C + lane + 32 * i, 0.f);
-        return;
+    constexpr int C = 768;
+    __shared__ __align__(16) float wt[7 * C];
+    for (int i = threadIdx.x; i < 7 * C; i += 256) {
+        const int j = i / C, c = i - j * C;
+        wt[i] = dw[c * 7 + j];
     }
-    float v[PER];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int rr = 0; rr < DW_ROWS / 8; ++rr) {
+        const long long row = (long long)blockIdx.x * DW_ROWS + warp * (DW_ROWS / 8) + rr;
+        if (row >= (long long)B * Lp) return;
+        const int b = (int)(row / Lp), t = (int)(row - (long long)b * Lp);
+        if (t >= L) {  // halo row of the padded row space
+            const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < PER; ++i) v[i] = db[lane + 32 * i];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) {
-        int tj = t - 3 + j;
-        if (tj < 0 || tj >= L) continue;
-        const float* xr = x + ((long long)b * Lp + tj) * C;
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            int c = lane + 32 * i;
-            v[i] = fmaf(dw[c * 7 + j], xr[c], v[i]);
+            for (int g = 0; g < 3; ++g) put8(out, row * C + g * 256 + lane * 8, z);
+            continue;
         }
-    }
-    float s = 0.f;
+        float v[3][8];
 #pragma unroll
-    for (int i = 0; i < PER; ++i) s += v[i];
-    const float mean = warp_sum(s) / (float)C;
-    float q = 0.f;
+        for (int g = 0; g < 3; ++g) load8(db + g * 256 + lane * 8, v[g]);
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { float d = v[i] - mean; q = fmaf(d, d, q); }
-    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+        for (int j = 0; j < 7; ++j) {
+            const int tj = t - 3 + j;
+            if (tj < 0 || tj >= L) continue;
+            const float* xr = x + ((long long)b * Lp + tj) * C;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        int c = lane + 32 * i;
-        put(out, row * C + c, (v[i] - mean) * rstd * scale[c] + shift[c]);
+            for (int g = 0; g < 3; ++g) {
+                float xv[8], wv[8];
+                load8(xr + g * 256 + lane * 8, xv);
+                load8(wt + j * C + g * 256 + lane * 8, wv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[g][k] = fmaf(wv[k], xv[k], v[g][k]);
+            }
+        }
+        ln_finish(v, scale, shift, out, row, lane, eps);
     }
 }
 
@@ -348,8 +424,9 @@ void launch_vt_planes(const __half* q_hi, const __half* q_lo, __half* vt_hi, __h
 void launch_groupnorm(const float* x, const float* w, const float* b, RowOut out, int B, int L, int Lp, int C,
                       int groups, float eps, int swish, cudaStream_t s) {
     if (B <= 0 || L <= 0) return;
-    dim3 grid(groups, B);
-    groupnorm_kernel<<<grid, 256, 0, s>>>(x, w, b, out, L, Lp, C, C / groups, eps, swish);
+    if (groups != 32 || C != 768) throw Error(1, "groupnorm: expected GroupNorm(32, 768)");
+    dim3 grid(C / 192, B);
+    groupnorm_kernel<<<grid, GN_THREADS, 0, s>>>(x, w, b, out, L, Lp, C, eps, swish);
     WT_CUDA(cudaGetLastError());
 }
 
@@ -357,7 +434,7 @@ void launch_layernorm(const float* x, const float* w, const float* b, RowOut out
                       cudaStream_t s) {
     if (M <= 0) return;
     if (C != 768) throw Error(1, "layernorm: backbone dim must be 768");
-    layernorm_kernel<24><<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, w, b, out, M, eps);
+    layernorm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, w, b, out, M, eps);
     WT_CUDA(cudaGetLastError());
 }
 
@@ -366,7 +443,7 @@ void launch_dwconv_ln(const float* x, const float* dw, const float* db, const fl
     if (B <= 0 || L <= 0) return;
     if (C != 768) throw Error(1, "dwconv_ln: backbone dim must be 768");
     long long M = (long long)B * Lp;
-    dwconv_ln_kernel<24><<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, dw, db, scale, shift, out, B, L, Lp, eps);
+    dwconv_ln_kernel<<<(unsigned)((M + DW_ROWS - 1) / DW_ROWS), 256, 0, s>>>(x, dw, db, scale, shift, out, B, L, Lp, eps);
     WT_CUDA(cudaGetLastError());
 }
 

@@ -331,6 +331,8 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+            const int ti = (tile - (int)blockIdx.x) / (int)gridDim.x;
+            if (lane == 0 && ti < 5) stamp(44 + 4 * ti);      // MMA may start tile ti (accumulator free)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
             for (int kb = 0; kb < num_kb; ++kb) {
@@ -354,7 +356,10 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                         }
                     }
                     umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
-                    if (kb == num_kb - 1) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                    if (kb == num_kb - 1) {
+                        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                        if (ti < 5) stamp(45 + 4 * ti);  // all MMAs of tile ti issued
+                    }
                 }
                 __syncwarp();
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -374,6 +379,8 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
             const int m = m_local + (int)(bz * g.o_brows);
             const int n0 = nt * BN;
             mbar_wait(tfull_bar(acc), acc_phase);
+            const int ti = (tile - (int)blockIdx.x) / (int)gridDim.x;
+            if (threadIdx.x == 64 && ti < 5) stamp(46 + 4 * ti);  // accumulator of tile ti ready
             if (tile == (int)blockIdx.x && threadIdx.x == 64) stamp(40);  // accumulator of the first tile ready
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -516,6 +523,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
+            if (threadIdx.x == 64 && ti < 5) stamp(47 + 4 * ti);  // epilogue of tile ti done (this warp)
             if (tile == (int)blockIdx.x && threadIdx.x == 64) stamp(41);  // epilogue of the first tile done
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -2,6 +2,7 @@
 // Host-side orchestration of the hot path: encode_infer -> VQ -> codes_to_features -> decode
 // (reference decoder/pretrained.py:186-239).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -19,7 +20,16 @@ namespace {
 
 thread_local std::string g_last_error;
 
-constexpr int ENC_CHUNK = 16;   // clips per encoder pass (early SEANet tensors are 9.2 MB per clip per tensor)
+constexpr int ENC_CHUNK_DEFAULT = 16;  // clips per encoder-front pass (early SEANet tensors: 9.2 MB per clip each)
+inline int enc_chunk() {
+    static int v = [] {
+        const char* e = std::getenv("WT_ENC_CHUNK");
+        int n = e ? std::atoi(e) : ENC_CHUNK_DEFAULT;
+        return n >= 1 && n <= 64 ? n : ENC_CHUNK_DEFAULT;
+    }();
+    return v;
+}
+#define ENC_CHUNK enc_chunk()
 constexpr int ENC_GROUP = 1024; // clips per LSTM / final-conv / VQ pass (the recurrent GEMM's M)
 constexpr int DEC_CHUNK = 128;  // clips per decoder pass
 
