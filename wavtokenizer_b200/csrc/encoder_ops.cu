@@ -76,10 +76,13 @@ __global__ void __launch_bounds__(256) conv0_planes_kernel(const float* __restri
     for (int i = threadIdx.x; i < C; i += blockDim.x) bs[i] = bias[i];
     __syncthreads();
     const int P = T + 2;
+    constexpr int G8 = C / 8;  // one thread per (padded position, group of 8 channels): 16-byte stores coalesce
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)B * P) return;
-    int b = (int)(gid / P);
-    int p = (int)(gid - (long long)b * P);
+    if (gid >= (long long)B * P * G8) return;
+    const int c8 = (int)(gid % G8);
+    const long long pos = gid / G8;
+    int b = (int)(pos / P);
+    int p = (int)(pos - (long long)b * P);
     int t = p - 1;
     if (t < 0) t = -t;
     if (t >= T) t = 2 * (T - 1) - t;
@@ -92,21 +95,18 @@ __global__ void __launch_bounds__(256) conv0_planes_kernel(const float* __restri
         if (ti >= T) ti = 2 * (T - 1) - ti;
         xv[j] = x[ti];
     }
+    float r[8], e[8];
 #pragma unroll
-    for (int c8 = 0; c8 < C / 8; ++c8) {
-        float r[8], e[8];
+    for (int u = 0; u < 8; ++u) {
+        int c = c8 * 8 + u;
+        float acc = 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            int c = c8 * 8 + u;
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < 7; ++j) acc = fmaf(ws[c * 7 + j], xv[j], acc);
-            r[u] = acc + bs[c];
-            e[u] = r[u] > 0.f ? r[u] : expm1f(r[u]);
-        }
-        split_store8(raw_hi, raw_lo, gid * C + c8 * 8, r);
-        split_store8(elu_hi, elu_lo, gid * C + c8 * 8, e);
+        for (int j = 0; j < 7; ++j) acc = fmaf(ws[c * 7 + j], xv[j], acc);
+        r[u] = acc + bs[c];
+        e[u] = r[u] > 0.f ? r[u] : expm1f(r[u]);
     }
+    split_store8(raw_hi, raw_lo, gid * 8, r);
+    split_store8(elu_hi, elu_lo, gid * 8, e);
 }
 
 // SLSTM skip connection y + x (reference encoder/modules/lstm.py:38; y and x in time-major rows) fused with the ELU in front of the last
@@ -200,7 +200,7 @@ void launch_conv0_planes(const float* wav, const float* w, const float* bias, __
                          __half* elu_hi, __half* elu_lo, int B, int T, int C, cudaStream_t s) {
     if (C != 32) throw Error(1, "conv0: n_filters must be 32");
     if (T < 4) throw Error(4, "conv0_planes: clip too short for the tcgen05 encoder layout");
-    long long n = (long long)B * (T + 2);
+    long long n = (long long)B * (T + 2) * (C / 8);
     conv0_planes_kernel<32><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wav, w, bias, raw_hi, raw_lo, elu_hi, elu_lo, B, T);
     WT_CUDA(cudaGetLastError());
 }

@@ -158,7 +158,14 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
 }
 
-// Store CW consecutive values of one row as split planes (16-byte vector stores).
+// 256-bit global store (sm_100a STG.E.256): one full 32-byte sector per lane per instruction.
+__device__ __forceinline__ void st256(void* p, const uint32_t* w) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                 "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+}
+
+// Store CW consecutive values of one row as split planes (32-byte stores when the row is 32-byte aligned).
 template <int CW, bool ELU>
 __device__ __forceinline__ void store_planes(__half* hi_p, __half* lo_p, long long off, const float (&v)[CW]) {
     uint32_t hi[CW / 2], lo[CW / 2];
@@ -167,6 +174,11 @@ __device__ __forceinline__ void store_planes(__half* hi_p, __half* lo_p, long lo
         float a = v[2 * i], b = v[2 * i + 1];
         if (ELU) { a = elu1(a); b = elu1(b); }
         split2(a, b, hi[i], lo[i]);
+    }
+    if (CW == 16 && (off & 15) == 0) {
+        st256(hi_p + off, hi);
+        if (lo_p) st256(lo_p + off, lo);
+        return;
     }
     uint4* oh = reinterpret_cast<uint4*>(hi_p + off);
 #pragma unroll
@@ -183,9 +195,19 @@ __device__ __forceinline__ void store_row(const TcGemm& g, long long row, int nb
     if (full) {
         if (g.out_f32) {
             float* o = g.out_f32 + row * g.ldo + nb;
+            if (CW % 8 == 0 && ((row * g.ldo + nb) & 7) == 0) {
 #pragma unroll
-            for (int i = 0; i < CW; i += 4)
-                *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                for (int i = 0; i < CW; i += 8) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) w[k] = __float_as_uint(v[i + k]);
+                    st256(o + i, w);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < CW; i += 4)
+                    *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
         }
         if (g.out_hi) {
             if (g.plane_shift) {

@@ -318,7 +318,8 @@ class WavTokenizer(nn.Module):
         return codes, quant
 
     def encode_decode_host(self, wav_host: torch.Tensor, bandwidth_id: int = 0):
-        """Whole hot path on HOST tensors (pinned recommended): H2D, encode, decode, D2H, sync."""
+        """Whole hot path on HOST tensors (pinned recommended): H2D, encode, decode, D2H, sync.
+        The returned tensors are reused by the next call with the same shapes (clone to keep them)."""
         h = self.native()
         if wav_host.device.type != "cpu" or wav_host.dtype != torch.float32 or wav_host.dim() != 2:
             raise ValueError("expected a float32 CPU tensor [B, T]")
@@ -326,8 +327,14 @@ class WavTokenizer(nn.Module):
         B, T = wav_host.shape
         L = self.cfg.frames_for(T)
         pin = wav_host.is_pinned()
-        codes = torch.empty(1, B, L, dtype=torch.int64, pin_memory=pin)
-        audio = torch.empty(B, L * self.cfg.hop_length, dtype=torch.float32, pin_memory=pin)
+        # pinned result buffers are cached per shape: cudaHostAlloc of ~75 MB costs more than the whole step
+        key = (B, L, pin)
+        cache = self.__dict__.setdefault("_host_out", {})
+        if key not in cache:
+            cache.clear()
+            cache[key] = (torch.empty(1, B, L, dtype=torch.int64, pin_memory=pin),
+                          torch.empty(B, L * self.cfg.hop_length, dtype=torch.float32, pin_memory=pin))
+        codes, audio = cache[key]
         with torch.cuda.device(self.device):
             _native.check(_native.lib().wt_encode_decode_host(h.ptr, wav_host.data_ptr(), B, T, int(bandwidth_id),
                                                               codes.data_ptr(), audio.data_ptr(), self._stream()))
