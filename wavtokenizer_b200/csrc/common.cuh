@@ -97,7 +97,7 @@ void launch_groupnorm(const float* x, const float* w, const float* b, RowOut out
                       int groups, float eps, int swish, cudaStream_t s);
 void launch_layernorm(const float* x, const float* w, const float* b, RowOut out, long long M, int C, float eps,
                       cudaStream_t s);
-void launch_dwconv_ln(const float* x, const float* dw /*[C,7]*/, const float* db, const float* scale,
+void launch_dwconv_ln(const float* x, const float* dw /*[7,C] (taps transposed at load)*/, const float* db, const float* scale,
                       const float* shift, RowOut out, int B, int L, int Lp, int C, float eps, cudaStream_t s);
 void launch_attention(const float* qkv /*[B*Lp, 3C]*/, RowOut out /*[B*Lp, C]*/, int B, int L, int Lp, int C,
                       cudaStream_t s);

@@ -181,51 +181,42 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // ConvNeXt front half: depthwise Conv1d(k=7, pad 3 zeros, groups=C) -> AdaLayerNorm
-// (reference decoder/modules.py:30-33, 49-53). One warp per frame; the depthwise weights sit transposed in
-// shared memory ([tap][channel]); the seven neighbouring rows are L1/L2 hits, so HBM traffic is one read and
-// one write of the activation.
-constexpr int DW_ROWS = 32;  // frames per block (8 warps x 4 frames)
-__global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ dw,
+// (reference decoder/modules.py:30-33, 49-53). One warp per frame; the depthwise taps arrive transposed
+// ([tap][channel], prepared at load) so every access is a coalesced 32-byte-per-lane vector; the seven
+// neighbouring rows are L1/L2 hits, so HBM traffic is one read and one write of the activation.
+__global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ dwT,
                                                         const float* __restrict__ db, const float* __restrict__ scale,
                                                         const float* __restrict__ shift, RowOut out, int B, int L,
                                                         int Lp, float eps) {
     constexpr int C = 768;
-    __shared__ __align__(16) float wt[7 * C];
-    for (int i = threadIdx.x; i < 7 * C; i += 256) {
-        const int j = i / C, c = i - j * C;
-        wt[i] = dw[c * 7 + j];
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= (long long)B * Lp) return;
+    const int b = (int)(row / Lp), t = (int)(row - (long long)b * Lp);
+    if (t >= L) {  // halo row of the padded row space
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int g = 0; g < 3; ++g) put8(out, row * C + g * 256 + lane * 8, z);
+        return;
     }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int rr = 0; rr < DW_ROWS / 8; ++rr) {
-        const long long row = (long long)blockIdx.x * DW_ROWS + warp * (DW_ROWS / 8) + rr;
-        if (row >= (long long)B * Lp) return;
-        const int b = (int)(row / Lp), t = (int)(row - (long long)b * Lp);
-        if (t >= L) {  // halo row of the padded row space
-            const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float v[3][8];
 #pragma unroll
-            for (int g = 0; g < 3; ++g) put8(out, row * C + g * 256 + lane * 8, z);
-            continue;
+    for (int g = 0; g < 3; ++g) load8(db + g * 256 + lane * 8, v[g]);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        const int tj = t - 3 + j;
+        if (tj < 0 || tj >= L) continue;
+        const float* xr = x + ((long long)b * Lp + tj) * C;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            float xv[8], wv[8];
+            load8(xr + g * 256 + lane * 8, xv);
+            load8(dwT + j * C + g * 256 + lane * 8, wv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[g][k] = fmaf(wv[k], xv[k], v[g][k]);
         }
-        float v[3][8];
-#pragma unroll
-        for (int g = 0; g < 3; ++g) load8(db + g * 256 + lane * 8, v[g]);
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            const int tj = t - 3 + j;
-            if (tj < 0 || tj >= L) continue;
-            const float* xr = x + ((long long)b * Lp + tj) * C;
-#pragma unroll
-            for (int g = 0; g < 3; ++g) {
-                float xv[8], wv[8];
-                load8(xr + g * 256 + lane * 8, xv);
-                load8(wt + j * C + g * 256 + lane * 8, wv);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[g][k] = fmaf(wv[k], xv[k], v[g][k]);
-            }
-        }
-        ln_finish(v, scale, shift, out, row, lane, eps);
     }
+    ln_finish(v, scale, shift, out, row, lane, eps);
 }
 
 // AttnBlock core (reference decoder/models.py:115-123): softmax(q k^T * C^-0.5) v, one head of width C
@@ -443,7 +434,7 @@ void launch_dwconv_ln(const float* x, const float* dw, const float* db, const fl
     if (B <= 0 || L <= 0) return;
     if (C != 768) throw Error(1, "dwconv_ln: backbone dim must be 768");
     long long M = (long long)B * Lp;
-    dwconv_ln_kernel<<<(unsigned)((M + DW_ROWS - 1) / DW_ROWS), 256, 0, s>>>(x, dw, db, scale, shift, out, B, L, Lp, eps);
+    dwconv_ln_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, dw, db, scale, shift, out, B, L, Lp, eps);
     WT_CUDA(cudaGetLastError());
 }
 

@@ -419,29 +419,29 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                 if (t <= g.map.Tvalid - 2 && t >= g.map.Tvalid - 1 - g.map.hr)
                     mir_r = base + (2 * (g.map.Tvalid - 1) - t) * st;
             }
-            if (BN == 128 && g.act == TC_ACT_LSTM) {
+            if (BN == 64 && g.act == TC_ACT_LSTM) {
                 // LSTM cell (reference encoder/modules/lstm.py:20; gates i, f, g, o). Tile columns hold
-                // [i | f | g | o] x 32 hidden units; the thread owns one batch row.
-                const int u0 = nt * 32 + cg * 8;  // this warp's 8 hidden units (4 warps per lane quarter)
-                {
+                // [i | f | g | o] x 16 hidden units; the thread owns one batch row, two warps per lane quarter work.
+                const int u0 = nt * 16 + cg * 8;  // this warp's 8 hidden units
+                if (cg < 2) {
                     uint32_t ri[8], rf[8], rg[8], ro[8];
                     __syncwarp();
                     tmem_ld(tbase + 0 + cg * 8, ri);
-                    tmem_ld(tbase + 32 + cg * 8, rf);
-                    tmem_ld(tbase + 64 + cg * 8, rg);
-                    tmem_ld(tbase + 96 + cg * 8, ro);
+                    tmem_ld(tbase + 16 + cg * 8, rf);
+                    tmem_ld(tbase + 32 + cg * 8, rg);
+                    tmem_ld(tbase + 48 + cg * 8, ro);
                     if (row_ok) {
                         const float* xr = g.res + (long long)m * g.ldres + n0 + cg * 8;
                         float* cr = g.cell + (long long)m * g.hidden + u0;
                         float xi[8], xf[8], xg[8], xo[8], cv[8];
                         *reinterpret_cast<float4*>(xi) = *reinterpret_cast<const float4*>(xr);
                         *reinterpret_cast<float4*>(xi + 4) = *reinterpret_cast<const float4*>(xr + 4);
-                        *reinterpret_cast<float4*>(xf) = *reinterpret_cast<const float4*>(xr + 32);
-                        *reinterpret_cast<float4*>(xf + 4) = *reinterpret_cast<const float4*>(xr + 36);
-                        *reinterpret_cast<float4*>(xg) = *reinterpret_cast<const float4*>(xr + 64);
-                        *reinterpret_cast<float4*>(xg + 4) = *reinterpret_cast<const float4*>(xr + 68);
-                        *reinterpret_cast<float4*>(xo) = *reinterpret_cast<const float4*>(xr + 96);
-                        *reinterpret_cast<float4*>(xo + 4) = *reinterpret_cast<const float4*>(xr + 100);
+                        *reinterpret_cast<float4*>(xf) = *reinterpret_cast<const float4*>(xr + 16);
+                        *reinterpret_cast<float4*>(xf + 4) = *reinterpret_cast<const float4*>(xr + 20);
+                        *reinterpret_cast<float4*>(xg) = *reinterpret_cast<const float4*>(xr + 32);
+                        *reinterpret_cast<float4*>(xg + 4) = *reinterpret_cast<const float4*>(xr + 36);
+                        *reinterpret_cast<float4*>(xo) = *reinterpret_cast<const float4*>(xr + 48);
+                        *reinterpret_cast<float4*>(xo + 4) = *reinterpret_cast<const float4*>(xr + 52);
                         *reinterpret_cast<float4*>(cv) = *reinterpret_cast<const float4*>(cr);
                         *reinterpret_cast<float4*>(cv + 4) = *reinterpret_cast<const float4*>(cr + 4);
                         float hv[8];
@@ -666,7 +666,7 @@ void launch_cfg(const TcGemm& g, cudaStream_t s) {
 
 template <int PASSES>
 void launch_bn(const TcGemm& g, cudaStream_t s) {
-    if (g.act == TC_ACT_LSTM) return launch_cfg<128, PASSES>(g, s);
+    if (g.act == TC_ACT_LSTM) return launch_cfg<64, PASSES>(g, s);
     if (g.N <= 16) return launch_cfg<16, PASSES>(g, s);
     if (g.N <= 32) return launch_cfg<32, PASSES>(g, s);
     if (g.N <= 64) return launch_cfg<64, PASSES>(g, s);
@@ -714,8 +714,8 @@ void launch_tap_gemm_tc(const TcGemm& g_in, cudaStream_t s) {
     if ((g.out_f32 && g.ldo % 4) || (g.res && g.ldres % 4) || (g.out_hi && g.ldh % 8) || (g.elu_hi && g.ldh2 % 8))
         throw Error(4, "gemm_tc: output pitches must keep 16-byte alignment");
     if (g.passes != 1 && g.passes != 3) throw Error(4, "gemm_tc: passes must be 1 or 3");
-    if (g.act == TC_ACT_LSTM && (g.N % 128 || !g.cell || !g.res || g.map.Pin))
-        throw Error(4, "gemm_tc: LSTM epilogue needs N % 128 == 0, a cell state and the input projection");
+    if (g.act == TC_ACT_LSTM && (g.N % 64 || !g.cell || !g.res || g.map.Pin))
+        throw Error(4, "gemm_tc: LSTM epilogue needs N % 64 == 0, a cell state and the input projection");
     if (g.act == TC_ACT_ARGMIN && (g.N % 256 || !g.best || !g.bias || g.map.Pin))
         throw Error(4, "gemm_tc: argmin epilogue needs N % 256 == 0, ||c||^2 and the packed best[] buffer");
     if (g.batch < 1 || (g.ldw && g.ldw % 8)) throw Error(4, "gemm_tc: bad batch / W pitch");

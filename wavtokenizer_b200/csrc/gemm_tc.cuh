@@ -64,7 +64,7 @@ struct TcGemm {
     __half* elu_hi = nullptr;  // split planes of ELU(v)
     __half* elu_lo = nullptr;
     int ldh2 = 0;
-    // TC_ACT_LSTM (see gemm_tc.cu): columns are [i | f | g | o] blocks of 32 units per 128-wide tile
+    // TC_ACT_LSTM (see gemm_tc.cu): columns are [i | f | g | o] blocks of 16 units per 64-wide tile
     float* cell = nullptr;     // [M, H] cell state, updated in place
     int hidden = 0;
     // split planes receive v - plane_shift[n] (the VQ reads frames centred on the codebook mean)

@@ -76,7 +76,7 @@ struct wt_handle {
     ConvW enc_last;
     // tcgen05 encoder weights: k3 conv padded to K % 64 == 0; conv1x1 and shortcut fused along K
     struct RbTc { HalfW w1; int Kp1 = 0; HalfW w2; int kb0 = 0, kb1 = 0; float* bias2 = nullptr; } rb_tc[4];
-    // LSTM weights with gate rows permuted so that each 128-wide tile holds [i | f | g | o] x 32 hidden units
+    // LSTM weights with gate rows permuted so that each 64-wide tile holds [i | f | g | o] x 16 hidden units
     struct LstmTc { HalfW w_ih, w_hh; float* bias = nullptr; } lstm_tc[4];
     float* zero_rows = nullptr;  // zero planes standing in for h_{-1}
     // vq
@@ -334,7 +334,7 @@ void prepare(wt_handle* h, const Table& t) {
             C *= 2;
         }
         const int D = c.dimension;
-        if (D % 32 == 0) {
+        if (D % 16 == 0) {
             for (int l = 0; l < c.lstm_layers; ++l) {
                 std::string p = E + std::to_string(idx) + ".lstm.";
                 std::string sfx = "_l" + std::to_string(l);
@@ -344,8 +344,8 @@ void prepare(wt_handle* h, const Table& t) {
                 const float* bh = t.get(p + "bias_hh" + sfx, 4 * D);
                 std::vector<float> pwi((size_t)4 * D * D), pwh((size_t)4 * D * D), pb((size_t)4 * D);
                 for (int np = 0; np < 4 * D; ++np) {
-                    const int nt = np / 128, gate = (np % 128) / 32, j = np % 32;
-                    const int src = gate * D + nt * 32 + j;
+                    const int nt = np / 64, gate = (np % 64) / 16, j = np % 16;
+                    const int src = gate * D + nt * 16 + j;
                     std::memcpy(&pwi[(size_t)np * D], wi + (size_t)src * D, D * sizeof(float));
                     std::memcpy(&pwh[(size_t)np * D], wh + (size_t)src * D, D * sizeof(float));
                     pb[np] = bi[src] + bh[src];
@@ -432,7 +432,13 @@ void prepare(wt_handle* h, const Table& t) {
     for (int i = 0; i < c.num_layers; ++i) {
         std::string p = "backbone.convnext." + std::to_string(i) + ".";
         auto& x = h->cnx[i];
-        x.dw = load_vec(h, t, p + "dwconv.weight", (int64_t)D * 7);
+        {   // depthwise taps transposed to [tap][channel] so that lanes read consecutive channels
+            const float* wp = t.get(p + "dwconv.weight", (int64_t)D * 7);
+            std::vector<float> wt((size_t)7 * D);
+            for (int cc = 0; cc < D; ++cc)
+                for (int j = 0; j < 7; ++j) wt[(size_t)j * D + cc] = wp[(size_t)cc * 7 + j];
+            x.dw = h->upload(wt);
+        }
         x.db = load_vec(h, t, p + "dwconv.bias", D);
         x.scale = load_vec(h, t, p + "norm.scale.weight", (int64_t)NE * D);
         x.shift = load_vec(h, t, p + "norm.shift.weight", (int64_t)NE * D);
