@@ -180,6 +180,7 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
     cfg = spec.load_config(cfg_path())
     L = cfg.frames_for(T)

@@ -60,7 +60,7 @@ def test_every_stage_matches_reference_taps(setup):
     ref_codes = torch.from_numpy(g["e2e_codes"].astype(np.int64))
     audio = m.decode(m.codes_to_features(ref_codes.cuda()), bandwidth_id=bw)
     torch.cuda.synchronize()
-    assert m.launch_count() - launches0 > 100
+    assert m.launch_count() - launches0 > 50
     worst = (None, 1e9)
     for n in names:
         t = taps.get(n)

@@ -58,8 +58,9 @@ void launch_lstm_pointwise(const float* gates /*row b*ldg, 4H wide*/, float* c /
                            int B, int H, long long ldg, long long ldy, cudaStream_t s);
 void launch_add(const float* a, const float* b, float* out, long long n, cudaStream_t s);
 // tcgen05 encoder helpers (padded, split-fp16 layouts; see model.cu encoder_front_tc)
-void launch_conv0_planes(const float* wav, const float* w, const float* bias, __half* raw_hi, __half* raw_lo,
-                         __half* elu_hi, __half* elu_lo, int B, int T, int C, cudaStream_t s);
+void launch_conv0_planes(const float* wav, const float* w, const float* bias, __half* win_hi /*[B*(T+2), 8]*/,
+                         __half* win_lo, __half* elu_hi /*[B*(T+2), C]*/, __half* elu_lo, int B, int T, int C,
+                         cudaStream_t s);
 void launch_lstm_skip_elu_pad(const float* y, const float* x, float* out_f32, __half* elu_hi, __half* elu_lo, int B,
                               int L, int D, cudaStream_t s);
 

@@ -62,13 +62,15 @@ __device__ __forceinline__ void split_store8(__half* hi, __half* lo, long long o
     *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// conv0 for the tcgen05 encoder: same arithmetic as conv0_kernel, but one thread per PADDED position of the
-// next layer's input layout (clip pitch T + 2, data at offset 1, reflect halo of 1 on both sides), writing
-// the split-fp16 planes of x (shortcut operand) and of ELU(x) (k3-conv operand).
+// conv0 for the tcgen05 encoder: same arithmetic as conv0_kernel, one thread per (PADDED position, group of 8
+// channels) of the next layer's input layout (clip pitch T + 2, data at offset 1, reflect halo of 1 on both
+// sides). Writes the split-fp16 planes of ELU(x) (k3-conv operand) and, instead of the planes of x itself, the
+// 8-wide window of raw audio samples around the position: the ResBlock shortcut conv1x1(conv0(wav)) is a single
+// k7 conv of the audio with composed weights (model.cu), which saves 96 B of HBM traffic per sample.
 template <int C>
 __global__ void __launch_bounds__(256) conv0_planes_kernel(const float* __restrict__ wav, const float* __restrict__ w,
-                                                           const float* __restrict__ bias, __half* __restrict__ raw_hi,
-                                                           __half* __restrict__ raw_lo, __half* __restrict__ elu_hi,
+                                                           const float* __restrict__ bias, __half* __restrict__ win_hi,
+                                                           __half* __restrict__ win_lo, __half* __restrict__ elu_hi,
                                                            __half* __restrict__ elu_lo, int B, int T) {
     __shared__ float ws[C * 7];
     __shared__ float bs[C];
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(256) conv0_planes_kernel(const float* __restri
     for (int i = threadIdx.x; i < C; i += blockDim.x) bs[i] = bias[i];
     __syncthreads();
     const int P = T + 2;
-    constexpr int G8 = C / 8;  // one thread per (padded position, group of 8 channels): 16-byte stores coalesce
+    constexpr int G8 = C / 8;  // 16-byte stores coalesce across the 4 threads of a position
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)B * P * G8) return;
     const int c8 = (int)(gid % G8);
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(256) conv0_planes_kernel(const float* __restri
     if (t < 0) t = -t;
     if (t >= T) t = 2 * (T - 1) - t;
     const float* x = wav + (long long)b * T;
-    float xv[7];
+    float xv[8];
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
         int ti = t - 3 + j;
@@ -95,18 +97,19 @@ __global__ void __launch_bounds__(256) conv0_planes_kernel(const float* __restri
         if (ti >= T) ti = 2 * (T - 1) - ti;
         xv[j] = x[ti];
     }
-    float r[8], e[8];
+    xv[7] = 0.f;
+    float e[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
         int c = c8 * 8 + u;
         float acc = 0.f;
 #pragma unroll
         for (int j = 0; j < 7; ++j) acc = fmaf(ws[c * 7 + j], xv[j], acc);
-        r[u] = acc + bs[c];
-        e[u] = r[u] > 0.f ? r[u] : expm1f(r[u]);
+        const float r = acc + bs[c];
+        e[u] = r > 0.f ? r : expm1f(r);
     }
-    split_store8(raw_hi, raw_lo, gid * 8, r);
     split_store8(elu_hi, elu_lo, gid * 8, e);
+    if (c8 == 0) split_store8(win_hi, win_lo, pos * 8, xv);
 }
 
 // SLSTM skip connection y + x (reference encoder/modules/lstm.py:38; y and x in time-major rows) fused with the ELU in front of the last
@@ -196,12 +199,12 @@ void launch_conv0(const float* wav, const float* w, const float* bias, float* ou
     WT_CUDA(cudaGetLastError());
 }
 
-void launch_conv0_planes(const float* wav, const float* w, const float* bias, __half* raw_hi, __half* raw_lo,
+void launch_conv0_planes(const float* wav, const float* w, const float* bias, __half* win_hi, __half* win_lo,
                          __half* elu_hi, __half* elu_lo, int B, int T, int C, cudaStream_t s) {
     if (C != 32) throw Error(1, "conv0: n_filters must be 32");
     if (T < 4) throw Error(4, "conv0_planes: clip too short for the tcgen05 encoder layout");
     long long n = (long long)B * (T + 2) * (C / 8);
-    conv0_planes_kernel<32><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wav, w, bias, raw_hi, raw_lo, elu_hi, elu_lo, B, T);
+    conv0_planes_kernel<32><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wav, w, bias, win_hi, win_lo, elu_hi, elu_lo, B, T);
     WT_CUDA(cudaGetLastError());
 }
 

@@ -563,6 +563,233 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Persistent LSTM layer (reference encoder/modules/lstm.py:20, nn.LSTM recurrence; gates i, f, g, o).
+//
+// One cooperative launch runs all L time steps of one layer. CTA (ns, mg) owns the 64 gate columns of
+// hidden units [16 ns, 16 ns + 16) (W_hh rows are permuted at load so that they are contiguous) and the batch
+// tiles mg, mg + MG, ...: its slice of W_hh (hi + lo planes, 128 KB) is loaded into shared memory ONCE and
+// stays resident for the whole layer. Per step it streams h_{t-1} of its batch tile through a 2-stage TMA
+// ring, accumulates W_hh h in TMEM with 3-pass split-fp16 tcgen05 MMAs, and the epilogue warps apply the
+// LSTM cell (adding the hoisted input projection) and publish h_t as fp32 rows and split-fp16 planes.
+// The 32 CTAs that share a batch tile synchronise once per step through an arrival counter in global memory
+// (release/acquire + proxy fences because h_t is written by threads and read back by TMA). All tensors are
+// time-major: row = t*B + b.
+// ---------------------------------------------------------------------------------------
+struct LstmArgs {
+    const float* xin;    // [L*B, 4D] W_ih x + b, gate-permuted ([i16 | f16 | g16 | o16] per 64 columns)
+    float* y;            // [L*B, D] h_t fp32
+    __half* h_hi;        // [L*B, D] h_t split planes (also this kernel's A operand through mapH)
+    __half* h_lo;
+    float* cell;         // [B, D]
+    int* counters;       // [m_tiles * L], zeroed before launch
+    int B, L, D, m_tiles;
+};
+
+constexpr int LSTM_EPI_WARPS = 8;
+constexpr int LSTM_THREADS = 64 + LSTM_EPI_WARPS * 32;
+constexpr int LSTM_KB = 8;                               // D = 512 = 8 k-blocks of 64
+constexpr int LSTM_W_BYTES = LSTM_KB * 2 * 64 * 128;     // resident W slice: 8 kb x (hi, lo) x [64 rows x 128 B]
+constexpr int LSTM_A_STAGE = 2 * BM * 128;               // hi + lo tile of h_{t-1}
+constexpr int LSTM_STAGES = 2;
+constexpr int LSTM_SMEM = LSTM_W_BYTES + LSTM_STAGES * LSTM_A_STAGE + 1024 + 256;
+
+__global__ void __launch_bounds__(LSTM_THREADS, 1)
+lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid_constant__ CUtensorMap mapH_lo,
+                       const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
+                       const LstmArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t w_base = smem_base;
+    const uint32_t a_base = smem_base + LSTM_W_BYTES;
+    const uint32_t bar_base = a_base + LSTM_STAGES * LSTM_A_STAGE;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (LSTM_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * LSTM_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * LSTM_STAGES + 2 + s); };
+    const uint32_t w_bar = bar_base + 8u * (2 * LSTM_STAGES + 4);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * LSTM_STAGES + 5);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ns = blockIdx.x;           // slice of 64 gate columns = 16 hidden units
+    const int mg = blockIdx.y, MG = gridDim.y;
+    const int n_slices = gridDim.x;      // CTAs that share a batch tile
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < LSTM_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), LSTM_EPI_WARPS); }
+        mbar_init(w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ---- producer: resident W slice once, then h_{t-1} tiles every step ----
+        if (lane == 0) {
+            mbar_expect_tx(w_bar, LSTM_W_BYTES);
+            for (int kb = 0; kb < LSTM_KB; ++kb) {
+                tma_load_2d(w_base + (kb * 2 + 0) * 8192, &mapW_hi, kb * BK, ns * 64, w_bar);
+                tma_load_2d(w_base + (kb * 2 + 1) * 8192, &mapW_lo, kb * BK, ns * 64, w_bar);
+            }
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 1; t < a.L; ++t) {
+            for (int mt = mg; mt < a.m_tiles; mt += MG) {
+                // wait until all CTAs sharing this batch tile have published h_{t-1}
+                if (lane == 0) {
+                    const int* cnt = a.counters + (long long)mt * a.L + (t - 1);
+                    int v = 0;
+                    uint32_t spins = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+                        if (v < n_slices && ++spins > (1u << 26)) asm volatile("trap;");
+                    } while (v < n_slices);
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+                __syncwarp();
+                const int r0 = (t - 1) * a.B + mt * BM;
+                for (int kb = 0; kb < LSTM_KB; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    if (lane == 0) {
+                        const uint32_t sa = a_base + stage * LSTM_A_STAGE;
+                        mbar_expect_tx(full_bar(stage), LSTM_A_STAGE);
+                        tma_load_2d(sa, &mapH_hi, kb * BK, r0, full_bar(stage));
+                        tma_load_2d(sa + BM * 128, &mapH_lo, kb * BK, r0, full_bar(stage));
+                    }
+                    __syncwarp();
+                    if (++stage == LSTM_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer ----
+        constexpr uint32_t idesc = umma_idesc_f16(64);
+        mbar_wait(w_bar, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = 1; t < a.L; ++t) {
+            for (int mt = mg; mt < a.m_tiles; mt += MG) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64);
+                for (int kb = 0; kb < LSTM_KB; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (lane == 0) {
+                        const uint32_t sa = a_base + stage * LSTM_A_STAGE;
+                        const uint32_t sw = w_base + kb * 2 * 8192;
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint32_t koff = k * UMMA_K * 2;
+                            const uint64_t a_hi = umma_desc_sw128(sa + koff), a_lo = umma_desc_sw128(sa + BM * 128 + koff);
+                            const uint64_t b_hi = umma_desc_sw128(sw + koff), b_lo = umma_desc_sw128(sw + 8192 + koff);
+                            umma_f16(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0);
+                            umma_f16(tmem_d, a_hi, b_lo, idesc, 1);
+                            umma_f16(tmem_d, a_lo, b_hi, idesc, 1);
+                        }
+                        umma_commit(empty_bar(stage));
+                        if (kb == LSTM_KB - 1) umma_commit(tfull_bar(acc));
+                    }
+                    __syncwarp();
+                    if (++stage == LSTM_STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ---- epilogue: LSTM cell, 8 warps = 4 TMEM lane quarters x 2 halves of the 16 hidden units ----
+        const int q = warp & 3;
+        const int hw = (warp - 2) >> 2;
+        const int u0 = ns * 16 + hw * 8;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = 0; t < a.L; ++t) {
+            for (int mt = mg; mt < a.m_tiles; mt += MG) {
+                const int b = mt * BM + q * 32 + lane;
+                const bool row_ok = b < a.B;
+                uint32_t ri[8], rf[8], rg[8], ro[8];
+                if (t > 0) {
+                    mbar_wait(tfull_bar(acc), acc_phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64 + hw * 8);
+                    __syncwarp();
+                    tmem_ld(tb + 0, ri);
+                    tmem_ld(tb + 16, rf);
+                    tmem_ld(tb + 32, rg);
+                    tmem_ld(tb + 48, ro);
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator is in registers: free it early
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) ri[i] = rf[i] = rg[i] = ro[i] = 0u;  // h_{-1} = 0
+                }
+                if (row_ok) {
+                    const long long row = (long long)t * a.B + b;
+                    const float* xr = a.xin + row * 4 * a.D + ns * 64 + hw * 8;
+                    float* cr = a.cell + (long long)b * a.D + u0;
+                    float xi[8], xf[8], xg[8], xo[8], cv[8], hv[8];
+                    *reinterpret_cast<float4*>(xi) = *reinterpret_cast<const float4*>(xr);
+                    *reinterpret_cast<float4*>(xi + 4) = *reinterpret_cast<const float4*>(xr + 4);
+                    *reinterpret_cast<float4*>(xf) = *reinterpret_cast<const float4*>(xr + 16);
+                    *reinterpret_cast<float4*>(xf + 4) = *reinterpret_cast<const float4*>(xr + 20);
+                    *reinterpret_cast<float4*>(xg) = *reinterpret_cast<const float4*>(xr + 32);
+                    *reinterpret_cast<float4*>(xg + 4) = *reinterpret_cast<const float4*>(xr + 36);
+                    *reinterpret_cast<float4*>(xo) = *reinterpret_cast<const float4*>(xr + 48);
+                    *reinterpret_cast<float4*>(xo + 4) = *reinterpret_cast<const float4*>(xr + 52);
+                    if (t > 0) {
+                        *reinterpret_cast<float4*>(cv) = *reinterpret_cast<const float4*>(cr);
+                        *reinterpret_cast<float4*>(cv + 4) = *reinterpret_cast<const float4*>(cr + 4);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) cv[i] = 0.f;  // c_{-1} = 0
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float ig = sigmoid1(__uint_as_float(ri[i]) + xi[i]);
+                        const float fg = sigmoid1(__uint_as_float(rf[i]) + xf[i]);
+                        const float gg = tanhf(__uint_as_float(rg[i]) + xg[i]);
+                        const float og = sigmoid1(__uint_as_float(ro[i]) + xo[i]);
+                        cv[i] = fg * cv[i] + ig * gg;
+                        hv[i] = og * tanhf(cv[i]);
+                    }
+                    *reinterpret_cast<float4*>(cr) = *reinterpret_cast<float4*>(cv);
+                    *reinterpret_cast<float4*>(cr + 4) = *reinterpret_cast<float4*>(cv + 4);
+                    float* yo = a.y + row * a.D + u0;
+                    *reinterpret_cast<float4*>(yo) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                    *reinterpret_cast<float4*>(yo + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                    store_planes<8, false>(a.h_hi, a.h_lo, row * a.D + u0, hv);
+                }
+                // publish h_t of this (batch tile, step): generic writes -> async proxy (TMA) readers in other CTAs
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"r"(LSTM_EPI_WARPS * 32) : "memory");
+                if (threadIdx.x == 64) {
+                    int* cnt = a.counters + (long long)mt * a.L + t;
+                    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(cnt) : "memory");
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -720,6 +947,31 @@ void launch_tap_gemm_tc(const TcGemm& g_in, cudaStream_t s) {
         throw Error(4, "gemm_tc: argmin epilogue needs N % 256 == 0, ||c||^2 and the packed best[] buffer");
     if (g.batch < 1 || (g.ldw && g.ldw % 8)) throw Error(4, "gemm_tc: bad batch / W pitch");
     if (g.passes == 3) launch_bn<3>(g, s); else launch_bn<1>(g, s);
+}
+
+void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_lo, float* cell, int* counters,
+                            const __half* w_hi, const __half* w_lo, int B, int L, int D, cudaStream_t s) {
+    if (D != 512) throw Error(4, "lstm_persistent: hidden size must be 512");
+    static bool attr = false;
+    if (!attr) {
+        WT_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LSTM_SMEM));
+        attr = true;
+    }
+    LstmArgs a;
+    a.xin = xin; a.y = y; a.h_hi = h_hi; a.h_lo = h_lo; a.cell = cell; a.counters = counters;
+    a.B = B; a.L = L; a.D = D; a.m_tiles = (B + BM - 1) / BM;
+    const int n_slices = 4 * D / 64;
+    int mgroups = a.m_tiles;
+    while (n_slices * mgroups > num_sms()) --mgroups;  // every CTA must be co-resident (they wait on each other)
+    if (mgroups < 1) throw Error(4, "lstm_persistent: device too small");
+    WT_CUDA(cudaMemsetAsync(counters, 0, (size_t)a.m_tiles * L * sizeof(int), s));
+    CUtensorMap mh_hi = make_map(h_hi, (long long)L * B, D, D, BM);
+    CUtensorMap mh_lo = make_map(h_lo, (long long)L * B, D, D, BM);
+    CUtensorMap mw_hi = make_map(w_hi, 4LL * D, D, D, 64);
+    CUtensorMap mw_lo = make_map(w_lo, 4LL * D, D, D, 64);
+    void* args[] = {&mh_hi, &mh_lo, &mw_hi, &mw_lo, &a};
+    WT_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_persistent_kernel, dim3(n_slices, mgroups), dim3(LSTM_THREADS),
+                                        args, (size_t)LSTM_SMEM, s));
 }
 
 void launch_split_f16(const float* x, __half* hi, __half* lo, long long rows, int cols, long long ld_in,

@@ -78,6 +78,9 @@ struct TcGemm {
 void set_debug_timeline(long long* dev_buf);
 
 void launch_tap_gemm_tc(const TcGemm& g, cudaStream_t s);
+// One LSTM layer, all L steps, in a single cooperative launch (see gemm_tc.cu). Time-major tensors.
+void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_lo, float* cell, int* counters,
+                            const __half* w_hi, const __half* w_lo, int B, int L, int D, cudaStream_t s);
 void launch_split_f16(const float* x, __half* hi, __half* lo, long long rows, int cols, long long ld_in,
                       long long ld_out, cudaStream_t s);
 

@@ -272,6 +272,7 @@ float* load_vec(wt_handle* h, const Table& t, const std::string& name, int64_t n
 
 void prepare(wt_handle* h, const Table& t) {
     const wt_config& c = h->cfg;
+    std::vector<float> h_conv0_w, h_conv0_b;  // host copies: the level-0 shortcut is composed with conv0
     const std::string E = "feature_extractor.encodec.encoder.model.";
     // ---- encoder (reference encoder/modules/seanet.py:105-141) ----
     {
@@ -279,8 +280,10 @@ void prepare(wt_handle* h, const Table& t) {
         const float* g = t.get(E + "0.conv.conv.weight_g", C);
         const float* v = t.get(E + "0.conv.conv.weight_v", (int64_t)C * 7);
         const float* b = t.get(E + "0.conv.conv.bias", C);
-        h->conv0_w = h->upload(fold_weight_norm(g, v, C, 1, 7));
-        h->conv0_b = h->upload(std::vector<float>(b, b + C));
+        h_conv0_w = fold_weight_norm(g, v, C, 1, 7);
+        h_conv0_b.assign(b, b + C);
+        h->conv0_w = h->upload(h_conv0_w);
+        h->conv0_b = h->upload(h_conv0_b);
     }
     int ch = c.n_filters, idx = 1;
     for (int i = 0; i < 4; ++i) {
@@ -326,8 +329,21 @@ void prepare(wt_handle* h, const Table& t) {
             std::vector<float> w2((size_t)C * K2, 0.f), b2(C);
             for (int n = 0; n < C; ++n) {
                 for (int k = 0; k < C / 2; ++k) w2[(size_t)n * K2 + k] = c2.hw[(size_t)n * (C / 2) + k];
-                for (int k = 0; k < C; ++k) w2[(size_t)n * K2 + 64 * rt.kb0 + k] = sc.hw[(size_t)n * C + k];
-                b2[n] = c2.hb[n] + sc.hb[n];
+                if (i == 0) {
+                    // level 0: shortcut(conv0(wav)) = (Wsc W0) * wav + Wsc b0 + b_sc, a k7 conv of the raw audio
+                    // (7 taps, padded to 8), composed in fp64; its A operand is the audio window conv0 writes
+                    double bacc = 0;
+                    for (int j = 0; j < 7; ++j) {
+                        double acc = 0;
+                        for (int k = 0; k < C; ++k) acc += (double)sc.hw[(size_t)n * C + k] * h_conv0_w[(size_t)k * 7 + j];
+                        w2[(size_t)n * K2 + 64 * rt.kb0 + j] = (float)acc;
+                    }
+                    for (int k = 0; k < C; ++k) bacc += (double)sc.hw[(size_t)n * C + k] * h_conv0_b[k];
+                    b2[n] = (float)((double)c2.hb[n] + (double)sc.hb[n] + bacc);
+                } else {
+                    for (int k = 0; k < C; ++k) w2[(size_t)n * K2 + 64 * rt.kb0 + k] = sc.hw[(size_t)n * C + k];
+                    b2[n] = c2.hb[n] + sc.hb[n];
+                }
             }
             rt.w2 = h->upload_split(w2);
             rt.bias2 = h->upload(b2);
@@ -548,6 +564,7 @@ size_t enc_back_floats(const wt_config& c, int Bg, int L) {
     a((size_t)Bg * (L + 6) * D);                       // ELU(lstm + skip) planes, reflect-padded
     a(M * D);                                          // centred z planes for the tcgen05 VQ
     a(M * 2);                                          // packed (distance, index) keys
+    a(((size_t)Bg + 127) / 128 * L + 64);              // per-(batch tile, step) arrival counters of the LSTM
     return tot;
 }
 
@@ -777,9 +794,11 @@ void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, int
     };
     auto want = [&](const std::string& name) { return b0 == 0 && h->taps.count(name) > 0; };
     int Tc = T, C = c.n_filters;
-    // X planes of level 0 come from the conv0 kernel
+    // level 0 operands come from the conv0 kernel: ELU(x0) planes and the 8-wide raw-audio windows that stand in
+    // for x0 in the shortcut (composed weights); deeper levels get x and ELU(x) planes from the strided conv
     size_t nX = (size_t)Bc * (Tc + 2) * C;
-    __half *xr_hi = halves(nX), *xr_lo = halves(nX), *xe_hi = halves(nX), *xe_lo = halves(nX);
+    const size_t nWin = (size_t)Bc * (Tc + 2) * 8;
+    __half *xr_hi = halves(nWin), *xr_lo = halves(nWin), *xe_hi = halves(nX), *xe_lo = halves(nX);
     {
         Scope sc(h, CAT_ENC_CONV, s);
         launch_conv0_planes(wav, h->conv0_w, h->conv0_b, xr_hi, xr_lo, xe_hi, xe_lo, Bc, T, C, s);
@@ -812,7 +831,8 @@ void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, int
             TcGemm g;
             g.nseg = 2;
             g.seg[0] = tc_window(he_hi, he_lo, rowsX * (C / 2), C / 2, C / 2);
-            g.seg[1] = tc_window(xr_hi, xr_lo, rowsX * C, C, C, /*shift0=*/1);
+            if (i == 0) g.seg[1] = tc_window(xr_hi, xr_lo, rowsX * 8, 8, 8, /*shift0=*/1);  // audio windows
+            else g.seg[1] = tc_window(xr_hi, xr_lo, rowsX * C, C, C, /*shift0=*/1);
             g.W_hi = rt.w2.hi; g.W_lo = rt.w2.lo; g.M = (int)rowsX; g.N = C; g.K = 64 * (rt.kb0 + rt.kb1); g.passes = 3;
             g.bias = rt.bias2;
             g.map.Pin = P; g.map.Tvalid = Tc; g.map.Pout = Py; g.map.off = left; g.map.hl = left; g.map.hr = right + extra;
@@ -878,6 +898,7 @@ float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, con
     }
     const __half *lin_hi = pre_hi, *lin_lo = pre_lo;
     const __half* zero = reinterpret_cast<const __half*>(h->zero_rows);
+    int* counters = reinterpret_cast<int*>(h->alloc((size_t)((Bg + 127) / 128) * L + 32));
     // all LSTM tensors are time-major: row t*Bg + b. Step t reads rows [(t-1)*Bg, t*Bg) of the hidden-state
     // planes through ONE tensor map (row shift (t-1)*Bg), so no descriptor is built inside the time loop.
     for (int l = 0; l < c.lstm_layers; ++l) {
@@ -889,6 +910,13 @@ float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, con
             g.bias = w.bias; g.out_f32 = xin; g.ldo = 4 * D;
             Scope sc(h, CAT_LSTM, s);
             launch_tap_gemm_tc(g, s);
+        }
+        static const bool stepwise = std::getenv("WT_LSTM_STEPWISE") != nullptr;
+        if (!stepwise) {
+            Scope sc(h, CAT_LSTM, s);
+            launch_lstm_persistent(xin, ybuf[l], yh_hi[l], yh_lo[l], cst, counters, w.w_hh.hi, w.w_hh.lo, Bg, L, D, s);
+            lin_hi = yh_hi[l]; lin_lo = yh_lo[l];
+            continue;
         }
         WT_CUDA(cudaMemsetAsync(cst, 0, (size_t)Bg * D * sizeof(float), s));
         for (int t = 0; t < L; ++t) {
