@@ -49,6 +49,14 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ wa
     }
 }
 
+// fast ELU, see gemm_tc.cu (same formula so that every producer of ELU planes agrees)
+__device__ __forceinline__ float elu_fast(float x) {
+    if (x > 0.f) return x;
+    const float p = x * fmaf(x, fmaf(x, fmaf(x, fmaf(x, 1.f / 120.f, 1.f / 24.f), 1.f / 6.f), 0.5f), 1.f);
+    const float e = __expf(x) - 1.f;
+    return x > -0.125f ? p : e;
+}
+
 __device__ __forceinline__ void split_store8(__half* hi, __half* lo, long long off, const float (&v)[8]) {
     uint32_t h[4], l[4];
 #pragma unroll
@@ -106,7 +114,7 @@ __global__ void __launch_bounds__(256) conv0_planes_kernel(const float* __restri
 #pragma unroll
         for (int j = 0; j < 7; ++j) acc = fmaf(ws[c * 7 + j], xv[j], acc);
         const float r = acc + bs[c];
-        e[u] = r > 0.f ? r : expm1f(r);
+        e[u] = elu_fast(r);
     }
     split_store8(elu_hi, elu_lo, gid * 8, e);
     if (c8 == 0) split_store8(win_hi, win_lo, pos * 8, xv);
@@ -135,7 +143,7 @@ __global__ void lstm_skip_elu_pad_kernel(const float* __restrict__ y, const floa
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         v[i] = y[src + i] + x[src + i];
-        e[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
+        e[i] = elu_fast(v[i]);
     }
     if (interior && out_f32) {
 #pragma unroll

@@ -137,6 +137,13 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[8]) {
 // Exact-erf GELU (reference decoder/modules.py:35, nn.GELU()). erf through the branch-free rational form of
 // Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, below the 2^-22 resolution of the split-fp16 operands the
 // result is stored in): two MUFU ops and ~12 FMAs per element instead of erff's divergent ~40-instruction paths.
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {
     const float z = fabsf(x) * 0.70710678118654752440f;
     const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
@@ -147,7 +154,15 @@ __device__ __forceinline__ float gelu_erf(float x) {
     const float e = 1.f - p * t * __expf(-z * z);
     return 0.5f * x * (1.f + copysignf(e, x));
 }
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+// ELU(alpha = 1) (reference encoder/modules/seanet.py:37). Negative branch: expm1 through a degree-5 Taylor
+// polynomial for x > -1/8 (error < 1e-8 relative) and __expf(x) - 1 below (<= 1e-6 relative): well under the
+// 2^-22 resolution of the split-fp16 planes the value is stored in, at a third of expm1f's instruction count.
+__device__ __forceinline__ float elu1(float x) {
+    if (x > 0.f) return x;
+    const float p = x * fmaf(x, fmaf(x, fmaf(x, fmaf(x, 1.f / 120.f, 1.f / 24.f), 1.f / 6.f), 0.5f), 1.f);
+    const float e = __expf(x) - 1.f;
+    return x > -0.125f ? p : e;
+}
 __device__ __forceinline__ float sigmoid1(float x) { return 1.f / (1.f + expf(-x)); }
 
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -169,11 +184,21 @@ __device__ __forceinline__ void st256(void* p, const uint32_t* w) {
 template <int CW, bool ELU>
 __device__ __forceinline__ void store_planes(__half* hi_p, __half* lo_p, long long off, const float (&v)[CW]) {
     uint32_t hi[CW / 2], lo[CW / 2];
+    if (lo_p) {
 #pragma unroll
-    for (int i = 0; i < CW / 2; ++i) {
-        float a = v[2 * i], b = v[2 * i + 1];
-        if (ELU) { a = elu1(a); b = elu1(b); }
-        split2(a, b, hi[i], lo[i]);
+        for (int i = 0; i < CW / 2; ++i) {
+            float a = v[2 * i], b = v[2 * i + 1];
+            if (ELU) { a = elu1(a); b = elu1(b); }
+            split2(a, b, hi[i], lo[i]);
+        }
+    } else {  // single-pass consumer: only the hi plane is read
+#pragma unroll
+        for (int i = 0; i < CW / 2; ++i) {
+            float a = v[2 * i], b = v[2 * i + 1];
+            if (ELU) { a = elu1(a); b = elu1(b); }
+            const __half2 h2 = __floats2half2_rn(a, b);
+            hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
     }
     if (CW == 16 && (off & 15) == 0) {
         st256(hi_p + off, hi);
@@ -583,14 +608,15 @@ struct LstmArgs {
     float* cell;         // [B, D]
     int* counters;       // [m_tiles * L], zeroed before launch
     int B, L, D, m_tiles;
+    long long* dbg;      // optional timeline of CTA (0,0): 8 stamps per step for steps 4..7
 };
 
-constexpr int LSTM_EPI_WARPS = 8;
+constexpr int LSTM_EPI_WARPS = 16;  // 4 per TMEM lane quarter, 4 hidden units each
 constexpr int LSTM_THREADS = 64 + LSTM_EPI_WARPS * 32;
 constexpr int LSTM_KB = 8;                               // D = 512 = 8 k-blocks of 64
 constexpr int LSTM_W_BYTES = LSTM_KB * 2 * 64 * 128;     // resident W slice: 8 kb x (hi, lo) x [64 rows x 128 B]
 constexpr int LSTM_A_STAGE = 2 * BM * 128;               // hi + lo tile of h_{t-1}
-constexpr int LSTM_STAGES = 2;
+constexpr int LSTM_STAGES = 3;
 constexpr int LSTM_SMEM = LSTM_W_BYTES + LSTM_STAGES * LSTM_A_STAGE + 1024 + 256;
 
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
@@ -613,6 +639,9 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ns = blockIdx.x;           // slice of 64 gate columns = 16 hidden units
     const int mg = blockIdx.y, MG = gridDim.y;
+    long long* dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? a.dbg : nullptr;
+    const long long t_begin = dbg ? clock64() : 0;
+    auto stamp = [&](int t, int slot) { if (dbg && t >= 4 && t < 8) dbg[(t - 4) * 8 + slot] = clock64() - t_begin; };
     const int n_slices = gridDim.x;      // CTAs that share a batch tile
 
     if (warp == 0 && lane == 0) {
@@ -648,11 +677,13 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                     const int* cnt = a.counters + (long long)mt * a.L + (t - 1);
                     int v = 0;
                     uint32_t spins = 0;
+                    const int target = n_slices * LSTM_EPI_WARPS;  // every epilogue warp of every CTA arrives once
                     do {
                         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
-                        if (v < n_slices && ++spins > (1u << 26)) asm volatile("trap;");
-                    } while (v < n_slices);
+                        if (v < target && ++spins > (1u << 26)) asm volatile("trap;");
+                    } while (v < target);
                     asm volatile("fence.proxy.async;" ::: "memory");
+                    stamp(t, 0);  // h_{t-1} published by everyone
                 }
                 __syncwarp();
                 const int r0 = (t - 1) * a.B + mt * BM;
@@ -663,6 +694,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                         mbar_expect_tx(full_bar(stage), LSTM_A_STAGE);
                         tma_load_2d(sa, &mapH_hi, kb * BK, r0, full_bar(stage));
                         tma_load_2d(sa + BM * 128, &mapH_lo, kb * BK, r0, full_bar(stage));
+                        if (kb == LSTM_KB - 1) stamp(t, 1);  // last k-block issued
                     }
                     __syncwarp();
                     if (++stage == LSTM_STAGES) { stage = 0; phase ^= 1; }
@@ -686,6 +718,8 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                     mbar_wait(full_bar(stage), phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (lane == 0) {
+                        if (kb == 0) stamp(t, 2);               // first k-block landed
+                        if (kb == LSTM_KB - 1) stamp(t, 3);     // last k-block landed
                         const uint32_t sa = a_base + stage * LSTM_A_STAGE;
                         const uint32_t sw = w_base + kb * 2 * 8192;
 #pragma unroll
@@ -707,21 +741,35 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
             }
         }
     } else {
-        // ---- epilogue: LSTM cell, 8 warps = 4 TMEM lane quarters x 2 halves of the 16 hidden units ----
+        // ---- epilogue: LSTM cell, 16 warps = 4 TMEM lane quarters x 4 groups of 4 hidden units ----
         const int q = warp & 3;
         const int hw = (warp - 2) >> 2;
-        const int u0 = ns * 16 + hw * 8;
+        const int u0 = ns * 16 + hw * 4;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = 0; t < a.L; ++t) {
             for (int mt = mg; mt < a.m_tiles; mt += MG) {
                 const int b = mt * BM + q * 32 + lane;
                 const bool row_ok = b < a.B;
-                uint32_t ri[8], rf[8], rg[8], ro[8];
+                const long long row = (long long)t * a.B + b;
+                // operands that do not depend on h_{t-1} are fetched before waiting for the accumulator
+                float4 xi = make_float4(0.f, 0.f, 0.f, 0.f), xf = xi, xg = xi, xo = xi, cv = xi;
+                float* cr = a.cell + (long long)b * a.D + u0;
+                if (row_ok) {
+                    const float* xr = a.xin + row * 4 * a.D + ns * 64 + hw * 4;
+                    xi = *reinterpret_cast<const float4*>(xr);
+                    xf = *reinterpret_cast<const float4*>(xr + 16);
+                    xg = *reinterpret_cast<const float4*>(xr + 32);
+                    xo = *reinterpret_cast<const float4*>(xr + 48);
+                    if (t > 0) cv = *reinterpret_cast<const float4*>(cr);  // c_{-1} = 0
+                }
+                uint32_t ri[4] = {0u, 0u, 0u, 0u}, rf[4] = {0u, 0u, 0u, 0u}, rg[4] = {0u, 0u, 0u, 0u},
+                         ro[4] = {0u, 0u, 0u, 0u};  // h_{-1} = 0
                 if (t > 0) {
                     mbar_wait(tfull_bar(acc), acc_phase);
+                    if (threadIdx.x == 64) stamp(t, 4);  // accumulator ready
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64 + hw * 8);
+                    const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64 + hw * 4);
                     __syncwarp();
                     tmem_ld(tb + 0, ri);
                     tmem_ld(tb + 16, rf);
@@ -731,54 +779,40 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator is in registers: free it early
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) ri[i] = rf[i] = rg[i] = ro[i] = 0u;  // h_{-1} = 0
                 }
                 if (row_ok) {
-                    const long long row = (long long)t * a.B + b;
-                    const float* xr = a.xin + row * 4 * a.D + ns * 64 + hw * 8;
-                    float* cr = a.cell + (long long)b * a.D + u0;
-                    float xi[8], xf[8], xg[8], xo[8], cv[8], hv[8];
-                    *reinterpret_cast<float4*>(xi) = *reinterpret_cast<const float4*>(xr);
-                    *reinterpret_cast<float4*>(xi + 4) = *reinterpret_cast<const float4*>(xr + 4);
-                    *reinterpret_cast<float4*>(xf) = *reinterpret_cast<const float4*>(xr + 16);
-                    *reinterpret_cast<float4*>(xf + 4) = *reinterpret_cast<const float4*>(xr + 20);
-                    *reinterpret_cast<float4*>(xg) = *reinterpret_cast<const float4*>(xr + 32);
-                    *reinterpret_cast<float4*>(xg + 4) = *reinterpret_cast<const float4*>(xr + 36);
-                    *reinterpret_cast<float4*>(xo) = *reinterpret_cast<const float4*>(xr + 48);
-                    *reinterpret_cast<float4*>(xo + 4) = *reinterpret_cast<const float4*>(xr + 52);
-                    if (t > 0) {
-                        *reinterpret_cast<float4*>(cv) = *reinterpret_cast<const float4*>(cr);
-                        *reinterpret_cast<float4*>(cv + 4) = *reinterpret_cast<const float4*>(cr + 4);
-                    } else {
+                    const float xiv[4] = {xi.x, xi.y, xi.z, xi.w}, xfv[4] = {xf.x, xf.y, xf.z, xf.w};
+                    const float xgv[4] = {xg.x, xg.y, xg.z, xg.w}, xov[4] = {xo.x, xo.y, xo.z, xo.w};
+                    float cvv[4] = {cv.x, cv.y, cv.z, cv.w}, hv[4];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) cv[i] = 0.f;  // c_{-1} = 0
+                    for (int i = 0; i < 4; ++i) {
+                        const float ig = sigmoid1(__uint_as_float(ri[i]) + xiv[i]);
+                        const float fg = sigmoid1(__uint_as_float(rf[i]) + xfv[i]);
+                        const float gg = tanhf(__uint_as_float(rg[i]) + xgv[i]);
+                        const float og = sigmoid1(__uint_as_float(ro[i]) + xov[i]);
+                        cvv[i] = fg * cvv[i] + ig * gg;
+                        hv[i] = og * tanhf(cvv[i]);
                     }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float ig = sigmoid1(__uint_as_float(ri[i]) + xi[i]);
-                        const float fg = sigmoid1(__uint_as_float(rf[i]) + xf[i]);
-                        const float gg = tanhf(__uint_as_float(rg[i]) + xg[i]);
-                        const float og = sigmoid1(__uint_as_float(ro[i]) + xo[i]);
-                        cv[i] = fg * cv[i] + ig * gg;
-                        hv[i] = og * tanhf(cv[i]);
-                    }
-                    *reinterpret_cast<float4*>(cr) = *reinterpret_cast<float4*>(cv);
-                    *reinterpret_cast<float4*>(cr + 4) = *reinterpret_cast<float4*>(cv + 4);
-                    float* yo = a.y + row * a.D + u0;
-                    *reinterpret_cast<float4*>(yo) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-                    *reinterpret_cast<float4*>(yo + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
-                    store_planes<8, false>(a.h_hi, a.h_lo, row * a.D + u0, hv);
+                    // h planes first: they are what the other CTAs wait for
+                    uint32_t h01, l01, h23, l23;
+                    split2(hv[0], hv[1], h01, l01);
+                    split2(hv[2], hv[3], h23, l23);
+                    *reinterpret_cast<uint2*>(a.h_hi + row * a.D + u0) = make_uint2(h01, h23);
+                    *reinterpret_cast<uint2*>(a.h_lo + row * a.D + u0) = make_uint2(l01, l23);
+                    *reinterpret_cast<float4*>(cr) = make_float4(cvv[0], cvv[1], cvv[2], cvv[3]);
+                    *reinterpret_cast<float4*>(a.y + row * a.D + u0) = make_float4(hv[0], hv[1], hv[2], hv[3]);
                 }
-                // publish h_t of this (batch tile, step): generic writes -> async proxy (TMA) readers in other CTAs
+                // publish h_t of this (batch tile, step): generic writes -> async-proxy (TMA) readers in other CTAs.
+                // Each warp arrives on its own: lanes fence, __syncwarp orders them before lane 0's release.
+                if (threadIdx.x == 64) stamp(t, 5);  // cell math + stores issued
                 asm volatile("fence.proxy.async;" ::: "memory");
                 __threadfence();
-                asm volatile("bar.sync 1, %0;" ::"r"(LSTM_EPI_WARPS * 32) : "memory");
-                if (threadIdx.x == 64) {
+                __syncwarp();
+                if (lane == 0) {
                     int* cnt = a.counters + (long long)mt * a.L + t;
                     asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(cnt) : "memory");
                 }
+                if (threadIdx.x == 64) stamp(t, 6);  // published
             }
         }
     }
@@ -960,6 +994,7 @@ void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_
     LstmArgs a;
     a.xin = xin; a.y = y; a.h_hi = h_hi; a.h_lo = h_lo; a.cell = cell; a.counters = counters;
     a.B = B; a.L = L; a.D = D; a.m_tiles = (B + BM - 1) / BM;
+    a.dbg = g_debug_timeline ? g_debug_timeline + 148 * 64 : nullptr;  // after the generic GEMMs' per-CTA slots
     const int n_slices = 4 * D / 64;
     int mgroups = a.m_tiles;
     while (n_slices * mgroups > num_sms()) --mgroups;  // every CTA must be co-resident (they wait on each other)
