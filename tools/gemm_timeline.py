@@ -33,11 +33,12 @@ def run(rows, Cin, taps, N, passes, act=0, label="", split=False):
     print("  prologue", int(c[0]), "| issue kb:", [int(x) for x in c[1:1 + min(nkb, 16)]])
     print("  landed kb:", [int(x) for x in c[17:17 + min(nkb, 16)]])
     print("  acc ready", int(c[40]), "epi done", int(c[41]), "end", int(c[42]))
+    print("  tile4 detail: producer issue kb0/kb1", int(c[33]), int(c[34]), "| landed kb0/kb1", int(c[35]), int(c[36]),
+          "| epi first chunk math done", int(c[38]))
     for ti in range(5):
         print(f"   tile {ti}: mma start {int(c[44 + 4 * ti])} issued {int(c[45 + 4 * ti])} acc ready {int(c[46 + 4 * ti])} "
               f"epi done {int(c[47 + 4 * ti])}")
 
 
-run(128 * 148 * 8, 128, 1, 32, 3, label="rb0 tail-like (K=128, N=32, split out)", split=True)
-run(128 * 148 * 8, 128, 1, 64, 3, label="down0-like (K=128, N=64, split out)", split=True)
-run(128 * 148 * 4, 768, 1, 2304, 1, act=1, label="pwconv1 1-pass GELU split out", split=True)
+run(128 * 148 * 8, 128, 1, 32, 3, label="K=128 N=32 split out", split=True)
+run(128 * 148 * 8, 128, 1, 32, 3, label="K=128 N=32 fp32 out", split=False)

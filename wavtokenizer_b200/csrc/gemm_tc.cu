@@ -100,6 +100,64 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint6
         : "memory");
 }
 
+// elect.sync: exactly one lane of a converged warp gets true. ptxas recognises an elect-guarded region as
+// single-threaded, which a `lane == 0` test does not give it.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// Warp-uniform issue: every lane of the role warp executes these with identical (uniform) operands and only the
+// leader's predicate is true. Issuing from inside an `if (lane == 0)` region instead makes the compiler wrap each
+// UTCHMMA / UTMALDG in an ELECT + BRA.U.ANY loop (one trip per active lane group) on the slow uniform datapath,
+// which costs the issuing thread on the order of 100 cycles per instruction and bounds every narrow-N GEMM.
+__device__ __forceinline__ void umma_f16_p(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate, uint32_t leader) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "setp.ne.b32 q, %5, 0;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint32_t bar, uint32_t leader) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %1, 0;\n"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(bar), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_p(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
+                                              uint32_t leader) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %5, 0;\n"
+        "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+        "}\n" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_p(uint32_t bar, uint32_t bytes, uint32_t leader) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %2, 0;\n"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+        "}\n" ::"r"(bar), "r"(bytes), "r"(leader)
+        : "memory");
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -278,7 +336,13 @@ struct Cfg {
     static constexpr int STAGE = PLANES * (A_PLANE + B_PLANE);
     static constexpr int STAGES = (200 * 1024) / STAGE > 8 ? 8 : (200 * 1024) / STAGE;
     static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator stages (power of two >= 32)
+    // An SS-mode MMA (M = 128, K = 16) costs >= ~128 cycles whatever N is (A-tile fetch from shared memory), so
+    // for N <= 128 the hi and lo weight tiles (adjacent in shared memory) are multiplied by A_hi in ONE MMA of
+    // N = 2*BN: hh lands in accumulator columns [0, BN), hl in [BN, 2*BN); A_lo x W_hi then adds lh to [0, BN).
+    // Two MMAs per k-step instead of three; the epilogue adds the two column blocks.
+    static constexpr bool FUSE = PASSES == 3 && BN <= 128;
+    static constexpr int ACC_COLS = FUSE ? 2 * BN : BN;          // TMEM columns per accumulator stage
+    static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;  // two stages (power of two >= 32)
     static constexpr int G = NEPI / 4;                           // epilogue warps per TMEM lane quarter
     static constexpr int CW = BN / G >= 16 ? 16 : 8;             // epilogue chunk width (columns per tcgen05.ld)
     static constexpr int EPI_SMEM = 0;
@@ -355,12 +419,12 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                 const int c0 = (kl - tap * kpt) * BK;
                 const int r0 = m0 + g.seg[si].shift0 + tap;
                 mbar_wait(empty_bar(stage), phase ^ 1);
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t sa = smem_base + stage * C::STAGE;
+                    const uint32_t sb = sa + C::PLANES * C::A_PLANE;
                     mbar_expect_tx(full_bar(stage), C::STAGE);
                     tma_load_2d(sa, &maps.a[si][0], c0, r0, full_bar(stage));
                     if (PASSES == 3) tma_load_2d(sa + C::A_PLANE, &maps.a[si][1], c0, r0, full_bar(stage));
-                    const uint32_t sb = sa + C::PLANES * C::A_PLANE;
                     tma_load_2d(sb, &maps.w[0], kb * BK, n0, full_bar(stage));
                     if (PASSES == 3) tma_load_2d(sb + C::B_PLANE, &maps.w[1], kb * BK, n0, full_bar(stage));
                     if (tile == (int)blockIdx.x) stamp(1 + kb);  // slots 1..16: producer issued k-block kb (first tile)
@@ -372,6 +436,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp loops; lane 0 issues) =====================
         constexpr uint32_t idesc = umma_idesc_f16(BN);
+        constexpr uint32_t idesc2 = umma_idesc_f16(C::FUSE ? 2 * BN : BN);  // A_hi x [W_hi; W_lo]
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -381,11 +446,11 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
             const int ti = (tile - (int)blockIdx.x) / (int)gridDim.x;
             if (lane == 0 && ti < 5) stamp(44 + 4 * ti);      // MMA may start tile ti (accumulator free)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * C::ACC_COLS);
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(full_bar(stage), phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
+                if (elect_one()) {
                     if (tile == (int)blockIdx.x) stamp(17 + kb);  // slots 17..32: data of k-block kb landed
                     const uint32_t sa = smem_base + stage * C::STAGE;
                     const uint32_t sb = sa + C::PLANES * C::A_PLANE;
@@ -394,12 +459,18 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                         const uint32_t koff = k * UMMA_K * 2;  // bytes inside the 128 B swizzle row
                         const uint64_t a_hi = umma_desc_sw128(sa + koff);
                         const uint64_t b_hi = umma_desc_sw128(sb + koff);
-                        umma_f16(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0);
-                        if (PASSES == 3) {
+                        if (C::FUSE) {
                             const uint64_t a_lo = umma_desc_sw128(sa + C::A_PLANE + koff);
-                            const uint64_t b_lo = umma_desc_sw128(sb + C::B_PLANE + koff);
-                            umma_f16(tmem_d, a_hi, b_lo, idesc, 1);
-                            umma_f16(tmem_d, a_lo, b_hi, idesc, 1);
+                            umma_f16(tmem_d, a_hi, b_hi, idesc2, (kb | k) != 0);  // [hh | hl], W_lo tile follows W_hi
+                            umma_f16(tmem_d, a_lo, b_hi, idesc, 1);               // + lh into the first BN columns
+                        } else {
+                            umma_f16(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0);
+                            if (PASSES == 3) {
+                                const uint64_t a_lo = umma_desc_sw128(sa + C::A_PLANE + koff);
+                                const uint64_t b_lo = umma_desc_sw128(sb + C::B_PLANE + koff);
+                                umma_f16(tmem_d, a_hi, b_lo, idesc, 1);
+                                umma_f16(tmem_d, a_lo, b_hi, idesc, 1);
+                            }
                         }
                     }
                     umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
@@ -430,7 +501,17 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
             if (threadIdx.x == 64 && ti < 5) stamp(46 + 4 * ti);  // accumulator of tile ti ready
             if (tile == (int)blockIdx.x && threadIdx.x == 64) stamp(40);  // accumulator of the first tile ready
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::ACC_COLS);
+            // accumulator chunk = columns [col, col+n) (+ the hl block BN columns further when the passes are fused)
+            auto ld_acc8 = [&](uint32_t col, uint32_t (&r)[8]) {
+                tmem_ld(tbase + col, r);
+                if (C::FUSE) {
+                    uint32_t t2[8];
+                    tmem_ld(tbase + (uint32_t)BN + col, t2);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(t2[i]));
+                }
+            };
             bool row_ok = m_local < g.M;
             // destination rows (identity, or re-mapped into the consumer's reflect-padded layout)
             long long dst = m, mir_l = -1, mir_r = -1;
@@ -451,10 +532,10 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                 if (cg < 2) {
                     uint32_t ri[8], rf[8], rg[8], ro[8];
                     __syncwarp();
-                    tmem_ld(tbase + 0 + cg * 8, ri);
-                    tmem_ld(tbase + 16 + cg * 8, rf);
-                    tmem_ld(tbase + 32 + cg * 8, rg);
-                    tmem_ld(tbase + 48 + cg * 8, ro);
+                    ld_acc8(0 + cg * 8, ri);
+                    ld_acc8(16 + cg * 8, rf);
+                    ld_acc8(32 + cg * 8, rg);
+                    ld_acc8(48 + cg * 8, ro);
                     if (row_ok) {
                         const float* xr = g.res + (long long)m * g.ldres + n0 + cg * 8;
                         float* cr = g.cell + (long long)m * g.hidden + u0;
@@ -518,6 +599,12 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                     uint32_t r[CW];
                     __syncwarp();  // tcgen05.ld is .sync.aligned: re-converge after the predicated stores below
                     tmem_ld(tbase + (uint32_t)(c * CW), r);
+                    if (C::FUSE) {
+                        uint32_t t2[CW];
+                        tmem_ld(tbase + (uint32_t)(BN + c * CW), t2);
+#pragma unroll
+                        for (int i = 0; i < CW; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(t2[i]));
+                    }
                     const int nb = n0 + c * CW;
                     if (!row_ok || nb >= g.N) continue;
                     float v[CW];
@@ -651,7 +738,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -661,7 +748,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
 
     if (warp == 0) {
         // ---- producer: resident W slice once, then h_{t-1} tiles every step ----
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(w_bar, LSTM_W_BYTES);
             for (int kb = 0; kb < LSTM_KB; ++kb) {
                 tma_load_2d(w_base + (kb * 2 + 0) * 8192, &mapW_hi, kb * BK, ns * 64, w_bar);
@@ -689,7 +776,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                 const int r0 = (t - 1) * a.B + mt * BM;
                 for (int kb = 0; kb < LSTM_KB; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
-                    if (lane == 0) {
+                    if (elect_one()) {
                         const uint32_t sa = a_base + stage * LSTM_A_STAGE;
                         mbar_expect_tx(full_bar(stage), LSTM_A_STAGE);
                         tma_load_2d(sa, &mapH_hi, kb * BK, r0, full_bar(stage));
@@ -704,6 +791,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
     } else if (warp == 1) {
         // ---- MMA issuer ----
         constexpr uint32_t idesc = umma_idesc_f16(64);
+        constexpr uint32_t idesc2 = umma_idesc_f16(128);  // h_hi x [W_hi; W_lo]: the lo tile follows the hi tile
         mbar_wait(w_bar, 0);
         int stage = 0;
         uint32_t phase = 0;
@@ -713,11 +801,11 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
             for (int mt = mg; mt < a.m_tiles; mt += MG) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 128);
                 for (int kb = 0; kb < LSTM_KB; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (lane == 0) {
+                    if (elect_one()) {
                         if (kb == 0) stamp(t, 2);               // first k-block landed
                         if (kb == LSTM_KB - 1) stamp(t, 3);     // last k-block landed
                         const uint32_t sa = a_base + stage * LSTM_A_STAGE;
@@ -726,10 +814,9 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             const uint32_t koff = k * UMMA_K * 2;
                             const uint64_t a_hi = umma_desc_sw128(sa + koff), a_lo = umma_desc_sw128(sa + BM * 128 + koff);
-                            const uint64_t b_hi = umma_desc_sw128(sw + koff), b_lo = umma_desc_sw128(sw + 8192 + koff);
-                            umma_f16(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0);
-                            umma_f16(tmem_d, a_hi, b_lo, idesc, 1);
-                            umma_f16(tmem_d, a_lo, b_hi, idesc, 1);
+                            const uint64_t b_hi = umma_desc_sw128(sw + koff);
+                            umma_f16(tmem_d, a_hi, b_hi, idesc2, (kb | k) != 0);  // [hh | hl] in one MMA (N = 128)
+                            umma_f16(tmem_d, a_lo, b_hi, idesc, 1);               // + lh into columns [0, 64)
                         }
                         umma_commit(empty_bar(stage));
                         if (kb == LSTM_KB - 1) umma_commit(tfull_bar(acc));
@@ -769,12 +856,19 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                     mbar_wait(tfull_bar(acc), acc_phase);
                     if (threadIdx.x == 64) stamp(t, 4);  // accumulator ready
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64 + hw * 4);
+                    const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + hw * 4);
                     __syncwarp();
-                    tmem_ld(tb + 0, ri);
-                    tmem_ld(tb + 16, rf);
-                    tmem_ld(tb + 32, rg);
-                    tmem_ld(tb + 48, ro);
+                    auto ld2 = [&](uint32_t col, uint32_t (&r)[4]) {  // hh + lh block, plus the hl block 64 columns on
+                        uint32_t t2[4];
+                        tmem_ld(tb + col, r);
+                        tmem_ld(tb + 64 + col, t2);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(t2[i]));
+                    };
+                    ld2(0, ri);
+                    ld2(16, rf);
+                    ld2(32, rg);
+                    ld2(48, ro);
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator is in registers: free it early
@@ -819,7 +913,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
     }
 }
 

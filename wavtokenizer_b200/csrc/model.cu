@@ -149,11 +149,11 @@ struct wt_handle {
             hi[i] = __float2half_rn(v[i]);
             lo[i] = __float2half_rn(v[i] - __half2float(hi[i]));
         }
-        HalfW w;
-        WT_CUDA(cudaMalloc(&w.hi, std::max<size_t>(v.size(), 1) * sizeof(__half)));
+        HalfW w;  // one allocation, lo right after hi: a single 3-D TMA box fetches both planes of a tile
+        const size_t n8 = align_up(std::max<size_t>(v.size(), 1), 8);
+        WT_CUDA(cudaMalloc(&w.hi, 2 * n8 * sizeof(__half)));
         owned.push_back(w.hi);
-        WT_CUDA(cudaMalloc(&w.lo, std::max<size_t>(v.size(), 1) * sizeof(__half)));
-        owned.push_back(w.lo);
+        w.lo = w.hi + n8;
         WT_CUDA(cudaMemcpy(w.hi, hi.data(), v.size() * sizeof(__half), cudaMemcpyHostToDevice));
         WT_CUDA(cudaMemcpy(w.lo, lo.data(), v.size() * sizeof(__half), cudaMemcpyHostToDevice));
         return w;
@@ -497,7 +497,7 @@ void prepare(wt_handle* h, const Table& t) {
     WT_CUDA(cudaMemset(h->err_flag, 0, sizeof(int)));
     {
         void* z = nullptr;
-        const size_t bytes = (size_t)ENC_GROUP * c.dimension * sizeof(__half);
+        const size_t bytes = 2 * (size_t)ENC_GROUP * c.dimension * sizeof(__half);  // hi and lo zero planes
         WT_CUDA(cudaMalloc(&z, bytes));
         WT_CUDA(cudaMemset(z, 0, bytes));
         h->owned.push_back(z);
@@ -922,7 +922,7 @@ float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, con
         for (int t = 0; t < L; ++t) {
             TcGemm g;
             if (t == 0) {
-                g.seg[0] = tc_taps(zero, zero, Bg, D, D, 1, 0);  // h_{-1} = 0
+                g.seg[0] = tc_taps(zero, zero + (size_t)ENC_GROUP * D, Bg, D, D, 1, 0);  // h_{-1} = 0
             } else {
                 g.seg[0] = tc_taps(yh_hi[l], yh_lo[l], M, D, D, 1, 0);
                 g.seg[0].shift0 = (t - 1) * Bg;
@@ -1470,10 +1470,10 @@ int wt_test_tap_gemm(int32_t device, const float* A, int32_t rows, int32_t Cin, 
         cudaStream_t s = (cudaStream_t)stream;
         const long long K = (long long)taps * Cin;
         __half *a_hi, *a_lo, *w_hi, *w_lo, *o_hi = nullptr, *o_lo = nullptr;
-        WT_CUDA(cudaMalloc(&a_hi, (size_t)rows * Cin * 2));
-        WT_CUDA(cudaMalloc(&a_lo, (size_t)rows * Cin * 2));
-        WT_CUDA(cudaMalloc(&w_hi, (size_t)N * K * 2));
-        WT_CUDA(cudaMalloc(&w_lo, (size_t)N * K * 2));
+        WT_CUDA(cudaMalloc(&a_hi, (size_t)rows * Cin * 2 * 2));  // hi plane, then lo plane
+        a_lo = a_hi + (size_t)rows * Cin;
+        WT_CUDA(cudaMalloc(&w_hi, (size_t)N * K * 2 * 2));
+        w_lo = w_hi + (size_t)N * K;
         const int ldh = (N + 7) / 8 * 8;
         if (out_split) {
             WT_CUDA(cudaMalloc(&o_hi, (size_t)rows * ldh * 2));
@@ -1499,7 +1499,7 @@ int wt_test_tap_gemm(int32_t device, const float* A, int32_t rows, int32_t Cin, 
                     sum[r * N + n] = __half2float(hh[r * ldh + n]) + __half2float(hl[r * ldh + n]);
             WT_CUDA(cudaMemcpy(out_split, sum.data(), sum.size() * 4, cudaMemcpyHostToDevice));
         }
-        for (void* p : {(void*)a_hi, (void*)a_lo, (void*)w_hi, (void*)w_lo, (void*)o_hi, (void*)o_lo})
+        for (void* p : {(void*)a_hi, (void*)w_hi, (void*)o_hi, (void*)o_lo})
             if (p) cudaFree(p);
         return WT_OK;
     } catch (const Error& e) {
