@@ -22,7 +22,7 @@ def t(rows, Cin, N, passes, mode):
                                        args[0], args[1], None))
     lib.wt_debug_timeline(None)
     d = dbg.view(148, 64).cpu()
-    return int(d[:, 42].max())  # cycles until the slowest CTA finished all roles
+    return int(d[:, 43].max())  # cycles until the slowest CTA's epilogue finished its last tile
 
 
 for rows, Cin, N in [(4 * 72002, 128, 16), (4 * 72002, 128, 32), (4 * 36001, 128, 64), (8 * 9001, 512, 128)]:

@@ -404,22 +404,24 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     if (threadIdx.x == 0) stamp(0);  // prologue done
 
     if (warp == 0) {
-        // ===================== TMA producer (whole warp loops; lane 0 issues) =====================
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int bz = tile / per_batch, rem = tile - bz * per_batch;
-            const int mt = rem / n_tiles, nt = rem - mt * n_tiles;
-            const int m0 = mt * BM + (int)(bz * g.a_brows), n0 = nt * BN + (int)(bz * g.w_brows);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int si = kb < nkb0 ? 0 : 1;
-                const int kl = si ? kb - nkb0 : kb;
-                const int kpt = g.seg[si].kb_per_tap;
-                const int tap = kl / kpt;
-                const int c0 = (kl - tap * kpt) * BK;
-                const int r0 = m0 + g.seg[si].shift0 + tap;
-                mbar_wait(empty_bar(stage), phase ^ 1);
-                if (elect_one()) {
+        // ===================== TMA producer: ONE elected thread runs the whole persistent loop =====================
+        // (elect.sync lets ptxas treat the region as single-threaded: no per-instruction ELECT/R2UR waterfall around
+        // UTMALDG, and the mbarrier is polled by one thread; the other 31 lanes wait at the teardown barrier)
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int bz = tile / per_batch, rem = tile - bz * per_batch;
+                const int mt = rem / n_tiles, nt = rem - mt * n_tiles;
+                const int m0 = mt * BM + (int)(bz * g.a_brows), n0 = nt * BN + (int)(bz * g.w_brows);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int si = kb < nkb0 ? 0 : 1;
+                    const int kl = si ? kb - nkb0 : kb;
+                    const int kpt = g.seg[si].kb_per_tap;
+                    const int tap = kl / kpt;
+                    const int c0 = (kl - tap * kpt) * BK;
+                    const int r0 = m0 + g.seg[si].shift0 + tap;
+                    mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * C::STAGE;
                     const uint32_t sb = sa + C::PLANES * C::A_PLANE;
                     mbar_expect_tx(full_bar(stage), C::STAGE);
@@ -428,34 +430,53 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                     tma_load_2d(sb, &maps.w[0], kb * BK, n0, full_bar(stage));
                     if (PASSES == 3) tma_load_2d(sb + C::B_PLANE, &maps.w[1], kb * BK, n0, full_bar(stage));
                     if (tile == (int)blockIdx.x) stamp(1 + kb);  // slots 1..16: producer issued k-block kb (first tile)
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (whole warp loops; lane 0 issues) =====================
-        constexpr uint32_t idesc = umma_idesc_f16(BN);
-        constexpr uint32_t idesc2 = umma_idesc_f16(C::FUSE ? 2 * BN : BN);  // A_hi x [W_hi; W_lo]
-        int stage = 0;
-        uint32_t phase = 0;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-            const int ti = (tile - (int)blockIdx.x) / (int)gridDim.x;
-            if (lane == 0 && ti < 5) stamp(44 + 4 * ti);      // MMA may start tile ti (accumulator free)
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * C::ACC_COLS);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(full_bar(stage), phase);
+        // ===================== MMA issuer: ONE elected thread =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_f16(BN);
+            constexpr uint32_t idesc2 = umma_idesc_f16(C::FUSE ? 2 * BN : BN);  // A_hi x [W_hi; W_lo]
+            // k16 steps that hold real columns in the LAST k-block of a segment row: narrow operands (16 channels,
+            // 8 audio taps, k*C = 96) are zero-padded to 64 by TMA, and an SS-mode MMA costs ~110 cycles whatever it
+            // multiplies, so the all-zero steps are simply not issued
+            int tail0 = BK / UMMA_K, tail1 = BK / UMMA_K;
+            {
+                const long long r0 = g.seg[0].inner - (long long)(g.seg[0].kb_per_tap - 1) * BK;
+                if (r0 < BK) tail0 = (int)((r0 + UMMA_K - 1) / UMMA_K);
+                if (g.nseg > 1) {
+                    const long long r1 = g.seg[1].inner - (long long)(g.seg[1].kb_per_tap - 1) * BK;
+                    if (r1 < BK) tail1 = (int)((r1 + UMMA_K - 1) / UMMA_K);
+                }
+            }
+            const int kpt0 = g.seg[0].kb_per_tap, kpt1 = g.nseg > 1 ? g.seg[1].kb_per_tap : 1;
+            const bool any_tail = tail0 < BK / UMMA_K || tail1 < BK / UMMA_K;
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                const int ti = (tile - (int)blockIdx.x) / (int)gridDim.x;
+                if (ti < 5) stamp(44 + 4 * ti);  // MMA may start tile ti (accumulator free)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (elect_one()) {
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * C::ACC_COLS);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (tile == (int)blockIdx.x) stamp(17 + kb);  // slots 17..32: data of k-block kb landed
                     const uint32_t sa = smem_base + stage * C::STAGE;
                     const uint32_t sb = sa + C::PLANES * C::A_PLANE;
+                    int nk16 = BK / UMMA_K;
+                    if (any_tail) {
+                        if (kb < nkb0) { if ((kb + 1) % kpt0 == 0) nk16 = tail0; }
+                        else if ((kb - nkb0 + 1) % kpt1 == 0) nk16 = tail1;
+                    }
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
+                        if (k >= nk16) break;
                         const uint32_t koff = k * UMMA_K * 2;  // bytes inside the 128 B swizzle row
                         const uint64_t a_hi = umma_desc_sw128(sa + koff);
                         const uint64_t b_hi = umma_desc_sw128(sb + koff);
@@ -478,11 +499,10 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                         umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
                         if (ti < 5) stamp(45 + 4 * ti);  // all MMAs of tile ti issued
                     }
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
@@ -664,9 +684,10 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
         }
     }
 
+    if (threadIdx.x == 64) stamp(43);  // this epilogue warp finished its last tile (a reliable "CTA done" time)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x == 0) stamp(42);  // all roles finished
+    if (threadIdx.x == 0) stamp(42);  // barrier issued (BAR.SYNC.DEFER_BLOCKING: not the release time)
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"((uint32_t)C::TMEM_COLS)
