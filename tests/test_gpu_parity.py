@@ -258,3 +258,40 @@ def test_full_size_properties(plan):
     rep = O.vq_tie_report(z.permute(0, 2, 1).reshape(-1, 512), codebook(sd), codes[:, idx].cpu(), c_ref)
     assert rep["hard_mismatches"] == 0 and rep["match_pct"] >= 98.0, rep
     assert helpers.snr_db(a_ref, audio[idx].cpu()) >= SNR_BAR_DB
+
+
+def test_decode_only_long_streams():
+    """BASELINE.json config 4 shape: codes_to_features + decode of 10 s random token streams (L = 750 at 75 tok/s),
+    more streams than one decoder chunk; a sampled stream is checked against the oracle."""
+    cfg, sd = helpers.model("small320")
+    m = native_model("small320", 2)
+    gen = torch.Generator().manual_seed(4)
+    codes = torch.randint(0, cfg.vq_bins, (1, 130, 750), generator=gen)
+    bw = torch.tensor([1])
+    audio = m.decode(m.codes_to_features(codes.cuda()), bandwidth_id=bw.cuda())
+    assert audio.shape == (130, 750 * cfg.hop_length) and bool(torch.isfinite(audio).all())
+    for i in (0, 129):
+        with torch.inference_mode():
+            ref = O.decode(sd, cfg, O.codes_to_features(sd, cfg, codes[:, i:i + 1]), bw)
+        assert helpers.snr_db(ref, audio[i:i + 1].cpu()) >= SNR_BAR_DB, i
+
+
+@pytest.mark.parametrize("plan", [0, 2])
+def test_vq_sweep_one_million_frames(plan):
+    """BASELINE.json config 5 at N = 1e6 frames: codes in range, quantized rows are exact codebook rows, idempotent
+    (quantising the quantised frames returns the same codes), and a sampled slice matches the oracle."""
+    cfg, sd = helpers.model("small320")
+    m = native_model("small320", plan)
+    cb = codebook(sd)
+    gen = torch.Generator().manual_seed(8)
+    N = 1_000_000
+    x = (cb[torch.randint(0, cb.shape[0], (N,), generator=gen)] + 2e-3 * torch.randn(N, 512, generator=gen)).cuda()
+    codes, quant = m.vq(x)
+    assert codes.shape == (N,) and int(codes.min()) >= 0 and int(codes.max()) < cfg.vq_bins
+    assert torch.equal(quant, cb.cuda()[codes])
+    codes2, _ = m.vq(quant)
+    assert torch.equal(codes2, codes)  # codebook rows are fixed points (duplicates would resolve to the first index)
+    sl = slice(123_000, 127_000)
+    ref = O.vq_quantize(x[sl].cpu(), cb)
+    rep = O.vq_tie_report(x[sl].cpu(), cb, codes[sl].cpu(), ref)
+    assert rep["hard_mismatches"] == 0 and rep["match_pct"] >= 98.0, rep
