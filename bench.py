@@ -196,8 +196,7 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
     sd = make_state(cfg, 1, enc)
     model.load_state_dict(sd)
     model = model.to(dev)
-    if args.plan:
-        model.set_plan(args.plan)
+    model.set_plan(args.plan)
     B = CLIPS_PER_GPU
     model.reserve(B, T)
     lib, hptr = _native.lib(), model.native().ptr

@@ -142,7 +142,7 @@ int wt_debug_timeline(long long* dev_buf);
 
 /* Compute plan: 0 = fp32 CUDA-core contractions everywhere (bit-conservative);
  * 1 = tcgen05 tensor-core contractions with split-fp16 operands, 3 passes (hi*hi + hi*lo + lo*hi);
- * 2 = as 1, but the 24 ConvNeXt pointwise GEMMs run single-pass fp16. */
+ * 2 = as 1, but the 24 ConvNeXt pointwise GEMMs run single-pass fp16. Default: 2. */
 int wt_set_plan(wt_handle* h, int32_t plan);
 
 const char* wt_last_error(void);

@@ -15,8 +15,7 @@ def native_model(tag: str, plan: int = 0) -> WavTokenizer:
     m = WavTokenizer(cfg)
     m.load_state_dict(sd)
     m = m.to("cuda:0")
-    if plan:
-        m.set_plan(plan)
+    m.set_plan(plan)  # the library default is plan 2
     return m
 
 

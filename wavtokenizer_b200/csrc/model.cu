@@ -64,7 +64,7 @@ using namespace wt;
 struct wt_handle {
     wt_config cfg{};
     int device = 0;
-    int plan = 0;
+    int plan = 2;  // default: tcgen05 everywhere, single-pass fp16 for the ConvNeXt GEMMs (wt_set_plan)
     int64_t launches = 0;
     std::vector<void*> owned;  // weight allocations
 
