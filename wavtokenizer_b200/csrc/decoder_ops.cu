@@ -68,10 +68,11 @@ __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
 
 // Normalize = GroupNorm(32, C, eps=1e-6, affine) (+ x*sigmoid(x)) (reference decoder/models.py:10-16,
 // 58-78, 107-110). Statistics span all L frames of a clip. One block per (clip, slab of 8 groups = 192
-// channels): 48 lanes x float4 read whole 768-byte row slabs coalesced, 5 row phases; pass 1 accumulates
+// channels): 48 lanes x float4 read whole 768-byte row slabs coalesced, 20 row phases (960 threads, four
+// independent loads in flight per thread); pass 1 accumulates
 // sum / sum-of-squares (combined in fp64), pass 2 re-reads the slab (L2-resident), normalises and stores
 // fp32 rows or split-fp16 planes with 8-byte vectors. Halo rows of the padded row space are written as zeros.
-constexpr int GN_LANES = 48, GN_PH = 5, GN_THREADS = GN_LANES * GN_PH;
+constexpr int GN_LANES = 48, GN_PH = 20, GN_THREADS = GN_LANES * GN_PH;
 __global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                const float* __restrict__ bsh, RowOut out, int L, int Lp,
                                                                int C, float eps, int swish) {
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __re
     const int c = slab * 192 + lane * 4;
     const long long base = (long long)b * Lp * C + c;
     float s = 0.f, q = 0.f;
+#pragma unroll 4
     for (int t = ph; t < L; t += GN_PH) {
         const float4 v = *reinterpret_cast<const float4*>(x + base + (long long)t * C);
         s += (v.x + v.y) + (v.z + v.w);
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __re
     __syncthreads();
     const float mean = s_mean[lane / 6], rstd = s_rstd[lane / 6];
     const float4 wv = *reinterpret_cast<const float4*>(w + c), bv = *reinterpret_cast<const float4*>(bsh + c);
+#pragma unroll 4
     for (int t = ph; t < Lp; t += GN_PH) {
         float y[4] = {0.f, 0.f, 0.f, 0.f};
         if (t < L) {
@@ -181,42 +184,111 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // ConvNeXt front half: depthwise Conv1d(k=7, pad 3 zeros, groups=C) -> AdaLayerNorm
-// (reference decoder/modules.py:30-33, 49-53). One warp per frame; the depthwise taps arrive transposed
-// ([tap][channel], prepared at load) so every access is a coalesced 32-byte-per-lane vector; the seven
-// neighbouring rows are L1/L2 hits, so HBM traffic is one read and one write of the activation.
-__global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ dwT,
-                                                        const float* __restrict__ db, const float* __restrict__ scale,
-                                                        const float* __restrict__ shift, RowOut out, int B, int L,
-                                                        int Lp, float eps) {
-    constexpr int C = 768;
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= (long long)B * Lp) return;
-    const int b = (int)(row / Lp), t = (int)(row - (long long)b * Lp);
-    if (t >= L) {  // halo row of the padded row space
-        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+// (reference decoder/modules.py:30-33, 49-53). One block per (clip, run of DW_TT frames); a thread owns 4
+// consecutive channels for the whole run: its 28 taps live in registers, the DW_TT + 6 input rows are read once
+// each as coalesced float4 (all loads issued up front), the conv slides over them in registers, and the
+// LayerNorm statistics of the DW_TT frames are reduced together (a 16-value butterfly: 16 shuffles instead of
+// 80 per pass, then one shared-memory exchange between the 6 warps). Two-pass variance (mean, then centred sum
+// of squares) as in the per-row LayerNorm kernel. HBM traffic: one read of x, one write of the operand planes.
+constexpr int DW_TT = 16, DW_THREADS = 192;
+
+// Sums v[i] over the 32 lanes for 16 values at once. On return v[0] of lane l holds the total of value (l >> 1).
+__device__ __forceinline__ void warp_sum16(float (&v)[16], int lane) {
 #pragma unroll
-        for (int g = 0; g < 3; ++g) put8(out, row * C + g * 256 + lane * 8, z);
-        return;
-    }
-    float v[3][8];
+    for (int o = 16, n = 16; n > 1; o >>= 1, n >>= 1) {
+        const bool upper = (lane & o) != 0;
 #pragma unroll
-    for (int g = 0; g < 3; ++g) load8(db + g * 256 + lane * 8, v[g]);
-#pragma unroll
-    for (int j = 0; j < 7; ++j) {
-        const int tj = t - 3 + j;
-        if (tj < 0 || tj >= L) continue;
-        const float* xr = x + ((long long)b * Lp + tj) * C;
-#pragma unroll
-        for (int g = 0; g < 3; ++g) {
-            float xv[8], wv[8];
-            load8(xr + g * 256 + lane * 8, xv);
-            load8(dwT + j * C + g * 256 + lane * 8, wv);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[g][k] = fmaf(wv[k], xv[k], v[g][k]);
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = upper ? v[i] : v[i + n / 2];
+            const float keep = upper ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
         }
     }
-    ln_finish(v, scale, shift, out, row, lane, eps);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+__global__ void __launch_bounds__(DW_THREADS, 2) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ dwT,
+                                                                  const float* __restrict__ db, const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift, RowOut out, int L, int Lp,
+                                                                  float eps) {
+    constexpr int C = 768, NW = DW_THREADS / 32;
+    __shared__ __align__(16) float red[2][DW_TT][8];  // [pass][frame][warp] partial sums (6 used)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, t0 = blockIdx.x * DW_TT;
+    const int c = threadIdx.x * 4;
+    const float* xb = x + (long long)b * Lp * C + c;
+    float4 xr[DW_TT + 6];
+#pragma unroll
+    for (int r = 0; r < DW_TT + 6; ++r) {
+        const int t = t0 - 3 + r;
+        xr[r] = (t >= 0 && t < L) ? *reinterpret_cast<const float4*>(xb + (long long)t * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 w[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) w[j] = *reinterpret_cast<const float4*>(dwT + j * C + c);
+    const float4 bias = *reinterpret_cast<const float4*>(db + c);
+    float4 v[DW_TT];
+    float part[16];
+#pragma unroll
+    for (int i = 0; i < DW_TT; ++i) {
+        float4 a = bias;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            a.x = fmaf(w[j].x, xr[i + j].x, a.x);
+            a.y = fmaf(w[j].y, xr[i + j].y, a.y);
+            a.z = fmaf(w[j].z, xr[i + j].z, a.z);
+            a.w = fmaf(w[j].w, xr[i + j].w, a.w);
+        }
+        v[i] = a;
+        part[i] = (a.x + a.y) + (a.z + a.w);
+    }
+    warp_sum16(part, lane);
+    if ((lane & 1) == 0) red[0][lane >> 1][warp] = part[0];
+    __syncthreads();
+    float mean[DW_TT];
+#pragma unroll
+    for (int i = 0; i < DW_TT; ++i) {
+        const float4 p0 = *reinterpret_cast<const float4*>(&red[0][i][0]);
+        const float2 p1 = *reinterpret_cast<const float2*>(&red[0][i][4]);
+        static_assert(NW == 6, "six warps cover the 768 channels");
+        mean[i] = (((p0.x + p0.y) + (p0.z + p0.w)) + (p1.x + p1.y)) * (1.f / (float)C);
+        const float dx = v[i].x - mean[i], dy = v[i].y - mean[i], dz = v[i].z - mean[i], dw = v[i].w - mean[i];
+        part[i] = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
+    }
+    warp_sum16(part, lane);
+    if ((lane & 1) == 0) red[1][lane >> 1][warp] = part[0];
+    __syncthreads();
+    const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+#pragma unroll
+    for (int i = 0; i < DW_TT; ++i) {
+        const int t = t0 + i;
+        if (t >= Lp) break;
+        float y[4] = {0.f, 0.f, 0.f, 0.f};
+        if (t < L) {
+            const float4 p0 = *reinterpret_cast<const float4*>(&red[1][i][0]);
+            const float2 p1 = *reinterpret_cast<const float2*>(&red[1][i][4]);
+            const float var = (((p0.x + p0.y) + (p0.z + p0.w)) + (p1.x + p1.y)) * (1.f / (float)C);
+            const float rstd = rsqrtf(var + eps);
+            y[0] = (v[i].x - mean[i]) * rstd * sc.x + sh.x;
+            y[1] = (v[i].y - mean[i]) * rstd * sc.y + sh.y;
+            y[2] = (v[i].z - mean[i]) * rstd * sc.z + sh.z;
+            y[3] = (v[i].w - mean[i]) * rstd * sc.w + sh.w;
+        }  // else: halo row of the padded row space, written as zeros
+        const long long idx = ((long long)b * Lp + t) * C + c;
+        if (out.f32) *reinterpret_cast<float4*>(out.f32 + idx) = make_float4(y[0], y[1], y[2], y[3]);
+        if (out.hi) {
+            const __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
+            *reinterpret_cast<uint2*>(out.hi + idx) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+            if (out.lo) {
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn(y[0] - f01.x, y[1] - f01.y);
+                const __half2 l23 = __floats2half2_rn(y[2] - f23.x, y[3] - f23.y);
+                *reinterpret_cast<uint2*>(out.lo + idx) =
+                    make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+            }
+        }
+    }
 }
 
 // AttnBlock core (reference decoder/models.py:115-123): softmax(q k^T * C^-0.5) v, one head of width C
@@ -276,20 +348,23 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
 
 // ISTFTHead spectral step (reference decoder/heads.py:55-65): z = [log-mag | phase] (row pitch ldz) ->
 // S = [min(exp(m), 100) cos p | min(exp(m), 100) sin p], zero-filled to ldS columns (the K of the iDFT GEMM).
-__global__ void spectral_kernel(const float* __restrict__ z, int ldz, RowOut S, long long M, int half, int ldS) {
+// One thread per (row, bin): both outputs of a bin share one exp and one sincos; threads past the last bin zero the pad.
+__global__ void __launch_bounds__(256) spectral_kernel(const float* __restrict__ z, int ldz, RowOut S, long long M, int half,
+                                                       int ldS) {
+    const int W = ldS - half;  // bins, then the zero pad columns [2*half, ldS)
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= M * ldS) return;
-    long long m = gid / ldS;
-    int c = (int)(gid - m * ldS);
-    float v = 0.f;
-    if (c < 2 * half) {
-        int i = c < half ? c : c - half;
-        float mag = fminf(expf(z[m * ldz + i]), 100.f);
+    if (gid >= M * W) return;
+    const long long m = gid / W;
+    const int i = (int)(gid - m * W);
+    if (i < half) {
+        const float mag = fminf(expf(z[m * ldz + i]), 100.f);
         float sn, cs;
         sincosf(z[m * ldz + half + i], &sn, &cs);
-        v = c < half ? mag * cs : mag * sn;
+        put(S, m * ldS + i, mag * cs);
+        put(S, m * ldS + half + i, mag * sn);
+    } else {
+        put(S, m * ldS + half + i, 0.f);
     }
-    put(S, gid, v);
 }
 
 // ISTFT "same" overlap-add + envelope normalisation (reference decoder/spectral_ops.py:58-73).
@@ -433,8 +508,8 @@ void launch_dwconv_ln(const float* x, const float* dw, const float* db, const fl
                       RowOut out, int B, int L, int Lp, int C, float eps, cudaStream_t s) {
     if (B <= 0 || L <= 0) return;
     if (C != 768) throw Error(1, "dwconv_ln: backbone dim must be 768");
-    long long M = (long long)B * Lp;
-    dwconv_ln_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, dw, db, scale, shift, out, B, L, Lp, eps);
+    dim3 grid((Lp + DW_TT - 1) / DW_TT, B);
+    dwconv_ln_kernel<<<grid, DW_THREADS, 0, s>>>(x, dw, db, scale, shift, out, L, Lp, eps);
     WT_CUDA(cudaGetLastError());
 }
 
@@ -455,7 +530,8 @@ void launch_attention(const float* qkv, RowOut out, int B, int L, int Lp, int C,
 
 void launch_spectral(const float* z, int ldz, RowOut S, long long M, int half, int ldS, cudaStream_t s) {
     if (M <= 0) return;
-    long long n = M * ldS;
+    if (ldS < 2 * half) throw Error(1, "spectral: ldS must cover both halves");
+    long long n = M * (ldS - half);
     spectral_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(z, ldz, S, M, half, ldS);
     WT_CUDA(cudaGetLastError());
 }

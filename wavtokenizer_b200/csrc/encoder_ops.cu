@@ -2,6 +2,8 @@
 // pointwise update and layout transposes.
 #include <cuda_fp16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace wt {
@@ -80,44 +82,48 @@ __global__ void __launch_bounds__(256) conv0_planes_kernel(const float* __restri
                                                            const float* __restrict__ bias, __half* __restrict__ win_hi,
                                                            __half* __restrict__ win_lo, __half* __restrict__ elu_hi,
                                                            __half* __restrict__ elu_lo, int B, int T) {
-    __shared__ float ws[C * 7];
-    __shared__ float bs[C];
-    for (int i = threadIdx.x; i < C * 7; i += blockDim.x) ws[i] = w[i];
-    for (int i = threadIdx.x; i < C; i += blockDim.x) bs[i] = bias[i];
-    __syncthreads();
     const int P = T + 2;
-    constexpr int G8 = C / 8;  // 16-byte stores coalesce across the 4 threads of a position
-    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)B * P * G8) return;
-    const int c8 = (int)(gid % G8);
-    const long long pos = gid / G8;
-    int b = (int)(pos / P);
-    int p = (int)(pos - (long long)b * P);
-    int t = p - 1;
-    if (t < 0) t = -t;
-    if (t >= T) t = 2 * (T - 1) - t;
-    const float* x = wav + (long long)b * T;
-    float xv[8];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) {
-        int ti = t - 3 + j;
-        if (ti < 0) ti = -ti;
-        if (ti >= T) ti = 2 * (T - 1) - ti;
-        xv[j] = x[ti];
-    }
-    xv[7] = 0.f;
-    float e[8];
+    constexpr int G8 = C / 8;  // 16-byte stores coalesce across the G8 threads of a position
+    static_assert(256 % G8 == 0, "a thread keeps the same channel group for every position it visits");
+    // the thread's 8 x 7 taps stay in registers for the whole grid-stride loop (no shared-memory operand per FMA)
+    const int c8 = threadIdx.x % G8;
+    float wr[8][7], br[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-        int c = c8 * 8 + u;
-        float acc = 0.f;
+        br[u] = bias[c8 * 8 + u];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) acc = fmaf(ws[c * 7 + j], xv[j], acc);
-        const float r = acc + bs[c];
-        e[u] = elu_fast(r);
+        for (int j = 0; j < 7; ++j) wr[u][j] = w[(c8 * 8 + u) * 7 + j];
     }
-    split_store8(elu_hi, elu_lo, gid * 8, e);
-    if (c8 == 0) split_store8(win_hi, win_lo, pos * 8, xv);
+    const long long total = (long long)B * P * G8;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += (long long)gridDim.x * blockDim.x) {
+        const long long pos = gid / G8;
+        int b = (int)(pos / P);
+        int p = (int)(pos - (long long)b * P);
+        int t = p - 1;
+        if (t < 0) t = -t;
+        if (t >= T) t = 2 * (T - 1) - t;
+        const float* x = wav + (long long)b * T;
+        float xv[8];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            int ti = t - 3 + j;
+            if (ti < 0) ti = -ti;
+            if (ti >= T) ti = 2 * (T - 1) - ti;
+            xv[j] = x[ti];
+        }
+        xv[7] = 0.f;
+        float e[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) acc = fmaf(wr[u][j], xv[j], acc);
+            e[u] = elu_fast(acc + br[u]);
+        }
+        split_store8(elu_hi, elu_lo, gid * 8, e);
+        if (c8 == 0) split_store8(win_hi, win_lo, pos * 8, xv);
+    }
 }
 
 // SLSTM skip connection y + x (reference encoder/modules/lstm.py:38; y and x in time-major rows) fused with the ELU in front of the last
@@ -212,7 +218,8 @@ void launch_conv0_planes(const float* wav, const float* w, const float* bias, __
     if (C != 32) throw Error(1, "conv0: n_filters must be 32");
     if (T < 4) throw Error(4, "conv0_planes: clip too short for the tcgen05 encoder layout");
     long long n = (long long)B * (T + 2) * (C / 8);
-    conv0_planes_kernel<32><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(wav, w, bias, win_hi, win_lo, elu_hi, elu_lo, B, T);
+    const long long blocks = std::min<long long>((n + 255) / 256, 148 * 8);  // grid-stride, 8 blocks per SM
+    conv0_planes_kernel<32><<<(unsigned)blocks, 256, 0, s>>>(wav, w, bias, win_hi, win_lo, elu_hi, elu_lo, B, T);
     WT_CUDA(cudaGetLastError());
 }
 

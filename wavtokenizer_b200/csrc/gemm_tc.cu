@@ -215,11 +215,11 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // ELU(alpha = 1) (reference encoder/modules/seanet.py:37). Negative branch: expm1 through a degree-5 Taylor
 // polynomial for x > -1/8 (error < 1e-8 relative) and __expf(x) - 1 below (<= 1e-6 relative): well under the
 // 2^-22 resolution of the split-fp16 planes the value is stored in, at a third of expm1f's instruction count.
-__device__ __forceinline__ float elu1(float x) {
-    if (x > 0.f) return x;
+__device__ __forceinline__ float elu1(float x) {  // branch-free: three selects
     const float p = x * fmaf(x, fmaf(x, fmaf(x, fmaf(x, 1.f / 120.f, 1.f / 24.f), 1.f / 6.f), 0.5f), 1.f);
     const float e = __expf(x) - 1.f;
-    return x > -0.125f ? p : e;
+    const float n = x > -0.125f ? p : e;
+    return x > 0.f ? x : n;
 }
 __device__ __forceinline__ float sigmoid1(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -342,8 +342,16 @@ struct Cfg {
     // Two MMAs per k-step instead of three; the epilogue adds the two column blocks.
     static constexpr bool FUSE = PASSES == 3 && BN <= 128;
     static constexpr int ACC_COLS = FUSE ? 2 * BN : BN;          // TMEM columns per accumulator stage
-    static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;  // two stages (power of two >= 32)
-    static constexpr int G = NEPI / 4;                           // epilogue warps per TMEM lane quarter
+    // Epilogue organisation. Wide accumulators (256 columns): two TMEM stages, all 16 epilogue warps drain one tile
+    // together (4 warps per TMEM lane quarter share its columns). Narrow accumulators (<= 128 columns): FOUR TMEM
+    // stages and four independent epilogue groups of 4 warps (one per lane quarter); group i owns stage i and
+    // handles tiles i, i+4, ... of this CTA, so four tiles are in flight in the epilogue and the per-tile fixed
+    // cost (barrier wait, tile decode, row re-map) is paid by 4 warps instead of 16 - the narrow encoder GEMMs were
+    // bound by exactly that instruction overhead (profiles/r01_enc_chunk_s3_summary.md).
+    static constexpr int NGRP = ACC_COLS <= 128 ? 4 : 1;
+    static constexpr int NACC = NGRP == 4 ? 4 : 2;
+    static constexpr int TMEM_COLS = NACC * ACC_COLS < 32 ? 32 : NACC * ACC_COLS;  // power of two >= 32
+    static constexpr int G = NEPI / 4 / NGRP;                    // epilogue warps per TMEM lane quarter per tile
     static constexpr int CW = BN / G >= 16 ? 16 : 8;             // epilogue chunk width (columns per tcgen05.ld)
     static constexpr int EPI_SMEM = 0;
 };
@@ -361,12 +369,12 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + C::STAGES * C::STAGE;
-    // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address slot
+    // barriers: full[STAGES], empty[STAGES], tmem_full[NACC], tmem_empty[NACC], then the TMEM base address slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + C::NACC + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 2 * C::NACC);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -379,15 +387,16 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     const int total_tiles = per_batch * g.batch;
     const int nkb0 = g.seg[0].num_kb;
     const int num_kb = nkb0 + (g.nseg > 1 ? g.seg[1].num_kb : 0);
+    const bool simple_tiles = total_tiles == m_tiles;  // one column tile, one batch: tile index = row tile
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < C::NACC; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), NEPI);  // one arrive per epilogue warp
+            mbar_init(tempty_bar(s), NEPI / C::NGRP);  // one arrive per epilogue warp of the group that drains it
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -411,8 +420,12 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int bz = tile / per_batch, rem = tile - bz * per_batch;
-                const int mt = rem / n_tiles, nt = rem - mt * n_tiles;
+                int bz = 0, mt = tile, nt = 0;
+                if (!simple_tiles) {
+                    bz = tile / per_batch;
+                    const int rem = tile - bz * per_batch;
+                    mt = rem / n_tiles; nt = rem - mt * n_tiles;
+                }
                 const int m0 = mt * BM + (int)(bz * g.a_brows), n0 = nt * BN + (int)(bz * g.w_brows);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const int si = kb < nkb0 ? 0 : 1;
@@ -457,9 +470,10 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            int ti = -1;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-                const int ti = (tile - (int)blockIdx.x) / (int)gridDim.x;
+                ++ti;
                 if (ti < 5) stamp(44 + 4 * ti);  // MMA may start tile ti (accumulator free)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * C::ACC_COLS);
@@ -501,23 +515,29 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                     }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == C::NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int q = warp & 3;        // TMEM lane quarter this warp may read (hardware: warp id % 4)
-        const int cg = (warp - 2) >> 2;  // which share of the tile's columns this warp handles
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int bz = tile / per_batch, rem = tile - bz * per_batch;
-            const int mt = rem / n_tiles, nt = rem - mt * n_tiles;
+        // ===================== epilogue (warps 2..17) =====================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may read (hardware: warp id % 4)
+        const int grp = ((warp - 2) >> 2) / C::G;  // epilogue group: handles this CTA's tiles grp, grp + NGRP, ...
+        const int cg = ((warp - 2) >> 2) % C::G;   // which share of the tile's columns this warp handles
+        for (int ti = grp;; ti += C::NGRP) {
+            const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+            if (tile >= total_tiles) break;
+            const int acc = ti % C::NACC;
+            const uint32_t acc_phase = (uint32_t)(ti / C::NACC) & 1u;
+            int bz = 0, mt = tile, nt = 0;
+            if (!simple_tiles) {
+                bz = tile / per_batch;
+                const int rem = tile - bz * per_batch;
+                mt = rem / n_tiles; nt = rem - mt * n_tiles;
+            }
             const int m_local = mt * BM + q * 32 + lane;
             const int m = m_local + (int)(bz * g.o_brows);
             const int n0 = nt * BN;
             mbar_wait(tfull_bar(acc), acc_phase);
-            const int ti = (tile - (int)blockIdx.x) / (int)gridDim.x;
             if (threadIdx.x == 64 && ti < 5) stamp(46 + 4 * ti);  // accumulator of tile ti ready
             if (tile == (int)blockIdx.x && threadIdx.x == 64) stamp(40);  // accumulator of the first tile ready
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -548,16 +568,17 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
             if (BN == 64 && g.act == TC_ACT_LSTM) {
                 // LSTM cell (reference encoder/modules/lstm.py:20; gates i, f, g, o). Tile columns hold
                 // [i | f | g | o] x 16 hidden units; the thread owns one batch row, two warps per lane quarter work.
-                const int u0 = nt * 16 + cg * 8;  // this warp's 8 hidden units
-                if (cg < 2) {
+#pragma unroll 1
+                for (int hs = cg; hs < 2; hs += C::G) {  // two blocks of 8 hidden units per tile
+                    const int u0 = nt * 16 + hs * 8;
                     uint32_t ri[8], rf[8], rg[8], ro[8];
                     __syncwarp();
-                    ld_acc8(0 + cg * 8, ri);
-                    ld_acc8(16 + cg * 8, rf);
-                    ld_acc8(32 + cg * 8, rg);
-                    ld_acc8(48 + cg * 8, ro);
+                    ld_acc8(0 + hs * 8, ri);
+                    ld_acc8(16 + hs * 8, rf);
+                    ld_acc8(32 + hs * 8, rg);
+                    ld_acc8(48 + hs * 8, ro);
                     if (row_ok) {
-                        const float* xr = g.res + (long long)m * g.ldres + n0 + cg * 8;
+                        const float* xr = g.res + (long long)m * g.ldres + n0 + hs * 8;
                         float* cr = g.cell + (long long)m * g.hidden + u0;
                         float xi[8], xf[8], xg[8], xo[8], cv[8];
                         *reinterpret_cast<float4*>(xi) = *reinterpret_cast<const float4*>(xr);
@@ -680,7 +701,6 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
             if (threadIdx.x == 64 && ti < 5) stamp(47 + 4 * ti);  // epilogue of tile ti done (this warp)
             if (tile == (int)blockIdx.x && threadIdx.x == 64) stamp(41);  // epilogue of the first tile done
             if (lane == 0) mbar_arrive(tempty_bar(acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 

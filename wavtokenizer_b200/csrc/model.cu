@@ -1128,7 +1128,7 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
     r.cat = CAT_PWCONV;
     for (int i = 0; i < c.num_layers; ++i) {
         const auto& p = h->cnx[i];
-        { Scope sc(h, CAT_MEM, s); launch_dwconv_ln(x, p.dw, p.db, p.scale + (size_t)bw * D, p.shift + (size_t)bw * D, out_split(a_hi, a_lo), Bc, L, Lp, D, eps, s); }
+        { Scope sc(h, CAT_MEM, s); launch_dwconv_ln(x, p.dw, p.db, p.scale + (size_t)bw * D, p.shift + (size_t)bw * D, out_split(a_hi, pw_passes == 3 ? a_lo : nullptr), Bc, L, Lp, D, eps, s); }
         gemm(a_hi, a_lo, D, 1, p.w1_h.hi, p.w1_h.lo, Hd, pw_passes, p.b1, ACT_GELU, nullptr, nullptr, nullptr, 0,
              g_hi, pw_passes == 3 ? g_lo : nullptr, Hd);
         gemm(g_hi, g_lo, Hd, 1, p.w2_h.hi, p.w2_h.lo, D, pw_passes, p.b2, ACT_NONE, p.gamma, x, x, D, nullptr, nullptr, 0);

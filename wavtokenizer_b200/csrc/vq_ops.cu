@@ -157,29 +157,39 @@ __global__ void gather_rows_kernel(const float4* __restrict__ cb, const long lon
 }
 
 // features[b, c, t] = sum_k codebooks[k*bins + codes[k, b, t]][c]; tile of 32 frames per block,
-// transposed through shared memory so both the codebook reads and the [B, D, L] writes coalesce.
+// transposed through shared memory so both the codebook reads (float4 per lane, the 32 codes of the tile staged
+// once in shared memory, four independent row gathers in flight per thread) and the [B, D, L] writes coalesce.
 __global__ void __launch_bounds__(256) codes_to_features_kernel(const float* __restrict__ cbs,
                                                                 const long long* __restrict__ codes,
                                                                 float* __restrict__ out, int K, int B, int L, int D,
                                                                 int bins, int* err) {
     extern __shared__ float tile[];  // [32][D + 1]
+    __shared__ int scode[32];
     const int b = blockIdx.y, t0 = blockIdx.x * 32;
     const int ldt = D + 1;
-    for (int i = threadIdx.x; i < 32 * D; i += blockDim.x) {
-        int tt = i / D, c = i - tt * D;
-        int t = t0 + tt;
-        float v = 0.f;
-        if (t < L) {
-            for (int k = 0; k < K; ++k) {
-                long long code = codes[((long long)k * B + b) * L + t];
-                if (code < 0 || code >= bins) {
-                    if (err) atomicExch(err, 1);
-                    code = 0;
-                }
-                v += cbs[((long long)k * bins + code) * D + c];
+    const int D4 = D >> 2;
+    for (int k = 0; k < K; ++k) {
+        if (k) __syncthreads();
+        if (threadIdx.x < 32) {
+            const int t = t0 + threadIdx.x;
+            long long code = t < L ? codes[((long long)k * B + b) * L + t] : 0;
+            if (code < 0 || code >= bins) {
+                if (err) atomicExch(err, 1);
+                code = 0;
             }
+            scode[threadIdx.x] = (int)code;
         }
-        tile[tt * ldt + c] = v;
+        __syncthreads();
+#pragma unroll 4
+        for (int i = threadIdx.x; i < 32 * D4; i += blockDim.x) {
+            const int tt = i / D4, c4 = i - tt * D4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t0 + tt < L)
+                v = *reinterpret_cast<const float4*>(cbs + ((long long)k * bins + scode[tt]) * D + c4 * 4);
+            float* tp = tile + tt * ldt + c4 * 4;
+            if (k == 0) { tp[0] = v.x; tp[1] = v.y; tp[2] = v.z; tp[3] = v.w; }
+            else { tp[0] += v.x; tp[1] += v.y; tp[2] += v.z; tp[3] += v.w; }
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 32 * D; i += blockDim.x) {
@@ -245,6 +255,7 @@ void launch_gather_rows(const float* codebook, const long long* codes, float* ou
 void launch_codes_to_features(const float* codebooks, const long long* codes, float* out, int K, int B, int L, int D,
                               int bins, int* err_flag, cudaStream_t s) {
     if (B <= 0 || L <= 0) return;
+    if (D % 4) throw Error(1, "codes_to_features: codebook dim must be a multiple of 4");
     size_t smem = (size_t)32 * (D + 1) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
