@@ -50,11 +50,12 @@ __device__ __forceinline__ void put8(const RowOut& o, long long idx, const float
     if (o.hi) {
         uint32_t h[4], l[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
-            __half l0 = __float2half_rn(v[2 * i] - __half2float(h0)), l1 = __float2half_rn(v[2 * i + 1] - __half2float(h1));
-            h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        for (int i = 0; i < 4; ++i) {  // packed conversions (ALU pipe) rather than scalar F2F (XU pipe)
+            const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            const float2 f = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+            h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+            l[i] = *reinterpret_cast<const uint32_t*>(&ll);
         }
         *reinterpret_cast<uint4*>(o.hi + idx) = make_uint4(h[0], h[1], h[2], h[3]);
         if (o.lo) *reinterpret_cast<uint4*>(o.lo + idx) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __re
             y[3] = (v.w - mean) * rstd * wv.w + bv.w;
             if (swish) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) y[i] = y[i] / (1.f + expf(-y[i]));
+                for (int i = 0; i < 4; ++i) y[i] = __fdividef(y[i], 1.f + __expf(-y[i]));
             }
         }
         const long long idx = base + (long long)t * C;
@@ -129,10 +130,11 @@ __global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __re
             uint32_t h[2], l[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                __half h0 = __float2half_rn(y[2 * i]), h1 = __float2half_rn(y[2 * i + 1]);
-                __half l0 = __float2half_rn(y[2 * i] - __half2float(h0)), l1 = __float2half_rn(y[2 * i + 1] - __half2float(h1));
-                h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                const __half2 hh = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+                const float2 f = __half22float2(hh);
+                const __half2 ll = __floats2half2_rn(y[2 * i] - f.x, y[2 * i + 1] - f.y);
+                h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+                l[i] = *reinterpret_cast<const uint32_t*>(&ll);
             }
             *reinterpret_cast<uint2*>(out.hi + idx) = make_uint2(h[0], h[1]);
             if (out.lo) *reinterpret_cast<uint2*>(out.lo + idx) = make_uint2(l[0], l[1]);

@@ -62,11 +62,12 @@ __device__ __forceinline__ float elu_fast(float x) {
 __device__ __forceinline__ void split_store8(__half* hi, __half* lo, long long off, const float (&v)[8]) {
     uint32_t h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
-        __half l0 = __float2half_rn(v[2 * i] - __half2float(h0)), l1 = __float2half_rn(v[2 * i + 1] - __half2float(h1));
-        h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-        l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    for (int i = 0; i < 4; ++i) {  // packed conversions (ALU pipe) rather than scalar F2F (XU pipe)
+        const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 f = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
     }
     *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -82,11 +83,14 @@ __global__ void __launch_bounds__(256) conv0_planes_kernel(const float* __restri
                                                            const float* __restrict__ bias, __half* __restrict__ win_hi,
                                                            __half* __restrict__ win_lo, __half* __restrict__ elu_hi,
                                                            __half* __restrict__ elu_lo, int B, int T) {
+    // One thread = 8 channels x 4 consecutive padded positions of one clip (blockIdx.y): its 56 taps stay in
+    // registers, the 10 audio samples under the 4 windows are loaded once, and there is no index division.
     const int P = T + 2;
     constexpr int G8 = C / 8;  // 16-byte stores coalesce across the G8 threads of a position
-    static_assert(256 % G8 == 0, "a thread keeps the same channel group for every position it visits");
-    // the thread's 8 x 7 taps stay in registers for the whole grid-stride loop (no shared-memory operand per FMA)
     const int c8 = threadIdx.x % G8;
+    const int p0 = (blockIdx.x * (256 / G8) + threadIdx.x / G8) * 4;
+    const int b = blockIdx.y;
+    if (p0 >= P) return;
     float wr[8][7], br[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -94,35 +98,48 @@ __global__ void __launch_bounds__(256) conv0_planes_kernel(const float* __restri
 #pragma unroll
         for (int j = 0; j < 7; ++j) wr[u][j] = w[(c8 * 8 + u) * 7 + j];
     }
-    const long long total = (long long)B * P * G8;
-    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
-         gid += (long long)gridDim.x * blockDim.x) {
-        const long long pos = gid / G8;
-        int b = (int)(pos / P);
-        int p = (int)(pos - (long long)b * P);
-        int t = p - 1;
-        if (t < 0) t = -t;
-        if (t >= T) t = 2 * (T - 1) - t;
-        const float* x = wav + (long long)b * T;
-        float xv[8];
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            int ti = t - 3 + j;
-            if (ti < 0) ti = -ti;
-            if (ti >= T) ti = 2 * (T - 1) - ti;
-            xv[j] = x[ti];
-        }
-        xv[7] = 0.f;
+    const float* x = wav + (long long)b * T;
+    const long long row0 = (long long)b * P + p0;
+    auto emit = [&](int q, const float (&xv)[8]) {  // position p0 + q from its 7-sample window
         float e[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            float acc = 0.f;
+            float acc = br[u];
 #pragma unroll
             for (int j = 0; j < 7; ++j) acc = fmaf(wr[u][j], xv[j], acc);
-            e[u] = elu_fast(acc + br[u]);
+            e[u] = elu_fast(acc);
         }
-        split_store8(elu_hi, elu_lo, gid * 8, e);
-        if (c8 == 0) split_store8(win_hi, win_lo, pos * 8, xv);
+        split_store8(elu_hi, elu_lo, ((row0 + q) * G8 + c8) * 8, e);
+        if (c8 == 0) split_store8(win_hi, win_lo, (row0 + q) * 8, xv);
+    };
+    if (p0 >= 4 && p0 + 6 <= T) {  // interior: samples t0 - 3 .. t0 + 6 with t0 = p0 - 1, no reflection
+        float xs[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) xs[j] = x[p0 - 4 + j];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float xv[8];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) xv[j] = xs[q + j];
+            xv[7] = 0.f;
+            emit(q, xv);
+        }
+    } else {  // clip edges: reflect the position (halo rows), then the taps (reference conv.py:79-96)
+        for (int q = 0; q < 4 && p0 + q < P; ++q) {
+            int t = p0 + q - 1;
+            if (t < 0) t = -t;
+            if (t >= T) t = 2 * (T - 1) - t;
+            float xv[8];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                int ti = t - 3 + j;
+                if (ti < 0) ti = -ti;
+                if (ti >= T) ti = 2 * (T - 1) - ti;
+                xv[j] = x[ti];
+            }
+            xv[7] = 0.f;
+            emit(q, xv);
+        }
     }
 }
 
@@ -217,9 +234,8 @@ void launch_conv0_planes(const float* wav, const float* w, const float* bias, __
                          __half* elu_hi, __half* elu_lo, int B, int T, int C, cudaStream_t s) {
     if (C != 32) throw Error(1, "conv0: n_filters must be 32");
     if (T < 4) throw Error(4, "conv0_planes: clip too short for the tcgen05 encoder layout");
-    long long n = (long long)B * (T + 2) * (C / 8);
-    const long long blocks = std::min<long long>((n + 255) / 256, 148 * 8);  // grid-stride, 8 blocks per SM
-    conv0_planes_kernel<32><<<(unsigned)blocks, 256, 0, s>>>(wav, w, bias, win_hi, win_lo, elu_hi, elu_lo, B, T);
+    dim3 grid((unsigned)((T + 2 + 255) / 256), (unsigned)B);  // 256 padded positions per block
+    conv0_planes_kernel<32><<<grid, 256, 0, s>>>(wav, w, bias, win_hi, win_lo, elu_hi, elu_lo, B, T);
     WT_CUDA(cudaGetLastError());
 }
 

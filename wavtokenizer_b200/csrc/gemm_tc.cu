@@ -192,9 +192,7 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Exact-erf GELU (reference decoder/modules.py:35, nn.GELU()). erf through the branch-free rational form of
-// Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, below the 2^-22 resolution of the split-fp16 operands the
-// result is stored in): two MUFU ops and ~12 FMAs per element instead of erff's divergent ~40-instruction paths.
+// Exact-erf GELU (reference decoder/modules.py:35, nn.GELU()): see gelu_erf below.
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[4]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -203,14 +201,18 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[4]) {
 }
 
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float e = 1.f - p * t * __expf(-z * z);
-    return 0.5f * x * (1.f + copysignf(e, x));
+    // erfc(z) = 2^P(z) on [0, 4], P of degree 7 without constant term (weighted minimax fit, |erf error| <= 1.6e-7
+    // evaluated in fp32; erfc(4) = 1.5e-8 so z is clamped there): one MUFU.EX2, no reciprocal, no branch.
+    const float z = fminf(fabsf(x) * 0.70710678118654752440f, 4.f);
+    float p = fmaf(1.00181106e-04f, z, -4.61322709e-04f);
+    p = fmaf(p, z, -2.30282884e-03f);
+    p = fmaf(p, z, 2.94531747e-02f);
+    p = fmaf(p, z, -1.48964027e-01f);
+    p = fmaf(p, z, -9.18328559e-01f);
+    p = fmaf(p, z, -1.62791374e+00f);
+    const float erfa = 1.f - exp2f(p * z);  // erf(|x| / sqrt(2))
+    const float h = 0.5f * x;
+    return fmaf(fabsf(h), erfa, h);         // 0.5 x (1 + sign(x) erf(|x|/sqrt 2))
 }
 // ELU(alpha = 1) (reference encoder/modules/seanet.py:37). Negative branch: expm1 through a degree-5 Taylor
 // polynomial for x > -1/8 (error < 1e-8 relative) and __expf(x) - 1 below (<= 1e-6 relative): well under the
@@ -222,13 +224,22 @@ __device__ __forceinline__ float elu1(float x) {  // branch-free: three selects
     return x > 0.f ? x : n;
 }
 __device__ __forceinline__ float sigmoid1(float x) { return 1.f / (1.f + expf(-x)); }
+// LSTM gates on the recurrent critical path: MUFU.EX2 + MUFU.RCP forms (absolute error ~1e-7, the resolution of the
+// split-fp16 planes h_t is published in) instead of the ~25-instruction expf / IEEE-divide / tanhf sequences.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float xc = fminf(fmaxf(x, -15.f), 15.f);
+    return fmaf(-2.f, __fdividef(1.f, 1.f + __expf(2.f * xc)), 1.f);
+}
 
+// Split a pair into packed hi / lo halves. Packed conversions (F2FP.F16.F32.PACK_AB, ALU pipe) instead of scalar
+// F2F (XU pipe, 16 lanes/clk/SM): the narrow-N epilogues were conversion-throughput bound.
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    __half h0 = __float2half_rn(a), h1 = __float2half_rn(b);
-    __half l0 = __float2half_rn(a - __half2float(h0));
-    __half l1 = __float2half_rn(b - __half2float(h1));
-    hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // 256-bit global store (sm_100a STG.E.256): one full 32-byte sector per lane per instruction.
@@ -921,12 +932,12 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                     float cvv[4] = {cv.x, cv.y, cv.z, cv.w}, hv[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float ig = sigmoid1(__uint_as_float(ri[i]) + xiv[i]);
-                        const float fg = sigmoid1(__uint_as_float(rf[i]) + xfv[i]);
-                        const float gg = tanhf(__uint_as_float(rg[i]) + xgv[i]);
-                        const float og = sigmoid1(__uint_as_float(ro[i]) + xov[i]);
+                        const float ig = sigmoid_fast(__uint_as_float(ri[i]) + xiv[i]);
+                        const float fg = sigmoid_fast(__uint_as_float(rf[i]) + xfv[i]);
+                        const float gg = tanh_fast(__uint_as_float(rg[i]) + xgv[i]);
+                        const float og = sigmoid_fast(__uint_as_float(ro[i]) + xov[i]);
                         cvv[i] = fg * cvv[i] + ig * gg;
-                        hv[i] = og * tanhf(cvv[i]);
+                        hv[i] = og * tanh_fast(cvv[i]);
                     }
                     // h planes first: they are what the other CTAs wait for
                     uint32_t h01, l01, h23, l23;
