@@ -200,6 +200,40 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[4]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Two accumulator chunks (hh + lh columns and the hl columns BN further) in flight behind ONE wait; the registers
+// pass through the wait ("+r") so that no use can be scheduled above it.
+__device__ __forceinline__ void tmem_ld_pair(uint32_t a0, uint32_t (&r)[16], uint32_t a1, uint32_t (&t)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(a0));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+                 : "r"(a1));
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+                 :
+                 : "memory");
+}
+// Two accumulator chunks (hh + lh columns and the hl columns BN further) in flight behind ONE wait; the registers
+// pass through the wait ("+r") so that no use can be scheduled above it.
+__device__ __forceinline__ void tmem_ld_pair(uint32_t a0, uint32_t (&r)[8], uint32_t a1, uint32_t (&t)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(a0));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7])
+                 : "r"(a1));
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_nowait(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {
     // erfc(z) = 2^P(z) on [0, 4], P of degree 7 without constant term (weighted minimax fit, |erf error| <= 1.6e-7
     // evaluated in fp32; erfc(4) = 1.5e-8 so z is clamped there): one MUFU.EX2, no reciprocal, no branch.
@@ -214,14 +248,12 @@ __device__ __forceinline__ float gelu_erf(float x) {
     const float h = 0.5f * x;
     return fmaf(fabsf(h), erfa, h);         // 0.5 x (1 + sign(x) erf(|x|/sqrt 2))
 }
-// ELU(alpha = 1) (reference encoder/modules/seanet.py:37). Negative branch: expm1 through a degree-5 Taylor
-// polynomial for x > -1/8 (error < 1e-8 relative) and __expf(x) - 1 below (<= 1e-6 relative): well under the
-// 2^-22 resolution of the split-fp16 planes the value is stored in, at a third of expm1f's instruction count.
-__device__ __forceinline__ float elu1(float x) {  // branch-free: three selects
-    const float p = x * fmaf(x, fmaf(x, fmaf(x, fmaf(x, 1.f / 120.f, 1.f / 24.f), 1.f / 6.f), 0.5f), 1.f);
+// ELU(alpha = 1) (reference encoder/modules/seanet.py:37). Negative branch exp(x) - 1 through MUFU.EX2: absolute
+// error <= ~1.2e-7 (one ulp of the exponential near 1), i.e. the 2^-22 resolution the value is then stored with
+// in split-fp16 planes at the O(0.1..1) activation scale of the encoder; five instructions, no branch.
+__device__ __forceinline__ float elu1(float x) {
     const float e = __expf(x) - 1.f;
-    const float n = x > -0.125f ? p : e;
-    return x > 0.f ? x : n;
+    return x > 0.f ? x : e;
 }
 __device__ __forceinline__ float sigmoid1(float x) { return 1.f / (1.f + expf(-x)); }
 // LSTM gates on the recurrent critical path: MUFU.EX2 + MUFU.RCP forms (absolute error ~1e-7, the resolution of the
@@ -339,7 +371,7 @@ __device__ __forceinline__ void store_row(const TcGemm& g, long long row, int nb
     }
 }
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, bool LSTM_EPI = false>
 struct Cfg {
     static constexpr int A_PLANE = BM * BK * 2;  // bytes
     static constexpr int B_PLANE = BN * BK * 2;
@@ -372,7 +404,8 @@ struct Maps {
     CUtensorMap w[2];     // [plane]
 };
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, bool LSTM_EPI>
+// 18 warps are allocated as 20 (warp granularity 4): 65536 / (20 * 32) = 102 -> 96 registers per thread.
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     using C = Cfg<BN, PASSES>;
@@ -576,7 +609,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                 if (t <= g.map.Tvalid - 2 && t >= g.map.Tvalid - 1 - g.map.hr)
                     mir_r = base + (2 * (g.map.Tvalid - 1) - t) * st;
             }
-            if (BN == 64 && g.act == TC_ACT_LSTM) {
+            if (LSTM_EPI) {  // separate instantiation: keeps the cell's registers out of the generic kernels
                 // LSTM cell (reference encoder/modules/lstm.py:20; gates i, f, g, o). Tile columns hold
                 // [i | f | g | o] x 16 hidden units; the thread owns one batch row, two warps per lane quarter work.
 #pragma unroll 1
@@ -622,7 +655,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                         if (g.out_hi) store_planes<8, false>(g.out_hi, g.out_lo, (long long)m * g.ldh + u0, hv);
                     }
                 }
-            } else if (g.act == TC_ACT_ARGMIN) {
+            } else if (BN == 256 && PASSES == 3 && g.act == TC_ACT_ARGMIN) {
                 // nearest code (reference encoder/quantization/core_vq.py:175-183): argmin_n ||x - c_n||^2 =
                 // argmin_n (||c_n||^2 - 2 x.c_n); operands are centred on the codebook mean (distance-invariant),
                 // first index wins ties (packed (distance, index) keys under a 64-bit atomicMin).
@@ -650,12 +683,13 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                 for (int c = cg; c < BN / CW; c += C::G) {
                     uint32_t r[CW];
                     __syncwarp();  // tcgen05.ld is .sync.aligned: re-converge after the predicated stores below
-                    tmem_ld(tbase + (uint32_t)(c * CW), r);
                     if (C::FUSE) {
                         uint32_t t2[CW];
-                        tmem_ld(tbase + (uint32_t)(BN + c * CW), t2);
+                        tmem_ld_pair(tbase + (uint32_t)(c * CW), r, tbase + (uint32_t)(BN + c * CW), t2);
 #pragma unroll
                         for (int i = 0; i < CW; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(t2[i]));
+                    } else {
+                        tmem_ld(tbase + (uint32_t)(c * CW), r);
                     }
                     const int nb = n0 + c * CW;
                     if (!row_ok || nb >= g.N) continue;
@@ -745,7 +779,7 @@ struct LstmArgs {
     __half* h_hi;        // [L*B, D] h_t split planes (also this kernel's A operand through mapH)
     __half* h_lo;
     float* cell;         // [B, D]
-    int* counters;       // [m_tiles * L], zeroed before launch
+    int* counters;       // [m_tiles * L * LSTM_KB * LSTM_CNT_PITCH], zeroed before launch
     int B, L, D, m_tiles;
     long long* dbg;      // optional timeline of CTA (0,0): 8 stamps per step for steps 4..7
 };
@@ -757,6 +791,8 @@ constexpr int LSTM_W_BYTES = LSTM_KB * 2 * 64 * 128;     // resident W slice: 8 
 constexpr int LSTM_A_STAGE = 2 * BM * 128;               // hi + lo tile of h_{t-1}
 constexpr int LSTM_STAGES = 3;
 constexpr int LSTM_SMEM = LSTM_W_BYTES + LSTM_STAGES * LSTM_A_STAGE + 1024 + 256;
+constexpr int LSTM_CTAS_PER_KB = 4 * 16;  // arrivals per k-block of 64 hidden units: four CTAs x 16 epilogue warps
+constexpr int LSTM_CNT_PITCH = 8;     // ints between counters (one 32-byte sector each)
 
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid_constant__ CUtensorMap mapH_lo,
@@ -811,32 +847,41 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
         uint32_t phase = 0;
         for (int t = 1; t < a.L; ++t) {
             for (int mt = mg; mt < a.m_tiles; mt += MG) {
-                // wait until all CTAs sharing this batch tile have published h_{t-1}
-                if (lane == 0) {
-                    const int* cnt = a.counters + (long long)mt * a.L + (t - 1);
-                    int v = 0;
-                    uint32_t spins = 0;
-                    const int target = n_slices * LSTM_EPI_WARPS;  // every epilogue warp of every CTA arrives once
-                    do {
-                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
-                        if (v < target && ++spins > (1u << 26)) asm volatile("trap;");
-                    } while (v < target);
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                    stamp(t, 0);  // h_{t-1} published by everyone
-                }
-                __syncwarp();
+                // k-block kb of h_{t-1} (hidden units [64 kb, 64 kb + 64)) is produced by the four CTAs ns = 4 kb ..
+                // 4 kb + 3 of this batch tile: wait for exactly those (one counter per k-block), so the loads of the
+                // early k-blocks overlap the skew of the late publishers instead of starting after the last one
                 const int r0 = (t - 1) * a.B + mt * BM;
-                for (int kb = 0; kb < LSTM_KB; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1);
-                    if (elect_one()) {
-                        const uint32_t sa = a_base + stage * LSTM_A_STAGE;
-                        mbar_expect_tx(full_bar(stage), LSTM_A_STAGE);
-                        tma_load_2d(sa, &mapH_hi, kb * BK, r0, full_bar(stage));
-                        tma_load_2d(sa + BM * 128, &mapH_lo, kb * BK, r0, full_bar(stage));
-                        if (kb == LSTM_KB - 1) stamp(t, 1);  // last k-block issued
+                const int* cnt0 = a.counters + ((long long)mt * a.L + (t - 1)) * LSTM_KB * LSTM_CNT_PITCH;
+                int issued = 0;
+                uint32_t spins = 0;
+                while (issued < LSTM_KB) {
+                    // lanes 0..7 poll the eight k-block counters in parallel (one L2 round trip per poll round)
+                    int v = LSTM_CTAS_PER_KB;
+                    if (lane < LSTM_KB)
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt0 + lane * LSTM_CNT_PITCH) : "memory");
+                    const unsigned ready = __ballot_sync(0xffffffffu, v >= LSTM_CTAS_PER_KB);
+                    __syncwarp();  // memory ordering between the polling lanes and the issuing lane
+                    int n = issued;
+                    while (n < LSTM_KB && ((ready >> n) & 1u)) ++n;
+                    if (n == issued) {
+                        if (++spins > (1u << 24)) asm volatile("trap;");
+                        continue;
                     }
-                    __syncwarp();
-                    if (++stage == LSTM_STAGES) { stage = 0; phase ^= 1; }
+                    if (issued == 0 && lane == 0) stamp(t, 0);  // first k-block(s) of h_{t-1} published
+                    for (int kb = issued; kb < n; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        if (elect_one()) {
+                            if (kb == issued) asm volatile("fence.proxy.async;" ::: "memory");
+                            const uint32_t sa = a_base + stage * LSTM_A_STAGE;
+                            mbar_expect_tx(full_bar(stage), LSTM_A_STAGE);
+                            tma_load_2d(sa, &mapH_hi, kb * BK, r0, full_bar(stage));
+                            tma_load_2d(sa + BM * 128, &mapH_lo, kb * BK, r0, full_bar(stage));
+                            if (kb == LSTM_KB - 1) stamp(t, 1);  // last k-block issued
+                        }
+                        __syncwarp();
+                        if (++stage == LSTM_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    issued = n;
                 }
             }
         }
@@ -910,17 +955,32 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + hw * 4);
                     __syncwarp();
-                    auto ld2 = [&](uint32_t col, uint32_t (&r)[4]) {  // hh + lh block, plus the hl block 64 columns on
-                        uint32_t t2[4];
-                        tmem_ld(tb + col, r);
-                        tmem_ld(tb + 64 + col, t2);
+                    // eight 4-column loads (hh + lh blocks and the hl blocks 64 columns on) in flight, ONE wait
+                    uint32_t ti2[4], tf2[4], tg2[4], to2[4];
+                    tmem_ld_nowait(tb + 0, ri);
+                    tmem_ld_nowait(tb + 16, rf);
+                    tmem_ld_nowait(tb + 32, rg);
+                    tmem_ld_nowait(tb + 48, ro);
+                    tmem_ld_nowait(tb + 64 + 0, ti2);
+                    tmem_ld_nowait(tb + 64 + 16, tf2);
+                    tmem_ld_nowait(tb + 64 + 32, tg2);
+                    tmem_ld_nowait(tb + 64 + 48, to2);
+                    // the registers pass THROUGH the wait ("+r") so that no use can be scheduled above it
+                    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                                 : "+r"(ri[0]), "+r"(ri[1]), "+r"(ri[2]), "+r"(ri[3]), "+r"(rf[0]), "+r"(rf[1]), "+r"(rf[2]),
+                                   "+r"(rf[3]), "+r"(rg[0]), "+r"(rg[1]), "+r"(rg[2]), "+r"(rg[3]), "+r"(ro[0]), "+r"(ro[1]),
+                                   "+r"(ro[2]), "+r"(ro[3]), "+r"(ti2[0]), "+r"(ti2[1]), "+r"(ti2[2]), "+r"(ti2[3]),
+                                   "+r"(tf2[0]), "+r"(tf2[1]), "+r"(tf2[2]), "+r"(tf2[3]), "+r"(tg2[0]), "+r"(tg2[1]),
+                                   "+r"(tg2[2]), "+r"(tg2[3]), "+r"(to2[0]), "+r"(to2[1]), "+r"(to2[2]), "+r"(to2[3])
+                                 :
+                                 : "memory");
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(t2[i]));
-                    };
-                    ld2(0, ri);
-                    ld2(16, rf);
-                    ld2(32, rg);
-                    ld2(48, ro);
+                    for (int i = 0; i < 4; ++i) {
+                        ri[i] = __float_as_uint(__uint_as_float(ri[i]) + __uint_as_float(ti2[i]));
+                        rf[i] = __float_as_uint(__uint_as_float(rf[i]) + __uint_as_float(tf2[i]));
+                        rg[i] = __float_as_uint(__uint_as_float(rg[i]) + __uint_as_float(tg2[i]));
+                        ro[i] = __float_as_uint(__uint_as_float(ro[i]) + __uint_as_float(to2[i]));
+                    }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator is in registers: free it early
@@ -949,13 +1009,14 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                     *reinterpret_cast<float4*>(a.y + row * a.D + u0) = make_float4(hv[0], hv[1], hv[2], hv[3]);
                 }
                 // publish h_t of this (batch tile, step): generic writes -> async-proxy (TMA) readers in other CTAs.
-                // Each warp arrives on its own: lanes fence, __syncwarp orders them before lane 0's release.
+                // Each warp arrives on its own (lanes fence, __syncwarp orders them before lane 0's release) on the
+                // counter of the k-block this CTA's 16 hidden units belong to.
                 if (threadIdx.x == 64) stamp(t, 5);  // cell math + stores issued
                 asm volatile("fence.proxy.async;" ::: "memory");
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) {
-                    int* cnt = a.counters + (long long)mt * a.L + t;
+                    int* cnt = a.counters + (((long long)mt * a.L + t) * LSTM_KB + (ns >> 2)) * LSTM_CNT_PITCH;
                     asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(cnt) : "memory");
                 }
                 if (threadIdx.x == 64) stamp(t, 6);  // published
@@ -1047,12 +1108,12 @@ int num_sms() {
     return n;
 }
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, bool LSTM_EPI = false>
 void launch_cfg(const TcGemm& g, cudaStream_t s) {
     using C = Cfg<BN, PASSES>;
     static bool attr = false;
     if (!attr) {
-        WT_CUDA(cudaFuncSetAttribute(tap_gemm_tc_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        WT_CUDA(cudaFuncSetAttribute(tap_gemm_tc_kernel<BN, PASSES, LSTM_EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::SMEM));
         attr = true;
     }
@@ -1067,13 +1128,13 @@ void launch_cfg(const TcGemm& g, cudaStream_t s) {
     maps.w[1] = make_map(PASSES == 3 ? g.W_lo : g.W_hi, w_rows, g.K, ldw, BN);
     const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.batch;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    tap_gemm_tc_kernel<BN, PASSES><<<grid, NUM_THREADS, C::SMEM, s>>>(maps, g);
+    tap_gemm_tc_kernel<BN, PASSES, LSTM_EPI><<<grid, NUM_THREADS, C::SMEM, s>>>(maps, g);
     WT_CUDA(cudaGetLastError());
 }
 
 template <int PASSES>
 void launch_bn(const TcGemm& g, cudaStream_t s) {
-    if (g.act == TC_ACT_LSTM) return launch_cfg<64, PASSES>(g, s);
+    if (g.act == TC_ACT_LSTM) return launch_cfg<64, PASSES, true>(g, s);
     if (g.N <= 16) return launch_cfg<16, PASSES>(g, s);
     if (g.N <= 32) return launch_cfg<32, PASSES>(g, s);
     if (g.N <= 64) return launch_cfg<64, PASSES>(g, s);
@@ -1129,6 +1190,8 @@ void launch_tap_gemm_tc(const TcGemm& g_in, cudaStream_t s) {
     if (g.passes == 3) launch_bn<3>(g, s); else launch_bn<1>(g, s);
 }
 
+size_t lstm_counter_ints(int B, int L) { return (size_t)((B + BM - 1) / BM) * L * LSTM_KB * LSTM_CNT_PITCH; }
+
 void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_lo, float* cell, int* counters,
                             const __half* w_hi, const __half* w_lo, int B, int L, int D, cudaStream_t s) {
     if (D != 512) throw Error(4, "lstm_persistent: hidden size must be 512");
@@ -1145,7 +1208,8 @@ void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_
     int mgroups = a.m_tiles;
     while (n_slices * mgroups > num_sms()) --mgroups;  // every CTA must be co-resident (they wait on each other)
     if (mgroups < 1) throw Error(4, "lstm_persistent: device too small");
-    WT_CUDA(cudaMemsetAsync(counters, 0, (size_t)a.m_tiles * L * sizeof(int), s));
+    if (4 * D / 64 != LSTM_KB * 4 || LSTM_CTAS_PER_KB != 4 * LSTM_EPI_WARPS) throw Error(4, "lstm_persistent: slice / k-block mapping");
+    WT_CUDA(cudaMemsetAsync(counters, 0, lstm_counter_ints(B, L) * sizeof(int), s));
     CUtensorMap mh_hi = make_map(h_hi, (long long)L * B, D, D, BM);
     CUtensorMap mh_lo = make_map(h_lo, (long long)L * B, D, D, BM);
     CUtensorMap mw_hi = make_map(w_hi, 4LL * D, D, D, 64);

@@ -79,6 +79,8 @@ void set_debug_timeline(long long* dev_buf);
 
 void launch_tap_gemm_tc(const TcGemm& g, cudaStream_t s);
 // One LSTM layer, all L steps, in a single cooperative launch (see gemm_tc.cu). Time-major tensors.
+// `counters` needs lstm_counter_ints(B, L) ints.
+size_t lstm_counter_ints(int B, int L);
 void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_lo, float* cell, int* counters,
                             const __half* w_hi, const __half* w_lo, int B, int L, int D, cudaStream_t s);
 void launch_split_f16(const float* x, __half* hi, __half* lo, long long rows, int cols, long long ld_in,

@@ -564,7 +564,7 @@ size_t enc_back_floats(const wt_config& c, int Bg, int L) {
     a((size_t)Bg * (L + 6) * D);                       // ELU(lstm + skip) planes, reflect-padded
     a(M * D);                                          // centred z planes for the tcgen05 VQ
     a(M * 2);                                          // packed (distance, index) keys
-    a(((size_t)Bg + 127) / 128 * L + 64);              // per-(batch tile, step) arrival counters of the LSTM
+    a(lstm_counter_ints(Bg, L) + 64);                  // per-(batch tile, step, k-block) arrival counters of the LSTM
     return tot;
 }
 
@@ -898,7 +898,7 @@ float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, con
     }
     const __half *lin_hi = pre_hi, *lin_lo = pre_lo;
     const __half* zero = reinterpret_cast<const __half*>(h->zero_rows);
-    int* counters = reinterpret_cast<int*>(h->alloc((size_t)((Bg + 127) / 128) * L + 32));
+    int* counters = reinterpret_cast<int*>(h->alloc(lstm_counter_ints(Bg, L) + 32));
     // all LSTM tensors are time-major: row t*Bg + b. Step t reads rows [(t-1)*Bg, t*Bg) of the hidden-state
     // planes through ONE tensor map (row shift (t-1)*Bg), so no descriptor is built inside the time loop.
     for (int l = 0; l < c.lstm_layers; ++l) {
