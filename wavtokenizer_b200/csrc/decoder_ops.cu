@@ -68,20 +68,21 @@ __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
 }
 
 // Normalize = GroupNorm(32, C, eps=1e-6, affine) (+ x*sigmoid(x)) (reference decoder/models.py:10-16,
-// 58-78, 107-110). Statistics span all L frames of a clip. One block per (clip, slab of 8 groups = 192
-// channels): 48 lanes x float4 read whole 768-byte row slabs coalesced, 20 row phases (960 threads, four
-// independent loads in flight per thread); pass 1 accumulates
-// sum / sum-of-squares (combined in fp64), pass 2 re-reads the slab (L2-resident), normalises and stores
-// fp32 rows or split-fp16 planes with 8-byte vectors. Halo rows of the padded row space are written as zeros.
-constexpr int GN_LANES = 48, GN_PH = 20, GN_THREADS = GN_LANES * GN_PH;
+// 58-78, 107-110). Statistics span all L frames of a clip. One block per (clip, slab of GN_GPB = 2 groups = 48
+// channels): 12 lanes x float4 read 192-byte row slabs (six full sectors), 32 row phases (384 threads, four
+// independent loads in flight each), 16 x B blocks so that the grid spreads evenly over the SMs. Pass 1
+// accumulates sum / sum-of-squares (combined in fp64), pass 2 re-reads the slab (L2-resident), normalises and
+// stores fp32 rows or split-fp16 planes with 8-byte vectors. Halo rows of the padded row space are written as zeros.
+constexpr int GN_GPB = 2, GN_LANES = GN_GPB * 6, GN_PH = 32, GN_THREADS = GN_LANES * GN_PH;
 __global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                const float* __restrict__ bsh, RowOut out, int L, int Lp,
                                                                int C, float eps, int swish) {
     __shared__ float ps[GN_THREADS], pq[GN_THREADS];
-    __shared__ float s_mean[8], s_rstd[8];
+    __shared__ double rs[GN_LANES], rq[GN_LANES];
+    __shared__ float s_mean[GN_GPB], s_rstd[GN_GPB];
     const int b = blockIdx.y, slab = blockIdx.x;
     const int lane = threadIdx.x % GN_LANES, ph = threadIdx.x / GN_LANES;
-    const int c = slab * 192 + lane * 4;
+    const int c = slab * (GN_GPB * 24) + lane * 4;
     const long long base = (long long)b * Lp * C + c;
     float s = 0.f, q = 0.f;
 #pragma unroll 4
@@ -93,13 +94,19 @@ __global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __re
     ps[threadIdx.x] = s;
     pq[threadIdx.x] = q;
     __syncthreads();
-    if (threadIdx.x < 8) {  // group g of the slab = lanes 6g..6g+5 in every phase
+    if (threadIdx.x < GN_LANES) {  // column sums over the phases
         double ds = 0, dq = 0;
-        for (int p = 0; p < GN_PH; ++p)
-            for (int l = 0; l < 6; ++l) {
-                ds += ps[p * GN_LANES + threadIdx.x * 6 + l];
-                dq += pq[p * GN_LANES + threadIdx.x * 6 + l];
-            }
+        for (int p = 0; p < GN_PH; ++p) {
+            ds += ps[p * GN_LANES + threadIdx.x];
+            dq += pq[p * GN_LANES + threadIdx.x];
+        }
+        rs[threadIdx.x] = ds;
+        rq[threadIdx.x] = dq;
+    }
+    __syncthreads();
+    if (threadIdx.x < GN_GPB) {  // group g of the slab = lanes 6g..6g+5
+        double ds = 0, dq = 0;
+        for (int l = 0; l < 6; ++l) { ds += rs[threadIdx.x * 6 + l]; dq += rq[threadIdx.x * 6 + l]; }
         const double n = (double)L * 24.0;
         const double mean = ds / n;
         double var = dq / n - mean * mean;
@@ -493,7 +500,7 @@ void launch_groupnorm(const float* x, const float* w, const float* b, RowOut out
                       int groups, float eps, int swish, cudaStream_t s) {
     if (B <= 0 || L <= 0) return;
     if (groups != 32 || C != 768) throw Error(1, "groupnorm: expected GroupNorm(32, 768)");
-    dim3 grid(C / 192, B);
+    dim3 grid(C / (GN_GPB * 24), B);
     groupnorm_kernel<<<grid, GN_THREADS, 0, s>>>(x, w, b, out, L, Lp, C, eps, swish);
     WT_CUDA(cudaGetLastError());
 }

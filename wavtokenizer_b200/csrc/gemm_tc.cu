@@ -83,6 +83,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// Same, for a k-block of kw = 64 / 32 / 16 elements: rows of 128 / 64 / 32 bytes under the matching TMA swizzle
+// (layout type 2 / 4 / 6, 8-row groups 8 * row bytes apart). `hi` carries every field but the start address.
+__device__ __forceinline__ uint64_t umma_desc_hi(int kw) {
+    const uint64_t layout = kw == 64 ? 2 : kw == 32 ? 4 : 6;
+    const uint64_t sbo = (uint64_t)(8 * kw * 2);
+    return ((uint64_t)1 << 16) | ((sbo >> 4) << 32) | ((uint64_t)1 << 46) | (layout << 61);
+}
+__device__ __forceinline__ uint64_t umma_desc_at(uint64_t hi, uint32_t smem_addr) {
+    return hi | (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+}
+
 // kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M = 128, N = BN.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
     return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) |
@@ -244,7 +255,9 @@ __device__ __forceinline__ float gelu_erf(float x) {
     p = fmaf(p, z, -1.48964027e-01f);
     p = fmaf(p, z, -9.18328559e-01f);
     p = fmaf(p, z, -1.62791374e+00f);
-    const float erfa = 1.f - exp2f(p * z);  // erf(|x| / sqrt(2))
+    float e2;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(p * z));  // bare MUFU.EX2 (exp2f adds a denormal-range fix-up)
+    const float erfa = 1.f - e2;  // erf(|x| / sqrt(2))
     const float h = 0.5f * x;
     return fmaf(fabsf(h), erfa, h);         // 0.5 x (1 + sign(x) erf(|x|/sqrt 2))
 }
@@ -301,9 +314,12 @@ __device__ __forceinline__ void store_planes(__half* hi_p, __half* lo_p, long lo
             hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
         }
     }
-    if (CW == 16 && (off & 15) == 0) {
-        st256(hi_p + off, hi);
-        if (lo_p) st256(lo_p + off, lo);
+    if (CW % 16 == 0 && (off & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < CW / 16; ++j) {
+            st256(hi_p + off + 16 * j, hi + 8 * j);
+            if (lo_p) st256(lo_p + off + 16 * j, lo + 8 * j);
+        }
         return;
     }
     uint4* oh = reinterpret_cast<uint4*>(hi_p + off);
@@ -395,7 +411,8 @@ struct Cfg {
     static constexpr int NACC = NGRP == 4 ? 4 : 2;
     static constexpr int TMEM_COLS = NACC * ACC_COLS < 32 ? 32 : NACC * ACC_COLS;  // power of two >= 32
     static constexpr int G = NEPI / 4 / NGRP;                    // epilogue warps per TMEM lane quarter per tile
-    static constexpr int CW = BN / G >= 16 ? 16 : 8;             // epilogue chunk width (columns per tcgen05.ld)
+    // epilogue chunk width (columns per tcgen05.ld) of the generic path; the GELU fast path below uses 32
+    static constexpr int CW = BN / G >= 16 ? 16 : 8;
     static constexpr int EPI_SMEM = 0;
 };
 
@@ -432,6 +449,10 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     const int nkb0 = g.seg[0].num_kb;
     const int num_kb = nkb0 + (g.nseg > 1 ? g.seg[1].num_kb : 0);
     const bool simple_tiles = total_tiles == m_tiles;  // one column tile, one batch: tile index = row tile
+    // k-block width: 64 elements (128-byte rows, SWIZZLE_128B) or, for narrow operands, 32 / 16 (64- / 32-byte rows
+    // under SWIZZLE_64B / _32B) so that TMA fetches exactly the bytes that exist instead of zero-filling 128-byte rows
+    const int kw = g.kw;
+    const uint32_t a_plane = (uint32_t)(BM * kw * 2), b_plane = (uint32_t)(BN * kw * 2);
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -476,16 +497,16 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                     const int kl = si ? kb - nkb0 : kb;
                     const int kpt = g.seg[si].kb_per_tap;
                     const int tap = kl / kpt;
-                    const int c0 = (kl - tap * kpt) * BK;
+                    const int c0 = (kl - tap * kpt) * kw;
                     const int r0 = m0 + g.seg[si].shift0 + tap;
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * C::STAGE;
-                    const uint32_t sb = sa + C::PLANES * C::A_PLANE;
-                    mbar_expect_tx(full_bar(stage), C::STAGE);
+                    const uint32_t sb = sa + C::PLANES * a_plane;
+                    mbar_expect_tx(full_bar(stage), C::PLANES * (a_plane + b_plane));
                     tma_load_2d(sa, &maps.a[si][0], c0, r0, full_bar(stage));
-                    if (PASSES == 3) tma_load_2d(sa + C::A_PLANE, &maps.a[si][1], c0, r0, full_bar(stage));
-                    tma_load_2d(sb, &maps.w[0], kb * BK, n0, full_bar(stage));
-                    if (PASSES == 3) tma_load_2d(sb + C::B_PLANE, &maps.w[1], kb * BK, n0, full_bar(stage));
+                    if (PASSES == 3) tma_load_2d(sa + a_plane, &maps.a[si][1], c0, r0, full_bar(stage));
+                    tma_load_2d(sb, &maps.w[0], kb * kw, n0, full_bar(stage));
+                    if (PASSES == 3) tma_load_2d(sb + b_plane, &maps.w[1], kb * kw, n0, full_bar(stage));
                     if (tile == (int)blockIdx.x) stamp(1 + kb);  // slots 1..16: producer issued k-block kb (first tile)
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -499,17 +520,19 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
             // k16 steps that hold real columns in the LAST k-block of a segment row: narrow operands (16 channels,
             // 8 audio taps, k*C = 96) are zero-padded to 64 by TMA, and an SS-mode MMA costs ~110 cycles whatever it
             // multiplies, so the all-zero steps are simply not issued
-            int tail0 = BK / UMMA_K, tail1 = BK / UMMA_K;
+            const int full16 = kw / UMMA_K;
+            int tail0 = full16, tail1 = full16;
             {
-                const long long r0 = g.seg[0].inner - (long long)(g.seg[0].kb_per_tap - 1) * BK;
-                if (r0 < BK) tail0 = (int)((r0 + UMMA_K - 1) / UMMA_K);
+                const long long r0 = g.seg[0].inner - (long long)(g.seg[0].kb_per_tap - 1) * kw;
+                if (r0 < kw) tail0 = (int)((r0 + UMMA_K - 1) / UMMA_K);
                 if (g.nseg > 1) {
-                    const long long r1 = g.seg[1].inner - (long long)(g.seg[1].kb_per_tap - 1) * BK;
-                    if (r1 < BK) tail1 = (int)((r1 + UMMA_K - 1) / UMMA_K);
+                    const long long r1 = g.seg[1].inner - (long long)(g.seg[1].kb_per_tap - 1) * kw;
+                    if (r1 < kw) tail1 = (int)((r1 + UMMA_K - 1) / UMMA_K);
                 }
             }
             const int kpt0 = g.seg[0].kb_per_tap, kpt1 = g.nseg > 1 ? g.seg[1].kb_per_tap : 1;
-            const bool any_tail = tail0 < BK / UMMA_K || tail1 < BK / UMMA_K;
+            const bool any_tail = tail0 < full16 || tail1 < full16;
+            const uint64_t dhi = umma_desc_hi(kw);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -526,8 +549,8 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (tile == (int)blockIdx.x) stamp(17 + kb);  // slots 17..32: data of k-block kb landed
                     const uint32_t sa = smem_base + stage * C::STAGE;
-                    const uint32_t sb = sa + C::PLANES * C::A_PLANE;
-                    int nk16 = BK / UMMA_K;
+                    const uint32_t sb = sa + C::PLANES * a_plane;
+                    int nk16 = full16;
                     if (any_tail) {
                         if (kb < nkb0) { if ((kb + 1) % kpt0 == 0) nk16 = tail0; }
                         else if ((kb - nkb0 + 1) % kpt1 == 0) nk16 = tail1;
@@ -535,18 +558,18 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         if (k >= nk16) break;
-                        const uint32_t koff = k * UMMA_K * 2;  // bytes inside the 128 B swizzle row
-                        const uint64_t a_hi = umma_desc_sw128(sa + koff);
-                        const uint64_t b_hi = umma_desc_sw128(sb + koff);
+                        const uint32_t koff = k * UMMA_K * 2;  // bytes inside the swizzle row
+                        const uint64_t a_hi = umma_desc_at(dhi, sa + koff);
+                        const uint64_t b_hi = umma_desc_at(dhi, sb + koff);
                         if (C::FUSE) {
-                            const uint64_t a_lo = umma_desc_sw128(sa + C::A_PLANE + koff);
+                            const uint64_t a_lo = umma_desc_at(dhi, sa + a_plane + koff);
                             umma_f16(tmem_d, a_hi, b_hi, idesc2, (kb | k) != 0);  // [hh | hl], W_lo tile follows W_hi
                             umma_f16(tmem_d, a_lo, b_hi, idesc, 1);               // + lh into the first BN columns
                         } else {
                             umma_f16(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0);
                             if (PASSES == 3) {
-                                const uint64_t a_lo = umma_desc_sw128(sa + C::A_PLANE + koff);
-                                const uint64_t b_lo = umma_desc_sw128(sb + C::B_PLANE + koff);
+                                const uint64_t a_lo = umma_desc_at(dhi, sa + a_plane + koff);
+                                const uint64_t b_lo = umma_desc_at(dhi, sb + b_plane + koff);
                                 umma_f16(tmem_d, a_hi, b_lo, idesc, 1);
                                 umma_f16(tmem_d, a_lo, b_hi, idesc, 1);
                             }
@@ -678,12 +701,44 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                     u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // order-preserving float -> uint
                     atomicMin(g.best + m, ((unsigned long long)u << 32) | (unsigned)bi);
                 }
+            } else if (PASSES == 1 && BN == 256 && g.act == TC_ACT_GELU && g.out_hi && !g.out_lo && !g.out_f32 &&
+                       !g.elu_hi && !g.map.Pin && !g.gamma && !g.res && n0 + BN <= g.N) {
+                // ConvNeXt GEMM-1 fast path (reference decoder/modules.py:54-55): bias + exact-erf GELU -> fp16 plane,
+                // 32 columns per tcgen05.ld so that the fixed per-chunk cost is paid half as often; nothing else live.
+                static_assert(BN / C::G == 64 || BN != 256 || PASSES != 1, "two 32-column chunks per warp");
+#pragma unroll 1
+                for (int c2 = 0; c2 < BN / C::G / 32; ++c2) {
+                    const int col = cg * (BN / C::G) + c2 * 32;
+                    uint32_t r[32];
+                    __syncwarp();
+                    tmem_ld(tbase + (uint32_t)col, r);
+                    if (row_ok) {
+                        const float* bp = g.bias + n0 + col;
+                        __half* op = g.out_hi + (long long)m * g.ldh + n0 + col;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            uint32_t w[8];
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 b = *reinterpret_cast<const float4*>(bp + 16 * j + i);
+                                const float v0 = gelu_erf(__uint_as_float(r[16 * j + i]) + b.x);
+                                const float v1 = gelu_erf(__uint_as_float(r[16 * j + i + 1]) + b.y);
+                                const float v2 = gelu_erf(__uint_as_float(r[16 * j + i + 2]) + b.z);
+                                const float v3 = gelu_erf(__uint_as_float(r[16 * j + i + 3]) + b.w);
+                                const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+                                w[i / 2] = *reinterpret_cast<const uint32_t*>(&h01);
+                                w[i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                            }
+                            st256(op + 16 * j, w);
+                        }
+                    }
+                }
             } else {
 #pragma unroll 1
                 for (int c = cg; c < BN / CW; c += C::G) {
                     uint32_t r[CW];
                     __syncwarp();  // tcgen05.ld is .sync.aligned: re-converge after the predicated stores below
-                    if (C::FUSE) {
+                    if constexpr (C::FUSE) {
                         uint32_t t2[CW];
                         tmem_ld_pair(tbase + (uint32_t)(c * CW), r, tbase + (uint32_t)(BN + c * CW), t2);
 #pragma unroll
@@ -1054,47 +1109,50 @@ EncodeTiledFn encode_fn() {
 // Descriptors are cached: the workspace arena hands out the same addresses call after call, and encoding
 // one costs ~10 us of host time (six per launch would leave the GPU idle between the ~700 launches of a step).
 struct MapKey {
-    const void* base; long long rows, inner, stride; int box;
+    const void* base; long long rows, inner, stride; int box, kw;
     bool operator==(const MapKey& o) const {
-        return base == o.base && rows == o.rows && inner == o.inner && stride == o.stride && box == o.box;
+        return base == o.base && rows == o.rows && inner == o.inner && stride == o.stride && box == o.box && kw == o.kw;
     }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const {
         size_t h = reinterpret_cast<size_t>(k.base);
         auto mix = [&](size_t v) { h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
-        mix((size_t)k.rows); mix((size_t)k.inner); mix((size_t)k.stride); mix((size_t)k.box);
+        mix((size_t)k.rows); mix((size_t)k.inner); mix((size_t)k.stride); mix((size_t)k.box); mix((size_t)k.kw);
         return h;
     }
 };
 
-CUtensorMap encode_map(const __half* base, long long rows, long long inner, long long stride, int box_rows);
+CUtensorMap encode_map(const __half* base, long long rows, long long inner, long long stride, int box_rows, int kw);
 
-const CUtensorMap& make_map(const __half* base, long long rows, long long inner, long long stride, int box_rows) {
+const CUtensorMap& make_map(const __half* base, long long rows, long long inner, long long stride, int box_rows,
+                            int kw = BK) {
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
     static std::mutex mu;
     if (rows < 1) rows = 1;
     std::lock_guard<std::mutex> lock(mu);
-    MapKey key{base, rows, inner, stride, box_rows};
+    MapKey key{base, rows, inner, stride, box_rows, kw};
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     if (cache.size() > (1u << 16)) cache.clear();
-    return cache.emplace(key, encode_map(base, rows, inner, stride, box_rows)).first->second;
+    return cache.emplace(key, encode_map(base, rows, inner, stride, box_rows, kw)).first->second;
 }
 
-CUtensorMap encode_map(const __half* base, long long rows, long long inner, long long stride, int box_rows) {
+CUtensorMap encode_map(const __half* base, long long rows, long long inner, long long stride, int box_rows, int kw) {
     CUtensorMap m;
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)stride * sizeof(__half)};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)kw, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = kw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : kw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box,
-                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         throw Error(4, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r) + " (rows " +
                            std::to_string(rows) + ", inner " + std::to_string(inner) + ", stride " +
-                           std::to_string(stride) + ")");
+                           std::to_string(stride) + ", kw " + std::to_string(kw) + ")");
     return m;
 }
 
@@ -1120,12 +1178,12 @@ void launch_cfg(const TcGemm& g, cudaStream_t s) {
     Maps maps;
     for (int si = 0; si < 2; ++si) {
         const TcSeg& sg = g.seg[si < g.nseg ? si : 0];
-        maps.a[si][0] = make_map(sg.hi, sg.rows, sg.inner, sg.stride, BM);
-        maps.a[si][1] = make_map(PASSES == 3 ? sg.lo : sg.hi, sg.rows, sg.inner, sg.stride, BM);
+        maps.a[si][0] = make_map(sg.hi, sg.rows, sg.inner, sg.stride, BM, g.kw);
+        maps.a[si][1] = make_map(PASSES == 3 ? sg.lo : sg.hi, sg.rows, sg.inner, sg.stride, BM, g.kw);
     }
     const long long ldw = g.ldw ? g.ldw : g.K, w_rows = g.w_rows ? g.w_rows : g.N;
-    maps.w[0] = make_map(g.W_hi, w_rows, g.K, ldw, BN);
-    maps.w[1] = make_map(PASSES == 3 ? g.W_lo : g.W_hi, w_rows, g.K, ldw, BN);
+    maps.w[0] = make_map(g.W_hi, w_rows, g.K, ldw, BN, g.kw);
+    maps.w[1] = make_map(PASSES == 3 ? g.W_lo : g.W_hi, w_rows, g.K, ldw, BN, g.kw);
     const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.batch;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     tap_gemm_tc_kernel<BN, PASSES, LSTM_EPI><<<grid, NUM_THREADS, C::SMEM, s>>>(maps, g);
@@ -1178,7 +1236,10 @@ void launch_tap_gemm_tc(const TcGemm& g_in, cudaStream_t s) {
             throw Error(4, "gemm_tc: A planes must be 16-byte aligned");
         kbs += sg.num_kb;
     }
-    if (g.nseg < 1 || g.nseg > 2 || g.K != kbs * BK) throw Error(4, "gemm_tc: K must equal 64 * total k-blocks");
+    if (g.kw != 64 && g.kw != 32 && g.kw != 16) throw Error(4, "gemm_tc: k-block width must be 64, 32 or 16");
+    if (g.kw != 64 && (g.batch != 1 || g.act == TC_ACT_LSTM || g.act == TC_ACT_ARGMIN))
+        throw Error(4, "gemm_tc: narrow k-blocks are for plain conv GEMMs");
+    if (g.nseg < 1 || g.nseg > 2 || g.K != kbs * g.kw) throw Error(4, "gemm_tc: K must equal kw * total k-blocks");
     if ((g.out_f32 && g.ldo % 4) || (g.res && g.ldres % 4) || (g.out_hi && g.ldh % 8) || (g.elu_hi && g.ldh2 % 8))
         throw Error(4, "gemm_tc: output pitches must keep 16-byte alignment");
     if (g.passes != 1 && g.passes != 3) throw Error(4, "gemm_tc: passes must be 1 or 3");

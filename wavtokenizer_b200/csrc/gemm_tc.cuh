@@ -45,6 +45,9 @@ struct TcGemm {
     long long ldw = 0;     // row pitch of W in elements (0: K)
     long long w_rows = 0;  // rows of the W tensor (0: N)
     int passes = 3;  // 3: hi*hi + hi*lo + lo*hi; 1: hi*hi only
+    // k-block width in elements shared by all segments and W: 64 (128-byte swizzle rows), or 32 / 16 for narrow
+    // operands (64- / 32-byte rows): TMA then moves only bytes that exist. num_kb / kb_per_tap count kw-wide blocks.
+    int kw = 64;
     // batched mode (attention): `batch` independent problems of M x N x K; problem z reads A rows shifted by
     // z*a_brows, W rows shifted by z*w_brows and writes rows shifted by z*o_brows
     int batch = 1;
@@ -95,11 +98,11 @@ inline TcSeg tc_taps(const __half* hi, const __half* lo, long long rows, int Cin
 }
 // Window-mode segment: row r = elements [r*stride, r*stride + inner) of a flat buffer holding total_elems.
 inline TcSeg tc_window(const __half* hi, const __half* lo, long long total_elems, long long inner, long long stride,
-                       int shift0 = 0) {
+                       int shift0 = 0, int kw = 64) {
     TcSeg s;
     s.hi = hi; s.lo = lo; s.inner = inner; s.stride = stride;
     s.rows = total_elems >= inner ? (total_elems - inner) / stride + 1 : 0;
-    s.num_kb = (int)((inner + 63) / 64); s.kb_per_tap = s.num_kb; s.shift0 = shift0;
+    s.num_kb = (int)((inner + kw - 1) / kw); s.kb_per_tap = s.num_kb; s.shift0 = shift0;
     return s;
 }
 

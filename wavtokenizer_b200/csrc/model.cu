@@ -75,7 +75,7 @@ struct wt_handle {
     struct Lstm { float *w_ih = nullptr, *w_hh = nullptr, *bias = nullptr; } lstm[4];
     ConvW enc_last;
     // tcgen05 encoder weights: k3 conv padded to K % 64 == 0; conv1x1 and shortcut fused along K
-    struct RbTc { HalfW w1; int Kp1 = 0; HalfW w2; int kb0 = 0, kb1 = 0; float* bias2 = nullptr; } rb_tc[4];
+    struct RbTc { HalfW w1; int Kp1 = 0, kw1 = 64; HalfW w2; int kb0 = 0, kb1 = 0, kw2 = 64; float* bias2 = nullptr; } rb_tc[4];
     // LSTM weights with gate rows permuted so that each 64-wide tile holds [i | f | g | o] x 16 hidden units
     struct LstmTc { HalfW w_ih, w_hh; float* bias = nullptr; } lstm_tc[4];
     float* zero_rows = nullptr;  // zero planes standing in for h_{-1}
@@ -318,14 +318,20 @@ void prepare(wt_handle* h, const Table& t) {
             const ConvW& c2 = h->rb[i].c2;
             const ConvW& sc = h->rb[i].sc;
             const int K1 = 3 * C;
-            rt.Kp1 = (int)align_up(K1, 64);
+            // k-block widths that fit the operands exactly (gemm_tc.cuh `kw`): the k3 window of 3C elements and the
+            // [C/2 | C] (level 0: [16 | 8 audio taps]) halves of the fused 1x1 convs
+            rt.kw1 = K1 % 64 == 0 ? 64 : 32;
+            rt.Kp1 = (int)align_up(K1, rt.kw1);
             std::vector<float> w1((size_t)(C / 2) * rt.Kp1, 0.f);
             for (int n = 0; n < C / 2; ++n)
                 for (int k = 0; k < K1; ++k) w1[(size_t)n * rt.Kp1 + k] = c1.hw[(size_t)n * K1 + k];
             rt.w1 = h->upload_split(w1);
-            rt.kb0 = (C / 2 + 63) / 64;
-            rt.kb1 = (C + 63) / 64;
-            const int K2 = 64 * (rt.kb0 + rt.kb1);
+            rt.kw2 = std::min(64, C / 2);
+            const int Cx = i == 0 ? 8 : C;  // shortcut operand: the raw-audio window at level 0
+            rt.kb0 = (C / 2 + rt.kw2 - 1) / rt.kw2;
+            rt.kb1 = (Cx + rt.kw2 - 1) / rt.kw2;
+            const int K2 = rt.kw2 * (rt.kb0 + rt.kb1);
+            const int off1 = rt.kw2 * rt.kb0;  // first K column of the shortcut half
             std::vector<float> w2((size_t)C * K2, 0.f), b2(C);
             for (int n = 0; n < C; ++n) {
                 for (int k = 0; k < C / 2; ++k) w2[(size_t)n * K2 + k] = c2.hw[(size_t)n * (C / 2) + k];
@@ -336,12 +342,12 @@ void prepare(wt_handle* h, const Table& t) {
                     for (int j = 0; j < 7; ++j) {
                         double acc = 0;
                         for (int k = 0; k < C; ++k) acc += (double)sc.hw[(size_t)n * C + k] * h_conv0_w[(size_t)k * 7 + j];
-                        w2[(size_t)n * K2 + 64 * rt.kb0 + j] = (float)acc;
+                        w2[(size_t)n * K2 + off1 + j] = (float)acc;
                     }
                     for (int k = 0; k < C; ++k) bacc += (double)sc.hw[(size_t)n * C + k] * h_conv0_b[k];
                     b2[n] = (float)((double)c2.hb[n] + (double)sc.hb[n] + bacc);
                 } else {
-                    for (int k = 0; k < C; ++k) w2[(size_t)n * K2 + 64 * rt.kb0 + k] = sc.hw[(size_t)n * C + k];
+                    for (int k = 0; k < C; ++k) w2[(size_t)n * K2 + off1 + k] = sc.hw[(size_t)n * C + k];
                     b2[n] = c2.hb[n] + sc.hb[n];
                 }
             }
@@ -815,7 +821,8 @@ void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, int
         __half *he_hi = halves(nH), *he_lo = halves(nH);
         {
             TcGemm g;
-            g.seg[0] = tc_window(xe_hi, xe_lo, rowsX * C, 3 * C, C);
+            g.kw = rt.kw1;
+            g.seg[0] = tc_window(xe_hi, xe_lo, rowsX * C, 3 * C, C, 0, rt.kw1);
             g.W_hi = rt.w1.hi; g.W_lo = rt.w1.lo; g.M = (int)rowsX; g.N = C / 2; g.K = rt.Kp1; g.passes = 3;
             g.bias = h->rb[i].c1.b;
             g.elu_hi = he_hi; g.elu_lo = he_lo; g.ldh2 = C / 2;
@@ -830,10 +837,11 @@ void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, int
         {
             TcGemm g;
             g.nseg = 2;
-            g.seg[0] = tc_window(he_hi, he_lo, rowsX * (C / 2), C / 2, C / 2);
-            if (i == 0) g.seg[1] = tc_window(xr_hi, xr_lo, rowsX * 8, 8, 8, /*shift0=*/1);  // audio windows
-            else g.seg[1] = tc_window(xr_hi, xr_lo, rowsX * C, C, C, /*shift0=*/1);
-            g.W_hi = rt.w2.hi; g.W_lo = rt.w2.lo; g.M = (int)rowsX; g.N = C; g.K = 64 * (rt.kb0 + rt.kb1); g.passes = 3;
+            g.kw = rt.kw2;
+            g.seg[0] = tc_window(he_hi, he_lo, rowsX * (C / 2), C / 2, C / 2, 0, rt.kw2);
+            if (i == 0) g.seg[1] = tc_window(xr_hi, xr_lo, rowsX * 8, 8, 8, /*shift0=*/1, rt.kw2);  // audio windows
+            else g.seg[1] = tc_window(xr_hi, xr_lo, rowsX * C, C, C, /*shift0=*/1, rt.kw2);
+            g.W_hi = rt.w2.hi; g.W_lo = rt.w2.lo; g.M = (int)rowsX; g.N = C; g.K = rt.kw2 * (rt.kb0 + rt.kb1); g.passes = 3;
             g.bias = rt.bias2;
             g.map.Pin = P; g.map.Tvalid = Tc; g.map.Pout = Py; g.map.off = left; g.map.hl = left; g.map.hr = right + extra;
             g.elu_hi = ye_hi; g.elu_lo = ye_lo; g.ldh2 = C;
