@@ -61,6 +61,11 @@ void launch_add(const float* a, const float* b, float* out, long long n, cudaStr
 void launch_conv0_planes(const float* wav, const float* w, const float* bias, __half* win_hi /*[B*(T+2), 8]*/,
                          __half* win_lo, __half* elu_hi /*[B*(T+2), C]*/, __half* elu_lo, int B, int T, int C,
                          cudaStream_t s);
+// level 0 (conv0 + ResBlock 0) fused, fp32 CUDA cores (encoder_ops.cu). pack: w0t[7][32] b0[32] w1t[96][16] b1[16]
+// w2t[16][32] wsct[8][32] b2[32]; output ELU(y) planes [B*Py, 32] with data at row `left` and reflect halo left / hr.
+int resblock0_pack_floats();
+void launch_resblock0_fused(const float* wav, const float* pack, __half* ye_hi, __half* ye_lo, float* y_f32, int B, int T,
+                            int Py, int left, int hr, cudaStream_t s);
 void launch_lstm_skip_elu_pad(const float* y, const float* x, float* out_f32, __half* elu_hi, __half* elu_lo, int B,
                               int L, int D, cudaStream_t s);
 

@@ -141,6 +141,184 @@ __global__ void __launch_bounds__(256) conv0_planes_kernel(const float* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Level 0 of the SEANet encoder in ONE kernel, fp32 on the CUDA cores:
+//   x0 = conv0(wav) (1 -> 32, k7, reflect)                       reference encoder/modules/seanet.py:107-110
+//   h1 = conv_k3(ELU(x0)) (32 -> 16, reflect pad 1)              seanet.py:45-63 (block), conv.py:195-211
+//   y  = conv1x1(ELU(h1)) + shortcut1x1(x0)  (-> 32)             seanet.py:61-63 (true_skip = False)
+//   out = ELU(y) as split-fp16 planes in the padded layout of the strided conv that follows (seanet.py:123-129)
+// The contractions are K = 7 / 96 / 16 + 7 wide with N = 32 / 16 / 32: as tcgen05 tiles they are bound by the
+// per-tile epilogue latency, not by the MMA (profiles/r01_enc_chunk_s3_summary.md), and their operands (2.4 GB per
+// 256 clips each) round-trip through HBM. Here a block owns 512 consecutive samples of a clip: ELU(x0) and ELU(h1)
+// live in shared memory only, weights are staged in shared memory once per block, every thread register-tiles
+// 4 positions x 8 (16) channels so that one 128-bit shared load feeds >= 8 FMAs, and HBM sees 4 B in and 128 B out
+// per sample. The shortcut conv1x1(conv0(wav)) is the composed k7 conv of the raw audio (weights composed in fp64
+// at load time). Bound: fp32 FMA issue (2.5 kFMA per sample).
+// ---------------------------------------------------------------------------------------
+constexpr int RB0_TILE = 512, RB0_THREADS = 256, RB0_LD = RB0_TILE + 4;
+// packed weights (floats): w0t[7][32] b0[32] w1t[96][16] b1[16] w2t[16][32] wsct[8][32] b2[32]
+constexpr int RB0_W0 = 0, RB0_B0 = 224, RB0_W1 = 256, RB0_B1 = 1792, RB0_W2 = 1808, RB0_WSC = 2320, RB0_B2 = 2576,
+              RB0_PACK = 2608, RB0_PACK_PAD = 2624, RB0_A = RB0_TILE + 8, RB0_A_PAD = RB0_TILE + 16;
+constexpr int RB0_SMEM = (RB0_PACK_PAD + RB0_A_PAD + 32 * RB0_LD + 16 * RB0_TILE) * 4;
+
+__global__ void __launch_bounds__(RB0_THREADS, 2)
+resblock0_fused_kernel(const float* __restrict__ wav, const float* __restrict__ pack, __half* __restrict__ ye_hi,
+                       __half* __restrict__ ye_lo, float* __restrict__ y_f32, int T, int Py, int left, int hr) {
+    extern __shared__ __align__(16) float sm[];
+    float* sW = sm;
+    float* sA = sW + RB0_PACK_PAD;
+    float* sE0 = sA + RB0_A_PAD;          // [32][RB0_LD], column col <-> sample t = t0 - 1 + col
+    float* sH1 = sE0 + 32 * RB0_LD;       // [16][RB0_TILE], ELU(h1)
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y, t0 = blockIdx.x * RB0_TILE;
+    const float* x = wav + (long long)b * T;
+
+    // ---- stage 0: weights and the audio samples t0 - 4 .. t0 + TILE + 3 (tap reflection, conv.py:79-96) ----
+    for (int i = tid; i < RB0_PACK / 4; i += RB0_THREADS)
+        reinterpret_cast<float4*>(sW)[i] = reinterpret_cast<const float4*>(pack)[i];
+    for (int i = tid; i < RB0_A; i += RB0_THREADS) {
+        int idx = t0 - 4 + i;
+        if (idx < 0) idx = -idx;
+        if (idx >= T) idx = 2 * (T - 1) - idx;
+        sA[i] = (idx >= 0 && idx < T) ? x[idx] : 0.f;
+    }
+    __syncthreads();
+
+    // ---- stage A: ELU(conv0) for columns 0 .. TILE + 1 ----
+    for (int col = tid; col < RB0_TILE + 2; col += RB0_THREADS) {
+        float xv[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) xv[j] = sA[col + j];
+#pragma unroll 1  // (fully unrolled, the 56 weight vectors get hoisted out of the column loop: 224 registers)
+        for (int c4 = 0; c4 < 8; ++c4) {
+            float4 acc = *reinterpret_cast<const float4*>(sW + RB0_B0 + c4 * 4);
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const float4 w = *reinterpret_cast<const float4*>(sW + RB0_W0 + j * 32 + c4 * 4);
+                acc.x = fmaf(w.x, xv[j], acc.x); acc.y = fmaf(w.y, xv[j], acc.y);
+                acc.z = fmaf(w.z, xv[j], acc.z); acc.w = fmaf(w.w, xv[j], acc.w);
+            }
+            sE0[(c4 * 4 + 0) * RB0_LD + col] = elu_fast(acc.x);
+            sE0[(c4 * 4 + 1) * RB0_LD + col] = elu_fast(acc.y);
+            sE0[(c4 * 4 + 2) * RB0_LD + col] = elu_fast(acc.z);
+            sE0[(c4 * 4 + 3) * RB0_LD + col] = elu_fast(acc.w);
+        }
+    }
+    __syncthreads();
+    // reflect padding of ELU(x0) for the k3 conv: sample -1 mirrors sample 1, sample T mirrors sample T - 2
+    if (tid < 32) {
+        if (t0 == 0) sE0[tid * RB0_LD] = sE0[tid * RB0_LD + 2];
+        const int cT = T - t0 + 1;
+        if (cT >= 2 && cT <= RB0_TILE + 1) sE0[tid * RB0_LD + cT] = sE0[tid * RB0_LD + cT - 2];
+    }
+    __syncthreads();
+
+    const int half = tid >> 7;         // warp-uniform channel half
+    const int pos0 = (tid & 127) * 4;  // four consecutive samples t0 + pos0 .. + 3
+    // ---- stage B: h1 = conv_k3(ELU(x0)), channels half*8 .. +7 ----
+    {
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float bb = sW[RB0_B1 + half * 8 + i];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q][i] = bb;
+        }
+#pragma unroll 2
+        for (int c = 0; c < 32; ++c) {
+            const float4 ea = *reinterpret_cast<const float4*>(sE0 + c * RB0_LD + pos0);
+            const float2 eb = *reinterpret_cast<const float2*>(sE0 + c * RB0_LD + pos0 + 4);
+            const float e[6] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y};
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float4 w0 = *reinterpret_cast<const float4*>(sW + RB0_W1 + (j * 32 + c) * 16 + half * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(sW + RB0_W1 + (j * 32 + c) * 16 + half * 8 + 4);
+                const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[q][i] = fmaf(w[i], e[q + j], acc[q][i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(sH1 + (half * 8 + i) * RB0_TILE + pos0) =
+                make_float4(elu_fast(acc[0][i]), elu_fast(acc[1][i]), elu_fast(acc[2][i]), elu_fast(acc[3][i]));
+    }
+    __syncthreads();
+
+    // ---- stage C: y = conv1x1(ELU(h1)) + composed shortcut k7 of the raw audio; two passes of 8 channels ----
+    float a10[10];  // samples t - 3 .. t + 6 of the first position = sA[pos0 + 1 ..]
+#pragma unroll
+    for (int j = 0; j < 10; ++j) a10[j] = sA[pos0 + 1 + j];
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const int ch0 = half * 16 + pass * 8;
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float bb = sW[RB0_B2 + ch0 + i];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q][i] = bb;
+        }
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+            const float4 hv = *reinterpret_cast<const float4*>(sH1 + k * RB0_TILE + pos0);
+            const float hq[4] = {hv.x, hv.y, hv.z, hv.w};
+            const float4 w0 = *reinterpret_cast<const float4*>(sW + RB0_W2 + k * 32 + ch0);
+            const float4 w1 = *reinterpret_cast<const float4*>(sW + RB0_W2 + k * 32 + ch0 + 4);
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[q][i] = fmaf(w[i], hq[q], acc[q][i]);
+        }
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const float4 w0 = *reinterpret_cast<const float4*>(sW + RB0_WSC + j * 32 + ch0);
+            const float4 w1 = *reinterpret_cast<const float4*>(sW + RB0_WSC + j * 32 + ch0 + 4);
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[q][i] = fmaf(w[i], a10[q + j], acc[q][i]);
+        }
+        // output: ELU(y) planes, row b*Py + left + t plus the reflect halo rows of the strided conv's layout
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int t = t0 + pos0 + q;
+            if (t < T) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float ea = elu_fast(acc[q][2 * i]), eb = elu_fast(acc[q][2 * i + 1]);
+                    const __half2 hh = __floats2half2_rn(ea, eb);
+                    const float2 f = __half22float2(hh);
+                    const __half2 ll = __floats2half2_rn(ea - f.x, eb - f.y);
+                    hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
+                    lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
+                }
+                const long long base = (long long)b * Py + left;
+                const long long r0 = base + t;
+                const long long r1 = (t >= 1 && t <= left) ? base - t : -1;
+                const long long r2 = (t <= T - 2 && t >= T - 1 - hr) ? base + 2 * (T - 1) - t : -1;
+                auto put_row = [&](long long row) {
+                    const long long off = row * 32 + ch0;
+                    *reinterpret_cast<uint4*>(ye_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(ye_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    if (y_f32) {
+                        *reinterpret_cast<float4*>(y_f32 + off) = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+                        *reinterpret_cast<float4*>(y_f32 + off + 4) = make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]);
+                    }
+                };
+                put_row(r0);
+                if (r1 >= 0) put_row(r1);
+                if (r2 >= 0) put_row(r2);
+            }
+        }
+    }
+}
+
 // SLSTM skip connection y + x (reference encoder/modules/lstm.py:38; y and x in time-major rows) fused with the ELU in front of the last
 // encoder conv: writes fp32 rows [B*L, D] (tap) and the split planes of ELU(y + x) in the reflect-padded layout
 // of the k7 conv (clip pitch L + 6, data at offset 3).
@@ -234,6 +412,22 @@ void launch_conv0_planes(const float* wav, const float* w, const float* bias, __
     if (T < 4) throw Error(4, "conv0_planes: clip too short for the tcgen05 encoder layout");
     dim3 grid((unsigned)((T + 2 + 255) / 256), (unsigned)B);  // 256 padded positions per block
     conv0_planes_kernel<32><<<grid, 256, 0, s>>>(wav, w, bias, win_hi, win_lo, elu_hi, elu_lo, B, T);
+    WT_CUDA(cudaGetLastError());
+}
+
+int resblock0_pack_floats() { return RB0_PACK; }
+
+void launch_resblock0_fused(const float* wav, const float* pack, __half* ye_hi, __half* ye_lo, float* y_f32, int B, int T,
+                            int Py, int left, int hr, cudaStream_t s) {
+    if (B <= 0) return;
+    if (T < 8) throw Error(4, "resblock0_fused: clip too short");
+    static bool attr = false;
+    if (!attr) {
+        WT_CUDA(cudaFuncSetAttribute(resblock0_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RB0_SMEM));
+        attr = true;
+    }
+    dim3 grid((unsigned)((T + RB0_TILE - 1) / RB0_TILE), (unsigned)B);
+    resblock0_fused_kernel<<<grid, RB0_THREADS, RB0_SMEM, s>>>(wav, pack, ye_hi, ye_lo, y_f32, T, Py, left, hr);
     WT_CUDA(cudaGetLastError());
 }
 

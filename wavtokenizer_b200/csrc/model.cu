@@ -78,6 +78,7 @@ struct wt_handle {
     struct RbTc { HalfW w1; int Kp1 = 0, kw1 = 64; HalfW w2; int kb0 = 0, kb1 = 0, kw2 = 64; float* bias2 = nullptr; } rb_tc[4];
     // LSTM weights with gate rows permuted so that each 64-wide tile holds [i | f | g | o] x 16 hidden units
     struct LstmTc { HalfW w_ih, w_hh; float* bias = nullptr; } lstm_tc[4];
+    float* rb0_pack = nullptr;   // level-0 fused kernel weights (encoder_ops.cu resblock0_fused_kernel)
     float* zero_rows = nullptr;  // zero planes standing in for h_{-1}
     // vq
     float* codebooks = nullptr;  // [num_quantizers * bins, D]
@@ -320,13 +321,15 @@ void prepare(wt_handle* h, const Table& t) {
             const int K1 = 3 * C;
             // k-block widths that fit the operands exactly (gemm_tc.cuh `kw`): the k3 window of 3C elements and the
             // [C/2 | C] (level 0: [16 | 8 audio taps]) halves of the fused 1x1 convs
-            rt.kw1 = K1 % 64 == 0 ? 64 : 32;
+            // (measured: 32-byte rows and three 64-byte k-blocks per tile are slower than zero-filled 128-byte rows at
+            //  level 0, profiles/r01_enc_chunk_s3_summary.md, so only the [32 | 64] halves of level 1 go narrow)
+            rt.kw1 = 64;
             rt.Kp1 = (int)align_up(K1, rt.kw1);
             std::vector<float> w1((size_t)(C / 2) * rt.Kp1, 0.f);
             for (int n = 0; n < C / 2; ++n)
                 for (int k = 0; k < K1; ++k) w1[(size_t)n * rt.Kp1 + k] = c1.hw[(size_t)n * K1 + k];
             rt.w1 = h->upload_split(w1);
-            rt.kw2 = std::min(64, C / 2);
+            rt.kw2 = C / 2 == 32 ? 32 : 64;
             const int Cx = i == 0 ? 8 : C;  // shortcut operand: the raw-audio window at level 0
             rt.kb0 = (C / 2 + rt.kw2 - 1) / rt.kw2;
             rt.kb1 = (Cx + rt.kw2 - 1) / rt.kw2;
@@ -353,6 +356,29 @@ void prepare(wt_handle* h, const Table& t) {
             }
             rt.w2 = h->upload_split(w2);
             rt.bias2 = h->upload(b2);
+            if (i == 0 && C == 32) {
+                // fused level-0 kernel: w0t[7][32] b0[32] w1t[96][16] b1[16] w2t[16][32] wsct[8][32] b2[32]
+                std::vector<float> pk((size_t)resblock0_pack_floats(), 0.f);
+                float* q = pk.data();
+                for (int j = 0; j < 7; ++j)
+                    for (int n = 0; n < 32; ++n) q[j * 32 + n] = h_conv0_w[(size_t)n * 7 + j];
+                q += 224;
+                for (int n = 0; n < 32; ++n) q[n] = h_conv0_b[n];
+                q += 32;
+                for (int k = 0; k < 96; ++k)
+                    for (int n = 0; n < 16; ++n) q[k * 16 + n] = c1.hw[(size_t)n * 96 + k];
+                q += 1536;
+                for (int n = 0; n < 16; ++n) q[n] = c1.hb[n];
+                q += 16;
+                for (int k = 0; k < 16; ++k)
+                    for (int n = 0; n < 32; ++n) q[k * 32 + n] = c2.hw[(size_t)n * 16 + k];
+                q += 512;
+                for (int j = 0; j < 7; ++j)
+                    for (int n = 0; n < 32; ++n) q[j * 32 + n] = w2[(size_t)n * K2 + off1 + j];
+                q += 256;
+                for (int n = 0; n < 32; ++n) q[n] = b2[n];
+                h->rb0_pack = h->upload(pk);
+            }
             C *= 2;
         }
         const int D = c.dimension;
@@ -802,10 +828,15 @@ void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, int
     int Tc = T, C = c.n_filters;
     // level 0 operands come from the conv0 kernel: ELU(x0) planes and the 8-wide raw-audio windows that stand in
     // for x0 in the shortcut (composed weights); deeper levels get x and ELU(x) planes from the strided conv
+    // Level 0 (conv0 + ResBlock 0) runs as ONE fp32 CUDA-core kernel that keeps ELU(x0) / ELU(h1) in shared memory
+    // (K = 7 / 96 / 24 is too small for the MMA pipeline to pay); WT_ENC_L0_TC=1 selects the tcgen05 formulation.
+    static const bool l0_tc = std::getenv("WT_ENC_L0_TC") != nullptr;
+    const bool fused0 = !l0_tc && h->rb0_pack != nullptr;
     size_t nX = (size_t)Bc * (Tc + 2) * C;
     const size_t nWin = (size_t)Bc * (Tc + 2) * 8;
-    __half *xr_hi = halves(nWin), *xr_lo = halves(nWin), *xe_hi = halves(nX), *xe_lo = halves(nX);
-    {
+    __half *xr_hi = nullptr, *xr_lo = nullptr, *xe_hi = nullptr, *xe_lo = nullptr;
+    if (!fused0) {
+        xr_hi = halves(nWin); xr_lo = halves(nWin); xe_hi = halves(nX); xe_lo = halves(nX);
         Scope sc(h, CAT_ENC_CONV, s);
         launch_conv0_planes(wav, h->conv0_w, h->conv0_b, xr_hi, xr_lo, xe_hi, xe_lo, Bc, T, C, s);
     }
@@ -816,10 +847,11 @@ void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, int
         const int P = Tc + 2;
         const long long rowsX = (long long)Bc * P;
         const auto& rt = h->rb_tc[i];
+        const bool fused = fused0 && i == 0;
         // ---- G1: h1 = conv_k3(ELU(x)) -> ELU(h1) planes, same row space ----
         const size_t nH = (size_t)rowsX * (C / 2);
-        __half *he_hi = halves(nH), *he_lo = halves(nH);
-        {
+        __half *he_hi = fused ? nullptr : halves(nH), *he_lo = fused ? nullptr : halves(nH);
+        if (!fused) {
             TcGemm g;
             g.kw = rt.kw1;
             g.seg[0] = tc_window(xe_hi, xe_lo, rowsX * C, 3 * C, C, 0, rt.kw1);
@@ -834,7 +866,10 @@ void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, int
         const size_t nY = (size_t)Bc * Py * C;
         __half *ye_hi = halves(nY), *ye_lo = halves(nY);
         float* y_tap = want("enc" + std::to_string(idx)) ? h->alloc(nY) : nullptr;
-        {
+        if (fused) {
+            Scope sc(h, CAT_ENC_CONV, s);
+            launch_resblock0_fused(wav, h->rb0_pack, ye_hi, ye_lo, y_tap, Bc, Tc, Py, left, right + extra, s);
+        } else {
             TcGemm g;
             g.nseg = 2;
             g.kw = rt.kw2;
