@@ -41,6 +41,9 @@ METRIC = "encode+decode audio-sec/sec (24 kHz)"
 UNIT = "audio-s/s"
 CPU_SAMPLE_CLIPS = 4
 # algorithmic FLOPs per frame of the ConvNeXt pointwise GEMMs: 12 x 2 x (2*768*2304)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, one `ncu --set full` capture of the kernel's modal launch shape
+# in this workload (decoder k3 conv 768 -> 768 over 128 clips; ConvNeXt GEMM-1): profiles/r01_final_summary.md
+DOMINANT_TRAFFIC = {"tap_gemm_tc_kernel<256, 3>": 240.9e6, "tap_gemm_tc_kernel<256, 1>": 132.9e6}
 CATS = ["enc_conv", "lstm", "vq", "dec_conv", "pwconv", "head_idft", "attention", "memory_bound"]
 
 
@@ -270,6 +273,18 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
         breakdown[name] = {"ms": round(t_ms.value, 3), "launches": n.value,
                            "algorithmic_tflops": round(flops[name] * B / 1e12, 4),
                            "tflops_per_s": round(flops[name] * B / max(t_ms.value, 1e-9) / 1e9, 2)}
+    # ---- same record per tcgen05 GEMM kernel variant (kern = BN * 10 + passes) ----
+    kernels = {}
+    for bn in (16, 32, 64, 128, 256):
+        for passes in (3, 1):
+            t_ms, n, fl = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+            _native.check(lib.wt_timing_read_kernel(hptr, bn * 10 + passes, ctypes.byref(t_ms), ctypes.byref(n),
+                                                    ctypes.byref(fl)))
+            if n.value:
+                kernels[f"tap_gemm_tc_kernel<{bn}, {passes}>"] = {
+                    "ms": round(t_ms.value, 3), "launches": n.value, "passes": passes,
+                    "algorithmic_tflops": round(fl.value / 1e12, 4),
+                    "tflops_per_s": round(fl.value / max(t_ms.value, 1e-9) / 1e9, 2)}
     _native.check(lib.wt_timing_enable(hptr, 0))
     peaks = {}
     try:
@@ -279,14 +294,20 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md sustained)"
-    dom = max((k for k in CATS if flops[k] > 0), key=lambda k: breakdown[k]["ms"])
-    d = breakdown[dom]
-    achieved = flops[dom] * B / (d["ms"] * 1e-3) / 1e12
+    # dominant kernel = the kernel (by name) with the largest share of the step
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    d = kernels[dom]
+    achieved = d["tflops_per_s"]
     roofline = {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 2), "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": round(achieved / peak_tf, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak_tf, 4), "traffic": DOMINANT_TRAFFIC.get(dom), "peak_source": peak_src,
                 "launches_per_step": d["launches"], "avg_launch_ms": round(d["ms"] / max(d["launches"], 1), 4),
-                "note": "algorithmic FLOPs of the category (split-precision passes not counted) / summed CUDA-event "
-                        "time of its launches in one step"}
+                "share_of_step": round(d["ms"] / ms, 3),
+                "executed_frac": round(achieved * d["passes"] / peak_tf, 4),
+                "note": "achieved = algorithmic FLOPs (2*M*N*K per launch, split-precision passes NOT counted) of all "
+                        "launches of this kernel in one step / their summed CUDA-event time on the launching stream; "
+                        "executed_frac counts the 3 split-fp16 MMA passes the parity bar requires (SURVEY.md App. D); "
+                        "traffic = dram read+write bytes per launch of the modal launch shape, ncu --set full "
+                        "(profiles/r01_final_summary.md)"}
 
     if rank == 0:
         cpu = None
@@ -301,7 +322,7 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
                            "plan": args.plan, "l2": "256 MiB flush between timed iterations; activations per step "
                            "(> 10 GB) exceed the 126 MB L2", "sharding": f"by clip, {world} rank(s), all-gather of codes"},
                 "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "clocks": clocks.summary(), "breakdown": breakdown,
+                "clocks": clocks.summary(), "breakdown": breakdown, "kernels": kernels,
                 "algorithmic_gflop_per_audio_s": round(sum(flops.values()) / 3 / 1e9, 3)}
         print(json.dumps(line), flush=True)
     if world > 1:

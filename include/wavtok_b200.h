@@ -125,6 +125,9 @@ int64_t wt_launch_count(const wt_handle* h);
  * wt_timing_enable(h, on) clears the record; wt_timing_read synchronises and sums one category. */
 int wt_timing_enable(wt_handle* h, int32_t on);
 int wt_timing_read(wt_handle* h, int32_t category, double* total_ms, int64_t* n_launches);
+/* Same record, summed per tcgen05 GEMM kernel variant: kern = BN * 10 + passes (2563 = tap_gemm_tc_kernel<256, 3>);
+ * flops = algorithmic 2*M*N*K of those launches (split-precision passes not counted). */
+int wt_timing_read_kernel(wt_handle* h, int32_t kern, double* total_ms, int64_t* n_launches, double* flops);
 
 /* Kernel-level test hook for the tcgen05 tap-GEMM (handle-free; allocates and frees its own scratch,
  * synchronises). out[m, n] = epi(sum_{j<taps} sum_c A[m + j - (taps-1)/2, c] * W[n, j*Cin + c]) over the

@@ -184,24 +184,39 @@ resblock0_fused_kernel(const float* __restrict__ wav, const float* __restrict__ 
     }
     __syncthreads();
 
-    // ---- stage A: ELU(conv0) for columns 0 .. TILE + 1 ----
-    for (int col = tid; col < RB0_TILE + 2; col += RB0_THREADS) {
-        float xv[7];
+    // ---- stage A: ELU(conv0) for columns 0 .. TILE + 1: two columns per thread share every weight vector ----
+    {
+        float xa[7], xb[7];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) xv[j] = sA[col + j];
-#pragma unroll 1  // (fully unrolled, the 56 weight vectors get hoisted out of the column loop: 224 registers)
+        for (int j = 0; j < 7; ++j) { xa[j] = sA[tid + j]; xb[j] = sA[tid + RB0_THREADS + j]; }
+#pragma unroll 1  // (fully unrolled, the 56 weight vectors get hoisted: 224 registers)
         for (int c4 = 0; c4 < 8; ++c4) {
-            float4 acc = *reinterpret_cast<const float4*>(sW + RB0_B0 + c4 * 4);
+            const float4 bb = *reinterpret_cast<const float4*>(sW + RB0_B0 + c4 * 4);
+            float4 a = bb, c = bb;
 #pragma unroll
             for (int j = 0; j < 7; ++j) {
                 const float4 w = *reinterpret_cast<const float4*>(sW + RB0_W0 + j * 32 + c4 * 4);
-                acc.x = fmaf(w.x, xv[j], acc.x); acc.y = fmaf(w.y, xv[j], acc.y);
-                acc.z = fmaf(w.z, xv[j], acc.z); acc.w = fmaf(w.w, xv[j], acc.w);
+                a.x = fmaf(w.x, xa[j], a.x); a.y = fmaf(w.y, xa[j], a.y);
+                a.z = fmaf(w.z, xa[j], a.z); a.w = fmaf(w.w, xa[j], a.w);
+                c.x = fmaf(w.x, xb[j], c.x); c.y = fmaf(w.y, xb[j], c.y);
+                c.z = fmaf(w.z, xb[j], c.z); c.w = fmaf(w.w, xb[j], c.w);
             }
-            sE0[(c4 * 4 + 0) * RB0_LD + col] = elu_fast(acc.x);
-            sE0[(c4 * 4 + 1) * RB0_LD + col] = elu_fast(acc.y);
-            sE0[(c4 * 4 + 2) * RB0_LD + col] = elu_fast(acc.z);
-            sE0[(c4 * 4 + 3) * RB0_LD + col] = elu_fast(acc.w);
+            float* e = sE0 + (c4 * 4) * RB0_LD + tid;
+            e[0] = elu_fast(a.x); e[RB0_LD] = elu_fast(a.y); e[2 * RB0_LD] = elu_fast(a.z); e[3 * RB0_LD] = elu_fast(a.w);
+            e += RB0_THREADS;
+            e[0] = elu_fast(c.x); e[RB0_LD] = elu_fast(c.y); e[2 * RB0_LD] = elu_fast(c.z); e[3 * RB0_LD] = elu_fast(c.w);
+        }
+        if (tid < 2) {  // the last two columns (TILE, TILE + 1)
+            const int col = RB0_TILE + tid;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) xa[j] = sA[col + j];
+#pragma unroll 1
+            for (int ch = 0; ch < 32; ++ch) {
+                float acc = sW[RB0_B0 + ch];
+#pragma unroll
+                for (int j = 0; j < 7; ++j) acc = fmaf(sW[RB0_W0 + j * 32 + ch], xa[j], acc);
+                sE0[ch * RB0_LD + col] = elu_fast(acc);
+            }
         }
     }
     __syncthreads();

@@ -1186,6 +1186,8 @@ void launch_cfg(const TcGemm& g, cudaStream_t s) {
     maps.w[1] = make_map(PASSES == 3 ? g.W_lo : g.W_hi, w_rows, g.K, ldw, BN, g.kw);
     const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.batch;
     const int grid = tiles < num_sms() ? tiles : num_sms();
+    last_launch_info().kern = BN * 10 + PASSES;
+    last_launch_info().flops = 2.0 * g.M * g.N * g.K * g.batch;
     tap_gemm_tc_kernel<BN, PASSES, LSTM_EPI><<<grid, NUM_THREADS, C::SMEM, s>>>(maps, g);
     WT_CUDA(cudaGetLastError());
 }
@@ -1219,6 +1221,11 @@ __global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict
 }
 
 }  // namespace
+
+LaunchInfo& last_launch_info() {
+    static thread_local LaunchInfo info;
+    return info;
+}
 
 static long long* g_debug_timeline = nullptr;
 void set_debug_timeline(long long* dev_buf) { g_debug_timeline = dev_buf; }

@@ -80,6 +80,11 @@ struct TcGemm {
 
 void set_debug_timeline(long long* dev_buf);
 
+// What the last launch_tap_gemm_tc on this thread ran: kernel variant id (BN * 10 + passes, e.g. 2563 =
+// tap_gemm_tc_kernel<256, 3>) and its algorithmic FLOPs 2*M*N*K*batch (split-precision passes not counted).
+struct LaunchInfo { int kern = 0; double flops = 0; };
+LaunchInfo& last_launch_info();
+
 void launch_tap_gemm_tc(const TcGemm& g, cudaStream_t s);
 // One LSTM layer, all L steps, in a single cooperative launch (see gemm_tc.cu). Time-major tensors.
 // `counters` needs lstm_counter_ints(B, L) ints.

@@ -115,7 +115,7 @@ struct wt_handle {
 
     // optional per-category kernel timing (CUDA events on the launching stream; bench.py's roofline)
     bool timing = false;
-    struct Ev { cudaEvent_t a, b; int cat; };
+    struct Ev { cudaEvent_t a, b; int cat; int kern = 0; double flops = 0; };
     std::vector<Ev> evs;
     std::vector<cudaEvent_t> ev_pool;
     cudaEvent_t get_event() {
@@ -641,13 +641,18 @@ struct Scope {
         ++h->launches;
         if (h->timing) {
             wt_handle::Ev e{h->get_event(), h->get_event(), cat};
+            last_launch_info() = LaunchInfo{};
             cudaEventRecord(e.a, s);
             h->evs.push_back(e);
             idx = (int)h->evs.size() - 1;
         }
     }
     ~Scope() {
-        if (idx >= 0) cudaEventRecord(h->evs[idx].b, s);
+        if (idx >= 0) {
+            cudaEventRecord(h->evs[idx].b, s);
+            h->evs[idx].kern = last_launch_info().kern;   // set by the tcgen05 GEMM launcher, 0 for other kernels
+            h->evs[idx].flops = last_launch_info().flops;
+        }
     }
 };
 
@@ -1502,6 +1507,25 @@ int wt_timing_read(wt_handle* h, int32_t category, double* total_ms, int64_t* n_
         }
         if (total_ms) *total_ms = ms;
         if (n_launches) *n_launches = n;
+    });
+}
+
+int wt_timing_read_kernel(wt_handle* h, int32_t kern, double* total_ms, int64_t* n_launches, double* flops) {
+    return guarded(h, [&] {
+        WT_CUDA(cudaDeviceSynchronize());
+        double ms = 0, fl = 0;
+        int64_t n = 0;
+        for (auto& e : h->evs) {
+            if (e.kern != kern) continue;
+            float t = 0;
+            WT_CUDA(cudaEventElapsedTime(&t, e.a, e.b));
+            ms += t;
+            fl += e.flops;
+            ++n;
+        }
+        if (total_ms) *total_ms = ms;
+        if (n_launches) *n_launches = n;
+        if (flops) *flops = fl;
     });
 }
 
