@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -108,6 +109,11 @@ struct wt_handle {
     // persistent staging for the host-buffer entry point
     char* stage = nullptr;
     size_t stage_cap = 0;
+    // host-buffer entry point: copy stream + events so that H2D of encoder chunk i+1 overlaps the encoder of chunk
+    // i and D2H of decoder chunk i overlaps the decoder of chunk i+1; hooks are set only inside that entry point
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copy_evs;
+    std::function<void(int /*first clip*/, int /*clips*/)> before_enc_chunk, after_dec_chunk;
     int* err_flag = nullptr;  // device
     int* err_host = nullptr;  // pinned
 
@@ -129,6 +135,8 @@ struct wt_handle {
         cudaSetDevice(device);
         for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         for (auto e : ev_pool) cudaEventDestroy(e);
+        for (auto e : copy_evs) cudaEventDestroy(e);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         for (void* p : owned) cudaFree(p);
         if (arena) cudaFree(arena);
         if (stage) cudaFree(stage);
@@ -1228,6 +1236,7 @@ void do_encode(wt_handle* h, const float* wav, int B, int T, float* features_out
             h->arena_off = mark;
             const size_t ro = (size_t)b0 * L * D;
             const size_t to = (size_t)b0 * D;  // time-major: clip b0 starts at row b0 of every time step
+            if (h->before_enc_chunk) h->before_enc_chunk(g0 + b0, Bc);
             if (tc) encoder_front_tc(h, wav + (size_t)(g0 + b0) * T, Bc, T, g0 + b0, Bg, pre + to, pre_hi + to, pre_lo + to, s);
             else encoder_front(h, wav + (size_t)(g0 + b0) * T, Bc, T, g0 + b0, pre + ro, s);
         }
@@ -1269,6 +1278,7 @@ void do_decode(wt_handle* h, const float* features, int B, int L, int bw, float*
         h->arena_off = 0;
         decoder_chunk(h, features + (size_t)b0 * c.dimension * L, Bc, L, bw,
                       audio + (size_t)b0 * L * c.hop_length, b0, s);
+        if (h->after_dec_chunk) h->after_dec_chunk(b0, Bc);
     }
 }
 
@@ -1449,12 +1459,59 @@ int wt_encode_decode_host(wt_handle* h, const float* wav_host, int32_t B, int32_
         float* feat = (float*)p; p += align_up(n_feat * 4, 256);
         int64_t* codes = (int64_t*)p; p += align_up(n_codes * 8, 256);
         float* audio = (float*)p;
-        WT_CUDA(cudaMemcpyAsync(wav, wav_host, n_wav * 4, cudaMemcpyHostToDevice, s));
+        // Copies run on a second stream, chunk by chunk: the encoder front of chunk i waits only for ITS clips, and the
+        // audio of decoder chunk i leaves while chunk i+1 is computed (pinned host buffers make these true async DMAs).
+        if (!h->copy_stream) WT_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        cudaStream_t cs = h->copy_stream;
+        size_t ev_next = 0;
+        auto next_event = [&]() {
+            if (ev_next == h->copy_evs.size()) {
+                cudaEvent_t e;
+                WT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                h->copy_evs.push_back(e);
+            }
+            return h->copy_evs[ev_next++];
+        };
+        {   // the copy stream starts after everything already queued on s (the staging buffers may still be in use)
+            cudaEvent_t e = next_event();
+            WT_CUDA(cudaEventRecord(e, s));
+            WT_CUDA(cudaStreamWaitEvent(cs, e, 0));
+        }
+        std::unordered_map<int, cudaEvent_t> h2d;  // first clip of an encoder chunk -> its wav is on the device
+        for (int g0 = 0; g0 < B; g0 += ENC_GROUP)  // same chunking as do_encode
+            for (int b0 = g0; b0 < std::min(B, g0 + ENC_GROUP); b0 += ENC_CHUNK) {
+                const int Bc = std::min(ENC_CHUNK, std::min(B, g0 + ENC_GROUP) - b0);
+                WT_CUDA(cudaMemcpyAsync(wav + (size_t)b0 * T, wav_host + (size_t)b0 * T, (size_t)Bc * T * 4,
+                                        cudaMemcpyHostToDevice, cs));
+                cudaEvent_t e = next_event();
+                WT_CUDA(cudaEventRecord(e, cs));
+                h2d[b0] = e;
+            }
+        struct Clear {
+            wt_handle* h;
+            ~Clear() { h->before_enc_chunk = nullptr; h->after_dec_chunk = nullptr; }
+        } clear{h};
+        h->before_enc_chunk = [&](int b0, int) { WT_CUDA(cudaStreamWaitEvent(s, h2d.at(b0), 0)); };
         do_encode(h, wav, B, T, feat, codes, nullptr, s);
+        h->before_enc_chunk = nullptr;
+        {
+            cudaEvent_t e = next_event();
+            WT_CUDA(cudaEventRecord(e, s));
+            WT_CUDA(cudaStreamWaitEvent(cs, e, 0));
+            WT_CUDA(cudaMemcpyAsync(codes_host, codes, n_codes * 8, cudaMemcpyDeviceToHost, cs));
+        }
+        const size_t per_clip = (size_t)L * c.hop_length;
+        h->after_dec_chunk = [&](int b0, int Bc) {
+            cudaEvent_t e = next_event();
+            WT_CUDA(cudaEventRecord(e, s));
+            WT_CUDA(cudaStreamWaitEvent(cs, e, 0));
+            WT_CUDA(cudaMemcpyAsync(audio_host + (size_t)b0 * per_clip, audio + (size_t)b0 * per_clip,
+                                    (size_t)Bc * per_clip * 4, cudaMemcpyDeviceToHost, cs));
+        };
         do_decode(h, feat, B, L, bandwidth_id, audio, s);
-        WT_CUDA(cudaMemcpyAsync(codes_host, codes, n_codes * 8, cudaMemcpyDeviceToHost, s));
-        WT_CUDA(cudaMemcpyAsync(audio_host, audio, n_audio * 4, cudaMemcpyDeviceToHost, s));
+        h->after_dec_chunk = nullptr;
         WT_CUDA(cudaStreamSynchronize(s));
+        WT_CUDA(cudaStreamSynchronize(cs));
     });
 }
 
