@@ -53,8 +53,9 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ wa
 
 // fast ELU, see gemm_tc.cu (same formula so that every producer of ELU planes agrees)
 __device__ __forceinline__ float elu_fast(float x) {
-    const float e = __expf(x) - 1.f;
-    return x > 0.f ? x : e;
+    float e;  // bare MUFU.EX2 (__expf adds a denormal-range fix-up: FSETP + two predicated FMULs per call)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return x > 0.f ? x : e - 1.f;
 }
 
 __device__ __forceinline__ void split_store8(__half* hi, __half* lo, long long off, const float (&v)[8]) {

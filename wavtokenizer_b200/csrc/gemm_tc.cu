@@ -265,8 +265,9 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // error <= ~1.2e-7 (one ulp of the exponential near 1), i.e. the 2^-22 resolution the value is then stored with
 // in split-fp16 planes at the O(0.1..1) activation scale of the encoder; five instructions, no branch.
 __device__ __forceinline__ float elu1(float x) {
-    const float e = __expf(x) - 1.f;
-    return x > 0.f ? x : e;
+    float e;  // bare MUFU.EX2 (__expf adds a denormal-range fix-up: FSETP + two predicated FMULs per call)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return x > 0.f ? x : e - 1.f;
 }
 __device__ __forceinline__ float sigmoid1(float x) { return 1.f / (1.f + expf(-x)); }
 // LSTM gates on the recurrent critical path: MUFU.EX2 + MUFU.RCP forms (absolute error ~1e-7, the resolution of the

@@ -21,12 +21,12 @@ namespace {
 
 thread_local std::string g_last_error;
 
-constexpr int ENC_CHUNK_DEFAULT = 32;  // clips per encoder-front pass (early SEANet tensors: 9.2 MB per clip each)
+constexpr int ENC_CHUNK_DEFAULT = 64;  // clips per encoder-front pass (early SEANet tensors: 9.2 MB per clip each)
 inline int enc_chunk() {
     static int v = [] {
         const char* e = std::getenv("WT_ENC_CHUNK");
         int n = e ? std::atoi(e) : ENC_CHUNK_DEFAULT;
-        return n >= 1 && n <= 64 ? n : ENC_CHUNK_DEFAULT;
+        return n >= 1 && n <= 256 ? n : ENC_CHUNK_DEFAULT;
     }();
     return v;
 }
