@@ -20,6 +20,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -166,6 +168,34 @@ __device__ __forceinline__ void mbar_expect_tx_p(uint32_t bar, uint32_t bytes, u
         "setp.ne.b32 q, %2, 0;\n"
         "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
         "}\n" ::"r"(bar), "r"(bytes), "r"(leader)
+        : "memory");
+}
+
+// ---- 2-CTA cluster helpers (W tiles are loaded once per CTA pair and multicast into both CTAs) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose box lands at the same shared-memory offset of every CTA in `mask`, each CTA's mbarrier at the same
+// offset receiving the complete_tx for the bytes written into it.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, "
+        "%3}], [%4], %5;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+        : "memory");
+}
+// commit whose mbarrier arrive is delivered to the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(mask)
         : "memory");
 }
 
@@ -388,7 +418,7 @@ __device__ __forceinline__ void store_row(const TcGemm& g, long long row, int nb
     }
 }
 
-template <int BN, int PASSES, bool LSTM_EPI = false>
+template <int BN, int PASSES>
 struct Cfg {
     static constexpr int A_PLANE = BM * BK * 2;  // bytes
     static constexpr int B_PLANE = BN * BK * 2;
@@ -419,10 +449,15 @@ struct Cfg {
 
 struct Maps {
     CUtensorMap a[2][2];  // [segment][plane]
-    CUtensorMap w[2];     // [plane]
+    CUtensorMap w[2];     // [plane]; box of BN rows (BN / 2 rows in the 2-CTA cluster variant: each CTA loads one half)
 };
 
-template <int BN, int PASSES, bool LSTM_EPI>
+// CL2: the kernel runs as clusters of two CTAs that work on two consecutive row tiles of the SAME column tile in
+// lockstep. Each CTA loads its own A tiles and one HALF of every W k-block, multicast into both CTAs, so the W bytes
+// cross L2 -> SM once per pair: the single-pass 128 x 256 tiles need 94 B/clk/SM of operands otherwise and were bound
+// by that (profiles/r01_final_summary.md). Shared-memory stages are recycled when BOTH CTAs' MMAs have read them
+// (tcgen05.commit multicast onto both CTAs' empty barriers).
+template <int BN, int PASSES, bool LSTM_EPI = false, bool CL2 = false>
 // 18 warps are allocated as 20 (warp granularity 4): 65536 / (20 * 32) = 102 -> 96 registers per thread.
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
@@ -449,7 +484,25 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     const int total_tiles = per_batch * g.batch;
     const int nkb0 = g.seg[0].num_kb;
     const int num_kb = nkb0 + (g.nseg > 1 ? g.seg[1].num_kb : 0);
-    const bool simple_tiles = total_tiles == m_tiles;  // one column tile, one batch: tile index = row tile
+    const bool simple_tiles = !CL2 && total_tiles == m_tiles;  // one column tile, one batch: tile index = row tile
+    // work distribution: CTA (or CTA pair) `wid` of `nworkers` takes work items wid, wid + nworkers, ...; an item is
+    // one output tile, or in the cluster variant a pair of row tiles (2 mp, 2 mp + 1) x one column tile
+    const uint32_t cta_rank = CL2 ? cluster_ctarank() : 0u;
+    const int wid = CL2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int nworkers = CL2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int total_items = CL2 ? ((m_tiles + 1) / 2) * n_tiles : total_tiles;
+    auto decode = [&](int item, int& bz, int& mt, int& nt) {
+        if (CL2) {
+            const int mp = item / n_tiles;
+            bz = 0; nt = item - mp * n_tiles; mt = 2 * mp + (int)cta_rank;
+        } else if (simple_tiles) {
+            bz = 0; mt = item; nt = 0;
+        } else {
+            bz = item / per_batch;
+            const int rem = item - bz * per_batch;
+            mt = rem / n_tiles; nt = rem - mt * n_tiles;
+        }
+    };
     // k-block width: 64 elements (128-byte rows, SWIZZLE_128B) or, for narrow operands, 32 / 16 (64- / 32-byte rows
     // under SWIZZLE_64B / _32B) so that TMA fetches exactly the bytes that exist instead of zero-filling 128-byte rows
     const int kw = g.kw;
@@ -458,7 +511,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), CL2 ? 2 : 1);  // cluster variant: both CTAs' MMAs must have read the stage
         }
         for (int s = 0; s < C::NACC; ++s) {
             mbar_init(tfull_bar(s), 1);
@@ -474,6 +527,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL2) cluster_sync_all();  // the peer's barriers exist before anything is multicast at them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
     if (threadIdx.x == 0) stamp(0);  // prologue done
@@ -485,13 +539,9 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                int bz = 0, mt = tile, nt = 0;
-                if (!simple_tiles) {
-                    bz = tile / per_batch;
-                    const int rem = tile - bz * per_batch;
-                    mt = rem / n_tiles; nt = rem - mt * n_tiles;
-                }
+            for (int tile = wid; tile < total_items; tile += nworkers) {
+                int bz, mt, nt;
+                decode(tile, bz, mt, nt);
                 const int m0 = mt * BM + (int)(bz * g.a_brows), n0 = nt * BN + (int)(bz * g.w_brows);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const int si = kb < nkb0 ? 0 : 1;
@@ -506,9 +556,16 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                     mbar_expect_tx(full_bar(stage), C::PLANES * (a_plane + b_plane));
                     tma_load_2d(sa, &maps.a[si][0], c0, r0, full_bar(stage));
                     if (PASSES == 3) tma_load_2d(sa + a_plane, &maps.a[si][1], c0, r0, full_bar(stage));
-                    tma_load_2d(sb, &maps.w[0], kb * kw, n0, full_bar(stage));
-                    if (PASSES == 3) tma_load_2d(sb + b_plane, &maps.w[1], kb * kw, n0, full_bar(stage));
-                    if (tile == (int)blockIdx.x) stamp(1 + kb);  // slots 1..16: producer issued k-block kb (first tile)
+                    if (CL2) {  // this CTA's half of the W rows, delivered to both CTAs of the pair
+                        const uint32_t hoff = cta_rank * (b_plane / 2);
+                        const int nh = n0 + (int)cta_rank * (BN / 2);
+                        tma_load_2d_mc(sb + hoff, &maps.w[0], kb * kw, nh, full_bar(stage), (uint16_t)3);
+                        if (PASSES == 3) tma_load_2d_mc(sb + b_plane + hoff, &maps.w[1], kb * kw, nh, full_bar(stage), (uint16_t)3);
+                    } else {
+                        tma_load_2d(sb, &maps.w[0], kb * kw, n0, full_bar(stage));
+                        if (PASSES == 3) tma_load_2d(sb + b_plane, &maps.w[1], kb * kw, n0, full_bar(stage));
+                    }
+                    if (tile == wid) stamp(1 + kb);  // slots 1..16: producer issued k-block kb (first tile)
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -539,7 +596,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
             int acc = 0;
             uint32_t acc_phase = 0;
             int ti = -1;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = wid; tile < total_items; tile += nworkers) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 ++ti;
                 if (ti < 5) stamp(44 + 4 * ti);  // MMA may start tile ti (accumulator free)
@@ -548,7 +605,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (tile == (int)blockIdx.x) stamp(17 + kb);  // slots 17..32: data of k-block kb landed
+                    if (tile == wid) stamp(17 + kb);  // slots 17..32: data of k-block kb landed
                     const uint32_t sa = smem_base + stage * C::STAGE;
                     const uint32_t sb = sa + C::PLANES * a_plane;
                     int nk16 = full16;
@@ -576,7 +633,8 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                             }
                         }
                     }
-                    umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+                    if (CL2) umma_commit_mc(empty_bar(stage), (uint16_t)3);  // ... in BOTH CTAs: the peer's W half lives here too
+                    else umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
                     if (kb == num_kb - 1) {
                         umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
                         if (ti < 5) stamp(45 + 4 * ti);  // all MMAs of tile ti issued
@@ -592,22 +650,18 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
         const int grp = ((warp - 2) >> 2) / C::G;  // epilogue group: handles this CTA's tiles grp, grp + NGRP, ...
         const int cg = ((warp - 2) >> 2) % C::G;   // which share of the tile's columns this warp handles
         for (int ti = grp;; ti += C::NGRP) {
-            const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-            if (tile >= total_tiles) break;
+            const int tile = wid + ti * nworkers;
+            if (tile >= total_items) break;
             const int acc = ti % C::NACC;
             const uint32_t acc_phase = (uint32_t)(ti / C::NACC) & 1u;
-            int bz = 0, mt = tile, nt = 0;
-            if (!simple_tiles) {
-                bz = tile / per_batch;
-                const int rem = tile - bz * per_batch;
-                mt = rem / n_tiles; nt = rem - mt * n_tiles;
-            }
+            int bz, mt, nt;
+            decode(tile, bz, mt, nt);
             const int m_local = mt * BM + q * 32 + lane;
             const int m = m_local + (int)(bz * g.o_brows);
             const int n0 = nt * BN;
             mbar_wait(tfull_bar(acc), acc_phase);
             if (threadIdx.x == 64 && ti < 5) stamp(46 + 4 * ti);  // accumulator of tile ti ready
-            if (tile == (int)blockIdx.x && threadIdx.x == 64) stamp(40);  // accumulator of the first tile ready
+            if (tile == wid && threadIdx.x == 64) stamp(40);  // accumulator of the first tile ready
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::ACC_COLS);
             // accumulator chunk = columns [col, col+n) (+ the hl block BN columns further when the passes are fused)
@@ -800,7 +854,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (threadIdx.x == 64 && ti < 5) stamp(47 + 4 * ti);  // epilogue of tile ti done (this warp)
-            if (tile == (int)blockIdx.x && threadIdx.x == 64) stamp(41);  // epilogue of the first tile done
+            if (tile == wid && threadIdx.x == 64) stamp(41);  // epilogue of the first tile done
             if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
     }
@@ -808,6 +862,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     if (threadIdx.x == 64) stamp(43);  // this epilogue warp finished its last tile (a reliable "CTA done" time)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL2) cluster_sync_all();  // the peer may still multicast into this CTA's stages / arrive on its barriers
     if (threadIdx.x == 0) stamp(42);  // barrier issued (BAR.SYNC.DEFER_BLOCKING: not the release time)
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -1167,13 +1222,26 @@ int num_sms() {
     return n;
 }
 
-template <int BN, int PASSES, bool LSTM_EPI = false>
+template <int BN, int PASSES, bool LSTM_EPI = false, bool CL2 = false>
 void launch_cfg(const TcGemm& g, cudaStream_t s) {
     using C = Cfg<BN, PASSES>;
+    auto kernel = tap_gemm_tc_kernel<BN, PASSES, LSTM_EPI, CL2>;
     static bool attr = false;
+    static int max_ctas = 0;  // cluster variant: CTAs that can be co-resident as pairs
     if (!attr) {
-        WT_CUDA(cudaFuncSetAttribute(tap_gemm_tc_kernel<BN, PASSES, LSTM_EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     C::SMEM));
+        WT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        if (CL2) {
+            cudaLaunchConfig_t qc = {};
+            qc.gridDim = dim3(num_sms() & ~1); qc.blockDim = dim3(NUM_THREADS); qc.dynamicSmemBytes = C::SMEM;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            qc.attrs = qa; qc.numAttrs = 1;
+            int nc = 0;
+            WT_CUDA(cudaOccupancyMaxActiveClusters(&nc, kernel, &qc));
+            max_ctas = 2 * nc;
+            if (max_ctas < 2) throw Error(4, "gemm_tc: no room for a 2-CTA cluster");
+        }
         attr = true;
     }
     Maps maps;
@@ -1183,13 +1251,27 @@ void launch_cfg(const TcGemm& g, cudaStream_t s) {
         maps.a[si][1] = make_map(PASSES == 3 ? sg.lo : sg.hi, sg.rows, sg.inner, sg.stride, BM, g.kw);
     }
     const long long ldw = g.ldw ? g.ldw : g.K, w_rows = g.w_rows ? g.w_rows : g.N;
-    maps.w[0] = make_map(g.W_hi, w_rows, g.K, ldw, BN, g.kw);
-    maps.w[1] = make_map(PASSES == 3 ? g.W_lo : g.W_hi, w_rows, g.K, ldw, BN, g.kw);
-    const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.batch;
-    const int grid = tiles < num_sms() ? tiles : num_sms();
+    const int wbox = CL2 ? BN / 2 : BN;
+    maps.w[0] = make_map(g.W_hi, w_rows, g.K, ldw, wbox, g.kw);
+    maps.w[1] = make_map(PASSES == 3 ? g.W_lo : g.W_hi, w_rows, g.K, ldw, wbox, g.kw);
+    const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
     last_launch_info().kern = BN * 10 + PASSES;
     last_launch_info().flops = 2.0 * g.M * g.N * g.K * g.batch;
-    tap_gemm_tc_kernel<BN, PASSES, LSTM_EPI><<<grid, NUM_THREADS, C::SMEM, s>>>(maps, g);
+    if (CL2) {
+        const int items = ((m_tiles + 1) / 2) * n_tiles;
+        const int grid = std::min(2 * items, std::min(num_sms() & ~1, max_ctas));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        WT_CUDA(cudaLaunchKernelEx(&cfg, kernel, maps, g));
+    } else {
+        const int tiles = m_tiles * n_tiles * g.batch;
+        const int grid = tiles < num_sms() ? tiles : num_sms();
+        kernel<<<grid, NUM_THREADS, C::SMEM, s>>>(maps, g);
+    }
     WT_CUDA(cudaGetLastError());
 }
 
@@ -1201,7 +1283,12 @@ void launch_bn(const TcGemm& g, cudaStream_t s) {
     if (g.N <= 64) return launch_cfg<64, PASSES>(g, s);
     if (g.N <= 128) return launch_cfg<128, PASSES>(g, s);
     const bool wide = g.N % 256 == 0 || g.N > 1024;
-    if (wide) launch_cfg<256, PASSES>(g, s); else launch_cfg<128, PASSES>(g, s);
+    if (!wide) return launch_cfg<128, PASSES>(g, s);
+    // 2-CTA clusters with multicast W loads for the wide tiles (WT_TC_CLUSTER=0 keeps single CTAs)
+    static const bool cluster_on = [] { const char* e = std::getenv("WT_TC_CLUSTER"); return !e || std::atoi(e) != 0; }();
+    const int m_tiles = (g.M + BM - 1) / BM;
+    if (cluster_on && g.batch == 1 && g.kw == 64 && m_tiles >= 2) launch_cfg<256, PASSES, false, true>(g, s);
+    else launch_cfg<256, PASSES>(g, s);
 }
 
 // fp32 -> split fp16 planes (weights at load time; activations whose producer is not fused yet)
