@@ -43,7 +43,7 @@ CPU_SAMPLE_CLIPS = 4
 # algorithmic FLOPs per frame of the ConvNeXt pointwise GEMMs: 12 x 2 x (2*768*2304)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, one `ncu --set full` capture of the kernel's modal launch shape
 # in this workload (decoder k3 conv 768 -> 768 over 128 clips; ConvNeXt GEMM-1): profiles/r01_final_summary.md
-DOMINANT_TRAFFIC = {"tap_gemm_tc_kernel<256, 3>": 240.9e6, "tap_gemm_tc_kernel<256, 1>": 132.9e6}
+DOMINANT_TRAFFIC = {"tap_gemm_tc_kernel<256, 3>": 249.5e6, "tap_gemm_tc_kernel<256, 1>": 135.0e6}
 CATS = ["enc_conv", "lstm", "vq", "dec_conv", "pwconv", "head_idft", "attention", "memory_bound"]
 
 
