@@ -309,6 +309,34 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
                         "traffic = dram read+write bytes per launch of the modal launch shape, ncu --set full "
                         "(profiles/r01_final_summary.md)"}
 
+    # ---- the convert_audio front-end (44.1 kHz stereo -> 24 kHz mono, 171 taps) ----
+    from wavtokenizer_b200 import convert_audio
+    sr_in = 44100
+    t_in = T * sr_in // SR
+    raw = torch.randn(B, 2, t_in, device=dev).clamp_(-1, 1)
+    for _ in range(3):
+        mono = convert_audio(raw, sr_in, SR, 1)
+    ca = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ca:
+        flush.zero_()
+        a.record()
+        mono = convert_audio(raw, sr_in, SR, 1)
+        b.record()
+    torch.cuda.synchronize()
+    ca_ms = sum(a.elapsed_time(b) for a, b in ca) / args.steps
+    ca_bytes = raw.numel() * 4 + mono.numel() * 4
+    hbm_peak = float(peaks.get("hbm_gbs", 6500.0))
+    next_rows = {"convert_audio": {
+        "workload": f"{B} clips x 3 s, {sr_in} Hz stereo -> {SR} Hz mono (polyphase sinc, 171 taps x 80 phases)",
+        "ms": round(ca_ms, 3), "audio_s_per_s": round(B * T / SR / (ca_ms * 1e-3), 1),
+        "roofline": {"bound": "hbm", "achieved": round(ca_bytes / (ca_ms * 1e-3) / 1e9, 1), "peak": hbm_peak,
+                     "unit": "GB/s", "frac": round(ca_bytes / (ca_ms * 1e-3) / 1e9 / hbm_peak, 4),
+                     "algorithmic_bytes": ca_bytes,
+                     "note": "compulsory bytes (stereo in + mono out) / CUDA-event time; this ratio is 171 FMA per output "
+                             "sample, so the kernel is fp32-FMA bound before it is HBM bound: "
+                             f"{round(B * T * 171 / (ca_ms * 1e-3) / 1e12, 2)} TFMA/s achieved"}}}
+    del raw, mono
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -322,7 +350,7 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
                            "plan": args.plan, "l2": "256 MiB flush between timed iterations; activations per step "
                            "(> 10 GB) exceed the 126 MB L2", "sharding": f"by clip, {world} rank(s), all-gather of codes"},
                 "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "clocks": clocks.summary(), "breakdown": breakdown, "kernels": kernels,
+                "clocks": clocks.summary(), "breakdown": breakdown, "kernels": kernels, "next_rows": next_rows,
                 "algorithmic_gflop_per_audio_s": round(sum(flops.values()) / 3 / 1e9, 3)}
         print(json.dumps(line), flush=True)
     if world > 1:

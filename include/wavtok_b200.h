@@ -129,6 +129,16 @@ int wt_timing_read(wt_handle* h, int32_t category, double* total_ms, int64_t* n_
  * flops = algorithmic 2*M*N*K of those launches (split-precision passes not counted). */
 int wt_timing_read_kernel(wt_handle* h, int32_t kern, double* total_ms, int64_t* n_launches, double* flops);
 
+/* convert_audio front-end: replaces encoder/utils.py:79-92, i.e. the channel mix
+ * (target_channels == 1: mean over channels; == 2 or mono input: expand) followed by
+ * torchaudio.transforms.Resample(sr, target_sr) (polyphase windowed sinc: sinc_interp_hann, lowpass_filter_width 6,
+ * rolloff 0.99). Handle-free. wav [B, channels, T] and out [B, target_channels, wt_convert_audio_length(T, sr,
+ * target_sr)] are fp32 DEVICE memory on `device`. Errors mirror the reference: channels not in {1, 2} -> WT_ERR_VALUE
+ * ("Audio must be mono or stereo."), impossible channel conversion -> WT_ERR_RUNTIME. */
+int64_t wt_convert_audio_length(int64_t T, int64_t sr, int64_t target_sr);
+int wt_convert_audio(int32_t device, const float* wav, int64_t B, int32_t channels, int64_t T, int64_t sr,
+                     int64_t target_sr, int32_t target_channels, float* out, void* stream);
+
 /* Kernel-level test hook for the tcgen05 tap-GEMM (handle-free; allocates and frees its own scratch,
  * synchronises). out[m, n] = epi(sum_{j<taps} sum_c A[m + j - (taps-1)/2, c] * W[n, j*Cin + c]) over the
  * rows of A [rows, Cin] (rows outside are zero); W [N, taps*Cin]; all pointers fp32 DEVICE memory; bias /

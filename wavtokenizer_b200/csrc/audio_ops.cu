@@ -1,0 +1,262 @@
+// convert_audio front-end (reference encoder/utils.py:79-92): channel mix
+// (mean to mono / expand) fused with torchaudio.transforms.Resample(sr -> target_sr), i.e. the polyphase
+// windowed-sinc FIR of torchaudio.functional._get_sinc_resample_kernel / _apply_sinc_resample_kernel
+// (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99; torchaudio 2.x, a dependency of the reference that is
+// not vendored in it: requirements.txt pins torchaudio==2.0.1, same algorithm).
+//
+//   out[j*new + p] = sum_k xpad[j*orig + k] * kernel[p][k],  xpad = zero-pad(x, width, width + orig),
+//   K = 2*width + orig taps, output cut to ceil(new * T / orig) samples.
+//
+// One block = 256 consecutive output samples of one (clip, output channel): the input span they touch
+// ((256/new + 1)*orig + K samples, channel-mixed on the fly) is staged in shared memory once; the tap table is
+// stored transposed [k][phase] so that consecutive threads (consecutive phases) read consecutive addresses.
+// Bound: HBM for the common ratios (K = 16..28 taps), fp32 FMA issue for 44.1 kHz -> 24 kHz (171 taps).
+#include <cmath>
+#include <map>
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/wavtok_b200.h"
+#include "common.cuh"
+
+namespace wt {
+
+long long gcd_ll(long long a, long long b) { return b ? gcd_ll(b, a % b) : a; }
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+
+__global__ void __launch_bounds__(RS_THREADS)
+resample_mix_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ tabT, int C_in,
+                    int C_out, int mix_mean, long long T, long long Tout, int orig, int new_, int width, int K) {
+    extern __shared__ float xs[];
+    const int bc = blockIdx.y;
+    const int b = bc / C_out, co = bc - b * C_out;
+    const long long i0 = (long long)blockIdx.x * RS_THREADS;
+    long long i_last = i0 + RS_THREADS - 1;
+    if (i_last > Tout - 1) i_last = Tout - 1;
+    const long long j_lo = i0 / new_, j_hi = i_last / new_;
+    const int span = (int)((j_hi - j_lo) * orig) + K;
+    const long long t_base = j_lo * orig - width;
+    const float* xb = in + (long long)b * C_in * T;
+    const float inv_c = 1.f / (float)C_in;
+    for (int s = threadIdx.x; s < span; s += RS_THREADS) {
+        const long long t = t_base + s;
+        float v = 0.f;
+        if (t >= 0 && t < T) {
+            if (mix_mean) {  // wav.mean(-2): sum over channels, then divide (reference encoder/utils.py:84)
+                float acc = 0.f;
+                for (int c = 0; c < C_in; ++c) acc += xb[(long long)c * T + t];
+                v = C_in == 1 ? acc : acc * inv_c;
+            } else {
+                v = xb[(long long)(C_in == 1 ? 0 : co) * T + t];  // expand
+            }
+        }
+        xs[s] = v;
+    }
+    __syncthreads();
+    const long long i = i0 + threadIdx.x;
+    if (i >= Tout) return;
+    const long long j = i / new_;
+    const int p = (int)(i - j * new_);
+    const float* x0 = xs + (int)((j - j_lo) * orig);
+    const float* w = tabT + p;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) acc = fmaf(x0[k], w[(long long)k * new_], acc);
+    out[((long long)b * C_out + co) * Tout + i] = acc;
+}
+
+// Register-tiled variant for phase counts that are multiples of 4 (44.1 kHz -> 24 kHz: 80 phases x 171 taps): a block owns
+// RT_FRAMES output frames x all phases, a thread 4 frames x 4 phases, so every tap costs one 128-bit table load and four
+// shared-memory loads for 16 FMAs (the one-output-per-thread kernel above pays two loads per FMA).
+constexpr int RT_FRAMES = 32;
+
+__global__ void __launch_bounds__(1024)
+resample_mix_tiled_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ tabT, int C_in,
+                          int C_out, int mix_mean, long long T, long long Tout, int orig, int new_, int width, int K) {
+    extern __shared__ float xs[];
+    const int bc = blockIdx.y;
+    const int b = bc / C_out, co = bc - b * C_out;
+    const long long j_lo = (long long)blockIdx.x * RT_FRAMES;
+    const int span = (RT_FRAMES - 1) * orig + K;
+    const long long t_base = j_lo * orig - width;
+    const float* xb = in + (long long)b * C_in * T;
+    const float inv_c = 1.f / (float)C_in;
+    for (int s = threadIdx.x; s < span; s += blockDim.x) {
+        const long long t = t_base + s;
+        float v = 0.f;
+        if (t >= 0 && t < T) {
+            if (mix_mean) {
+                float acc = 0.f;
+                for (int c = 0; c < C_in; ++c) acc += xb[(long long)c * T + t];
+                v = C_in == 1 ? acc : acc * inv_c;
+            } else {
+                v = xb[(long long)(C_in == 1 ? 0 : co) * T + t];
+            }
+        }
+        xs[s] = v;
+    }
+    __syncthreads();
+    const int npg = new_ >> 2;
+    const int jg = threadIdx.x / npg, pg = threadIdx.x - jg * npg;
+    const int p0 = pg * 4;
+    const float* x0 = xs + (4 * jg) * orig;
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+        const float4 w = *reinterpret_cast<const float4*>(tabT + (long long)k * new_ + p0);
+        const float xv[4] = {x0[k], x0[orig + k], x0[2 * orig + k], x0[3 * orig + k]};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            acc[r][0] = fmaf(xv[r], w.x, acc[r][0]);
+            acc[r][1] = fmaf(xv[r], w.y, acc[r][1]);
+            acc[r][2] = fmaf(xv[r], w.z, acc[r][2]);
+            acc[r][3] = fmaf(xv[r], w.w, acc[r][3]);
+        }
+    }
+    float* ob = out + ((long long)b * C_out + co) * Tout;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const long long i = (j_lo + 4 * jg + r) * new_ + p0;
+        if (i + 3 < Tout && ((reinterpret_cast<uintptr_t>(ob + i) & 15) == 0)) {
+            *reinterpret_cast<float4*>(ob + i) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (i + c < Tout) ob[i + c] = acc[r][c];
+        }
+    }
+}
+
+struct Table {
+    int orig = 0, new_ = 0, width = 0, K = 0;
+    float* dev = nullptr;  // [K][new_]
+};
+
+// torchaudio.functional._get_sinc_resample_kernel, evaluated like the reference does: sample positions in fp64,
+// the phase offset -p/new in fp32 (an int64 tensor divided by a Python int), window and sinc in fp64, cast to fp32.
+const Table& get_table(int device, long long sr, long long target) {
+    static std::map<std::tuple<int, long long, long long>, Table> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_tuple(device, sr, target);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    const long long g = gcd_ll(sr, target);
+    Table t;
+    t.orig = (int)(sr / g);
+    t.new_ = (int)(target / g);
+    if (sr == target) {  // torchaudio.transforms.Resample.forward returns its input when the rates agree: mix only
+        t.width = 0; t.K = 1;
+        const float one = 1.f;
+        WT_CUDA(cudaMalloc(&t.dev, sizeof(float)));
+        WT_CUDA(cudaMemcpy(t.dev, &one, sizeof(float), cudaMemcpyHostToDevice));
+        return cache.emplace(key, t).first->second;
+    }
+    const double lowpass = 6.0, rolloff = 0.99;
+    const double base = (double)std::min(t.orig, t.new_) * rolloff;
+    t.width = (int)std::ceil(lowpass * t.orig / base);
+    t.K = 2 * t.width + t.orig;
+    std::vector<float> tab((size_t)t.K * t.new_);
+    const double pi = 3.14159265358979323846;
+    const double scale = base / t.orig;
+    for (int p = 0; p < t.new_; ++p) {
+        const double ph = (double)((float)(-p) / (float)t.new_);
+        for (int k = 0; k < t.K; ++k) {
+            double x = (ph + (double)(k - t.width) / (double)t.orig) * base;
+            if (x < -lowpass) x = -lowpass;
+            if (x > lowpass) x = lowpass;
+            const double c = std::cos(x * pi / lowpass / 2.0);
+            const double window = c * c;
+            x *= pi;
+            const double s = x == 0.0 ? 1.0 : std::sin(x) / x;
+            tab[(size_t)k * t.new_ + p] = (float)(s * window * scale);
+        }
+    }
+    WT_CUDA(cudaMalloc(&t.dev, tab.size() * sizeof(float)));
+    WT_CUDA(cudaMemcpy(t.dev, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return cache.emplace(key, t).first->second;
+}
+
+}  // namespace
+
+}  // namespace wt
+
+extern "C" {
+
+int64_t wt_convert_audio_length(int64_t T, int64_t sr, int64_t target_sr) {
+    if (T < 0 || sr <= 0 || target_sr <= 0) return -1;
+    if (sr == target_sr) return T;
+    const long long g = wt::gcd_ll(sr, target_sr);
+    const long long orig = sr / g, nw = target_sr / g;
+    return (nw * T + orig - 1) / orig;  // ceil(new * T / orig)
+}
+
+int wt_convert_audio(int32_t device, const float* wav, int64_t B, int32_t channels, int64_t T, int64_t sr,
+                     int64_t target_sr, int32_t target_channels, float* out, void* stream) {
+    using namespace wt;
+    try {
+        if (!wav || !out) throw Error(WT_ERR_VALUE, "wt_convert_audio: null buffer");
+        if (B < 0 || T < 0 || sr <= 0 || target_sr <= 0) throw Error(WT_ERR_VALUE, "wt_convert_audio: bad sizes");
+        if (channels != 1 && channels != 2) throw Error(WT_ERR_VALUE, "Audio must be mono or stereo.");
+        if (target_channels != 1 && target_channels != 2 && channels != 1)
+            throw Error(WT_ERR_RUNTIME, "Impossible to convert from " + std::to_string(channels) + " to " +
+                                            std::to_string(target_channels));
+        if (target_channels < 1) throw Error(WT_ERR_VALUE, "wt_convert_audio: target_channels must be >= 1");
+        WT_CUDA(cudaSetDevice(device));
+        cudaStream_t s = (cudaStream_t)stream;
+        const long long Tout = wt_convert_audio_length(T, sr, target_sr);
+        if (B == 0 || Tout == 0) return WT_OK;
+        const int mix = target_channels == 1 ? 1 : 0;
+        if (sr == target_sr && !mix && channels == target_channels) {  // Resample(orig == new) returns its input
+            WT_CUDA(cudaMemcpyAsync(out, wav, (size_t)B * channels * T * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            return WT_OK;
+        }
+        const Table& t = get_table(device, sr, target_sr);
+        const long long by = B * target_channels;
+        if (by > 65535) throw Error(WT_ERR_VALUE, "wt_convert_audio: more than 65535 (clip, channel) rows per call");
+        static size_t attr_a = 48 * 1024, attr_b = 48 * 1024;
+        const size_t smem_t = ((size_t)(RT_FRAMES - 1) * t.orig + t.K) * sizeof(float);
+        const int threads_t = (RT_FRAMES / 4) * (t.new_ / 4);
+        if (t.new_ % 4 == 0 && threads_t <= 1024 && threads_t >= 32 && smem_t <= 160 * 1024) {
+            if (smem_t > attr_b) {
+                WT_CUDA(cudaFuncSetAttribute(resample_mix_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                attr_b = 160 * 1024;
+            }
+            const long long frames = (Tout + t.new_ - 1) / t.new_;
+            dim3 grid((unsigned)((frames + RT_FRAMES - 1) / RT_FRAMES), (unsigned)by);
+            resample_mix_tiled_kernel<<<grid, threads_t, smem_t, s>>>(wav, out, t.dev, channels, target_channels, mix, T, Tout,
+                                                                      t.orig, t.new_, t.width, t.K);
+        } else {
+            const int span_max = (RS_THREADS / t.new_ + 2) * t.orig + t.K;
+            const size_t smem = (size_t)span_max * sizeof(float);
+            if (smem > 200 * 1024) throw Error(WT_ERR_VALUE, "wt_convert_audio: resampling ratio too extreme for the on-chip window");
+            if (smem > attr_a) {
+                WT_CUDA(cudaFuncSetAttribute(resample_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_a = 200 * 1024;
+            }
+            dim3 grid((unsigned)((Tout + RS_THREADS - 1) / RS_THREADS), (unsigned)by);
+            resample_mix_kernel<<<grid, RS_THREADS, smem, s>>>(wav, out, t.dev, channels, target_channels, mix, T, Tout, t.orig,
+                                                               t.new_, t.width, t.K);
+        }
+        WT_CUDA(cudaGetLastError());
+        return WT_OK;
+    } catch (const Error& e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return WT_ERR_RUNTIME;
+    }
+}
+
+}  // extern "C"

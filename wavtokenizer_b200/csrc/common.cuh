@@ -14,6 +14,9 @@ struct Error : std::runtime_error {
     Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
 };
 
+// thread-local message behind wt_last_error() (model.cu)
+void set_last_error(const std::string& msg);
+
 #define WT_CUDA(expr)                                                                          \
     do {                                                                                       \
         cudaError_t _e = (expr);                                                               \

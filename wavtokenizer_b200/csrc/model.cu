@@ -21,6 +21,12 @@ namespace {
 
 thread_local std::string g_last_error;
 
+}  // namespace
+
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+
 constexpr int ENC_CHUNK_DEFAULT = 64;  // clips per encoder-front pass (early SEANet tensors: 9.2 MB per clip each)
 inline int enc_chunk() {
     static int v = [] {
