@@ -73,6 +73,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+// L2 prefetch of a tensor-map box (no shared-memory destination, no barrier): pulls the A rows of a k-block that is
+// still a few stages away from HBM into L2, so that the TMA load that later fills the freed stage is an L2 hit.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+
 // K-major, 128-byte swizzled operand tile (rows of 64 fp16 = 128 B, 8-row groups 1024 B apart):
 // start address >> 4 | LBO (ignored for swizzled K-major) | SBO = 1024 B | version 1 | SWIZZLE_128B.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -445,6 +453,8 @@ struct Cfg {
     // epilogue chunk width (columns per tcgen05.ld) of the generic path; the GELU fast path below uses 32
     static constexpr int CW = BN / G >= 16 ? 16 : 8;
     static constexpr int EPI_SMEM = 0;
+    // k-blocks of look-ahead for the L2 prefetch of the streamed (A) operand; the smem ring itself holds STAGES
+    static constexpr int PF = STAGES + 2;
 };
 
 struct Maps {
@@ -484,6 +494,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     const int total_tiles = per_batch * g.batch;
     const int nkb0 = g.seg[0].num_kb;
     const int num_kb = nkb0 + (g.nseg > 1 ? g.seg[1].num_kb : 0);
+    const int PF_DIST = g.prefetch ? C::PF : 0;
     const bool simple_tiles = !CL2 && total_tiles == m_tiles;  // one column tile, one batch: tile index = row tile
     // work distribution: CTA (or CTA pair) `wid` of `nworkers` takes work items wid, wid + nworkers, ...; an item is
     // one output tile, or in the cluster variant a pair of row tiles (2 mp, 2 mp + 1) x one column tile
@@ -564,6 +575,15 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                     } else {
                         tma_load_2d(sb, &maps.w[0], kb * kw, n0, full_bar(stage));
                         if (PASSES == 3) tma_load_2d(sb + b_plane, &maps.w[1], kb * kw, n0, full_bar(stage));
+                    }
+                    if (PF_DIST > 0 && kb + PF_DIST < num_kb) {  // A operand of a later k-block of this tile -> L2
+                        const int kf = kb + PF_DIST;
+                        const int sf = kf < nkb0 ? 0 : 1;
+                        const int kfl = sf ? kf - nkb0 : kf;
+                        const int kptf = g.seg[sf].kb_per_tap;
+                        const int tapf = kfl / kptf;
+                        tma_prefetch_2d(&maps.a[sf][0], (kfl - tapf * kptf) * kw, m0 + g.seg[sf].shift0 + tapf);
+                        if (PASSES == 3) tma_prefetch_2d(&maps.a[sf][1], (kfl - tapf * kptf) * kw, m0 + g.seg[sf].shift0 + tapf);
                     }
                     if (tile == wid) stamp(1 + kb);  // slots 1..16: producer issued k-block kb (first tile)
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }

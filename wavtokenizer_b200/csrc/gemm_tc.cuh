@@ -48,6 +48,8 @@ struct TcGemm {
     // k-block width in elements shared by all segments and W: 64 (128-byte swizzle rows), or 32 / 16 for narrow
     // operands (64- / 32-byte rows): TMA then moves only bytes that exist. num_kb / kb_per_tap count kw-wide blocks.
     int kw = 64;
+    // L2 prefetch of the A operand a few k-blocks ahead of the TMA ring (long-K GEMMs whose A streams from HBM)
+    int prefetch = 0;
     // batched mode (attention): `batch` independent problems of M x N x K; problem z reads A rows shifted by
     // z*a_brows, W rows shifted by z*w_brows and writes rows shifted by z*o_brows
     int batch = 1;

@@ -37,6 +37,10 @@ inline int enc_chunk() {
     return v;
 }
 #define ENC_CHUNK enc_chunk()
+inline int tc_prefetch() {
+    static const int v = [] { const char* e = std::getenv("WT_TC_PREFETCH"); return e ? std::atoi(e) : 0; }();
+    return v;
+}
 constexpr int ENC_GROUP = 1024; // clips per LSTM / final-conv / VQ pass (the recurrent GEMM's M)
 constexpr int DEC_CHUNK = 128;  // clips per decoder pass
 
@@ -840,6 +844,7 @@ void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, int
     const wt_config& c = h->cfg;
     auto halves = [&](size_t n) { return reinterpret_cast<__half*>(h->alloc((n + 1) / 2)); };
     auto run = [&](TcGemm& g) {
+        g.prefetch = tc_prefetch();
         Scope sc(h, CAT_ENC_CONV, s);
         launch_tap_gemm_tc(g, s);
     };
@@ -1126,6 +1131,7 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
         g.W_hi = whi; g.W_lo = wlo; g.M = (int)R; g.N = N; g.K = taps * Cin; g.passes = passes;
         g.bias = bias; g.act = act; g.gamma = gamma; g.res = res; g.ldres = ldo;
         g.out_f32 = of32; g.ldo = ldo; g.out_hi = ohi; g.out_lo = olo; g.ldh = ldh;
+        g.prefetch = tc_prefetch();
         Scope sc(h, r.cat, s);
         launch_tap_gemm_tc(g, s);
     };
