@@ -135,50 +135,6 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-// Warp-uniform issue: every lane of the role warp executes these with identical (uniform) operands and only the
-// leader's predicate is true. Issuing from inside an `if (lane == 0)` region instead makes the compiler wrap each
-// UTCHMMA / UTMALDG in an ELECT + BRA.U.ANY loop (one trip per active lane group) on the slow uniform datapath,
-// which costs the issuing thread on the order of 100 cycles per instruction and bounds every narrow-N GEMM.
-__device__ __forceinline__ void umma_f16_p(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                           uint32_t accumulate, uint32_t leader) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p, q;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "setp.ne.b32 q, %5, 0;\n"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_p(uint32_t bar, uint32_t leader) {
-    asm volatile(
-        "{\n"
-        ".reg .pred q;\n"
-        "setp.ne.b32 q, %1, 0;\n"
-        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
-        "}\n" ::"r"(bar), "r"(leader)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_p(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
-                                              uint32_t leader) {
-    asm volatile(
-        "{\n"
-        ".reg .pred q;\n"
-        "setp.ne.b32 q, %5, 0;\n"
-        "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
-        "}\n" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar), "r"(leader)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx_p(uint32_t bar, uint32_t bytes, uint32_t leader) {
-    asm volatile(
-        "{\n"
-        ".reg .pred q;\n"
-        "setp.ne.b32 q, %2, 0;\n"
-        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
-        "}\n" ::"r"(bar), "r"(bytes), "r"(leader)
-        : "memory");
-}
-
 // ---- 2-CTA cluster helpers (W tiles are loaded once per CTA pair and multicast into both CTAs) ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -242,12 +198,6 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[8]) {
 }
 
 // Exact-erf GELU (reference decoder/modules.py:35, nn.GELU()): see gelu_erf below.
-__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[4]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // Two accumulator chunks (hh + lh columns and the hl columns BN further) in flight behind ONE wait; the registers
 // pass through the wait ("+r") so that no use can be scheduled above it.
@@ -260,20 +210,6 @@ __device__ __forceinline__ void tmem_ld_pair(uint32_t a0, uint32_t (&r)[16], uin
                  : "r"(a1));
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
-                 :
-                 : "memory");
-}
-// Two accumulator chunks (hh + lh columns and the hl columns BN further) in flight behind ONE wait; the registers
-// pass through the wait ("+r") so that no use can be scheduled above it.
-__device__ __forceinline__ void tmem_ld_pair(uint32_t a0, uint32_t (&r)[8], uint32_t a1, uint32_t (&t)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(a0));
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7])
-                 : "r"(a1));
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7])
                  :
                  : "memory");
 }
@@ -452,7 +388,6 @@ struct Cfg {
     static constexpr int G = NEPI / 4 / NGRP;                    // epilogue warps per TMEM lane quarter per tile
     // epilogue chunk width (columns per tcgen05.ld) of the generic path; the GELU fast path below uses 32
     static constexpr int CW = BN / G >= 16 ? 16 : 8;
-    static constexpr int EPI_SMEM = 0;
     // k-blocks of look-ahead for the L2 prefetch of the streamed (A) operand; the smem ring itself holds STAGES
     static constexpr int PF = STAGES + 2;
 };
@@ -948,7 +883,6 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
     long long* dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? a.dbg : nullptr;
     const long long t_begin = dbg ? clock64() : 0;
     auto stamp = [&](int t, int slot) { if (dbg && t >= 4 && t < 8) dbg[(t - 4) * 8 + slot] = clock64() - t_begin; };
-    const int n_slices = gridDim.x;      // CTAs that share a batch tile
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < LSTM_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
