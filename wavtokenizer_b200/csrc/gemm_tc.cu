@@ -847,6 +847,7 @@ struct LstmArgs {
     float* cell;         // [B, D]
     int* counters;       // [m_tiles * L * LSTM_KB * LSTM_CNT_PITCH], zeroed before launch
     int B, L, D, m_tiles;
+    int t_begin, t_end;  // this launch runs steps [t_begin, t_end): h, c and the counters of earlier steps are in place
     long long* dbg;      // optional timeline of CTA (0,0): 8 stamps per step for steps 4..7
 };
 
@@ -910,7 +911,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
         }
         int stage = 0;
         uint32_t phase = 0;
-        for (int t = 1; t < a.L; ++t) {
+        for (int t = (a.t_begin > 1 ? a.t_begin : 1); t < a.t_end; ++t) {
             for (int mt = mg; mt < a.m_tiles; mt += MG) {
                 // k-block kb of h_{t-1} (hidden units [64 kb, 64 kb + 64)) is produced by the four CTAs ns = 4 kb ..
                 // 4 kb + 3 of this batch tile: wait for exactly those (one counter per k-block), so the loads of the
@@ -959,7 +960,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = 1; t < a.L; ++t) {
+        for (int t = (a.t_begin > 1 ? a.t_begin : 1); t < a.t_end; ++t) {
             for (int mt = mg; mt < a.m_tiles; mt += MG) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -996,7 +997,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
         const int u0 = ns * 16 + hw * 4;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = 0; t < a.L; ++t) {
+        for (int t = a.t_begin; t < a.t_end; ++t) {
             for (int mt = mg; mt < a.m_tiles; mt += MG) {
                 const int b = mt * BM + q * 32 + lane;
                 const bool row_ok = b < a.B;
@@ -1213,7 +1214,8 @@ void launch_cfg(const TcGemm& g, cudaStream_t s) {
     last_launch_info().flops = 2.0 * g.M * g.N * g.K * g.batch;
     if (CL2) {
         const int items = ((m_tiles + 1) / 2) * n_tiles;
-        const int grid = std::min(2 * items, std::min(num_sms() & ~1, max_ctas));
+        int grid = std::min(2 * items, std::min(num_sms() & ~1, max_ctas));
+        if (g.max_ctas > 0) grid = std::max(2, std::min(grid, g.max_ctas & ~1));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = s;
         cudaLaunchAttribute at[1];
@@ -1223,7 +1225,8 @@ void launch_cfg(const TcGemm& g, cudaStream_t s) {
         WT_CUDA(cudaLaunchKernelEx(&cfg, kernel, maps, g));
     } else {
         const int tiles = m_tiles * n_tiles * g.batch;
-        const int grid = tiles < num_sms() ? tiles : num_sms();
+        int grid = tiles < num_sms() ? tiles : num_sms();
+        if (g.max_ctas > 0) grid = std::max(1, std::min(grid, g.max_ctas));
         kernel<<<grid, NUM_THREADS, C::SMEM, s>>>(maps, g);
     }
     WT_CUDA(cudaGetLastError());
@@ -1303,7 +1306,8 @@ void launch_tap_gemm_tc(const TcGemm& g_in, cudaStream_t s) {
 size_t lstm_counter_ints(int B, int L) { return (size_t)((B + BM - 1) / BM) * L * LSTM_KB * LSTM_CNT_PITCH; }
 
 void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_lo, float* cell, int* counters,
-                            const __half* w_hi, const __half* w_lo, int B, int L, int D, cudaStream_t s) {
+                            const __half* w_hi, const __half* w_lo, int B, int L, int D, cudaStream_t s, int t_begin,
+                            int t_end) {
     if (D != 512) throw Error(4, "lstm_persistent: hidden size must be 512");
     static bool attr = false;
     if (!attr) {
@@ -1313,13 +1317,16 @@ void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_
     LstmArgs a;
     a.xin = xin; a.y = y; a.h_hi = h_hi; a.h_lo = h_lo; a.cell = cell; a.counters = counters;
     a.B = B; a.L = L; a.D = D; a.m_tiles = (B + BM - 1) / BM;
+    if (t_end < 0) t_end = L;
+    if (t_begin < 0 || t_begin >= t_end || t_end > L) throw Error(4, "lstm_persistent: bad step range");
+    a.t_begin = t_begin; a.t_end = t_end;
     a.dbg = g_debug_timeline ? g_debug_timeline + 148 * 64 : nullptr;  // after the generic GEMMs' per-CTA slots
     const int n_slices = 4 * D / 64;
     int mgroups = a.m_tiles;
     while (n_slices * mgroups > num_sms()) --mgroups;  // every CTA must be co-resident (they wait on each other)
     if (mgroups < 1) throw Error(4, "lstm_persistent: device too small");
     if (4 * D / 64 != LSTM_KB * 4 || LSTM_CTAS_PER_KB != 4 * LSTM_EPI_WARPS) throw Error(4, "lstm_persistent: slice / k-block mapping");
-    WT_CUDA(cudaMemsetAsync(counters, 0, lstm_counter_ints(B, L) * sizeof(int), s));
+    if (t_begin == 0) WT_CUDA(cudaMemsetAsync(counters, 0, lstm_counter_ints(B, L) * sizeof(int), s));
     CUtensorMap mh_hi = make_map(h_hi, (long long)L * B, D, D, BM);
     CUtensorMap mh_lo = make_map(h_lo, (long long)L * B, D, D, BM);
     CUtensorMap mw_hi = make_map(w_hi, 4LL * D, D, D, 64);
@@ -1327,6 +1334,13 @@ void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_
     void* args[] = {&mh_hi, &mh_lo, &mw_hi, &mw_lo, &a};
     WT_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_persistent_kernel, dim3(n_slices, mgroups), dim3(LSTM_THREADS),
                                         args, (size_t)LSTM_SMEM, s));
+}
+
+int lstm_ctas(int B, int D) {
+    const int n_slices = 4 * D / 64;
+    int mgroups = (B + BM - 1) / BM;
+    while (mgroups > 1 && n_slices * mgroups > num_sms()) --mgroups;
+    return n_slices * mgroups;
 }
 
 void launch_split_f16(const float* x, __half* hi, __half* lo, long long rows, int cols, long long ld_in,

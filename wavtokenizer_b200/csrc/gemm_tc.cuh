@@ -50,6 +50,9 @@ struct TcGemm {
     int kw = 64;
     // L2 prefetch of the A operand a few k-blocks ahead of the TMA ring (long-K GEMMs whose A streams from HBM)
     int prefetch = 0;
+    // cap on the persistent grid (0: one CTA per SM): lets the kernel share the GPU with a resident cooperative
+    // kernel (the LSTM wavefront) instead of queueing CTAs behind it
+    int max_ctas = 0;
     // batched mode (attention): `batch` independent problems of M x N x K; problem z reads A rows shifted by
     // z*a_brows, W rows shifted by z*w_brows and writes rows shifted by z*o_brows
     int batch = 1;
@@ -91,8 +94,12 @@ void launch_tap_gemm_tc(const TcGemm& g, cudaStream_t s);
 // One LSTM layer, all L steps, in a single cooperative launch (see gemm_tc.cu). Time-major tensors.
 // `counters` needs lstm_counter_ints(B, L) ints.
 size_t lstm_counter_ints(int B, int L);
+// Runs steps [t_begin, t_end) (t_end < 0: L); the counters are zeroed by the launch that starts at step 0, later
+// segments rely on h / c / counters of the earlier ones. lstm_ctas(B): CTAs the launch keeps resident.
 void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_lo, float* cell, int* counters,
-                            const __half* w_hi, const __half* w_lo, int B, int L, int D, cudaStream_t s);
+                            const __half* w_hi, const __half* w_lo, int B, int L, int D, cudaStream_t s, int t_begin = 0,
+                            int t_end = -1);
+int lstm_ctas(int B, int D);
 void launch_split_f16(const float* x, __half* hi, __half* lo, long long rows, int cols, long long ld_in,
                       long long ld_out, cudaStream_t s);
 

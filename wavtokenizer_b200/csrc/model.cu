@@ -122,6 +122,8 @@ struct wt_handle {
     // host-buffer entry point: copy stream + events so that H2D of encoder chunk i+1 overlaps the encoder of chunk
     // i and D2H of decoder chunk i overlaps the decoder of chunk i+1; hooks are set only inside that entry point
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;   // second layer of the LSTM wavefront (encoder_back_tc)
+    std::vector<cudaEvent_t> aux_evs;
     std::vector<cudaEvent_t> copy_evs;
     std::function<void(int /*first clip*/, int /*clips*/)> before_enc_chunk, after_dec_chunk;
     int* err_flag = nullptr;  // device
@@ -146,6 +148,8 @@ struct wt_handle {
         for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         for (auto e : ev_pool) cudaEventDestroy(e);
         for (auto e : copy_evs) cudaEventDestroy(e);
+        for (auto e : aux_evs) cudaEventDestroy(e);
+        if (aux_stream) cudaStreamDestroy(aux_stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         for (void* p : owned) cudaFree(p);
         if (arena) cudaFree(arena);
@@ -603,7 +607,10 @@ size_t enc_back_floats(const wt_config& c, int Bg, int L) {
     auto a = [&](size_t n) { tot += align_up(n * sizeof(float), 256) / sizeof(float); };
     const size_t M = (size_t)Bg * L, D = c.dimension;
     a(M * D);                                          // pre-LSTM rows of the group
-    a(M * 4 * D);                                      // xin
+    a(M * 4 * D);                                      // xin (layer 1)
+    a(M * 4 * D);                                      // xin (layer 2: the two layers overlap as a wavefront)
+    a((size_t)Bg * D);                                 // c (layer 2)
+    a(lstm_counter_ints(Bg, L) + 64);                  // counters (layer 2)
     for (int l = 0; l < c.lstm_layers; ++l) a(M * D);  // y_l
     a((size_t)Bg * 4 * D);                             // gates
     a((size_t)Bg * D);                                 // c
@@ -968,17 +975,70 @@ float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, con
     int* counters = reinterpret_cast<int*>(h->alloc(lstm_counter_ints(Bg, L) + 32));
     // all LSTM tensors are time-major: row t*Bg + b. Step t reads rows [(t-1)*Bg, t*Bg) of the hidden-state
     // planes through ONE tensor map (row shift (t-1)*Bg), so no descriptor is built inside the time loop.
+    static const bool stepwise = std::getenv("WT_LSTM_STEPWISE") != nullptr;
+    static const bool no_wave = std::getenv("WT_LSTM_NO_WAVEFRONT") != nullptr;
+    auto input_projection = [&](int l, const __half* ahi, const __half* alo, float* out, long long row0, long long rows,
+                                int max_ctas, cudaStream_t st) {
+        // xin = W_ih x + b_ih + b_hh for `rows` time-major rows (gate rows permuted like the recurrent tile)
+        const auto& w = h->lstm_tc[l];
+        TcGemm g;
+        g.seg[0] = tc_taps(ahi + row0 * D, alo + row0 * D, rows, D, D, 1, 0);
+        g.W_hi = w.w_ih.hi; g.W_lo = w.w_ih.lo; g.M = (int)rows; g.N = 4 * D; g.K = D; g.passes = 3;
+        g.bias = w.bias; g.out_f32 = out + row0 * 4 * D; g.ldo = 4 * D;
+        g.max_ctas = max_ctas;
+        Scope sc(h, CAT_LSTM, st);
+        launch_tap_gemm_tc(g, st);
+    };
+    const int lstm_sms = lstm_ctas(Bg, D);
+    int sms = 0;
+    WT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    const bool wavefront = !stepwise && !no_wave && c.lstm_layers == 2 && L >= 16 && 2 * lstm_sms <= sms;
+    if (wavefront) {
+        // Layer wavefront: the recurrence of either layer keeps only lstm_sms (64 of 148) SMs busy and
+        // is a pure latency chain, so the time axis is cut into NSEG segments and layer 2 of segment k runs on a second
+        // stream WHILE layer 1 runs segment k+1. Per segment on the main stream: layer-1 steps, then the layer-2 input
+        // projection of those steps on the SMs the resident layer-2 kernel leaves free (grid cap). 5 segment-times
+        // instead of 8 for NSEG = 4.
+        constexpr int NSEG = 4;
+        if (!h->aux_stream) WT_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+        while (h->aux_evs.size() < (size_t)NSEG + 2) {
+            cudaEvent_t e;
+            WT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h->aux_evs.push_back(e);
+        }
+        cudaStream_t s2 = h->aux_stream;
+        float* xin2 = h->alloc((size_t)M * 4 * D);
+        float* cst2 = h->alloc((size_t)Bg * D);
+        int* counters2 = reinterpret_cast<int*>(h->alloc(lstm_counter_ints(Bg, L) + 32));
+        // the second stream starts after everything queued so far (its buffers may still be read by earlier work)
+        WT_CUDA(cudaEventRecord(h->aux_evs[NSEG], s));
+        WT_CUDA(cudaStreamWaitEvent(s2, h->aux_evs[NSEG], 0));
+        input_projection(0, pre_hi, pre_lo, xin, 0, M, 0, s);
+        for (int k = 0; k < NSEG; ++k) {
+            const int t0 = (int)((long long)L * k / NSEG), t1 = (int)((long long)L * (k + 1) / NSEG);
+            {
+                Scope sc(h, CAT_LSTM, s);
+                launch_lstm_persistent(xin, ybuf[0], yh_hi[0], yh_lo[0], cst, counters, h->lstm_tc[0].w_hh.hi,
+                                       h->lstm_tc[0].w_hh.lo, Bg, L, D, s, t0, t1);
+            }
+            // layer-2 input projection of steps [t0, t1): leaves room for the layer-2 recurrence of segment k-1
+            input_projection(1, yh_hi[0], yh_lo[0], xin2, (long long)t0 * Bg, (long long)(t1 - t0) * Bg,
+                             k == 0 ? 0 : sms - lstm_sms, s);
+            WT_CUDA(cudaEventRecord(h->aux_evs[k], s));
+            WT_CUDA(cudaStreamWaitEvent(s2, h->aux_evs[k], 0));
+            {
+                Scope sc(h, CAT_LSTM, s2);
+                launch_lstm_persistent(xin2, ybuf[1], yh_hi[1], yh_lo[1], cst2, counters2, h->lstm_tc[1].w_hh.hi,
+                                       h->lstm_tc[1].w_hh.lo, Bg, L, D, s2, t0, t1);
+            }
+        }
+        WT_CUDA(cudaEventRecord(h->aux_evs[NSEG + 1], s2));
+        WT_CUDA(cudaStreamWaitEvent(s, h->aux_evs[NSEG + 1], 0));
+        lin_hi = yh_hi[1]; lin_lo = yh_lo[1];
+    } else
     for (int l = 0; l < c.lstm_layers; ++l) {
         const auto& w = h->lstm_tc[l];
-        {   // xin = W_ih x + b_ih + b_hh for all L steps at once (gate rows permuted like the recurrent tile)
-            TcGemm g;
-            g.seg[0] = tc_taps(lin_hi, lin_lo, M, D, D, 1, 0);
-            g.W_hi = w.w_ih.hi; g.W_lo = w.w_ih.lo; g.M = (int)M; g.N = 4 * D; g.K = D; g.passes = 3;
-            g.bias = w.bias; g.out_f32 = xin; g.ldo = 4 * D;
-            Scope sc(h, CAT_LSTM, s);
-            launch_tap_gemm_tc(g, s);
-        }
-        static const bool stepwise = std::getenv("WT_LSTM_STEPWISE") != nullptr;
+        input_projection(l, lin_hi, lin_lo, xin, 0, M, 0, s);
         if (!stepwise) {
             Scope sc(h, CAT_LSTM, s);
             launch_lstm_persistent(xin, ybuf[l], yh_hi[l], yh_lo[l], cst, counters, w.w_hh.hi, w.w_hh.lo, Bg, L, D, s);
