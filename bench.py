@@ -337,11 +337,69 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
                              f"{round(B * T * 171 / (ca_ms * 1e-3) / 1e12, 2)} TFMA/s achieved"}}}
     del raw, mono
 
+    def timed(fn, n):
+        for _ in range(2):
+            fn()
+        evp = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for a, b in evp:
+            flush.zero_()
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evp) / n
+
+    # ---- BASELINE.json configs[4]: VQ-only sweep (fused distance GEMM + argmin), 1e6 frames per GPU ----
+    n_vq = 1_000_000
+    cb = sd[spec.CODEBOOK_PREFIX + "0._codebook.embed"].to(dev)
+    g = torch.Generator(device=dev).manual_seed(11 + rank)
+    xs = cb[torch.randint(0, cb.shape[0], (n_vq,), device=dev, generator=g)]
+    xs = xs + 2e-3 * torch.randn(n_vq, cfg.dimension, device=dev, generator=g)
+    vq_ms = timed(lambda: model.vq(xs, return_quantized=False), args.steps)
+    vq_fl = 2.0 * n_vq * cfg.vq_bins * cfg.dimension
+    other = {"vq_only": {
+        "workload": f"{n_vq} frames x {cfg.dimension} fp32 vs {cfg.vq_bins} x {cfg.dimension} codebook per GPU, codes only",
+        "ms": round(vq_ms, 3), "frames_per_s": round(n_vq * world / (vq_ms * 1e-3), 1),
+        "roofline": {"bound": "tensor", "achieved": round(vq_fl / (vq_ms * 1e-3) / 1e12, 2), "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": round(vq_fl / (vq_ms * 1e-3) / 1e12 / peak_tf, 4),
+                     "executed_frac": round(3 * vq_fl / (vq_ms * 1e-3) / 1e12 / peak_tf, 4),
+                     "note": "4.194 algorithmic MFLOP per frame (SURVEY.md 8(d)); includes the fp32 -> split-fp16 "
+                             "plane conversion of the frames (2048 B read + 2048 B written per frame)"}}}
+    del xs
+    # ---- BASELINE.json configs[3]: decode-only detokenisation, 10 s random token streams (bounded: 256 per GPU) ----
+    n_st, l_st = 256, 750
+    rc = torch.randint(0, cfg.vq_bins, (1, n_st, l_st), device=dev, generator=g)
+    dec_ms = timed(lambda: model.decode(model.codes_to_features(rc), bandwidth_id=bw), args.steps)
+    other["decode_only"] = {
+        "workload": f"codes_to_features + decode of {n_st} random token streams x 10 s (L = {l_st}) per GPU",
+        "ms": round(dec_ms, 3), "audio_s_per_s": round(n_st * world * l_st * cfg.hop_length / SR / (dec_ms * 1e-3), 1),
+        "tokens_per_s": round(n_st * world * l_st / (dec_ms * 1e-3), 1)}
+    del rc
+
     if rank == 0:
         cpu = None
+        parity = None
         if world == 1 and not args.no_cpu:
             cpu_r = time_cpu(sd, cfg, CPU_SAMPLE_CLIPS, 2, 1)
             cpu = {k: cpu_r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            # BASELINE.json metric (iii): code match % of the measured path against the oracle on the same CPU sample
+            from oracle import wavtok_oracle as O  # checker only
+            wav_s = spec.synthetic_audio(CPU_SAMPLE_CLIPS, T, seed=100)
+            feats_n, codes_n = model.encode_infer(wav_s.to(dev), bandwidth_id=bw)
+            audio_n = model.decode(feats_n, bandwidth_id=bw)
+            with torch.inference_mode():
+                z = O.seanet_encoder(sd, cfg, wav_s.unsqueeze(1), library_lstm=True)
+                _, c_ref = O.vq_infer(sd, z)
+                a_ref = O.decode(sd, cfg, O.codes_to_features(sd, cfg, codes_n.cpu()), torch.tensor([0]))
+            rep = O.vq_tie_report(z.permute(0, 2, 1).reshape(-1, cfg.dimension), cb.cpu(), codes_n.cpu(), c_ref)
+            err = (a_ref - audio_n.cpu()).double()
+            parity = {"sample": f"{CPU_SAMPLE_CLIPS} x 3 s clips ({CPU_SAMPLE_CLIPS * L} frames), plan {args.plan} vs "
+                                "oracle/wavtok_oracle.py fp32",
+                      "code_match_pct": round(float(rep["match_pct"]), 4),
+                      "near_tie_mismatches": int(rep["near_ties"]),
+                      "hard_mismatches": int(rep["hard_mismatches"]),
+                      "waveform_snr_db": round(float(10 * torch.log10(a_ref.double().pow(2).sum() / err.pow(2).sum())), 2),
+                      "waveform_max_abs_err": float(err.abs().max())}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32" if args.plan == 0 else "split-f16x2 operands, f32 accumulate",
@@ -351,6 +409,7 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
                            "(> 10 GB) exceed the 126 MB L2", "sharding": f"by clip, {world} rank(s), all-gather of codes"},
                 "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "clocks": clocks.summary(), "breakdown": breakdown, "kernels": kernels, "next_rows": next_rows,
+                "other_configs": other, "parity_sample": parity,
                 "algorithmic_gflop_per_audio_s": round(sum(flops.values()) / 3 / 1e9, 3)}
         print(json.dumps(line), flush=True)
     if world > 1:

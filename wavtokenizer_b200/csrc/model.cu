@@ -999,7 +999,11 @@ float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, con
         // stream WHILE layer 1 runs segment k+1. Per segment on the main stream: layer-1 steps, then the layer-2 input
         // projection of those steps on the SMs the resident layer-2 kernel leaves free (grid cap). 5 segment-times
         // instead of 8 for NSEG = 4.
-        constexpr int NSEG = 4;
+        static const int NSEG = [] {
+            const char* e = std::getenv("WT_LSTM_NSEG");
+            const int v = e ? std::atoi(e) : 4;
+            return v < 2 ? 2 : (v > 16 ? 16 : v);
+        }();
         if (!h->aux_stream) WT_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
         while (h->aux_evs.size() < (size_t)NSEG + 2) {
             cudaEvent_t e;

@@ -15,7 +15,7 @@ from typing import Any, Dict, List, Optional, Tuple
 import torch
 from torch import nn
 
-from . import _native, spec
+from . import _native, ragged, spec
 from .spec import ModelConfig
 
 
@@ -316,6 +316,38 @@ class WavTokenizer(nn.Module):
             _native.check(_native.lib().wt_vq(h.ptr, x.data_ptr(), N, codes.data_ptr(),
                                               quant.data_ptr() if quant is not None else None, self._stream()))
         return codes, quant
+
+    @torch.inference_mode()
+    def encode_infer_ragged(self, clips, max_bucket: int = 0, **kwargs: Any):
+        """Clips of DIFFERENT lengths ([T_i] or [1, T_i] float32) -> per clip, in input order, exactly what the
+        reference's one-file-at-a-time loop returns (infer.py:44-54): ``(features [1, 512, L_i], codes [1, 1, L_i])``.
+        Equal-length clips are stacked and share one C-ABI call (``ragged.length_buckets``); nothing is padded."""
+        flat = []
+        for i, c in enumerate(clips):
+            if c.dim() == 2 and c.shape[0] == 1:
+                c = c[0]
+            if c.dim() != 1:
+                raise ValueError(f"clip {i}: expected [T] or [1, T], got {tuple(c.shape)}")
+            flat.append(c)
+
+        def fn(batch):
+            feats, codes = self.encode_infer(batch, **kwargs)
+            return (feats, 0), (codes, 1)
+        return [(f.unsqueeze(0), c.unsqueeze(1)) for f, c in ragged.run_bucketed(flat, fn, max_bucket)]
+
+    @torch.inference_mode()
+    def decode_ragged(self, features, max_bucket: int = 0, **kwargs: Any):
+        """Features of different lengths ([512, L_i] or [1, 512, L_i]) -> [audio [1, L_i * hop]] in input order,
+        each equal to a batch-of-one ``decode`` (reference decoder/pretrained.py:192-207)."""
+        flat = []
+        for i, f in enumerate(features):
+            if f.dim() == 3 and f.shape[0] == 1:
+                f = f[0]
+            if f.dim() != 2:
+                raise ValueError(f"features {i}: expected [C, L] or [1, C, L], got {tuple(f.shape)}")
+            flat.append(f)
+        return [a.unsqueeze(0) for (a,) in ragged.run_bucketed(
+            flat, lambda batch: ((self.decode(batch, **kwargs), 0),), max_bucket)]
 
     def encode_decode_host(self, wav_host: torch.Tensor, bandwidth_id: int = 0):
         """Whole hot path on HOST tensors (pinned recommended): H2D, encode, decode, D2H, sync.
