@@ -375,6 +375,21 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
         "ms": round(dec_ms, 3), "audio_s_per_s": round(n_st * world * l_st * cfg.hop_length / SR / (dec_ms * 1e-3), 1),
         "tokens_per_s": round(n_st * world * l_st / (dec_ms * 1e-3), 1)}
     del rc
+    # ---- SURVEY.md 8(f) row 1, second half: save_audio limiter + PCM_S 16 of the decoded batch ----
+    from wavtokenizer_b200 import pcm16
+    dec_audio = torch.randn(B, T, device=dev, generator=g) * 0.5
+    for mode in ("clamp", "rescale"):
+        p_ms = timed(lambda: pcm16(dec_audio, mode), args.steps)
+        p_bytes = dec_audio.numel() * (6 if mode == "clamp" else 10)
+        next_rows[f"save_audio_pcm16_{mode}"] = {
+            "workload": f"{B} clips x 3 s fp32 -> int16, limiter '{mode}' (encoder/utils.py:95-103)",
+            "ms": round(p_ms, 4), "audio_s_per_s": round(B * T / SR / (p_ms * 1e-3), 1),
+            "roofline": {"bound": "hbm", "achieved": round(p_bytes / (p_ms * 1e-3) / 1e9, 1), "peak": hbm_peak,
+                         "unit": "GB/s", "frac": round(p_bytes / (p_ms * 1e-3) / 1e9 / hbm_peak, 4),
+                         "algorithmic_bytes": p_bytes,
+                         "note": "4 B read + 2 B written per sample" + ("" if mode == "clamp" else
+                                 " + 4 B for the peak pass; two launches + a memset")}}
+    del dec_audio
 
     if rank == 0:
         cpu = None

@@ -139,6 +139,16 @@ int64_t wt_convert_audio_length(int64_t T, int64_t sr, int64_t target_sr);
 int wt_convert_audio(int32_t device, const float* wav, int64_t B, int32_t channels, int64_t T, int64_t sr,
                      int64_t target_sr, int32_t target_channels, float* out, void* stream);
 
+/* save_audio back-end: replaces the limiter of encoder/utils.py:95-103 and the
+ * float -> PCM_S 16 conversion inside torchaudio.save(..., encoding='PCM_S', bits_per_sample=16) (utils.py:103,
+ * infer.py:70). Handle-free. Each row of wav [B, T] (fp32 DEVICE memory) is one file. mode 0: no limiter
+ * (infer.py:70); 1: wav.clamp(-0.99, 0.99) (rescale=False); 2: wav * min(0.99 / max|wav|, 1) (rescale=True).
+ * peak [B] fp32 device (required for mode 2, where it receives max|wav| per file; unused otherwise); limited_out [B, T]
+ * (optional) the limited float samples handed to the writer; pcm_out [B, T] int16. The 16-bit conversion restates
+ * torchaudio 2.0.1 / libsox (round half up at 2^-16 of the 32-bit sample, clip at +32767); see csrc/audio_ops.cu. */
+int wt_save_audio_pcm16(int32_t device, const float* wav, int64_t B, int64_t T, int32_t mode, float* peak,
+                        float* limited_out, int16_t* pcm_out, void* stream);
+
 /* Kernel-level test hook for the tcgen05 tap-GEMM (handle-free; allocates and frees its own scratch,
  * synchronises). out[m, n] = epi(sum_{j<taps} sum_c A[m + j - (taps-1)/2, c] * W[n, j*Cin + c]) over the
  * rows of A [rows, Cin] (rows outside are zero); W [N, taps*Cin]; all pointers fp32 DEVICE memory; bias /

@@ -57,6 +57,7 @@ SYMBOLS = {
     "wt_timing_read": (ctypes.c_int, [_P, _I32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64)]),
     "wt_convert_audio_length": (_I64, [_I64, _I64, _I64]),
     "wt_convert_audio": (ctypes.c_int, [_I32, _P, _I64, _I32, _I64, _I64, _I64, _I32, _P, _P]),
+    "wt_save_audio_pcm16": (ctypes.c_int, [_I32, _P, _I64, _I64, _I32, _P, _P, _P, _P]),
     "wt_timing_read_kernel": (ctypes.c_int, [_P, _I32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64),
                                              ctypes.POINTER(ctypes.c_double)]),
     "wt_test_tap_gemm": (ctypes.c_int, [_I32, _P, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _I32, _I32, _P, _P, _P]),

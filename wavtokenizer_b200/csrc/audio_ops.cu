@@ -12,6 +12,7 @@
 // stored transposed [k][phase] so that consecutive threads (consecutive phases) read consecutive addresses.
 // Bound: HBM for the common ratios (K = 16..28 taps), fp32 FMA issue for 44.1 kHz -> 24 kHz (171 taps).
 #include <cmath>
+#include <cstdint>
 #include <map>
 #include <algorithm>
 #include <mutex>
@@ -187,6 +188,101 @@ const Table& get_table(int device, long long sr, long long target) {
     return cache.emplace(key, t).first->second;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// save_audio back-end (second half): the limiter of reference encoder/utils.py:95-103
+// fused with the float -> 16-bit signed PCM conversion behind torchaudio.save(..., encoding='PCM_S',
+// bits_per_sample=16) (also called bare in infer.py:70). Each row of wav [B, T] is one file.
+//   limiter (the reference's own arithmetic, pinned by goldens):
+//     mode 1  wav.clamp(-0.99, 0.99)
+//     mode 2  wav * min(0.99 / max|wav|, 1)   with torch's  scalar / tensor  = reciprocal(tensor) * scalar, in fp32
+//     mode 0  none (infer.py:70)
+//   quantiser (torchaudio==2.0.1 sox_io backend, NOT vendored and not runnable here: restated, parity unpinned):
+//     s32 = trunc(clamp(double(x) * 2^31, INT32_MIN, INT32_MAX));  s16 = s32 > INT32_MAX - 2^15 ? 32767
+//     : (uint32(s32 + 2^15) >> 16)      (libsox SOX_SAMPLE_TO_SIGNED_16BIT: round half up, clip at the top)
+// Memory-bound: 4 B read + 2 B written per sample (mode 2 reads twice; the second read is L2-resident for
+// batches below the 126 MB L2).
+constexpr int PCM_THREADS = 256, PCM_PER_THREAD = 8;
+
+__global__ void __launch_bounds__(PCM_THREADS)
+absmax_rows_kernel(const float* __restrict__ wav, long long T, int* __restrict__ peak_bits) {
+    __shared__ float red[PCM_THREADS / 32];
+    const float* row = wav + (long long)blockIdx.y * T;
+    const long long n0 = (long long)blockIdx.x * (PCM_THREADS * PCM_PER_THREAD) + threadIdx.x;
+    float m = 0.f;
+#pragma unroll
+    for (int k = 0; k < PCM_PER_THREAD; ++k) {
+        const long long n = n0 + (long long)k * PCM_THREADS;
+        if (n < T) m = fmaxf(m, fabsf(row[n]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 1; i < PCM_THREADS / 32; ++i) m = fmaxf(m, red[i]);
+        atomicMax(peak_bits + blockIdx.y, __float_as_int(m));  // non-negative floats order like their bit patterns
+    }
+}
+
+__device__ __forceinline__ int pcm16_sox(float x) {
+    // x * 2^31 is exact in fp32 (power-of-two scaling) and cvt.rzi.s32.f32 truncates toward zero and saturates to
+    // [INT32_MIN, INT32_MAX]: the same s32 as clamp(double(x) * 2^31).to(int32), without the fp64 pipe
+    const int s32 = __float2int_rz(x * 2147483648.f);
+    if (s32 > 2147483647 - 32768) return 32767;
+    return (int)(short)(unsigned short)(((unsigned int)s32 + 32768u) >> 16);
+}
+
+__device__ __forceinline__ float limit_sample(float v, int mode, float scale) {
+    if (mode == 1) return fminf(fmaxf(v, -0.99f), 0.99f);
+    if (mode == 2) return __fmul_rn(v, scale);
+    return v;
+}
+
+// VEC: every row starts 32-byte aligned (T % 8 == 0, aligned bases): a thread owns 8 consecutive samples, two
+// 16-byte loads and ONE 16-byte store of eight int16. Otherwise scalar, still coalesced.
+template <bool VEC>
+__global__ void __launch_bounds__(PCM_THREADS)
+limit_pcm16_kernel(const float* __restrict__ wav, long long T, int mode, const float* __restrict__ peak,
+                   float* __restrict__ limited, short* __restrict__ pcm) {
+    const long long base = (long long)blockIdx.y * T;
+    float scale = 1.f;
+    if (mode == 2) {
+        const float sc = __fmul_rn(__frcp_rn(peak[blockIdx.y]), 0.99f);  // 0.99 / mx as torch evaluates it
+        scale = 1.f < sc ? 1.f : sc;                                      // python min(tensor, 1)
+    }
+    if (VEC) {
+        const long long n = ((long long)blockIdx.x * PCM_THREADS + threadIdx.x) * PCM_PER_THREAD;
+        if (n >= T) return;
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(wav + base + n));
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(wav + base + n + 4));
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        unsigned int q[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = limit_sample(v[i], mode, scale);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            q[i] = ((unsigned int)pcm16_sox(v[2 * i]) & 0xFFFFu) | ((unsigned int)pcm16_sox(v[2 * i + 1]) << 16);
+        if (limited) {
+            *reinterpret_cast<float4*>(limited + base + n) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(limited + base + n + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        __stcs(reinterpret_cast<uint4*>(pcm + base + n), make_uint4(q[0], q[1], q[2], q[3]));
+    } else {
+        const long long n0 = (long long)blockIdx.x * (PCM_THREADS * PCM_PER_THREAD) + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < PCM_PER_THREAD; ++k) {
+            const long long n = n0 + (long long)k * PCM_THREADS;
+            if (n < T) {
+                const float v = limit_sample(wav[base + n], mode, scale);
+                if (limited) limited[base + n] = v;
+                pcm[base + n] = (short)pcm16_sox(v);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 }  // namespace wt
@@ -248,6 +344,39 @@ int wt_convert_audio(int32_t device, const float* wav, int64_t B, int32_t channe
             resample_mix_kernel<<<grid, RS_THREADS, smem, s>>>(wav, out, t.dev, channels, target_channels, mix, T, Tout, t.orig,
                                                                t.new_, t.width, t.K);
         }
+        WT_CUDA(cudaGetLastError());
+        return WT_OK;
+    } catch (const Error& e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return WT_ERR_RUNTIME;
+    }
+}
+
+int wt_save_audio_pcm16(int32_t device, const float* wav, int64_t B, int64_t T, int32_t mode, float* peak,
+                        float* limited_out, int16_t* pcm_out, void* stream) {
+    using namespace wt;
+    try {
+        if (!wav || !pcm_out) throw Error(WT_ERR_VALUE, "wt_save_audio_pcm16: null buffer");
+        if (B < 0 || T < 0) throw Error(WT_ERR_VALUE, "wt_save_audio_pcm16: bad sizes");
+        if (mode < 0 || mode > 2) throw Error(WT_ERR_VALUE, "wt_save_audio_pcm16: mode must be 0 (none), 1 (clamp) or 2 (rescale)");
+        if (mode == 2 && !peak) throw Error(WT_ERR_VALUE, "wt_save_audio_pcm16: rescale needs the per-file peak buffer");
+        if (B > 65535) throw Error(WT_ERR_VALUE, "wt_save_audio_pcm16: more than 65535 files per call");
+        if (B == 0 || T == 0) return WT_OK;
+        WT_CUDA(cudaSetDevice(device));
+        cudaStream_t s = (cudaStream_t)stream;
+        const long long per_block = (long long)PCM_THREADS * PCM_PER_THREAD;
+        dim3 grid((unsigned)((T + per_block - 1) / per_block), (unsigned)B);
+        if (peak && mode == 2) {
+            WT_CUDA(cudaMemsetAsync(peak, 0, (size_t)B * sizeof(float), s));
+            absmax_rows_kernel<<<grid, PCM_THREADS, 0, s>>>(wav, T, reinterpret_cast<int*>(peak));
+        }
+        const bool vec = T % PCM_PER_THREAD == 0 && ((uintptr_t)wav & 15) == 0 && ((uintptr_t)pcm_out & 15) == 0 &&
+                         (!limited_out || ((uintptr_t)limited_out & 15) == 0);
+        if (vec) limit_pcm16_kernel<true><<<grid, PCM_THREADS, 0, s>>>(wav, T, mode, peak, limited_out, pcm_out);
+        else limit_pcm16_kernel<false><<<grid, PCM_THREADS, 0, s>>>(wav, T, mode, peak, limited_out, pcm_out);
         WT_CUDA(cudaGetLastError());
         return WT_OK;
     } catch (const Error& e) {

@@ -73,7 +73,10 @@ __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
 // independent loads in flight each), 16 x B blocks so that the grid spreads evenly over the SMs. Pass 1
 // accumulates sum / sum-of-squares (combined in fp64), pass 2 re-reads the slab (L2-resident), normalises and
 // stores fp32 rows or split-fp16 planes with 8-byte vectors. Halo rows of the padded row space are written as zeros.
-constexpr int GN_GPB = 2, GN_LANES = GN_GPB * 6, GN_PH = 32, GN_THREADS = GN_LANES * GN_PH;
+// RES > 0: L <= RES * GN_PH, the thread's <= RES rows stay in registers between the two passes (all RES loads in
+// flight at once, no second read); RES == 0: any L, pass 2 re-reads the slab.
+constexpr int GN_GPB = 2, GN_LANES = GN_GPB * 6, GN_PH = 32, GN_THREADS = GN_LANES * GN_PH, GN_RES = 8;
+template <int RES>
 __global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                const float* __restrict__ bsh, RowOut out, int L, int Lp,
                                                                int C, float eps, int swish) {
@@ -85,11 +88,26 @@ __global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __re
     const int c = slab * (GN_GPB * 24) + lane * 4;
     const long long base = (long long)b * Lp * C + c;
     float s = 0.f, q = 0.f;
+    float4 keep[RES > 0 ? RES : 1];
+    if (RES > 0) {
+#pragma unroll
+        for (int i = 0; i < RES; ++i) {
+            const int t = ph + i * GN_PH;
+            keep[i] = t < L ? *reinterpret_cast<const float4*>(x + base + (long long)t * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < RES; ++i) {  // zero rows add nothing to either sum
+            const float4 v = keep[i];
+            s += (v.x + v.y) + (v.z + v.w);
+            q = fmaf(v.x, v.x, q); q = fmaf(v.y, v.y, q); q = fmaf(v.z, v.z, q); q = fmaf(v.w, v.w, q);
+        }
+    } else {
 #pragma unroll 4
-    for (int t = ph; t < L; t += GN_PH) {
-        const float4 v = *reinterpret_cast<const float4*>(x + base + (long long)t * C);
-        s += (v.x + v.y) + (v.z + v.w);
-        q = fmaf(v.x, v.x, q); q = fmaf(v.y, v.y, q); q = fmaf(v.z, v.z, q); q = fmaf(v.w, v.w, q);
+        for (int t = ph; t < L; t += GN_PH) {
+            const float4 v = *reinterpret_cast<const float4*>(x + base + (long long)t * C);
+            s += (v.x + v.y) + (v.z + v.w);
+            q = fmaf(v.x, v.x, q); q = fmaf(v.y, v.y, q); q = fmaf(v.z, v.z, q); q = fmaf(v.w, v.w, q);
+        }
     }
     ps[threadIdx.x] = s;
     pq[threadIdx.x] = q;
@@ -117,11 +135,9 @@ __global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __re
     __syncthreads();
     const float mean = s_mean[lane / 6], rstd = s_rstd[lane / 6];
     const float4 wv = *reinterpret_cast<const float4*>(w + c), bv = *reinterpret_cast<const float4*>(bsh + c);
-#pragma unroll 4
-    for (int t = ph; t < Lp; t += GN_PH) {
+    auto emit = [&](int t, const float4& v) {  // row t of the slab: normalised (+ swish) or, past L, a zero halo row
         float y[4] = {0.f, 0.f, 0.f, 0.f};
         if (t < L) {
-            const float4 v = *reinterpret_cast<const float4*>(x + base + (long long)t * C);
             y[0] = (v.x - mean) * rstd * wv.x + bv.x;
             y[1] = (v.y - mean) * rstd * wv.y + bv.y;
             y[2] = (v.z - mean) * rstd * wv.z + bv.z;
@@ -146,6 +162,19 @@ __global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __re
             *reinterpret_cast<uint2*>(out.hi + idx) = make_uint2(h[0], h[1]);
             if (out.lo) *reinterpret_cast<uint2*>(out.lo + idx) = make_uint2(l[0], l[1]);
         }
+    };
+    if (RES > 0) {
+#pragma unroll
+        for (int i = 0; i < RES; ++i) {
+            const int t = ph + i * GN_PH;
+            if (t < Lp) emit(t, keep[i]);
+        }
+        const int t = ph + RES * GN_PH;  // halo rows past RES * GN_PH (Lp <= L + GN_PH)
+        if (t < Lp) emit(t, make_float4(0.f, 0.f, 0.f, 0.f));
+    } else {
+#pragma unroll 4
+        for (int t = ph; t < Lp; t += GN_PH)
+            emit(t, t < L ? *reinterpret_cast<const float4*>(x + base + (long long)t * C) : make_float4(0.f, 0.f, 0.f, 0.f));
     }
 }
 
@@ -501,7 +530,8 @@ void launch_groupnorm(const float* x, const float* w, const float* b, RowOut out
     if (B <= 0 || L <= 0) return;
     if (groups != 32 || C != 768) throw Error(1, "groupnorm: expected GroupNorm(32, 768)");
     dim3 grid(C / (GN_GPB * 24), B);
-    groupnorm_kernel<<<grid, GN_THREADS, 0, s>>>(x, w, b, out, L, Lp, C, eps, swish);
+    if (L <= GN_RES * GN_PH && Lp <= L + GN_PH) groupnorm_kernel<GN_RES><<<grid, GN_THREADS, 0, s>>>(x, w, b, out, L, Lp, C, eps, swish);
+    else groupnorm_kernel<0><<<grid, GN_THREADS, 0, s>>>(x, w, b, out, L, Lp, C, eps, swish);
     WT_CUDA(cudaGetLastError());
 }
 
