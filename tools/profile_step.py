@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--plan", type=int, default=2)
     ap.add_argument("--tag", default="small320")
     ap.add_argument("--seconds", type=float, default=3.0)
+    ap.add_argument("--pcm", action="store_true", help="also run the save_audio back-end (clamp, rescale) on the output")
     args = ap.parse_args()
     m = native_model(args.tag, args.plan)
     T = int(args.seconds * 24000)
@@ -37,6 +38,10 @@ def main():
     f, c = m.encode_infer(wav, bandwidth_id=bw)
     a = m.decode(m.codes_to_features(c), bandwidth_id=bw)
     e1.record()
+    if args.pcm:
+        from wavtokenizer_b200 import pcm16
+        pcm16(a, "clamp")
+        pcm16(a, "rescale")
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStop()
     print(f"step: {e0.elapsed_time(e1):.2f} ms for {args.clips} clips x {args.seconds} s, plan {args.plan}, "
