@@ -295,3 +295,32 @@ def test_vq_sweep_one_million_frames(plan):
     ref = O.vq_quantize(x[sl].cpu(), cb)
     rep = O.vq_tie_report(x[sl].cpu(), cb, codes[sl].cpu(), ref)
     assert rep["hard_mismatches"] == 0 and rep["match_pct"] >= 98.0, rep
+
+
+def test_config3_rank_share_of_1024_clips():
+    """BASELINE.json configs[2]: the medium model, 8192 x 3 s clips over 8 ranks = 1024 clips per rank in one call.
+    Size-independent properties: the first and last 64 clips equal a separate 64-clip call (clips are independent;
+    group / chunk boundaries move), features are codebook rows, audio is finite; one clip is checked against the oracle."""
+    cfg, sd = helpers.model("medium")
+    m = native_model("medium", 2)
+    B = 1024
+    wav = spec.synthetic_audio(B, 72000, seed=91).cuda()
+    bw = torch.tensor([3]).cuda()
+    feats, codes = m.encode_infer(wav, bandwidth_id=bw)
+    assert codes.shape == (1, B, 225) and int(codes.min()) >= 0 and int(codes.max()) < cfg.vq_bins
+    for sl in (slice(0, 64), slice(B - 64, B)):
+        f2, c2 = m.encode_infer(wav[sl], bandwidth_id=bw)
+        assert torch.equal(c2[0], codes[0, sl])
+        assert torch.equal(f2, feats[sl])
+    audio = m.decode(feats, bandwidth_id=bw)
+    assert audio.shape == (B, 72000) and bool(torch.isfinite(audio).all())
+    a2 = m.decode(feats[B - 64:], bandwidth_id=bw)
+    assert helpers.snr_db(audio[B - 64:], a2) >= 90
+    i = 777
+    with torch.inference_mode():
+        z = O.seanet_encoder(sd, cfg, wav[i:i + 1].cpu().unsqueeze(1), library_lstm=True)
+        _, c_ref = O.vq_infer(sd, z)
+        a_ref = O.decode(sd, cfg, O.codes_to_features(sd, cfg, codes[:, i:i + 1].cpu()), torch.tensor([3]))
+    rep = O.vq_tie_report(z.permute(0, 2, 1).reshape(-1, 512), codebook(sd), codes[:, i:i + 1].cpu(), c_ref)
+    assert rep["hard_mismatches"] == 0 and rep["match_pct"] >= 98.0, rep
+    assert helpers.snr_db(a_ref, audio[i:i + 1].cpu()) >= SNR_BAR_DB
