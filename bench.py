@@ -10,6 +10,9 @@ each rank owns its own 256 clips; the only collective is the all-gather of codes
   e2e          same metric through the host-buffer C-ABI entry (pinned host wav in, codes+audio out)
   roofline     dominant contraction category, timed live with CUDA events on its stream
   cpu_baseline the CPU oracle port (oracle/) on a bounded sample of the same workload, host cores
+  parity_sample  code match % / waveform SNR of the measured path against the oracle on that CPU sample
+  other_configs  BASELINE.json's VQ-only sweep (1e6 frames) and decode-only detokenisation (256 x 10 s streams)
+  next_rows      SURVEY.md 8(f) row 1: convert_audio and the save_audio limiter + PCM16 back-end, HBM roofline each
 
 `--impl reference` times the reference algorithm's CPU port (oracle/, torch CPU ops, all host threads)
 on a bounded sample of the same workload: /root/reference is pure Python and does not exist on the GPU box.
@@ -87,25 +90,54 @@ def make_state(cfg, seed: int, encode_frames):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md clocks line). NVML (nvidia_ml_py) is
+    polled every 10 ms from a thread; if NVML cannot be loaded the same fields are read through nvidia-smi."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         self.index, self.rows, self._stop = index, [], threading.Event()
         self.thread = threading.Thread(target=self._run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            phys = int(ids[index]) if index < len(ids) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        bits = [getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8), getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)]
+        return [str(sm), str(self.max_sm)] + ["Active" if r & b else "Not Active" for b in bits]
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) == 6:
-                    self.rows.append(parts)
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                    parts = [p.strip() for p in out.strip().split(",")]
+                    if len(parts) == 6:
+                        self.rows.append(parts)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.01 if self.nvml is not None else 0.2)
 
     def __enter__(self):
         self.thread.start()
@@ -120,10 +152,9 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
         sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def oracle_step(sd, cfg, wav, bw):
@@ -273,6 +304,8 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
         breakdown[name] = {"ms": round(t_ms.value, 3), "launches": n.value,
                            "algorithmic_tflops": round(flops[name] * B / 1e12, 4),
                            "tflops_per_s": round(flops[name] * B / max(t_ms.value, 1e-9) / 1e9, 2)}
+    breakdown["lstm"]["note"] = ("the two LSTM layers run as a wavefront on two streams: ms sums intervals that overlap "
+                                 "in time (wall share of the step is about half of it)")
     # ---- same record per tcgen05 GEMM kernel variant (kern = BN * 10 + passes) ----
     kernels = {}
     for bn in (16, 32, 64, 128, 256):
