@@ -1052,6 +1052,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                     if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator is in registers: free it early
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
+                float4 c_out = cv, y_out = cv;
                 if (row_ok) {
                     const float xiv[4] = {xi.x, xi.y, xi.z, xi.w}, xfv[4] = {xf.x, xf.y, xf.z, xf.w};
                     const float xgv[4] = {xg.x, xg.y, xg.z, xg.w}, xov[4] = {xo.x, xo.y, xo.z, xo.w};
@@ -1071,8 +1072,8 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                     split2(hv[2], hv[3], h23, l23);
                     *reinterpret_cast<uint2*>(a.h_hi + row * a.D + u0) = make_uint2(h01, h23);
                     *reinterpret_cast<uint2*>(a.h_lo + row * a.D + u0) = make_uint2(l01, l23);
-                    *reinterpret_cast<float4*>(cr) = make_float4(cvv[0], cvv[1], cvv[2], cvv[3]);
-                    *reinterpret_cast<float4*>(a.y + row * a.D + u0) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                    c_out = make_float4(cvv[0], cvv[1], cvv[2], cvv[3]);
+                    y_out = make_float4(hv[0], hv[1], hv[2], hv[3]);
                 }
                 // publish h_t of this (batch tile, step): generic writes -> async-proxy (TMA) readers in other CTAs.
                 // Each warp arrives on its own (lanes fence, __syncwarp orders them before lane 0's release) on the
@@ -1086,6 +1087,12 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                     asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(cnt) : "memory");
                 }
                 if (threadIdx.x == 64) stamp(t, 6);  // published
+                // c_t (read back by this same thread at step t + 1) and y_t (read after the kernel) are stored AFTER the
+                // release: the fences above then only wait for the two h-plane stores the other CTAs are waiting for
+                if (row_ok) {
+                    *reinterpret_cast<float4*>(cr) = c_out;
+                    *reinterpret_cast<float4*>(a.y + row * a.D + u0) = y_out;
+                }
             }
         }
     }
