@@ -42,7 +42,16 @@ inline int tc_prefetch() {
     return v;
 }
 constexpr int ENC_GROUP = 1024; // clips per LSTM / final-conv / VQ pass (the recurrent GEMM's M)
-constexpr int DEC_CHUNK = 128;  // clips per decoder pass
+constexpr int DEC_CHUNK_DEFAULT = 128;  // clips per decoder pass (29 k rows: fp32 row tensors of 90 MB stay L2-resident)
+inline int dec_chunk() {
+    static const int v = [] {
+        const char* e = std::getenv("WT_DEC_CHUNK");
+        int n = e ? std::atoi(e) : DEC_CHUNK_DEFAULT;
+        return n >= 1 && n <= 1024 ? n : DEC_CHUNK_DEFAULT;
+    }();
+    return v;
+}
+#define DEC_CHUNK dec_chunk()
 
 struct ConvW {
     float* w = nullptr;  // [cout, k*cin], K index = tap*cin + c
