@@ -423,6 +423,21 @@ def run_native(args, rank: int, local_rank: int, world: int) -> None:
                          "note": "4 B read + 2 B written per sample" + ("" if mode == "clamp" else
                                  " + 4 B for the peak pass; two launches + a memset")}}
     del dec_audio
+    # ---- ragged input, 64 clips of 64 DISTINCT lengths (1 - 5 s), one bucket per clip ----
+    n_rag = 64
+    rag = [torch.randn(SR + i * (4 * SR // n_rag) + 7 * i, device=dev, generator=g).clamp_(-1, 1) for i in range(n_rag)]
+    rag_s = sum(x.numel() for x in rag) / SR
+
+    def rag_step(k):
+        enc = model.encode_infer_ragged(rag, streams=k, bandwidth_id=bw)
+        return model.decode_ragged([f for f, _ in enc], streams=k, bandwidth_id=bw)
+    ragged_row = {"workload": f"{n_rag} clips of {n_rag} distinct lengths, 1 - 5 s ({rag_s:.0f} audio-s): one batch-of-one "
+                              "bucket per clip, encode_infer_ragged + decode_ragged"}
+    for k in (1, 4):
+        r_ms = timed(lambda: rag_step(k), max(2, args.steps // 2))
+        ragged_row[f"streams_{k}"] = {"ms": round(r_ms, 2), "audio_s_per_s": round(rag_s / (r_ms * 1e-3), 1)}
+    next_rows["ragged_batches"] = ragged_row
+    del rag
 
     if rank == 0:
         cpu = None

@@ -35,6 +35,39 @@ def test_run_bucketed_scatter_matches_per_item_calls():
         ragged.run_bucketed([torch.zeros(2, 4), torch.zeros(3, 4)], fn)
 
 
+def test_assign_lanes_balances_samples():
+    b = ragged.length_buckets([9, 9, 5, 5, 5, 1, 3, 8])
+    lanes = ragged.assign_lanes(b, 2)
+    assert lanes == [0, 1, 1, 0, 0]  # loads: 18 | 8 + 15 = 23 ... then 3 and 1 go to the lighter lane
+    load = [0, 0]
+    for (n, idx), k in zip(b, lanes):
+        load[k] += n * len(idx)
+    assert abs(load[0] - load[1]) <= 9
+    assert ragged.assign_lanes(b, 1) == [0] * len(b)
+
+
+@pytest.mark.gpu
+def test_ragged_streams_give_identical_results():
+    from tests.gpu_util import native_model
+    from wavtokenizer_b200 import spec
+    m = native_model("small320", 2)
+    lens = [4000 + 777 * i for i in range(9)] + [4000, 4777]
+    wavs = [spec.synthetic_audio(1, n, seed=70 + i)[0].cuda() for i, n in enumerate(lens)]
+    bw = torch.tensor([1]).cuda()
+    one = m.encode_infer_ragged(wavs, bandwidth_id=bw)
+    three = m.encode_infer_ragged(wavs, streams=3, bandwidth_id=bw)
+    for (f1, c1), (f3, c3) in zip(one, three):
+        assert torch.equal(c1, c3) and torch.equal(f1, f3)
+    a1 = m.decode_ragged([f for f, _ in one], bandwidth_id=bw)
+    a3 = m.decode_ragged([f for f, _ in three], streams=3, bandwidth_id=bw)
+    torch.cuda.synchronize()
+    for x, y in zip(a1, a3):
+        assert torch.equal(x, y)
+    m.set_plan(0)  # replicas follow the plan
+    z = m.encode_infer_ragged(wavs[:4], streams=2, bandwidth_id=bw)
+    assert all(torch.equal(c, c1) for (_, c), (_, c1) in zip(z, one[:4]))
+
+
 @pytest.mark.gpu
 def test_ragged_batch_matches_one_clip_at_a_time_oracle():
     from oracle import wavtok_oracle as O

@@ -149,6 +149,8 @@ class WavTokenizer(nn.Module):
         if getattr(self, "_handle", None) is not None:
             self._handle.close()
         self._handle = None
+        self.__dict__.pop("_plan", None)          # a new handle starts on the library's default plan
+        self.__dict__.pop("_ragged_lanes", None)  # replicas hold copies of the old weights
 
     # ------------------------------------------------------------------ native plumbing
     @property
@@ -182,6 +184,9 @@ class WavTokenizer(nn.Module):
 
     def set_plan(self, plan: int) -> None:
         _native.check(_native.lib().wt_set_plan(self.native().ptr, int(plan)))
+        self.__dict__["_plan"] = int(plan)
+        for lane in self.__dict__.get("_ragged_lanes", []):
+            lane[2].set_plan(plan)
 
     def _bandwidth_index(self, kwargs: Dict[str, Any], need_list_semantics: bool) -> int:
         if "bandwidth_id" not in kwargs or kwargs["bandwidth_id"] is None:
@@ -317,11 +322,34 @@ class WavTokenizer(nn.Module):
                                               quant.data_ptr() if quant is not None else None, self._stream()))
         return codes, quant
 
+    def _lanes(self, n: int):
+        """``n`` (model, stream) lanes for ragged input: lane 0 is this model on the caller's stream, the others are
+        replicas with their own native handle, workspace and stream (a handle serves one stream at a time, SURVEY.md
+        8(b) threading contract)."""
+        lanes = self.__dict__.setdefault("_ragged_lanes", [])
+        dev = self.device
+        if lanes and (lanes[0][0] != dev or lanes[0][1] != id(self._handle)):
+            lanes.clear()  # device or weights changed: rebuild the replicas
+        while len(lanes) < n - 1:
+            m = WavTokenizer(self.cfg, self.config_path)
+            m.load_state_dict(self.state_dict())
+            m = m.to(dev)
+            m.set_plan(self.plan())
+            lanes.append((dev, id(self._handle), m, torch.cuda.Stream(device=dev)))
+        models = [self] + [lane[2] for lane in lanes[:n - 1]]
+        streams = [torch.cuda.current_stream(dev)] + [lane[3] for lane in lanes[:n - 1]]
+        return models, streams
+
+    def plan(self) -> int:
+        return int(self.__dict__.get("_plan", 2))
+
     @torch.inference_mode()
-    def encode_infer_ragged(self, clips, max_bucket: int = 0, **kwargs: Any):
+    def encode_infer_ragged(self, clips, max_bucket: int = 0, streams: int = 1, **kwargs: Any):
         """Clips of DIFFERENT lengths ([T_i] or [1, T_i] float32) -> per clip, in input order, exactly what the
         reference's one-file-at-a-time loop returns (infer.py:44-54): ``(features [1, 512, L_i], codes [1, 1, L_i])``.
-        Equal-length clips are stacked and share one C-ABI call (``ragged.length_buckets``); nothing is padded."""
+        Equal-length clips are stacked and share one C-ABI call (``ragged.length_buckets``); nothing is padded.
+        ``streams`` > 1 runs the buckets on that many CUDA streams (one model replica each) so that small buckets,
+        which cannot fill the GPU alone, overlap."""
         flat = []
         for i, c in enumerate(clips):
             if c.dim() == 2 and c.shape[0] == 1:
@@ -330,13 +358,21 @@ class WavTokenizer(nn.Module):
                 raise ValueError(f"clip {i}: expected [T] or [1, T], got {tuple(c.shape)}")
             flat.append(c)
 
-        def fn(batch):
-            feats, codes = self.encode_infer(batch, **kwargs)
-            return (feats, 0), (codes, 1)
-        return [(f.unsqueeze(0), c.unsqueeze(1)) for f, c in ragged.run_bucketed(flat, fn, max_bucket)]
+        def make(model):
+            def fn(batch):
+                feats, codes = model.encode_infer(batch, **kwargs)
+                return (feats, 0), (codes, 1)
+            return fn
+        if streams > 1 and len(flat) > 1:
+            self.native()
+            models, sts = self._lanes(int(streams))
+            out = ragged.run_bucketed(flat, [make(m) for m in models], max_bucket, sts)
+        else:
+            out = ragged.run_bucketed(flat, make(self), max_bucket)
+        return [(f.unsqueeze(0), c.unsqueeze(1)) for f, c in out]
 
     @torch.inference_mode()
-    def decode_ragged(self, features, max_bucket: int = 0, **kwargs: Any):
+    def decode_ragged(self, features, max_bucket: int = 0, streams: int = 1, **kwargs: Any):
         """Features of different lengths ([512, L_i] or [1, 512, L_i]) -> [audio [1, L_i * hop]] in input order,
         each equal to a batch-of-one ``decode`` (reference decoder/pretrained.py:192-207)."""
         flat = []
@@ -346,8 +382,16 @@ class WavTokenizer(nn.Module):
             if f.dim() != 2:
                 raise ValueError(f"features {i}: expected [C, L] or [1, C, L], got {tuple(f.shape)}")
             flat.append(f)
-        return [a.unsqueeze(0) for (a,) in ragged.run_bucketed(
-            flat, lambda batch: ((self.decode(batch, **kwargs), 0),), max_bucket)]
+
+        def make(model):
+            return lambda batch: ((model.decode(batch, **kwargs), 0),)
+        if streams > 1 and len(flat) > 1:
+            self.native()
+            models, sts = self._lanes(int(streams))
+            out = ragged.run_bucketed(flat, [make(m) for m in models], max_bucket, sts)
+        else:
+            out = ragged.run_bucketed(flat, make(self), max_bucket)
+        return [a.unsqueeze(0) for (a,) in out]
 
     def encode_decode_host(self, wav_host: torch.Tensor, bandwidth_id: int = 0):
         """Whole hot path on HOST tensors (pinned recommended): H2D, encode, decode, D2H, sync.

@@ -36,11 +36,25 @@ def length_buckets(lengths: Sequence[int], max_bucket: int = 0) -> List[Tuple[in
     return out
 
 
-def run_bucketed(items: Sequence[torch.Tensor], fn: Callable[[torch.Tensor], Tuple[torch.Tensor, ...]],
-                 max_bucket: int = 0) -> List[Tuple[torch.Tensor, ...]]:
-    """Stack ``items`` (tensors whose LAST dimension is the ragged one, equal leading shape) per length
-    bucket, call ``fn(batch)`` -> tuple of tensors with a batch dimension ``dims[k]``, and return the
-    per-item slices in input order. ``fn`` returns ``(tensor, batch_dim)`` pairs."""
+def assign_lanes(buckets: Sequence[Tuple[int, List[int]]], n_lanes: int) -> List[int]:
+    """Lane (stream) of every bucket: greedy longest-processing-time on samples per bucket (buckets arrive longest
+    first), so that the lanes finish together."""
+    load = [0] * max(1, n_lanes)
+    lanes = []
+    for n, idx in buckets:
+        k = min(range(len(load)), key=lambda i: (load[i], i))
+        lanes.append(k)
+        load[k] += n * len(idx)
+    return lanes
+
+
+def run_bucketed(items: Sequence[torch.Tensor], fn, max_bucket: int = 0, streams=None) -> List[Tuple[torch.Tensor, ...]]:
+    """Stack ``items`` (tensors whose LAST dimension is the ragged one, equal leading shape) per length bucket, call
+    ``fn(batch)`` -> tuple of ``(tensor, batch_dim)`` pairs, and return the per-item slices in input order.
+
+    With ``streams`` (a list of CUDA streams) ``fn`` is a list of callables, one per stream: bucket j runs
+    ``fn[lane](batch)`` on ``streams[lane]`` (``assign_lanes``), so that small buckets - which cannot fill the GPU on
+    their own - overlap. Every lane first waits for the caller's stream and the caller's stream waits for every lane."""
     if len(items) == 0:
         return []
     lead = items[0].shape[:-1]
@@ -48,9 +62,26 @@ def run_bucketed(items: Sequence[torch.Tensor], fn: Callable[[torch.Tensor], Tup
         if t.shape[:-1] != lead:
             raise ValueError(f"item {i} has shape {tuple(t.shape)}, expected {tuple(lead)} + [length]")
     results: List = [None] * len(items)
-    for _, idx in length_buckets([t.shape[-1] for t in items], max_bucket):
-        batch = torch.stack([items[i] for i in idx], dim=0)
-        outs = fn(batch)
+    buckets = length_buckets([t.shape[-1] for t in items], max_bucket)
+    if not streams:
+        for _, idx in buckets:
+            outs = fn(torch.stack([items[i] for i in idx], dim=0))
+            for k, i in enumerate(idx):
+                results[i] = tuple(o.select(d, k) for o, d in outs)
+        return results
+    cur = torch.cuda.current_stream(items[0].device)
+    batches = [torch.stack([items[i] for i in idx], dim=0) for _, idx in buckets]  # on the caller's stream
+    for st in streams:
+        st.wait_stream(cur)  # fork: the lanes start once the stacked inputs exist
+    for (_, idx), lane, batch in zip(buckets, assign_lanes(buckets, len(streams)), batches):
+        st = streams[lane]
+        batch.record_stream(st)
+        with torch.cuda.stream(st):
+            outs = fn[lane](batch)
+        for o, _ in outs:
+            o.record_stream(cur)  # allocated on the lane, consumed on the caller's stream
         for k, i in enumerate(idx):
             results[i] = tuple(o.select(d, k) for o, d in outs)
+    for st in streams:
+        cur.wait_stream(st)  # join
     return results
