@@ -92,6 +92,13 @@ int wt_encoder_forward(wt_handle* h, const float* wav, int32_t B, int32_t T, flo
 int wt_codes_to_features(wt_handle* h, const int64_t* codes, int32_t K, int32_t B, int32_t L,
                          float* features_out, void* stream);
 
+/* An out-of-range code (>= vq_bins; the reference raises IndexError from the embedding lookup, pretrained.py:236) is
+ * detected by the gather kernel and recorded in a sticky device flag. wt_codes_to_features does NOT synchronise to
+ * read it (the call stays asynchronous, like the reference on a CUDA device where the index assert is asynchronous
+ * too): the error is reported, as WT_ERR_INDEX, by the next call on the handle that finds the flag's read-back
+ * complete, by wt_encode_decode_host (which synchronises anyway), or by wt_check_errors, which waits for it. */
+int wt_check_errors(wt_handle* h);
+
 /* WavTokenizer.decode (decoder/pretrained.py:192-207): features [B, dimension, L] ->
  * audio [B, L*hop_length]. One bandwidth_id for the whole batch (decoder/modules.py:81-86). */
 int wt_decode(wt_handle* h, const float* features, int32_t B, int32_t L, int32_t bandwidth_id,
@@ -128,6 +135,12 @@ int wt_timing_read(wt_handle* h, int32_t category, double* total_ms, int64_t* n_
 /* Same record, summed per tcgen05 GEMM kernel variant: kern = BN * 10 + passes (2563 = tap_gemm_tc_kernel<256, 3>);
  * flops = algorithmic 2*M*N*K of those launches (split-precision passes not counted). */
 int wt_timing_read_kernel(wt_handle* h, int32_t kern, double* total_ms, int64_t* n_launches, double* flops);
+/* The other kernels of the step carry ids below 100: 1 lstm_persistent_kernel (flops = 16*D*D per clip and step),
+ * 2 resblock0_fused_kernel, 3 groupnorm_kernel, 4 dwconv_ln_kernel, 5 layernorm_kernel, 6 spectral_kernel,
+ * 7 overlap_add_kernel, 8 softmax_planes_kernel, 9 vt_planes_kernel, 10 features_to_rows_kernel,
+ * 11 codes_to_features_kernel, 12 lstm_skip_elu_pad_kernel. For these `bytes` is the ALGORITHMIC (compulsory) HBM
+ * traffic of the launches: the numerator of their bandwidth roofline. */
+int wt_timing_read_kernel_bytes(wt_handle* h, int32_t kern, double* total_ms, int64_t* n_launches, double* bytes);
 
 /* convert_audio front-end: replaces encoder/utils.py:79-92, i.e. the channel mix
  * (target_channels == 1: mean over channels; == 2 or mono input: expand) followed by

@@ -20,8 +20,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
-sys.path.insert(0, ROOT)
-sys.path.insert(1, REF)
+# the reference's own decoder/ and encoder/ packages must win over the repo's import-path shims of the same name
+sys.path.insert(0, REF)
+sys.path.insert(1, ROOT)
 warnings.filterwarnings("ignore")
 
 from wavtokenizer_b200 import spec  # noqa: E402

@@ -58,11 +58,40 @@ def test_checkpoint_round_trip_with_foreign_keys(tmp_path):
     got = m.state_dict()
     for k, v in sd.items():
         assert torch.equal(got[k], v), k
-    # folder averaging (from_pretrained0911) of two identical checkpoints is the identity
-    torch.save({"state_dict": ckpt}, tmp_path / "b.ckpt")
-    os.rename(path, tmp_path / "a.ckpt")
-    m2 = WavTokenizer.from_pretrained0911(config_path("small600"), str(tmp_path))
-    assert torch.equal(m2.state_dict()["head.out.weight"], sd["head.out.weight"])
+
+
+def test_from_pretrained0911_averages_the_three_best_vocos_checkpoints(tmp_path, monkeypatch):
+    """Reference decoder/pretrained.py:117-156: only 'vocos_*' files, ranked by the val-loss string in the file name
+    ([-11:-5]), best three averaged; anything else in the folder is ignored."""
+    cfg, sd = model("small600")
+    names = {"vocos_checkpoint_epoch=1_step=10_val_loss=5.3000.ckpt": 3.0,
+             "vocos_checkpoint_epoch=2_step=20_val_loss=5.1000.ckpt": 1.0,
+             "vocos_checkpoint_epoch=3_step=30_val_loss=9.9000.ckpt": 100.0,   # fourth best: dropped
+             "vocos_checkpoint_epoch=4_step=40_val_loss=5.2000.ckpt": 2.0,
+             "last.ckpt": 1000.0, "notes.txt": 1000.0}                          # no 'vocos_' prefix: ignored
+    for n in names:
+        (tmp_path / n).write_bytes(b"")
+    real_load = torch.load
+
+    def fake_load(path, *a, **k):
+        base = os.path.basename(str(path))
+        if base not in names:
+            return real_load(path, *a, **k)
+        d = {k2: v.clone() for k2, v in sd.items()}
+        d["head.out.bias"] = torch.full_like(sd["head.out.bias"], names[base])
+        d["discriminator.x"] = torch.zeros(1)
+        return {"state_dict": d}
+    monkeypatch.setattr(torch, "load", fake_load)
+    m = WavTokenizer.from_pretrained0911(config_path("small600"), str(tmp_path))
+    got = m.state_dict()
+    assert torch.equal(got["head.out.bias"], torch.full_like(sd["head.out.bias"], 2.0))  # mean of 1, 2, 3
+    assert torch.allclose(got["head.out.weight"], sd["head.out.weight"], rtol=0, atol=1e-7)
+    assert not m.training
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    (empty / "model.ckpt").write_bytes(b"")
+    with pytest.raises(FileNotFoundError):
+        WavTokenizer.from_pretrained0911(config_path("small600"), str(empty))
 
 
 def test_strict_load_rejects_missing_hot_path_key():
@@ -114,3 +143,17 @@ def test_bandwidth_id_semantics():
         m._bandwidth_index({}, False)
     with pytest.raises(TypeError):
         m._bandwidth_index({}, True)
+
+
+def test_reference_import_paths_resolve_to_the_native_classes():
+    """`from decoder.pretrained import WavTokenizer` / `from encoder.utils import convert_audio` (reference
+    README.md:50-53, infer.py:5-6) work unedited through the repo's shim packages."""
+    import importlib
+    import wavtokenizer_b200
+    dp = importlib.import_module("decoder.pretrained")
+    eu = importlib.import_module("encoder.utils")
+    assert dp.WavTokenizer is wavtokenizer_b200.WavTokenizer
+    assert eu.convert_audio is wavtokenizer_b200.convert_audio and eu.save_audio is wavtokenizer_b200.save_audio
+    for name in ("from_pretrained0802", "from_pretrained0911", "from_hparams0802", "encode_infer", "codes_to_features",
+                 "decode", "encode", "forward"):
+        assert hasattr(dp.WavTokenizer, name), name

@@ -73,8 +73,7 @@ def test_every_stage_matches_reference_taps(setup):
     taps.close()
     assert helpers.snr_db(torch.from_numpy(g["e2e_z"]), z) >= STAGE_BAR_DB[plan]
     rep = O.vq_tie_report(z.permute(0, 2, 1).reshape(-1, cfg.dimension), codebook(sd), codes.cpu(), ref_codes)
-    assert rep["hard_mismatches"] == 0, rep
-    assert rep["match_pct"] >= 98.0, rep
+    helpers.assert_code_parity(rep)
     # features are exactly the codebook rows of the returned codes (reference: torch.equal)
     assert codes.shape == (1, 2, cfg.frames_for(int(g["e2e_T"]))) and codes.dtype == torch.int64
     assert torch.equal(feats.cpu(), O.codes_to_features(sd, cfg, codes.cpu()))
@@ -92,7 +91,7 @@ def test_three_second_clip(setup):
     with torch.inference_mode():
         z = O.seanet_encoder(sd, cfg, wav.cpu().unsqueeze(1), library_lstm=True)
     rep = O.vq_tie_report(z.permute(0, 2, 1).reshape(-1, cfg.dimension), codebook(sd), codes.cpu(), ref_codes)
-    assert rep["hard_mismatches"] == 0 and rep["match_pct"] >= 98.0, rep
+    helpers.assert_code_parity(rep)
     audio = m.decode(m.codes_to_features(ref_codes.cuda()), bandwidth_id=bw)
     assert audio.shape == (1, 72000)
     assert helpers.snr_db(torch.from_numpy(g["c3s_audio_sub16"]), audio.cpu()[:, ::16]) >= SNR_BAR_DB
@@ -176,7 +175,7 @@ def test_vq_matches_oracle_on_calibration_like_frames():
     codes, quant = m.vq(x.cuda())
     ref = O.vq_quantize(x, cb)
     rep = O.vq_tie_report(x, cb, codes.cpu(), ref)
-    assert rep["hard_mismatches"] == 0 and rep["match_pct"] >= 98.0, rep
+    helpers.assert_code_parity(rep)
     assert torch.equal(quant.cpu(), cb[codes.cpu()])
     # exact ties resolve to the first index like torch.max (core_vq.py:182)
     cb2 = cb.clone()
@@ -208,8 +207,18 @@ def test_error_behaviour_mirrors_reference(setup):
         m.decode(torch.zeros(1, 512, 4).cuda())
     with pytest.raises(IndexError):
         m.decode(torch.zeros(1, 512, 4).cuda(), bandwidth_id=torch.tensor([4]).cuda())
+    # an out-of-range code: the call itself stays asynchronous (no host sync in the middle of a step; on a CUDA
+    # device the reference's embedding assert is asynchronous too), the IndexError is raised by check_errors() ...
+    bad = torch.full((1, 1, 4), 4096, dtype=torch.int64).cuda()
+    m.codes_to_features(bad)
     with pytest.raises(IndexError):
-        m.codes_to_features(torch.full((1, 1, 4), 4096, dtype=torch.int64).cuda())
+        m.check_errors()
+    m.check_errors()  # reported once, then clear
+    # ... or by the next call on the model once the flag's read-back has landed
+    m.codes_to_features(bad)
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):
+        m.decode(torch.zeros(1, 512, 4).cuda(), bandwidth_id=bw)
     # the C ABI itself reports the same classes
     lib, h = _native.lib(), m.native().ptr
     buf = torch.zeros(16).cuda()
@@ -256,7 +265,7 @@ def test_full_size_properties(plan):
         _, c_ref = O.vq_infer(sd, z)
         a_ref = O.decode(sd, cfg, O.codes_to_features(sd, cfg, codes[:, idx].cpu()), torch.tensor([0]))
     rep = O.vq_tie_report(z.permute(0, 2, 1).reshape(-1, 512), codebook(sd), codes[:, idx].cpu(), c_ref)
-    assert rep["hard_mismatches"] == 0 and rep["match_pct"] >= 98.0, rep
+    helpers.assert_code_parity(rep)
     assert helpers.snr_db(a_ref, audio[idx].cpu()) >= SNR_BAR_DB
 
 
@@ -294,7 +303,7 @@ def test_vq_sweep_one_million_frames(plan):
     sl = slice(123_000, 127_000)
     ref = O.vq_quantize(x[sl].cpu(), cb)
     rep = O.vq_tie_report(x[sl].cpu(), cb, codes[sl].cpu(), ref)
-    assert rep["hard_mismatches"] == 0 and rep["match_pct"] >= 98.0, rep
+    helpers.assert_code_parity(rep)
 
 
 def test_config3_rank_share_of_1024_clips():
@@ -322,5 +331,38 @@ def test_config3_rank_share_of_1024_clips():
         _, c_ref = O.vq_infer(sd, z)
         a_ref = O.decode(sd, cfg, O.codes_to_features(sd, cfg, codes[:, i:i + 1].cpu()), torch.tensor([3]))
     rep = O.vq_tie_report(z.permute(0, 2, 1).reshape(-1, 512), codebook(sd), codes[:, i:i + 1].cpu(), c_ref)
-    assert rep["hard_mismatches"] == 0 and rep["match_pct"] >= 98.0, rep
+    helpers.assert_code_parity(rep)
     assert helpers.snr_db(a_ref, audio[i:i + 1].cpu()) >= SNR_BAR_DB
+
+
+@pytest.mark.parametrize("tag", helpers.TAGS)
+def test_parity_report_48_clips(tag):
+    """BASELINE.json metric (iii) as a test (tools/parity_report.py at 48 x 3 s clips per YAML, the default plan 2):
+    code match % against the fp32 oracle with near-tie accounting under BOTH definitions, latent and waveform SNR.
+    The agreement floor is what the path achieves at benchmark scale (99.93 %, profiles/) minus a margin."""
+    cfg, sd = helpers.model(tag)
+    m = native_model(tag, 2)
+    clips = 48
+    wav = spec.synthetic_audio(clips, 72000, seed=2024)
+    bw = torch.tensor([1])
+    feats, codes = m.encode_infer(wav.cuda(), bandwidth_id=bw.cuda())
+    audio = m.decode(feats, bandwidth_id=bw.cuda()).cpu()
+    z_nat = m._encoder_forward(wav.cuda()).cpu()
+    codes = codes.cpu()
+    zs, cs, auds = [], [], []
+    with torch.inference_mode():
+        for i in range(0, clips, 16):
+            z = O.seanet_encoder(sd, cfg, wav[i:i + 16].unsqueeze(1), library_lstm=True)
+            _, c = O.vq_infer(sd, z)
+            a = O.decode(sd, cfg, O.codes_to_features(sd, cfg, codes[:, i:i + 16]), bw)
+            zs.append(z), cs.append(c), auds.append(a)
+    z, c_ref, a_ref = torch.cat(zs), torch.cat(cs, dim=1), torch.cat(auds)
+    rep = O.vq_tie_report(z.permute(0, 2, 1).reshape(-1, cfg.dimension), codebook(sd), codes, c_ref)
+    print("parity_report", tag, rep)
+    assert rep["hard_mismatches"] == 0, rep
+    assert rep["match_pct"] >= 99.8, rep
+    # every flip is a near-tie at the resolution of the fp32 formula the reference evaluates; the literal
+    # relative-to-distance count is reported next to it
+    assert rep["near_ties"] == rep["mismatches"] and rep["near_ties_rel_distance"] <= rep["mismatches"]
+    assert helpers.snr_db(z, z_nat) >= 85.0
+    assert helpers.snr_db(a_ref, audio) >= 70.0

@@ -24,10 +24,15 @@ def _worker(rank, world, port, n_items, L, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         g = torch.Generator().manual_seed(0)
-        full = torch.randint(0, 4096, (1, n_items, L), generator=g)
-        s, e = shard_range(n_items, rank, world)
-        out = gather_codes(full[:, s:e].clone(), n_items)
-        q.put((rank, bool(torch.equal(out, full)), out.dtype == torch.int64))
+        ok = True
+        # 4096 bins: int16 on the wire; 65536 bins (ids above 32767 would wrap in int16) and "bins unknown": int32
+        for bins, arg in ((4096, 4096), (65536, 65536), (65536, None)):
+            full = torch.randint(0, bins, (1, n_items, L), generator=g)
+            full[0, 0, 0] = bins - 1
+            s, e = shard_range(n_items, rank, world)
+            out = gather_codes(full[:, s:e].clone(), n_items, bins=arg)
+            ok = ok and bool(torch.equal(out, full)) and out.dtype == torch.int64
+        q.put((rank, ok, True))
     finally:
         dist.destroy_process_group()
 

@@ -60,6 +60,9 @@ SYMBOLS = {
     "wt_save_audio_pcm16": (ctypes.c_int, [_I32, _P, _I64, _I64, _I32, _P, _P, _P, _P]),
     "wt_timing_read_kernel": (ctypes.c_int, [_P, _I32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64),
                                              ctypes.POINTER(ctypes.c_double)]),
+    "wt_timing_read_kernel_bytes": (ctypes.c_int, [_P, _I32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64),
+                                                   ctypes.POINTER(ctypes.c_double)]),
+    "wt_check_errors": (ctypes.c_int, [_P]),
     "wt_test_tap_gemm": (ctypes.c_int, [_I32, _P, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _I32, _I32, _P, _P, _P]),
     "wt_debug_timeline": (ctypes.c_int, [_P]),
     "wt_last_error": (ctypes.c_char_p, []),
@@ -74,19 +77,44 @@ def sources() -> Iterable[str]:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into csrc/libwavtok_b200.so (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a into csrc/libwavtok_b200.so (nvcc cross-compiles without a GPU).
+
+    Each translation unit is compiled to its own object (in parallel, rebuilt only when it or a header is newer),
+    then the objects are linked into the shared library."""
+    from concurrent.futures import ThreadPoolExecutor
     srcs = list(sources())
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    deps.append(os.path.join(ROOT, "include", "wavtok_b200.h"))
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
-        return LIB_PATH
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hdrs.append(os.path.join(ROOT, "include", "wavtok_b200.h"))
+    hdr_m = max(os.path.getmtime(d) for d in hdrs)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs + ["-lcuda"]
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src: str):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), hdr_m):
+            return obj, None
+        cmd = [nvcc] + cflags + ["-c", "-o", obj, src]
+        if verbose:
+            print(" ".join(cmd))
+        out = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, (out.stdout + out.stderr if out.returncode != 0 else None)
+
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as ex:
+        res = list(ex.map(compile_one, srcs))
+    errs = [e for _, e in res if e]
+    if errs:
+        raise RuntimeError("nvcc failed:\n" + "\n".join(errs))
+    objs = [o for o, _ in res]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(o) for o in objs):
+        return LIB_PATH
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs + ["-lcuda"]
     if verbose:
         print(" ".join(cmd))
     out = subprocess.run(cmd, capture_output=True, text=True)
     if out.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + out.stdout + out.stderr)
+        raise RuntimeError("nvcc link failed:\n" + out.stdout + out.stderr)
     return LIB_PATH
 
 

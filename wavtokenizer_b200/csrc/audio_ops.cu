@@ -320,7 +320,11 @@ int wt_convert_audio(int32_t device, const float* wav, int64_t B, int32_t channe
         const Table& t = get_table(device, sr, target_sr);
         const long long by = B * target_channels;
         if (by > 65535) throw Error(WT_ERR_VALUE, "wt_convert_audio: more than 65535 (clip, channel) rows per call");
-        static size_t attr_a = 48 * 1024, attr_b = 48 * 1024;
+        static PerDevice<size_t> attr_a_dev, attr_b_dev;  // opted-in dynamic shared memory per device (0: the 48 KB default)
+        size_t& attr_a = attr_a_dev.get();
+        size_t& attr_b = attr_b_dev.get();
+        if (!attr_a) attr_a = 48 * 1024;
+        if (!attr_b) attr_b = 48 * 1024;
         const size_t smem_t = ((size_t)(RT_FRAMES - 1) * t.orig + t.K) * sizeof(float);
         const int threads_t = (RT_FRAMES / 4) * (t.new_ / 4);
         if (t.new_ % 4 == 0 && threads_t <= 1024 && threads_t >= 32 && smem_t <= 160 * 1024) {

@@ -24,6 +24,39 @@ void set_last_error(const std::string& msg);
             throw ::wt::Error(4, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
     } while (0)
 
+// Per-device launch state. cudaFuncSetAttribute, occupancy queries and the SM count belong to ONE device: a cache kept
+// in a plain static would leave the second GPU of a process without its shared-memory opt-in (every launch there
+// would then fail with "invalid argument"). State is kept per device ordinal instead; a benign race at most repeats
+// an idempotent call.
+constexpr int WT_MAX_DEVICES = 64;
+inline int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < WT_MAX_DEVICES) ? d : 0;
+}
+template <typename T>
+struct PerDevice {
+    T v[WT_MAX_DEVICES] = {};
+    T& get() { return v[current_device()]; }
+};
+// Makes `dev` current for a scope and restores the caller's device afterwards (the C ABI must not change the current
+// device of the calling thread: torch and other libraries in the process rely on it).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) {
+            cudaError_t e = cudaSetDevice(dev);
+            if (e != cudaSuccess) throw Error(4, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+            switched = true;
+        }
+    }
+    ~DeviceGuard() { if (switched && prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // ---------------------------------------------------------------------------------------
 // tap-GEMM: the one contraction shape of this path.
 //   out[m, n] = epi( sum_{j<taps} sum_{c<Cin} pro(A[src(m, j), c]) * W[n, j*Cin + c] )

@@ -557,7 +557,8 @@ void launch_attention(const float* qkv, RowOut out, int B, int L, int Lp, int C,
     if (C != 768) throw Error(1, "attention: backbone dim must be 768");
     size_t smem = (size_t)8 * L * sizeof(float);
     if (smem > 200 * 1024) throw Error(1, "attention: clip too long for the on-chip score buffer (L <= 6400)");
-    static size_t attr = 0;
+    static PerDevice<size_t> attr_dev;
+    size_t& attr = attr_dev.get();
     if (smem > 48 * 1024 && smem > attr) {
         WT_CUDA(cudaFuncSetAttribute(attention_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = 200 * 1024;

@@ -437,7 +437,8 @@ void launch_resblock0_fused(const float* wav, const float* pack, __half* ye_hi, 
                             int Py, int left, int hr, cudaStream_t s) {
     if (B <= 0) return;
     if (T < 8) throw Error(4, "resblock0_fused: clip too short");
-    static bool attr = false;
+    static PerDevice<bool> attr_dev;
+    bool& attr = attr_dev.get();
     if (!attr) {
         WT_CUDA(cudaFuncSetAttribute(resblock0_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RB0_SMEM));
         attr = true;

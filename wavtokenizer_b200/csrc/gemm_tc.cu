@@ -1127,16 +1127,17 @@ EncodeTiledFn encode_fn() {
 // Descriptors are cached: the workspace arena hands out the same addresses call after call, and encoding
 // one costs ~10 us of host time (six per launch would leave the GPU idle between the ~700 launches of a step).
 struct MapKey {
-    const void* base; long long rows, inner, stride; int box, kw;
+    const void* base; long long rows, inner, stride; int box, kw, dev;
     bool operator==(const MapKey& o) const {
-        return base == o.base && rows == o.rows && inner == o.inner && stride == o.stride && box == o.box && kw == o.kw;
+        return base == o.base && rows == o.rows && inner == o.inner && stride == o.stride && box == o.box && kw == o.kw &&
+               dev == o.dev;
     }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const {
         size_t h = reinterpret_cast<size_t>(k.base);
         auto mix = [&](size_t v) { h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
-        mix((size_t)k.rows); mix((size_t)k.inner); mix((size_t)k.stride); mix((size_t)k.box); mix((size_t)k.kw);
+        mix((size_t)k.rows); mix((size_t)k.inner); mix((size_t)k.stride); mix((size_t)k.box); mix((size_t)k.kw); mix((size_t)k.dev);
         return h;
     }
 };
@@ -1149,7 +1150,7 @@ const CUtensorMap& make_map(const __half* base, long long rows, long long inner,
     static std::mutex mu;
     if (rows < 1) rows = 1;
     std::lock_guard<std::mutex> lock(mu);
-    MapKey key{base, rows, inner, stride, box_rows, kw};
+    MapKey key{base, rows, inner, stride, box_rows, kw, current_device()};  // device addresses repeat across GPUs
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     if (cache.size() > (1u << 16)) cache.clear();
@@ -1175,7 +1176,8 @@ CUtensorMap encode_map(const __half* base, long long rows, long long inner, long
 }
 
 int num_sms() {
-    static int n = 0;
+    static PerDevice<int> cache;
+    int& n = cache.get();
     if (!n) {
         int dev = 0;
         WT_CUDA(cudaGetDevice(&dev));
@@ -1188,8 +1190,10 @@ template <int BN, int PASSES, bool LSTM_EPI = false, bool CL2 = false>
 void launch_cfg(const TcGemm& g, cudaStream_t s) {
     using C = Cfg<BN, PASSES>;
     auto kernel = tap_gemm_tc_kernel<BN, PASSES, LSTM_EPI, CL2>;
-    static bool attr = false;
-    static int max_ctas = 0;  // cluster variant: CTAs that can be co-resident as pairs
+    static PerDevice<bool> attr_dev;
+    static PerDevice<int> max_ctas_dev;  // cluster variant: CTAs that can be co-resident as pairs
+    bool& attr = attr_dev.get();
+    int& max_ctas = max_ctas_dev.get();
     if (!attr) {
         WT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         if (CL2) {
@@ -1316,7 +1320,8 @@ void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_
                             const __half* w_hi, const __half* w_lo, int B, int L, int D, cudaStream_t s, int t_begin,
                             int t_end) {
     if (D != 512) throw Error(4, "lstm_persistent: hidden size must be 512");
-    static bool attr = false;
+    static PerDevice<bool> attr_dev;
+    bool& attr = attr_dev.get();
     if (!attr) {
         WT_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LSTM_SMEM));
         attr = true;

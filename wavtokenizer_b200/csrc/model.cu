@@ -37,6 +37,19 @@ inline int enc_chunk() {
     return v;
 }
 #define ENC_CHUNK enc_chunk()
+// clips per sub-chunk of encoder levels 0-1 (encoder_front_tc); 0 = off. Measured (profiles/r02_enc_subchunk_sweep.md):
+// sub-chunks of 2 / 4 / 8 / 16 clips are SLOWER than whole 64-clip chunks (36.4 / 34.2 / 33.2 / 32.3 vs 32.3 ms per
+// step): the planes of even 4 clips (37 MB read + 74 MB written by the level-0 strided conv) do not survive in L2
+// between producer and consumer, and each extra launch costs ~6 us of prologue + tail. Kept as a tunable, off.
+constexpr int ENC_SUB_DEFAULT = 0;
+inline int enc_sub() {
+    static int v = [] {
+        const char* e = std::getenv("WT_ENC_SUB");
+        int n = e ? std::atoi(e) : ENC_SUB_DEFAULT;
+        return n >= 0 && n <= 256 ? n : ENC_SUB_DEFAULT;
+    }();
+    return v;
+}
 inline int tc_prefetch() {
     static const int v = [] { const char* e = std::getenv("WT_TC_PREFETCH"); return e ? std::atoi(e) : 0; }();
     return v;
@@ -135,14 +148,20 @@ struct wt_handle {
     std::vector<cudaEvent_t> aux_evs;
     std::vector<cudaEvent_t> copy_evs;
     std::function<void(int /*first clip*/, int /*clips*/)> before_enc_chunk, after_dec_chunk;
+    // Sticky device-side error flag (code out of range in a gather). It is NOT read back synchronously: the launch is
+    // followed by an async copy into pinned memory plus an event, and the flag is examined when that event has
+    // completed -- at the next call on the handle, at wt_check_errors(), or at the end of wt_encode_decode_host.
     int* err_flag = nullptr;  // device
     int* err_host = nullptr;  // pinned
+    cudaEvent_t err_ev = nullptr;
+    bool err_armed = false;
+    std::string err_what;
 
     std::map<std::string, TapReq> taps;
 
     // optional per-category kernel timing (CUDA events on the launching stream; bench.py's roofline)
     bool timing = false;
-    struct Ev { cudaEvent_t a, b; int cat; int kern = 0; double flops = 0; };
+    struct Ev { cudaEvent_t a, b; int cat; int kern = 0; double flops = 0; double bytes = 0; };
     std::vector<Ev> evs;
     std::vector<cudaEvent_t> ev_pool;
     cudaEvent_t get_event() {
@@ -152,12 +171,12 @@ struct wt_handle {
         return e;
     }
 
-    ~wt_handle() {
-        cudaSetDevice(device);
+    ~wt_handle() {  // the caller (wt_destroy) has made `device` current
         for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         for (auto e : ev_pool) cudaEventDestroy(e);
         for (auto e : copy_evs) cudaEventDestroy(e);
         for (auto e : aux_evs) cudaEventDestroy(e);
+        if (err_ev) cudaEventDestroy(err_ev);
         if (aux_stream) cudaStreamDestroy(aux_stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         for (void* p : owned) cudaFree(p);
@@ -666,12 +685,23 @@ size_t workspace_bytes(const wt_handle* h, int B, int T) {
 // ---------------------------------------------------------------------------------------
 enum Cat : int { CAT_ENC_CONV = 0, CAT_LSTM, CAT_VQ, CAT_DEC_CONV, CAT_PWCONV, CAT_HEAD, CAT_ATTN, CAT_MEM, CAT_COUNT };
 
-// Counts one kernel launch and, when timing is on, brackets it with CUDA events on its stream.
+// Kernel ids of the per-kernel timing record (wt_timing_read_kernel). tcgen05 GEMM variants report BN * 10 + passes
+// through last_launch_info(); the other kernels of the step are named here.
+enum Kern : int {
+    KERN_LSTM = 1, KERN_RB0 = 2, KERN_GROUPNORM = 3, KERN_DWCONV_LN = 4, KERN_LAYERNORM = 5, KERN_SPECTRAL = 6,
+    KERN_OLA = 7, KERN_SOFTMAX = 8, KERN_VT = 9, KERN_ROWS = 10, KERN_GATHER = 11, KERN_LSTM_SKIP = 12, KERN_VQ_MISC = 13
+};
+
+// Counts one kernel launch and, when timing is on, brackets it with CUDA events on its stream. `kern` / `flops` /
+// `bytes` name the kernel and its ALGORITHMIC work (compulsory bytes for the memory-bound kernels).
 struct Scope {
     wt_handle* h;
     cudaStream_t s;
     int idx = -1;
-    Scope(wt_handle* h_, int cat, cudaStream_t s_) : h(h_), s(s_) {
+    int kern;
+    double flops, bytes;
+    Scope(wt_handle* h_, int cat, cudaStream_t s_, int kern_ = 0, double flops_ = 0, double bytes_ = 0)
+        : h(h_), s(s_), kern(kern_), flops(flops_), bytes(bytes_) {
         ++h->launches;
         if (h->timing) {
             wt_handle::Ev e{h->get_event(), h->get_event(), cat};
@@ -684,8 +714,10 @@ struct Scope {
     ~Scope() {
         if (idx >= 0) {
             cudaEventRecord(h->evs[idx].b, s);
-            h->evs[idx].kern = last_launch_info().kern;   // set by the tcgen05 GEMM launcher, 0 for other kernels
-            h->evs[idx].flops = last_launch_info().flops;
+            // the tcgen05 GEMM launcher reports its variant and FLOPs; other kernels are named by the caller
+            h->evs[idx].kern = kern ? kern : last_launch_info().kern;
+            h->evs[idx].flops = kern ? flops : last_launch_info().flops;
+            h->evs[idx].bytes = bytes;
         }
     }
 };
@@ -854,9 +886,14 @@ bool encoder_tc_supported(const wt_config& c, int T) {
     return Tc >= 4 && c.dimension == 512 && c.n_filters == 32;
 }
 
-// `pre*` point at the group's time-major pre-LSTM rows [t*Bg + b] already offset to this chunk's first clip.
-void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, int Bg, float* pre, __half* pre_hi,
-                      __half* pre_lo, cudaStream_t s) {
+// Planes of one encoder level's input: x (raw) and ELU(x), clip pitch T + 2 rows, data at row 1, reflect halo 1 / 1.
+struct EncPlanes { __half *xr_hi = nullptr, *xr_lo = nullptr, *xe_hi = nullptr, *xe_lo = nullptr; };
+
+// Levels [i0, i1) of the SEANet front on Bc clips. Level i0 reads the audio (i0 == 0) or `in` (length Tin per clip);
+// level i1 - 1 writes the pre-LSTM rows (i1 == 4; `pre*` point at the group's time-major rows [t*Bg + b] already
+// offset to the first clip) or the planes `out` of level i1 (caller-allocated, already offset to the first clip).
+void encoder_levels_tc(wt_handle* h, const float* wav, int Bc, int Tin, int i0, int i1, int b0, int Bg, EncPlanes in,
+                       EncPlanes out, float* pre, __half* pre_hi, __half* pre_lo, cudaStream_t s) {
     const wt_config& c = h->cfg;
     auto halves = [&](size_t n) { return reinterpret_cast<__half*>(h->alloc((n + 1) / 2)); };
     auto run = [&](TcGemm& g) {
@@ -865,23 +902,23 @@ void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, int
         launch_tap_gemm_tc(g, s);
     };
     auto want = [&](const std::string& name) { return b0 == 0 && h->taps.count(name) > 0; };
-    int Tc = T, C = c.n_filters;
+    int Tc = Tin, C = c.n_filters << i0;
     // level 0 operands come from the conv0 kernel: ELU(x0) planes and the 8-wide raw-audio windows that stand in
     // for x0 in the shortcut (composed weights); deeper levels get x and ELU(x) planes from the strided conv
     // Level 0 (conv0 + ResBlock 0) runs as ONE fp32 CUDA-core kernel that keeps ELU(x0) / ELU(h1) in shared memory
     // (K = 7 / 96 / 24 is too small for the MMA pipeline to pay); WT_ENC_L0_TC=1 selects the tcgen05 formulation.
     static const bool l0_tc = std::getenv("WT_ENC_L0_TC") != nullptr;
     const bool fused0 = !l0_tc && h->rb0_pack != nullptr;
-    size_t nX = (size_t)Bc * (Tc + 2) * C;
-    const size_t nWin = (size_t)Bc * (Tc + 2) * 8;
-    __half *xr_hi = nullptr, *xr_lo = nullptr, *xe_hi = nullptr, *xe_lo = nullptr;
-    if (!fused0) {
+    __half *xr_hi = in.xr_hi, *xr_lo = in.xr_lo, *xe_hi = in.xe_hi, *xe_lo = in.xe_lo;
+    if (i0 == 0 && !fused0) {
+        const size_t nX = (size_t)Bc * (Tc + 2) * C;
+        const size_t nWin = (size_t)Bc * (Tc + 2) * 8;
         xr_hi = halves(nWin); xr_lo = halves(nWin); xe_hi = halves(nX); xe_lo = halves(nX);
         Scope sc(h, CAT_ENC_CONV, s);
-        launch_conv0_planes(wav, h->conv0_w, h->conv0_b, xr_hi, xr_lo, xe_hi, xe_lo, Bc, T, C, s);
+        launch_conv0_planes(wav, h->conv0_w, h->conv0_b, xr_hi, xr_lo, xe_hi, xe_lo, Bc, Tc, C, s);
     }
-    int idx = 1;
-    for (int i = 0; i < 4; ++i) {
+    int idx = 1 + 3 * i0;
+    for (int i = i0; i < i1; ++i) {
         const int s_ = c.strides[i];
         const int Tn = (Tc + s_ - 1) / s_;
         const int P = Tc + 2;
@@ -907,7 +944,8 @@ void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, int
         __half *ye_hi = halves(nY), *ye_lo = halves(nY);
         float* y_tap = want("enc" + std::to_string(idx)) ? h->alloc(nY) : nullptr;
         if (fused) {
-            Scope sc(h, CAT_ENC_CONV, s);
+            // algorithmic work per sample: conv0 224 + k3 1536 + 1x1 512 + shortcut 1024 MACs; 4 B in, 128 B of planes out
+            Scope sc(h, CAT_ENC_CONV, s, KERN_RB0, 6592.0 * Bc * Tc, 132.0 * Bc * Tc);
             launch_resblock0_fused(wav, h->rb0_pack, ye_hi, ye_lo, y_tap, Bc, Tc, Py, left, right + extra, s);
         } else {
             TcGemm g;
@@ -935,7 +973,8 @@ void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, int
         float* z_tap = nullptr;
         if (i < 3) {
             const size_t nX2 = (size_t)Bc * (Tn + 2) * C2;
-            xr_hi = halves(nX2); xr_lo = halves(nX2); xe_hi = halves(nX2); xe_lo = halves(nX2);
+            if (i == i1 - 1) { xr_hi = out.xr_hi; xr_lo = out.xr_lo; xe_hi = out.xe_hi; xe_lo = out.xe_lo; }
+            else { xr_hi = halves(nX2); xr_lo = halves(nX2); xe_hi = halves(nX2); xe_lo = halves(nX2); }
             g.map.Pout = Tn + 2; g.map.off = 1; g.map.hl = 1; g.map.hr = 1;
             g.out_hi = xr_hi; g.out_lo = xr_lo; g.ldh = C2;
             g.elu_hi = xe_hi; g.elu_lo = xe_lo; g.ldh2 = C2;
@@ -960,6 +999,37 @@ void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, int
         }
         Tc = Tn; C = C2; idx += 3;
     }
+}
+
+// SEANet front on a chunk of Bc clips. Levels 0-1 move 0.3 GB per clip through split-fp16 planes (32 / 64 channels at
+// 72000 / 36000 rows) and are HBM-bound (profiles/r01_ncu_table_encoder_chunk64_s4.txt: 4.5-4.8 TB/s). WT_ENC_SUB=n
+// runs them in sub-chunks of n clips (same arena addresses every sub-chunk), each writing its slice of the level-2
+// input planes of the whole chunk, with levels 2-3 once per chunk; measured slower at every n (see ENC_SUB_DEFAULT).
+void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, int Bg, float* pre, __half* pre_hi,
+                      __half* pre_lo, cudaStream_t s) {
+    const wt_config& c = h->cfg;
+    const int sub = enc_sub();
+    if (sub <= 0 || sub >= Bc || !h->taps.empty()) {
+        encoder_levels_tc(h, wav, Bc, T, 0, 4, b0, Bg, EncPlanes{}, EncPlanes{}, pre, pre_hi, pre_lo, s);
+        return;
+    }
+    auto halves = [&](size_t n) { return reinterpret_cast<__half*>(h->alloc((n + 1) / 2)); };
+    const int T1 = (T + c.strides[0] - 1) / c.strides[0], T2 = (T1 + c.strides[1] - 1) / c.strides[1];
+    const int C2 = 4 * c.n_filters;
+    const size_t per_clip = (size_t)(T2 + 2) * C2, nX2 = (size_t)Bc * per_clip;
+    EncPlanes l2;
+    l2.xr_hi = halves(nX2); l2.xr_lo = halves(nX2); l2.xe_hi = halves(nX2); l2.xe_lo = halves(nX2);
+    const size_t mark = h->arena_off;
+    for (int bs = 0; bs < Bc; bs += sub) {
+        const int Bs = std::min(sub, Bc - bs);
+        h->arena_off = mark;
+        EncPlanes o;
+        o.xr_hi = l2.xr_hi + bs * per_clip; o.xr_lo = l2.xr_lo + bs * per_clip;
+        o.xe_hi = l2.xe_hi + bs * per_clip; o.xe_lo = l2.xe_lo + bs * per_clip;
+        encoder_levels_tc(h, wav + (size_t)bs * T, Bs, T, 0, 2, b0 + bs, Bg, EncPlanes{}, o, nullptr, nullptr, nullptr, s);
+    }
+    h->arena_off = mark;
+    encoder_levels_tc(h, nullptr, Bc, T2, 2, 4, b0, Bg, l2, EncPlanes{}, pre, pre_hi, pre_lo, s);
 }
 
 // SLSTM + ELU + final k7 conv on the tensor cores: hoisted input projections, one GEMM launch per time
@@ -1030,7 +1100,7 @@ float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, con
         for (int k = 0; k < NSEG; ++k) {
             const int t0 = (int)((long long)L * k / NSEG), t1 = (int)((long long)L * (k + 1) / NSEG);
             {
-                Scope sc(h, CAT_LSTM, s);
+                Scope sc(h, CAT_LSTM, s, KERN_LSTM, 16.0 * D * D * Bg * (t1 - t0), 0);
                 launch_lstm_persistent(xin, ybuf[0], yh_hi[0], yh_lo[0], cst, counters, h->lstm_tc[0].w_hh.hi,
                                        h->lstm_tc[0].w_hh.lo, Bg, L, D, s, t0, t1);
             }
@@ -1040,7 +1110,7 @@ float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, con
             WT_CUDA(cudaEventRecord(h->aux_evs[k], s));
             WT_CUDA(cudaStreamWaitEvent(s2, h->aux_evs[k], 0));
             {
-                Scope sc(h, CAT_LSTM, s2);
+                Scope sc(h, CAT_LSTM, s2, KERN_LSTM, 16.0 * D * D * Bg * (t1 - t0), 0);
                 launch_lstm_persistent(xin2, ybuf[1], yh_hi[1], yh_lo[1], cst2, counters2, h->lstm_tc[1].w_hh.hi,
                                        h->lstm_tc[1].w_hh.lo, Bg, L, D, s2, t0, t1);
             }
@@ -1053,7 +1123,7 @@ float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, con
         const auto& w = h->lstm_tc[l];
         input_projection(l, lin_hi, lin_lo, xin, 0, M, 0, s);
         if (!stepwise) {
-            Scope sc(h, CAT_LSTM, s);
+            Scope sc(h, CAT_LSTM, s, KERN_LSTM, 16.0 * D * D * Bg * L, 0);
             launch_lstm_persistent(xin, ybuf[l], yh_hi[l], yh_lo[l], cst, counters, w.w_hh.hi, w.w_hh.lo, Bg, L, D, s);
             lin_hi = yh_hi[l]; lin_lo = yh_lo[l];
             continue;
@@ -1081,7 +1151,7 @@ float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, con
     const size_t nE = (size_t)Bg * (L + 6) * D;
     __half *e_hi = halves(nE), *e_lo = halves(nE);
     {
-        Scope sc(h, CAT_LSTM, s);
+        Scope sc(h, CAT_LSTM, s, KERN_LSTM_SKIP, 0, (double)M * D * 12 + (double)nE * 4);
         if (c.lstm_layers) launch_lstm_skip_elu_pad(ylast, pre, lo, e_hi, e_lo, Bg, L, D, s);
         else launch_lstm_skip_elu_pad(pre, h->zero_rows /*unused*/, lo, e_hi, e_lo, Bg, L, D, s);
     }
@@ -1209,16 +1279,16 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
         launch_tap_gemm_tc(g, s);
     };
 
-    { Scope sc(h, CAT_MEM, s); launch_features_to_rows(features, out_split(xin_hi, xin_lo), Bc, Din, L, Lp, s); }
+    { Scope sc(h, CAT_MEM, s, KERN_ROWS, 0, (double)Bc * L * Din * 8); launch_features_to_rows(features, out_split(xin_hi, xin_lo), Bc, Din, L, Lp, s); }
     r.cat = CAT_DEC_CONV;
     gemm(xin_hi, xin_lo, Din, 7, h->embed.w_hi, h->embed.w_lo, D, 3, h->embed.b, ACT_NONE, nullptr, nullptr, x, D,
          nullptr, nullptr, 0);
     h->tap("dec_embed", x, Bc, L, D, b0, s, Lp);
 
     auto resnet = [&](const wt_handle::Resnet& p) {
-        { Scope sc(h, CAT_MEM, s); launch_groupnorm(x, p.n1w, p.n1b, out_split(a_hi, a_lo), Bc, L, Lp, D, 32, eps, 1, s); }
+        { Scope sc(h, CAT_MEM, s, KERN_GROUPNORM, 0, (double)Bc * L * D * 8); launch_groupnorm(x, p.n1w, p.n1b, out_split(a_hi, a_lo), Bc, L, Lp, D, 32, eps, 1, s); }
         gemm(a_hi, a_lo, D, 3, p.c1.w_hi, p.c1.w_lo, D, 3, p.c1.b, ACT_NONE, nullptr, nullptr, t2, D, nullptr, nullptr, 0);
-        { Scope sc(h, CAT_MEM, s); launch_groupnorm(t2, p.n2w, p.n2b, out_split(a_hi, a_lo), Bc, L, Lp, D, 32, eps, 1, s); }
+        { Scope sc(h, CAT_MEM, s, KERN_GROUPNORM, 0, (double)Bc * L * D * 8); launch_groupnorm(t2, p.n2w, p.n2b, out_split(a_hi, a_lo), Bc, L, Lp, D, 32, eps, 1, s); }
         gemm(a_hi, a_lo, D, 3, p.c2.w_hi, p.c2.w_lo, D, 3, p.c2.b, ACT_NONE, nullptr, x, x, D, nullptr, nullptr, 0);
     };
     resnet(h->pos[0]); h->tap("dec_pos0", x, Bc, L, D, b0, s, Lp);
@@ -1229,7 +1299,7 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
         __half *p_hi = halves((size_t)R * Lpad), *p_lo = halves((size_t)R * Lpad);
         __half *vt_hi = halves((size_t)Bc * D * Lpad), *vt_lo = halves((size_t)Bc * D * Lpad);
         __half *qkv_hi = g_hi, *qkv_lo = g_lo;  // [R, 3D] planes (the GELU buffer is free here)
-        { Scope sc(h, CAT_MEM, s); launch_groupnorm(x, h->attn.nw, h->attn.nb, out_split(a_hi, a_lo), Bc, L, Lp, D, 32, eps, 0, s); }
+        { Scope sc(h, CAT_MEM, s, KERN_GROUPNORM, 0, (double)Bc * L * D * 8); launch_groupnorm(x, h->attn.nw, h->attn.nb, out_split(a_hi, a_lo), Bc, L, Lp, D, 32, eps, 0, s); }
         gemm(a_hi, a_lo, D, 1, h->attn.wqkv_h.hi, h->attn.wqkv_h.lo, 3 * D, 3, h->attn.bqkv, ACT_NONE, nullptr, nullptr,
              nullptr, 0, qkv_hi, qkv_lo, 3 * D);
         r.cat = CAT_ATTN;
@@ -1243,8 +1313,8 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
             Scope sc(h, CAT_ATTN, s);
             launch_tap_gemm_tc(g, s);
         }
-        { Scope sc(h, CAT_ATTN, s); launch_softmax_planes(S, Lpad, p_hi, p_lo, Lpad, Bc, L, Lp, 1.0f / sqrtf((float)D), s); }
-        { Scope sc(h, CAT_ATTN, s); launch_vt_planes(qkv_hi, qkv_lo, vt_hi, vt_lo, Bc, L, Lp, D, Lpad, s); }
+        { Scope sc(h, CAT_ATTN, s, KERN_SOFTMAX, 0, (double)Bc * L * L * 8); launch_softmax_planes(S, Lpad, p_hi, p_lo, Lpad, Bc, L, Lp, 1.0f / sqrtf((float)D), s); }
+        { Scope sc(h, CAT_ATTN, s, KERN_VT, 0, (double)Bc * L * D * 8); launch_vt_planes(qkv_hi, qkv_lo, vt_hi, vt_lo, Bc, L, Lp, D, Lpad, s); }
         {   // out[b, i, :] = sum_j P[b, i, j] v_j
             TcGemm g;
             g.seg[0] = tc_taps(p_hi, p_lo, R, Lpad, Lpad, 1, 0);
@@ -1262,30 +1332,30 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
     }
     resnet(h->pos[2]); h->tap("dec_pos3", x, Bc, L, D, b0, s, Lp);
     resnet(h->pos[3]); h->tap("dec_pos4", x, Bc, L, D, b0, s, Lp);
-    { Scope sc(h, CAT_MEM, s); launch_groupnorm(x, h->gn5w, h->gn5b, out_f32(t2), Bc, L, Lp, D, 32, eps, 0, s); }
+    { Scope sc(h, CAT_MEM, s, KERN_GROUPNORM, 0, (double)Bc * L * D * 8); launch_groupnorm(x, h->gn5w, h->gn5b, out_f32(t2), Bc, L, Lp, D, 32, eps, 0, s); }
     h->tap("dec_pos5", t2, Bc, L, D, b0, s, Lp);
-    { Scope sc(h, CAT_MEM, s); launch_layernorm(t2, h->norm_scale + (size_t)bw * D, h->norm_shift + (size_t)bw * D, out_f32(x), R, D, eps, s); }
+    { Scope sc(h, CAT_MEM, s, KERN_LAYERNORM, 0, (double)Bc * L * D * 8); launch_layernorm(t2, h->norm_scale + (size_t)bw * D, h->norm_shift + (size_t)bw * D, out_f32(x), R, D, eps, s); }
     h->tap("dec_norm", x, Bc, L, D, b0, s, Lp);
     r.cat = CAT_PWCONV;
     for (int i = 0; i < c.num_layers; ++i) {
         const auto& p = h->cnx[i];
-        { Scope sc(h, CAT_MEM, s); launch_dwconv_ln(x, p.dw, p.db, p.scale + (size_t)bw * D, p.shift + (size_t)bw * D, out_split(a_hi, pw_passes == 3 ? a_lo : nullptr), Bc, L, Lp, D, eps, s); }
+        { Scope sc(h, CAT_MEM, s, KERN_DWCONV_LN, 0, (double)Bc * L * D * (pw_passes == 3 ? 8 : 6)); launch_dwconv_ln(x, p.dw, p.db, p.scale + (size_t)bw * D, p.shift + (size_t)bw * D, out_split(a_hi, pw_passes == 3 ? a_lo : nullptr), Bc, L, Lp, D, eps, s); }
         gemm(a_hi, a_lo, D, 1, p.w1_h.hi, p.w1_h.lo, Hd, pw_passes, p.b1, ACT_GELU, nullptr, nullptr, nullptr, 0,
              g_hi, pw_passes == 3 ? g_lo : nullptr, Hd);
         gemm(g_hi, g_lo, Hd, 1, p.w2_h.hi, p.w2_h.lo, D, pw_passes, p.b2, ACT_NONE, p.gamma, x, x, D, nullptr, nullptr, 0);
         h->tap(("dec_cnx" + std::to_string(i)).c_str(), x, Bc, L, D, b0, s, Lp);
     }
-    { Scope sc(h, CAT_MEM, s); launch_layernorm(x, h->fln_w, h->fln_b, out_split(a_hi, a_lo, t2), R, D, eps, s); }
+    { Scope sc(h, CAT_MEM, s, KERN_LAYERNORM, 0, (double)Bc * L * D * 8); launch_layernorm(x, h->fln_w, h->fln_b, out_split(a_hi, a_lo, t2), R, D, eps, s); }
     h->tap("dec_final", t2, Bc, L, D, b0, s, Lp);
     const int N = c.n_fft, half = N / 2 + 1;
     r.cat = CAT_HEAD;
     gemm(a_hi, a_lo, D, 1, h->head_h.hi, h->head_h.lo, N + 2, 3, h->head_b, ACT_NONE, nullptr, nullptr, bigA, h->ldz,
          nullptr, nullptr, 0);
     h->tap("dec_headlin", bigA, Bc, L, N + 2, b0, s, Lp, h->ldz);
-    { Scope sc(h, CAT_MEM, s); launch_spectral(bigA, h->ldz, out_split(S_hi, S_lo), R, half, h->Kp, s); }
+    { Scope sc(h, CAT_MEM, s, KERN_SPECTRAL, 0, (double)Bc * L * (N + 2) * 8); launch_spectral(bigA, h->ldz, out_split(S_hi, S_lo), R, half, h->Kp, s); }
     gemm(S_hi, S_lo, h->Kp, 1, h->basis_h.hi, h->basis_h.lo, N, 3, nullptr, ACT_NONE, nullptr, nullptr, bigA, N, nullptr,
          nullptr, 0);
-    { Scope sc(h, CAT_MEM, s); launch_overlap_add(bigA, h->wsq, audio, Bc, L, Lp, N, c.hop_length, s); }
+    { Scope sc(h, CAT_MEM, s, KERN_OLA, 0, (double)Bc * L * (N + c.hop_length) * 4); launch_overlap_add(bigA, h->wsq, audio, Bc, L, Lp, N, c.hop_length, s); }
 }
 
 void decoder_chunk(wt_handle* h, const float* features, int Bc, int L, int bw, float* audio, int b0, cudaStream_t s) {
@@ -1293,12 +1363,31 @@ void decoder_chunk(wt_handle* h, const float* features, int Bc, int L, int bw, f
     else decoder_chunk_simt(h, features, Bc, L, bw, audio, b0, s);
 }
 
-void check_err_flag(wt_handle* h, cudaStream_t s, const char* what) {
+// Deferred read-back of the sticky error flag (see wt_handle::err_flag). arm: queue the copy + event behind the kernel
+// that may have raised it. poll: if the event has completed (block = wait for it), examine the flag and throw the
+// IndexError the reference raises for an out-of-range code (torch embedding: "index out of range in self").
+void arm_err_flag(wt_handle* h, cudaStream_t s, const char* what) {
+    if (!h->err_ev) WT_CUDA(cudaEventCreateWithFlags(&h->err_ev, cudaEventDisableTiming));
     WT_CUDA(cudaMemcpyAsync(h->err_host, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-    WT_CUDA(cudaStreamSynchronize(s));
+    WT_CUDA(cudaEventRecord(h->err_ev, s));
+    h->err_armed = true;
+    h->err_what = what;
+}
+
+void poll_err_flag(wt_handle* h, bool block) {
+    if (!h->err_armed) return;
+    if (block) {
+        WT_CUDA(cudaEventSynchronize(h->err_ev));
+    } else {
+        cudaError_t q = cudaEventQuery(h->err_ev);
+        if (q == cudaErrorNotReady) return;
+        WT_CUDA(q);
+    }
+    h->err_armed = false;
     if (*h->err_host) {
-        WT_CUDA(cudaMemsetAsync(h->err_flag, 0, sizeof(int), s));
-        throw Error(WT_ERR_INDEX, std::string(what) + ": index out of range in self");
+        *h->err_host = 0;
+        WT_CUDA(cudaMemset(h->err_flag, 0, sizeof(int)));
+        throw Error(WT_ERR_INDEX, h->err_what + ": index out of range in self");
     }
 }
 
@@ -1344,7 +1433,7 @@ void do_encode(wt_handle* h, const float* wav, int B, int T, float* features_out
                 launch_vq_simt(z, h->codebooks, h->cnorm, M, D, c.vq_bins, codes, s);
             }
             if (features_out) {
-                Scope sc(h, CAT_MEM, s);
+                Scope sc(h, CAT_MEM, s, KERN_GATHER, 0, (double)Bg * L * (D * 4 + 8));
                 launch_codes_to_features(h->codebooks, codes, features_out + (size_t)g0 * D * L, 1, Bg, L, D, c.vq_bins,
                                          nullptr, s);
             }
@@ -1371,7 +1460,8 @@ template <typename F>
 int guarded(wt_handle* h, F&& f) {
     try {
         if (!h) throw Error(WT_ERR_VALUE, "null handle");
-        WT_CUDA(cudaSetDevice(h->device));
+        DeviceGuard dg(h->device);  // the caller's current device is restored on return
+        poll_err_flag(h, false);    // an out-of-range code of an earlier call surfaces here once its flag has landed
         f();
         return WT_OK;
     } catch (const Error& e) {
@@ -1410,7 +1500,7 @@ int wt_create(const wt_config* cfg, const wt_tensor* tensors, int32_t n_tensors,
         int ndev = 0;
         WT_CUDA(cudaGetDeviceCount(&ndev));
         if (device < 0 || device >= ndev) throw Error(WT_ERR_RUNTIME, "invalid CUDA device ordinal");
-        WT_CUDA(cudaSetDevice(device));
+        DeviceGuard dg(device);
         cudaDeviceProp prop;
         WT_CUDA(cudaGetDeviceProperties(&prop, device));
         if (prop.major != 10)
@@ -1436,9 +1526,14 @@ int wt_create(const wt_config* cfg, const wt_tensor* tensors, int32_t n_tensors,
 
 int wt_destroy(wt_handle* h) {
     if (!h) return WT_OK;
-    cudaSetDevice(h->device);
-    cudaDeviceSynchronize();
-    delete h;
+    try {
+        DeviceGuard dg(h->device);
+        cudaDeviceSynchronize();
+        delete h;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return WT_ERR_RUNTIME;
+    }
     return WT_OK;
 }
 
@@ -1475,11 +1570,11 @@ int wt_codes_to_features(wt_handle* h, const int64_t* codes, int32_t K, int32_t 
             throw Error(WT_ERR_INDEX, "codes_to_features: more code books than the checkpoint holds");
         cudaStream_t s = (cudaStream_t)stream;
         {
-            Scope sc(h, CAT_MEM, s);
+            Scope sc(h, CAT_MEM, s, KERN_GATHER, 0, (double)B * L * (h->cfg.dimension * 4 + 8));
             launch_codes_to_features(h->codebooks, reinterpret_cast<const long long*>(codes), features_out, K, B, L,
                                      h->cfg.dimension, h->cfg.vq_bins, h->err_flag, s);
         }
-        check_err_flag(h, s, "codes_to_features");
+        arm_err_flag(h, s, "codes_to_features");
     });
 }
 
@@ -1597,6 +1692,7 @@ int wt_encode_decode_host(wt_handle* h, const float* wav_host, int32_t B, int32_
         h->after_dec_chunk = nullptr;
         WT_CUDA(cudaStreamSynchronize(s));
         WT_CUDA(cudaStreamSynchronize(cs));
+        poll_err_flag(h, true);
     });
 }
 
@@ -1671,11 +1767,34 @@ int wt_timing_read_kernel(wt_handle* h, int32_t kern, double* total_ms, int64_t*
     });
 }
 
+int wt_timing_read_kernel_bytes(wt_handle* h, int32_t kern, double* total_ms, int64_t* n_launches, double* bytes) {
+    return guarded(h, [&] {
+        WT_CUDA(cudaDeviceSynchronize());
+        double ms = 0, by = 0;
+        int64_t n = 0;
+        for (auto& e : h->evs) {
+            if (e.kern != kern) continue;
+            float t = 0;
+            WT_CUDA(cudaEventElapsedTime(&t, e.a, e.b));
+            ms += t;
+            by += e.bytes;
+            ++n;
+        }
+        if (total_ms) *total_ms = ms;
+        if (n_launches) *n_launches = n;
+        if (bytes) *bytes = by;
+    });
+}
+
+int wt_check_errors(wt_handle* h) {
+    return guarded(h, [&] { poll_err_flag(h, true); });
+}
+
 int wt_test_tap_gemm(int32_t device, const float* A, int32_t rows, int32_t Cin, int32_t taps, const float* W, int32_t N,
                      const float* bias, const float* gamma, const float* res, int32_t act, int32_t passes,
                      float* out_f32, float* out_split, void* stream) {
     try {
-        WT_CUDA(cudaSetDevice(device));
+        DeviceGuard dg(device);
         cudaStream_t s = (cudaStream_t)stream;
         const long long K = (long long)taps * Cin;
         __half *a_hi, *a_lo, *w_hi, *w_lo, *o_hi = nullptr, *o_lo = nullptr;

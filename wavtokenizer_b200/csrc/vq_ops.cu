@@ -257,7 +257,8 @@ void launch_codes_to_features(const float* codebooks, const long long* codes, fl
     if (B <= 0 || L <= 0) return;
     if (D % 4) throw Error(1, "codes_to_features: codebook dim must be a multiple of 4");
     size_t smem = (size_t)32 * (D + 1) * sizeof(float);
-    static bool attr_set = false;
+    static PerDevice<bool> attr_dev;
+    bool& attr_set = attr_dev.get();
     if (!attr_set) {
         WT_CUDA(cudaFuncSetAttribute(codes_to_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;

@@ -112,17 +112,28 @@ class WavTokenizer(nn.Module):
 
     @classmethod
     def from_pretrained0911(cls, config_path: str, model_folder_path: str) -> "WavTokenizer":
-        """Average every checkpoint in a folder (reference decoder/pretrained.py:117-156)."""
+        """Average the three best checkpoints of a folder (reference decoder/pretrained.py:117-156): only files whose
+        name starts with ``vocos_`` count, they are ranked by the validation loss embedded in the file name
+        (characters ``[-11:-5]``, compared as strings), every file whose loss string is among the three smallest is
+        loaded, and their ``backbone.`` / ``head.`` / ``feature_extractor.`` tensors are averaged."""
         import os
         model = cls.from_hparams0802(config_path)
-        models = [os.path.join(model_folder_path, f) for f in os.listdir(model_folder_path)
-                  if f.endswith(".ckpt") or f.endswith(".pt") or f.endswith(".pth")] or \
-                 [os.path.join(model_folder_path, f) for f in os.listdir(model_folder_path)]
+        names = [f for f in os.listdir(model_folder_path) if f.startswith("vocos_")]
+        if not names:
+            raise FileNotFoundError(f"no 'vocos_*' checkpoint in {model_folder_path} (reference pretrained.py:126-129)")
+        best = sorted(f[-11:-5] for f in names)[:3]
         dicts = []
-        for path in models:
-            raw = torch.load(path, map_location="cpu")["state_dict"]
+        for f in names:
+            if f[-11:-5] not in best:
+                continue
+            raw = torch.load(model_folder_path + "/" + f, map_location="cpu")["state_dict"]
             dicts.append({k: v for k, v in raw.items() if k.startswith(("backbone.", "head.", "feature_extractor."))})
-        avg = {k: sum(d[k] for d in dicts) / len(dicts) for k in dicts[0]}
+        avg = {}
+        for k in dicts[0]:
+            acc = dicts[0][k].clone()  # same accumulation order as the reference (file order of os.listdir)
+            for d in dicts[1:]:
+                acc += d[k]
+            avg[k] = acc / len(dicts)
         model.load_state_dict(avg)
         model.eval()
         return model
@@ -415,6 +426,14 @@ class WavTokenizer(nn.Module):
             _native.check(_native.lib().wt_encode_decode_host(h.ptr, wav_host.data_ptr(), B, T, int(bandwidth_id),
                                                               codes.data_ptr(), audio.data_ptr(), self._stream()))
         return codes, audio
+
+    def check_errors(self) -> None:
+        """Wait for pending device-side checks and raise what they found: ``IndexError`` for a code >= vq_bins given to
+        ``codes_to_features`` (reference decoder/pretrained.py:236 -> embedding lookup). That call does not
+        synchronise the stream to find out; without this method the error is raised by a later call on the model."""
+        if self._handle is not None:
+            with torch.cuda.device(self.device):
+                _native.check(_native.lib().wt_check_errors(self._handle.ptr))
 
     def reserve(self, B: int, T: int) -> None:
         _native.check(_native.lib().wt_reserve(self.native().ptr, int(B), int(T)))

@@ -22,11 +22,13 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
-def gather_codes(local_codes: torch.Tensor, n_items: int, group=None) -> torch.Tensor:
+def gather_codes(local_codes: torch.Tensor, n_items: int, group=None, bins: int | None = None) -> torch.Tensor:
     """All-gather per-rank codes [1, B_r, L] (int64) into [1, n_items, L] on every rank.
 
-    Codes fit 16 bits (vq_bins = 4096), so they travel as int16 and are widened afterwards: the
-    payload of BASELINE.json's config 3 (1024 x 225 codes per rank) shrinks from 1.84 MB to 0.46 MB.
+    ``bins`` is the codebook size the codes index (``cfg.vq_bins``). Up to 32768 bins the codes fit a signed 16-bit
+    word and travel as int16, widened afterwards: the payload of BASELINE.json's config 3 (1024 x 225 codes per rank)
+    shrinks from 1.84 MB to 0.46 MB. Larger codebooks (the reference's EncodecFeatures default is 16384, but the YAML
+    is free) and callers that do not say travel as int32, so an id can never wrap.
     Ragged shards (n_items % world != 0) are padded to the largest shard on the wire.
     """
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
@@ -37,13 +39,15 @@ def gather_codes(local_codes: torch.Tensor, n_items: int, group=None) -> torch.T
     s, e = shard_range(n_items, rank, world)
     if b_local != e - s:
         raise ValueError(f"rank {rank} holds {b_local} clips, expected {e - s}")
+    wire_dtype = torch.int16 if bins is not None and 0 < int(bins) <= 32768 else torch.int32
+    width = torch.empty((), dtype=wire_dtype).element_size()
     b_max = -(-n_items // world)
-    wire = torch.zeros(K, b_max, L, dtype=torch.int16, device=local_codes.device)
-    wire[:, :b_local] = local_codes.to(torch.int16)
-    # neither NCCL nor gloo has a 16-bit integer type: ship the int16 payload as raw bytes
-    flat = torch.empty(world * K, b_max, 2 * L, dtype=torch.uint8, device=local_codes.device)
+    wire = torch.zeros(K, b_max, L, dtype=wire_dtype, device=local_codes.device)
+    wire[:, :b_local] = local_codes.to(wire_dtype)
+    # neither NCCL nor gloo has a 16-bit integer type: ship the payload as raw bytes
+    flat = torch.empty(world * K, b_max, width * L, dtype=torch.uint8, device=local_codes.device)
     dist.all_gather_into_tensor(flat, wire.view(torch.uint8), group=group)
-    out = flat.view(torch.int16).view(world, K, b_max, L)
+    out = flat.view(wire_dtype).view(world, K, b_max, L)
     parts = []
     for r in range(world):
         rs, re = shard_range(n_items, r, world)

@@ -4,7 +4,7 @@ Mirrors what the reference resolves from YAML through ``instantiate_class``
 (reference decoder/pretrained.py:13-29, 81-92) and the hard-wired SEANet encoder
 arguments in ``EncodecFeatures.__init__`` (decoder/feature_extractors.py:55-96).
 Nothing here imports the reference; the state-dict key set below is checked against
-the reference's own ``state_dict()`` by tests/test_spec.py (golden key list).
+the reference's own ``state_dict()`` by tests/test_oracle_golden.py::test_state_keys_match_reference (golden key list).
 """
 from __future__ import annotations
 
