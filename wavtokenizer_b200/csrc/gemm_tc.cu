@@ -105,9 +105,9 @@ __device__ __forceinline__ uint64_t umma_desc_at(uint64_t hi, uint32_t smem_addr
 }
 
 // kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M = 128, N = BN.
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int n, int m = BM) {
     return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(BM >> 4) << 24);
+           ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -161,6 +161,46 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
         "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
         "h"(mask)
         : "memory");
+}
+
+// ---- CTA-pair MMA (cta_group::2): one tcgen05.mma of M = 256 runs on the tensor cores of BOTH SMs of a pair. Each CTA
+// holds its own 128 A rows and HALF of the B (weight) rows in shared memory; each SM reads its A tile and its B half
+// locally and receives the other B half from the peer, so the shared-memory reads per MMA drop from 12 KB to 8 KB per
+// SM (N = 256) and a k-block occupies 32 KB instead of 48 KB per SM. The leader CTA (rank 0) issues the MMAs and owns
+// the barriers the MMA thread waits on. ----
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+// TMA load into THIS CTA's shared memory whose complete_tx goes to an mbarrier that may live in the peer CTA
+// (`bar` is a shared::cluster address, e.g. the leader's full barrier)
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// commit of the pair's MMAs: the arrive is delivered to the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(mask)
+        : "memory");
+}
+// arrive on an mbarrier of another CTA of the cluster (`bar` is a shared::cluster address)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -362,10 +402,10 @@ __device__ __forceinline__ void store_row(const TcGemm& g, long long row, int nb
     }
 }
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, bool CG2 = false>
 struct Cfg {
     static constexpr int A_PLANE = BM * BK * 2;  // bytes
-    static constexpr int B_PLANE = BN * BK * 2;
+    static constexpr int B_PLANE = (CG2 ? BN / 2 : BN) * BK * 2;  // CTA-pair MMA: this CTA holds half of the W rows
     static constexpr int PLANES = PASSES == 3 ? 2 : 1;
     static constexpr int STAGE = PLANES * (A_PLANE + B_PLANE);
     static constexpr int STAGES = (200 * 1024) / STAGE > 8 ? 8 : (200 * 1024) / STAGE;
@@ -402,11 +442,15 @@ struct Maps {
 // cross L2 -> SM once per pair: the single-pass 128 x 256 tiles need 94 B/clk/SM of operands otherwise and were bound
 // by that (profiles/r01_final_summary.md). Shared-memory stages are recycled when BOTH CTAs' MMAs have read them
 // (tcgen05.commit multicast onto both CTAs' empty barriers).
-template <int BN, int PASSES, bool LSTM_EPI = false, bool CL2 = false>
+// CLM = 2 (cta_group::2): same pairing of CTAs and tiles, but the pair runs ONE tcgen05.mma of M = 256 per step, issued by
+// the leader CTA; each CTA keeps only its half of the W rows (no multicast copy), see the cta_group::2 helpers above.
+template <int BN, int PASSES, bool LSTM_EPI = false, int CLM = 0>
 // 18 warps are allocated as 20 (warp granularity 4): 65536 / (20 * 32) = 102 -> 96 registers per thread.
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
-    using C = Cfg<BN, PASSES>;
+    constexpr bool CL2 = CLM != 0;  // the kernel runs as clusters of two CTAs
+    constexpr bool CG2 = CLM == 2;  // ... whose tensor cores execute one M = 256 MMA together
+    using C = Cfg<BN, PASSES, CG2>;
     constexpr int CW = C::CW;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -452,24 +496,33 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     // k-block width: 64 elements (128-byte rows, SWIZZLE_128B) or, for narrow operands, 32 / 16 (64- / 32-byte rows
     // under SWIZZLE_64B / _32B) so that TMA fetches exactly the bytes that exist instead of zero-filling 128-byte rows
     const int kw = g.kw;
-    const uint32_t a_plane = (uint32_t)(BM * kw * 2), b_plane = (uint32_t)(BN * kw * 2);
+    const uint32_t a_plane = (uint32_t)(BM * kw * 2), b_plane = (uint32_t)((CG2 ? BN / 2 : BN) * kw * 2);
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), CL2 ? 2 : 1);  // cluster variant: both CTAs' MMAs must have read the stage
+            // multicast variant: both CTAs' MMAs must have read the stage; pair MMA: the leader's commit covers both
+            mbar_init(empty_bar(s), (CL2 && !CG2) ? 2 : 1);
         }
         for (int s = 0; s < C::NACC; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), NEPI / C::NGRP);  // one arrive per epilogue warp of the group that drains it
+            // one arrive per epilogue warp of the group that drains it (pair MMA: of BOTH CTAs, on the leader's barrier)
+            mbar_init(tempty_bar(s), (CG2 ? 2 : 1) * (NEPI / C::NGRP));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                     "r"((uint32_t)C::TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG2) {  // one warp of EACH CTA of the pair: the columns are allocated in both tensor memories
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                         "r"((uint32_t)C::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                         "r"((uint32_t)C::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -499,6 +552,20 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * C::STAGE;
                     const uint32_t sb = sa + C::PLANES * a_plane;
+                    if (CG2) {
+                        // pair MMA: both CTAs' loads complete on the LEADER's full barrier (its MMA thread is the only
+                        // consumer); the leader arms it with the bytes of both CTAs. Each CTA keeps its own A rows and
+                        // its own half of the W rows: nothing is multicast.
+                        const uint32_t fb = mapa_rank(full_bar(stage), 0);
+                        if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::PLANES * (a_plane + b_plane));
+                        const int nh = n0 + (int)cta_rank * (BN / 2);
+                        tma_load_2d_cg2(sa, &maps.a[si][0], c0, r0, fb);
+                        if (PASSES == 3) tma_load_2d_cg2(sa + a_plane, &maps.a[si][1], c0, r0, fb);
+                        tma_load_2d_cg2(sb, &maps.w[0], kb * kw, nh, fb);
+                        if (PASSES == 3) tma_load_2d_cg2(sb + b_plane, &maps.w[1], kb * kw, nh, fb);
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(full_bar(stage), C::PLANES * (a_plane + b_plane));
                     tma_load_2d(sa, &maps.a[si][0], c0, r0, full_bar(stage));
                     if (PASSES == 3) tma_load_2d(sa + a_plane, &maps.a[si][1], c0, r0, full_bar(stage));
@@ -526,9 +593,9 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer: ONE elected thread =====================
-        if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_f16(BN);
+        // ===================== MMA issuer: ONE elected thread (pair MMA: of the leader CTA only) =====================
+        if ((!CG2 || cta_rank == 0) && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_f16(BN, CG2 ? 2 * BM : BM);
             constexpr uint32_t idesc2 = umma_idesc_f16(C::FUSE ? 2 * BN : BN);  // A_hi x [W_hi; W_lo]
             // k16 steps that hold real columns in the LAST k-block of a segment row: narrow operands (16 channels,
             // 8 audio taps, k*C = 96) are zero-padded to 64 by TMA, and an SS-mode MMA costs ~110 cycles whatever it
@@ -578,6 +645,16 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                             const uint64_t a_lo = umma_desc_at(dhi, sa + a_plane + koff);
                             umma_f16(tmem_d, a_hi, b_hi, idesc2, (kb | k) != 0);  // [hh | hl], W_lo tile follows W_hi
                             umma_f16(tmem_d, a_lo, b_hi, idesc, 1);               // + lh into the first BN columns
+                        } else if (CG2) {
+                            // M = 256 over the pair: descriptors are this (leader) CTA's shared-memory offsets, the peer's
+                            // tensor core uses the same offsets in ITS shared memory
+                            umma_f16_cg2(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0);
+                            if (PASSES == 3) {
+                                const uint64_t a_lo = umma_desc_at(dhi, sa + a_plane + koff);
+                                const uint64_t b_lo = umma_desc_at(dhi, sb + b_plane + koff);
+                                umma_f16_cg2(tmem_d, a_hi, b_lo, idesc, 1);
+                                umma_f16_cg2(tmem_d, a_lo, b_hi, idesc, 1);
+                            }
                         } else {
                             umma_f16(tmem_d, a_hi, b_hi, idesc, (kb | k) != 0);
                             if (PASSES == 3) {
@@ -588,9 +665,12 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                             }
                         }
                     }
-                    if (CL2) umma_commit_mc(empty_bar(stage), (uint16_t)3);  // ... in BOTH CTAs: the peer's W half lives here too
+                    if (CG2) umma_commit_cg2(empty_bar(stage), (uint16_t)3);  // frees the stage in both CTAs
+                    else if (CL2) umma_commit_mc(empty_bar(stage), (uint16_t)3);  // ... in BOTH CTAs: the peer's W half lives here too
                     else umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
                     if (kb == num_kb - 1) {
+                        if (CG2) umma_commit_cg2(tfull_bar(acc), (uint16_t)3);  // both CTAs' epilogues drain their 128 rows
+                        else
                         umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
                         if (ti < 5) stamp(45 + 4 * ti);  // all MMAs of tile ti issued
                     }
@@ -810,7 +890,10 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
             __syncwarp();
             if (threadIdx.x == 64 && ti < 5) stamp(47 + 4 * ti);  // epilogue of tile ti done (this warp)
             if (tile == wid && threadIdx.x == 64) stamp(41);  // epilogue of the first tile done
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) {
+                if (CG2) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));  // the leader's MMA thread waits for both CTAs
+                else mbar_arrive(tempty_bar(acc));
+            }
         }
     }
 
@@ -820,9 +903,14 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     if (CL2) cluster_sync_all();  // the peer may still multicast into this CTA's stages / arrive on its barriers
     if (threadIdx.x == 0) stamp(42);  // barrier issued (BAR.SYNC.DEFER_BLOCKING: not the release time)
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"((uint32_t)C::TMEM_COLS)
-                     : "memory");
+        if (CG2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"((uint32_t)C::TMEM_COLS)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                         "r"((uint32_t)C::TMEM_COLS)
+                         : "memory");
     }
 }
 
@@ -848,6 +936,7 @@ struct LstmArgs {
     int* counters;       // [m_tiles * L * LSTM_KB * LSTM_CNT_PITCH], zeroed before launch
     int B, L, D, m_tiles;
     int t_begin, t_end;  // this launch runs steps [t_begin, t_end): h, c and the counters of earlier steps are in place
+    int publish;         // 0: every lane fences (fence.proxy.async + membar.gl) before the release; 1: one release per warp
     long long* dbg;      // optional timeline of CTA (0,0): 8 stamps per step for steps 4..7
 };
 
@@ -1079,8 +1168,13 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                 // Each warp arrives on its own (lanes fence, __syncwarp orders them before lane 0's release) on the
                 // counter of the k-block this CTA's 16 hidden units belong to.
                 if (threadIdx.x == 64) stamp(t, 5);  // cell math + stores issued
-                asm volatile("fence.proxy.async;" ::: "memory");
-                __threadfence();
+                // publish = 1: the stores of the warp's lanes are ordered before lane 0's release by __syncwarp (the release
+                // is cumulative over writes that happen-before it), so ONE fence round trip per warp instead of two; the
+                // generic -> async proxy ordering is established on the consumer side (fence.proxy.async after its acquire)
+                if (a.publish == 0) {
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __threadfence();
+                }
                 __syncwarp();
                 if (lane == 0) {
                     int* cnt = a.counters + (((long long)mt * a.L + t) * LSTM_KB + (ns >> 2)) * LSTM_CNT_PITCH;
@@ -1186,10 +1280,11 @@ int num_sms() {
     return n;
 }
 
-template <int BN, int PASSES, bool LSTM_EPI = false, bool CL2 = false>
+template <int BN, int PASSES, bool LSTM_EPI = false, int CLM = 0>
 void launch_cfg(const TcGemm& g, cudaStream_t s) {
-    using C = Cfg<BN, PASSES>;
-    auto kernel = tap_gemm_tc_kernel<BN, PASSES, LSTM_EPI, CL2>;
+    constexpr bool CL2 = CLM != 0;
+    using C = Cfg<BN, PASSES, CLM == 2>;
+    auto kernel = tap_gemm_tc_kernel<BN, PASSES, LSTM_EPI, CLM>;
     static PerDevice<bool> attr_dev;
     static PerDevice<int> max_ctas_dev;  // cluster variant: CTAs that can be co-resident as pairs
     bool& attr = attr_dev.get();
@@ -1252,10 +1347,13 @@ void launch_bn(const TcGemm& g, cudaStream_t s) {
     if (g.N <= 128) return launch_cfg<128, PASSES>(g, s);
     const bool wide = g.N % 256 == 0 || g.N > 1024;
     if (!wide) return launch_cfg<128, PASSES>(g, s);
-    // 2-CTA clusters with multicast W loads for the wide tiles (WT_TC_CLUSTER=0 keeps single CTAs)
-    static const bool cluster_on = [] { const char* e = std::getenv("WT_TC_CLUSTER"); return !e || std::atoi(e) != 0; }();
+    // wide tiles run as CTA pairs: WT_TC_CLUSTER=2 one tcgen05.mma.cta_group::2 of M = 256 per pair (each CTA holds half of
+    // W), =1 two cta_group::1 MMAs with the W halves multicast into both CTAs, =0 single CTAs
+    static const int cluster_mode = [] { const char* e = std::getenv("WT_TC_CLUSTER"); return e ? std::atoi(e) : 2; }();
     const int m_tiles = (g.M + BM - 1) / BM;
-    if (cluster_on && g.batch == 1 && g.kw == 64 && m_tiles >= 2) launch_cfg<256, PASSES, false, true>(g, s);
+    const bool pair_ok = g.batch == 1 && g.kw == 64 && m_tiles >= 2;
+    if (pair_ok && cluster_mode == 2) launch_cfg<256, PASSES, false, 2>(g, s);
+    else if (pair_ok && cluster_mode == 1) launch_cfg<256, PASSES, false, 1>(g, s);
     else launch_cfg<256, PASSES>(g, s);
 }
 
@@ -1332,6 +1430,8 @@ void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_
     if (t_end < 0) t_end = L;
     if (t_begin < 0 || t_begin >= t_end || t_end > L) throw Error(4, "lstm_persistent: bad step range");
     a.t_begin = t_begin; a.t_end = t_end;
+    static const int publish = [] { const char* e = std::getenv("WT_LSTM_PUBLISH"); return e ? std::atoi(e) : 1; }();
+    a.publish = publish;
     a.dbg = g_debug_timeline ? g_debug_timeline + 148 * 64 : nullptr;  // after the generic GEMMs' per-CTA slots
     const int n_slices = 4 * D / 64;
     int mgroups = a.m_tiles;

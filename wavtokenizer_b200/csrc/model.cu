@@ -380,7 +380,9 @@ void prepare(wt_handle* h, const Table& t) {
                 for (int k = 0; k < K1; ++k) w1[(size_t)n * rt.Kp1 + k] = c1.hw[(size_t)n * K1 + k];
             rt.w1 = h->upload_split(w1);
             rt.kw2 = C / 2 == 32 ? 32 : 64;
-            const int Cx = i == 0 ? 8 : C;  // shortcut operand: the raw-audio window at level 0
+            // shortcut operand: the raw-audio window at level 0; at level 1 the window of ELU(y0) the level-0 strided conv
+            // reads (composed shortcut, below); x itself deeper down
+            const int Cx = i == 0 ? 8 : (i == 1 ? 2 * c.strides[0] * (C / 2) : C);
             rt.kb0 = (C / 2 + rt.kw2 - 1) / rt.kw2;
             rt.kb1 = (Cx + rt.kw2 - 1) / rt.kw2;
             const int K2 = rt.kw2 * (rt.kb0 + rt.kb1);
@@ -398,6 +400,20 @@ void prepare(wt_handle* h, const Table& t) {
                         w2[(size_t)n * K2 + off1 + j] = (float)acc;
                     }
                     for (int k = 0; k < C; ++k) bacc += (double)sc.hw[(size_t)n * C + k] * h_conv0_b[k];
+                    b2[n] = (float)((double)c2.hb[n] + (double)sc.hb[n] + bacc);
+                } else if (i == 1) {
+                    // level 1: x1 = W_d * a + b_d with a the window of ELU(y0) planes the strided conv reads, so
+                    // shortcut(x1) = (W_sc W_d) * a + W_sc b_d + b_sc reads those planes too (composed in fp64) and the
+                    // strided conv no longer writes the raw-x planes (0.6 GB per 64 clips written and read back)
+                    const ConvW& dn = h->down[0];
+                    const int Kd = dn.k * dn.cin;
+                    for (int j = 0; j < Kd; ++j) {
+                        double acc = 0;
+                        for (int k = 0; k < C; ++k) acc += (double)sc.hw[(size_t)n * C + k] * dn.hw[(size_t)k * Kd + j];
+                        w2[(size_t)n * K2 + off1 + j] = (float)acc;
+                    }
+                    double bacc = 0;
+                    for (int k = 0; k < C; ++k) bacc += (double)sc.hw[(size_t)n * C + k] * dn.hb[k];
                     b2[n] = (float)((double)c2.hb[n] + (double)sc.hb[n] + bacc);
                 } else {
                     for (int k = 0; k < C; ++k) w2[(size_t)n * K2 + off1 + k] = sc.hw[(size_t)n * C + k];
@@ -622,7 +638,7 @@ size_t enc_front_tc_floats(const wt_config& c, int Bc, int T) {
         const size_t s_ = c.strides[i], Tn = (Tc + s_ - 1) / s_;
         for (int k = 0; k < 4; ++k) a((size_t)Bc * (Tc + 2) * C);
         for (int k = 0; k < 2; ++k) a((size_t)Bc * (Tc + 2) * (C / 2));
-        for (int k = 0; k < 2; ++k) a((size_t)Bc * (Tn + 1) * s_ * C);
+        for (int k = 0; k < 2; ++k) a((size_t)Bc * (Tn + 2) * s_ * C);  // (level 0 uses Tn + 2 window slots per clip)
         tot += align_up((size_t)Bc * (Tc + 2) * C * sizeof(float), 256) / sizeof(float);  // optional fp32 tap copies
         tot += align_up((size_t)Bc * (Tn + 2) * 2 * C * sizeof(float), 256) / sizeof(float);
         Tc = Tn; C *= 2;
@@ -910,6 +926,12 @@ void encoder_levels_tc(wt_handle* h, const float* wav, int Bc, int Tin, int i0, 
     static const bool l0_tc = std::getenv("WT_ENC_L0_TC") != nullptr;
     const bool fused0 = !l0_tc && h->rb0_pack != nullptr;
     __half *xr_hi = in.xr_hi, *xr_lo = in.xr_lo, *xe_hi = in.xe_hi, *xe_lo = in.xe_lo;
+    // Composed shortcut of level 1 (weights: prepare()): its ResBlock tail reads the ELU(y0) planes of level 0 instead of
+    // raw-x planes of its own. Both row spaces then need ONE clip pitch: level 1 works on T1 + 2 rows per clip, so the
+    // strided layout of level 0 gets T1 + 2 window slots per clip instead of T1 + 1.
+    const bool composed1 = fused0;
+    const __half *y0_hi = nullptr, *y0_lo = nullptr;  // ELU(y0) planes of level 0 and their size
+    long long nY0 = 0;
     if (i0 == 0 && !fused0) {
         const size_t nX = (size_t)Bc * (Tc + 2) * C;
         const size_t nWin = (size_t)Bc * (Tc + 2) * 8;
@@ -939,7 +961,8 @@ void encoder_levels_tc(wt_handle* h, const float* wav, int Bc, int Tin, int i0, 
         }
         // ---- G2: y = conv1x1(ELU(h1)) + shortcut(x) -> ELU(y) planes in the strided conv's padded layout ----
         const int right = s_ / 2, left = s_ - right, extra = Tn * s_ - Tc;
-        const int Py = (Tn + 1) * s_;
+        const int Q = Tn + ((composed1 && i == 0) ? 2 : 1);  // window slots per clip in the strided conv's row space
+        const int Py = Q * s_;
         const size_t nY = (size_t)Bc * Py * C;
         __half *ye_hi = halves(nY), *ye_lo = halves(nY);
         float* y_tap = want("enc" + std::to_string(idx)) ? h->alloc(nY) : nullptr;
@@ -953,6 +976,8 @@ void encoder_levels_tc(wt_handle* h, const float* wav, int Bc, int Tin, int i0, 
             g.kw = rt.kw2;
             g.seg[0] = tc_window(he_hi, he_lo, rowsX * (C / 2), C / 2, C / 2, 0, rt.kw2);
             if (i == 0) g.seg[1] = tc_window(xr_hi, xr_lo, rowsX * 8, 8, 8, /*shift0=*/1, rt.kw2);  // audio windows
+            else if (i == 1 && composed1)  // row m = b*(T1+2) + t of this GEMM <-> window slot m of the ELU(y0) planes
+                g.seg[1] = tc_window(y0_hi, y0_lo, nY0, 2LL * c.strides[0] * (C / 2), (long long)c.strides[0] * (C / 2), 0, rt.kw2);
             else g.seg[1] = tc_window(xr_hi, xr_lo, rowsX * C, C, C, /*shift0=*/1, rt.kw2);
             g.W_hi = rt.w2.hi; g.W_lo = rt.w2.lo; g.M = (int)rowsX; g.N = C; g.K = rt.kw2 * (rt.kb0 + rt.kb1); g.passes = 3;
             g.bias = rt.bias2;
@@ -963,7 +988,7 @@ void encoder_levels_tc(wt_handle* h, const float* wav, int Bc, int Tin, int i0, 
         }
         if (y_tap) h->tap(("enc" + std::to_string(idx)).c_str(), y_tap + (size_t)left * C, Bc, Tc, C, b0, s, Py);
         // ---- G3: z = strided conv(ELU(y)) -> next level's planes (x and ELU(x)), or the pre-LSTM rows ----
-        const int Q = Tn + 1;
+        if (i == 0) { y0_hi = ye_hi; y0_lo = ye_lo; nY0 = (long long)nY; }
         const int C2 = 2 * C;
         TcGemm g;
         g.seg[0] = tc_window(ye_hi, ye_lo, (long long)nY, 2 * s_ * C, (long long)s_ * C);
@@ -973,10 +998,14 @@ void encoder_levels_tc(wt_handle* h, const float* wav, int Bc, int Tin, int i0, 
         float* z_tap = nullptr;
         if (i < 3) {
             const size_t nX2 = (size_t)Bc * (Tn + 2) * C2;
+            const bool need_x = !(composed1 && i == 0 && i1 > 1);  // level 1's shortcut reads ELU(y0) instead
             if (i == i1 - 1) { xr_hi = out.xr_hi; xr_lo = out.xr_lo; xe_hi = out.xe_hi; xe_lo = out.xe_lo; }
-            else { xr_hi = halves(nX2); xr_lo = halves(nX2); xe_hi = halves(nX2); xe_lo = halves(nX2); }
+            else {
+                xr_hi = need_x ? halves(nX2) : nullptr; xr_lo = need_x ? halves(nX2) : nullptr;
+                xe_hi = halves(nX2); xe_lo = halves(nX2);
+            }
             g.map.Pout = Tn + 2; g.map.off = 1; g.map.hl = 1; g.map.hr = 1;
-            g.out_hi = xr_hi; g.out_lo = xr_lo; g.ldh = C2;
+            if (need_x) { g.out_hi = xr_hi; g.out_lo = xr_lo; g.ldh = C2; }
             g.elu_hi = xe_hi; g.elu_lo = xe_lo; g.ldh2 = C2;
             if (want("enc" + std::to_string(idx + 2))) { z_tap = h->alloc(nX2); g.out_f32 = z_tap; g.ldo = C2; }
         } else {
