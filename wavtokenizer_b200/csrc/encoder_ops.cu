@@ -263,13 +263,18 @@ resblock0_fused_kernel(const float* __restrict__ wav, const float* __restrict__ 
     }
     __syncthreads();
 
-    // ---- stage C: y = conv1x1(ELU(h1)) + composed shortcut k7 of the raw audio; two passes of 8 channels ----
-    float a10[10];  // samples t - 3 .. t + 6 of the first position = sA[pos0 + 1 ..]
-#pragma unroll
-    for (int j = 0; j < 10; ++j) a10[j] = sA[pos0 + 1 + j];
+    // ---- stage C: y = conv1x1(ELU(h1)) + composed shortcut k7 of the raw audio ----
+    // Two passes over POSITIONS (256 each); a thread owns 4 positions x 8 channels and adjacent lanes own the two
+    // 8-channel halves of the same rows, so that the 16-byte plane stores of a lane pair fill whole 32-byte sectors
+    // (channel passes left every sector half empty: ncu, 16 of 32 bytes per sector used).
+    const int cgrp = tid & 1;
+    const int ch0 = half * 16 + cgrp * 8;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-        const int ch0 = half * 16 + pass * 8;
+        const int pos0 = pass * 256 + ((tid & 127) >> 1) * 4;
+        float a10[10];  // samples t - 3 .. t + 6 of the first position = sA[pos0 + 1 ..]
+#pragma unroll
+        for (int j = 0; j < 10; ++j) a10[j] = sA[pos0 + 1 + j];
         float acc[4][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {

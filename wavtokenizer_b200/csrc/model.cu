@@ -929,7 +929,7 @@ void encoder_levels_tc(wt_handle* h, const float* wav, int Bc, int Tin, int i0, 
     // Composed shortcut of level 1 (weights: prepare()): its ResBlock tail reads the ELU(y0) planes of level 0 instead of
     // raw-x planes of its own. Both row spaces then need ONE clip pitch: level 1 works on T1 + 2 rows per clip, so the
     // strided layout of level 0 gets T1 + 2 window slots per clip instead of T1 + 1.
-    const bool composed1 = fused0;
+    const bool composed1 = true;
     const __half *y0_hi = nullptr, *y0_lo = nullptr;  // ELU(y0) planes of level 0 and their size
     long long nY0 = 0;
     if (i0 == 0 && !fused0) {
