@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <string>
 #include <unordered_map>
 
 #include "common.cuh"
@@ -1438,11 +1439,11 @@ void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_
     while (n_slices * mgroups > num_sms()) --mgroups;  // every CTA must be co-resident (they wait on each other)
     if (mgroups < 1) throw Error(4, "lstm_persistent: device too small");
     if (4 * D / 64 != LSTM_KB * 4 || LSTM_CTAS_PER_KB != 4 * LSTM_EPI_WARPS) throw Error(4, "lstm_persistent: slice / k-block mapping");
+    CUtensorMap mw_hi = make_map(w_hi, 4LL * D, D, D, 64);
+    CUtensorMap mw_lo = make_map(w_lo, 4LL * D, D, D, 64);
     if (t_begin == 0) WT_CUDA(cudaMemsetAsync(counters, 0, lstm_counter_ints(B, L) * sizeof(int), s));
     CUtensorMap mh_hi = make_map(h_hi, (long long)L * B, D, D, BM);
     CUtensorMap mh_lo = make_map(h_lo, (long long)L * B, D, D, BM);
-    CUtensorMap mw_hi = make_map(w_hi, 4LL * D, D, D, 64);
-    CUtensorMap mw_lo = make_map(w_lo, 4LL * D, D, D, 64);
     void* args[] = {&mh_hi, &mh_lo, &mw_hi, &mw_lo, &a};
     WT_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_persistent_kernel, dim3(n_slices, mgroups), dim3(LSTM_THREADS),
                                         args, (size_t)LSTM_SMEM, s));
