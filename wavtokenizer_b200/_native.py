@@ -90,6 +90,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
     cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+    if os.environ.get("WT_TIMELINE"):  # instrumented build for tools/gemm_timeline.py (per-CTA clock64 stamps)
+        cflags.append("-DWT_TIMELINE=1")
 
     def compile_one(src: str):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")

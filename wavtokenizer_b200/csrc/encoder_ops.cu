@@ -207,17 +207,12 @@ resblock0_fused_kernel(const float* __restrict__ wav, const float* __restrict__ 
             e += RB0_THREADS;
             e[0] = elu_fast(c.x); e[RB0_LD] = elu_fast(c.y); e[2 * RB0_LD] = elu_fast(c.z); e[3 * RB0_LD] = elu_fast(c.w);
         }
-        if (tid < 2) {  // the last two columns (TILE, TILE + 1)
-            const int col = RB0_TILE + tid;
+        if (tid < 64) {  // the last two columns (TILE, TILE + 1): one (column, channel) per thread of the first two warps
+            const int col = RB0_TILE + (tid >> 5), ch = tid & 31;
+            float acc = sW[RB0_B0 + ch];
 #pragma unroll
-            for (int j = 0; j < 7; ++j) xa[j] = sA[col + j];
-#pragma unroll 1
-            for (int ch = 0; ch < 32; ++ch) {
-                float acc = sW[RB0_B0 + ch];
-#pragma unroll
-                for (int j = 0; j < 7; ++j) acc = fmaf(sW[RB0_W0 + j * 32 + ch], xa[j], acc);
-                sE0[ch * RB0_LD + col] = elu_fast(acc);
-            }
+            for (int j = 0; j < 7; ++j) acc = fmaf(sW[RB0_W0 + j * 32 + ch], sA[col + j], acc);
+            sE0[ch * RB0_LD + col] = elu_fast(acc);
         }
     }
     __syncthreads();

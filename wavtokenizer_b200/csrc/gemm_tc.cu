@@ -12,11 +12,15 @@
 //   tensor are zero-filled by TMA) and "window" mode (rows of the tensor map OVERLAP: row stride =
 //   conv_stride*C, row length = k*C, i.e. the im2col matrix of a strided Conv1d without materialising it).
 //   Up to two segments accumulate into one tile (ResBlock: conv1x1(ELU(h)) + shortcut1x1(x)).
-// * One CTA per SM, persistent over output tiles (128 x BN). Warp 0 = TMA producer, warp 1 = MMA issuer
-//   (single thread, tcgen05.mma cta_group::1 kind::f16) + TMEM allocator, warps 2..5 = epilogue
-//   (tcgen05.ld 32x32b -> bias / GELU / layer-scale / residual / ELU / LSTM cell -> fp32 and/or
-//   split-fp16 stores, optionally re-mapped into the reflect-padded layout of the consumer).
-//   Two TMEM accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
+// * One CTA per SM, persistent over output tiles (128 x BN). Warp 0 = TMA producer (one elected thread), warp 1 = MMA
+//   issuer (one elected thread, tcgen05.mma kind::f16) + TMEM allocator, warps 2..17 = sixteen epilogue warps, four per
+//   TMEM lane quarter (tcgen05.ld 32x32b -> bias / GELU / layer-scale / residual / ELU / LSTM cell / VQ argmin -> fp32
+//   and/or split-fp16 stores, optionally re-mapped into the reflect-padded layout of the consumer). Wide accumulators
+//   (256 columns): two TMEM stages, all 16 warps drain one tile while the mainloop of the next runs; narrow accumulators
+//   (<= 128 columns): four TMEM stages and four independent groups of 4 warps (struct Cfg).
+// * 256-column tiles run as CTA PAIRS (cluster of 2, two consecutive row tiles of one column tile): by default one
+//   tcgen05.mma.cta_group::2 of M = 256 per step with each CTA holding half of the weight rows (CLM = 2); CLM = 1 is the
+//   earlier variant (two cta_group::1 MMAs, weight halves multicast into both CTAs).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -28,6 +32,10 @@
 
 #include "common.cuh"
 #include "gemm_tc.cuh"
+
+#ifndef WT_TIMELINE
+#define WT_TIMELINE 0
+#endif
 
 namespace wt {
 
@@ -200,8 +208,11 @@ __device__ __forceinline__ void umma_commit_cg2(uint32_t bar, uint16_t mask) {
         : "memory");
 }
 // arrive on an mbarrier of another CTA of the cluster (`bar` is a shared::cluster address)
+// Default semantics (.release at CTA scope): what is handed over is the TMEM accumulator stage, already ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync. A .release.cluster here costs MEMBAR.ALL.GPU + ERRBAR per tile,
+// i.e. a wait for the tile's global stores (ncu: 14.6 % of the ConvNeXt GEMM-1 stall samples).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -445,10 +456,14 @@ struct Maps {
 // (tcgen05.commit multicast onto both CTAs' empty barriers).
 // CLM = 2 (cta_group::2): same pairing of CTAs and tiles, but the pair runs ONE tcgen05.mma of M = 256 per step, issued by
 // the leader CTA; each CTA keeps only its half of the W rows (no multicast copy), see the cta_group::2 helpers above.
-template <int BN, int PASSES, bool LSTM_EPI = false, int CLM = 0>
+// EPI selects a specialised epilogue instantiation: 0 generic (+ VQ argmin), 1 LSTM cell, 2 ConvNeXt GEMM-1 only (bias +
+// erf-GELU -> fp16 plane). The specialised kernels do not carry the generic path's live state (row re-map, mirror rows,
+// three output forms), which the 96-register cap otherwise turns into local-memory traffic inside the tile loop.
+template <int BN, int PASSES, int EPI = 0, int CLM = 0>
 // 18 warps are allocated as 20 (warp granularity 4): 65536 / (20 * 32) = 102 -> 96 registers per thread.
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
+    constexpr bool LSTM_EPI = EPI == 1, GELU_EPI = EPI == 2;
     constexpr bool CL2 = CLM != 0;  // the kernel runs as clusters of two CTAs
     constexpr bool CG2 = CLM == 2;  // ... whose tensor cores execute one M = 256 MMA together
     using C = Cfg<BN, PASSES, CG2>;
@@ -465,9 +480,15 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per-CTA timeline stamps (tools/gemm_timeline.py) exist only in builds with -DWT_TIMELINE=1 (WT_TIMELINE=1 in the
+    // environment of _native.build): in the shipped kernels they cost registers the 96-register cap does not have
+#if WT_TIMELINE
     long long* dbg = g.dbg ? g.dbg + (long long)blockIdx.x * 64 : nullptr;
     const long long t_begin = dbg ? clock64() : 0;
     auto stamp = [&](int slot) { if (dbg && slot < 64) dbg[slot] = clock64() - t_begin; };
+#else
+    auto stamp = [](int) {};
+#endif
     const int m_tiles = (g.M + BM - 1) / BM;
     const int n_tiles = (g.N + BN - 1) / BN;
     const int per_batch = m_tiles * n_tiles;
@@ -713,7 +734,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
             bool row_ok = m_local < g.M;
             // destination rows (identity, or re-mapped into the consumer's reflect-padded layout)
             long long dst = m, mir_l = -1, mir_r = -1;
-            if (g.map.Pin) {
+            if (!GELU_EPI && g.map.Pin) {
                 const int b = m / g.map.Pin, t = m - b * g.map.Pin;
                 row_ok = row_ok && t < g.map.Tvalid;
                 const long long sb = g.map.sb ? g.map.sb : g.map.Pout, st = g.map.st ? g.map.st : 1;
@@ -723,7 +744,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                 if (t <= g.map.Tvalid - 2 && t >= g.map.Tvalid - 1 - g.map.hr)
                     mir_r = base + (2 * (g.map.Tvalid - 1) - t) * st;
             }
-            if (LSTM_EPI) {  // separate instantiation: keeps the cell's registers out of the generic kernels
+            if constexpr (LSTM_EPI) {  // separate instantiation: keeps the cell's registers out of the generic kernels
                 // LSTM cell (reference encoder/modules/lstm.py:20; gates i, f, g, o). Tile columns hold
                 // [i | f | g | o] x 16 hidden units; the thread owns one batch row, two warps per lane quarter work.
 #pragma unroll 1
@@ -769,7 +790,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                         if (g.out_hi) store_planes<8, false>(g.out_hi, g.out_lo, (long long)m * g.ldh + u0, hv);
                     }
                 }
-            } else if (BN == 256 && PASSES == 3 && g.act == TC_ACT_ARGMIN) {
+            } else if (!GELU_EPI && BN == 256 && PASSES == 3 && g.act == TC_ACT_ARGMIN) {
                 // nearest code (reference encoder/quantization/core_vq.py:175-183): argmin_n ||x - c_n||^2 =
                 // argmin_n (||c_n||^2 - 2 x.c_n); operands are centred on the codebook mean (distance-invariant),
                 // first index wins ties (packed (distance, index) keys under a 64-bit atomicMin).
@@ -792,8 +813,8 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                     u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // order-preserving float -> uint
                     atomicMin(g.best + m, ((unsigned long long)u << 32) | (unsigned)bi);
                 }
-            } else if (PASSES == 1 && BN == 256 && g.act == TC_ACT_GELU && g.out_hi && !g.out_lo && !g.out_f32 &&
-                       !g.elu_hi && !g.map.Pin && !g.gamma && !g.res && n0 + BN <= g.N) {
+            } else if (GELU_EPI || (PASSES == 1 && BN == 256 && g.act == TC_ACT_GELU && g.out_hi && !g.out_lo && !g.out_f32 &&
+                                    !g.elu_hi && !g.map.Pin && !g.gamma && !g.res && n0 + BN <= g.N)) {
                 // ConvNeXt GEMM-1 fast path (reference decoder/modules.py:54-55): bias + exact-erf GELU -> fp16 plane,
                 // 32 columns per tcgen05.ld so that the fixed per-chunk cost is paid half as often; nothing else live.
                 static_assert(BN / C::G == 64 || BN != 256 || PASSES != 1, "two 32-column chunks per warp");
@@ -824,7 +845,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                         }
                     }
                 }
-            } else {
+            } else if constexpr (!GELU_EPI) {
 #pragma unroll 1
                 for (int c = cg; c < BN / CW; c += C::G) {
                     uint32_t r[CW];
@@ -921,7 +942,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
 // One cooperative launch runs all L time steps of one layer. CTA (ns, mg) owns the 64 gate columns of
 // hidden units [16 ns, 16 ns + 16) (W_hh rows are permuted at load so that they are contiguous) and the batch
 // tiles mg, mg + MG, ...: its slice of W_hh (hi + lo planes, 128 KB) is loaded into shared memory ONCE and
-// stays resident for the whole layer. Per step it streams h_{t-1} of its batch tile through a 2-stage TMA
+// stays resident for the whole layer. Per step it streams h_{t-1} of its batch tile through a 3-stage TMA
 // ring, accumulates W_hh h in TMEM with 3-pass split-fp16 tcgen05 MMAs, and the epilogue warps apply the
 // LSTM cell (adding the hoisted input projection) and publish h_t as fp32 rows and split-fp16 planes.
 // The 32 CTAs that share a batch tile synchronise once per step through an arrival counter in global memory
@@ -1281,11 +1302,11 @@ int num_sms() {
     return n;
 }
 
-template <int BN, int PASSES, bool LSTM_EPI = false, int CLM = 0>
+template <int BN, int PASSES, int EPI = 0, int CLM = 0>
 void launch_cfg(const TcGemm& g, cudaStream_t s) {
     constexpr bool CL2 = CLM != 0;
     using C = Cfg<BN, PASSES, CLM == 2>;
-    auto kernel = tap_gemm_tc_kernel<BN, PASSES, LSTM_EPI, CLM>;
+    auto kernel = tap_gemm_tc_kernel<BN, PASSES, EPI, CLM>;
     static PerDevice<bool> attr_dev;
     static PerDevice<int> max_ctas_dev;  // cluster variant: CTAs that can be co-resident as pairs
     bool& attr = attr_dev.get();
@@ -1341,7 +1362,7 @@ void launch_cfg(const TcGemm& g, cudaStream_t s) {
 
 template <int PASSES>
 void launch_bn(const TcGemm& g, cudaStream_t s) {
-    if (g.act == TC_ACT_LSTM) return launch_cfg<64, PASSES, true>(g, s);
+    if (g.act == TC_ACT_LSTM) return launch_cfg<64, PASSES, 1>(g, s);
     if (g.N <= 16) return launch_cfg<16, PASSES>(g, s);
     if (g.N <= 32) return launch_cfg<32, PASSES>(g, s);
     if (g.N <= 64) return launch_cfg<64, PASSES>(g, s);
@@ -1353,8 +1374,14 @@ void launch_bn(const TcGemm& g, cudaStream_t s) {
     static const int cluster_mode = [] { const char* e = std::getenv("WT_TC_CLUSTER"); return e ? std::atoi(e) : 2; }();
     const int m_tiles = (g.M + BM - 1) / BM;
     const bool pair_ok = g.batch == 1 && g.kw == 64 && m_tiles >= 2;
-    if (pair_ok && cluster_mode == 2) launch_cfg<256, PASSES, false, 2>(g, s);
-    else if (pair_ok && cluster_mode == 1) launch_cfg<256, PASSES, false, 1>(g, s);
+    if constexpr (PASSES == 1) {
+        // ConvNeXt GEMM-1 (bias + erf-GELU -> one fp16 plane, whole column tiles): the specialised epilogue instantiation
+        const bool gelu_only = g.act == TC_ACT_GELU && g.out_hi && !g.out_lo && !g.out_f32 && !g.elu_hi && !g.map.Pin &&
+                               !g.gamma && !g.res && g.bias && g.N % 256 == 0;
+        if (gelu_only && pair_ok && cluster_mode == 2) return launch_cfg<256, 1, 2, 2>(g, s);
+    }
+    if (pair_ok && cluster_mode == 2) launch_cfg<256, PASSES, 0, 2>(g, s);
+    else if (pair_ok && cluster_mode == 1) launch_cfg<256, PASSES, 0, 1>(g, s);
     else launch_cfg<256, PASSES>(g, s);
 }
 
