@@ -578,14 +578,27 @@ def extras(m: dict, args, dev, rank: int, world: int, flush, peaks: dict) -> tup
     rag = [torch.randn(SR + i * (4 * SR // n_rag) + 7 * i, device=dev, generator=g).clamp_(-1, 1) for i in range(n_rag)]
     rag_s = sum(x.numel() for x in rag) / SR
 
-    def rag_step(k):
-        enc = model.encode_infer_ragged(rag, streams=k, bandwidth_id=bw)
+    def rag_step(k, batched):
+        enc = model.encode_infer_ragged(rag, streams=k, batched=batched, bandwidth_id=bw)
         return model.decode_ragged([f for f, _ in enc], streams=k, bandwidth_id=bw)
-    ragged_row = {"workload": f"{n_rag} clips of {n_rag} distinct lengths, 1 - 5 s ({rag_s:.0f} audio-s): one batch-of-one "
-                              "bucket per clip, encode_infer_ragged + decode_ragged"}
+    ragged_row = {"workload": f"{n_rag} clips of {n_rag} distinct lengths, 1 - 5 s ({rag_s:.0f} audio-s), "
+                              "encode_infer_ragged + decode_ragged; 'buckets': one batch-of-one call per clip on k streams; "
+                              "'batched': the ragged C-ABI entries (the default of encode_infer_ragged / decode_ragged)"}
     for k in (1, 4):
-        r_ms = event_ms(lambda: rag_step(k), 2, flush, warm=1)
-        ragged_row[f"streams_{k}"] = {"ms": round(r_ms, 2), "audio_s_per_s": round(rag_s / (r_ms * 1e-3), 1)}
+        r_ms = event_ms(lambda: rag_step(k, False), 2, flush, warm=1)
+        ragged_row[f"buckets_streams_{k}"] = {"ms": round(r_ms, 2), "audio_s_per_s": round(rag_s / (r_ms * 1e-3), 1)}
+    e_ms = event_ms(lambda: model.encode_infer_ragged(rag, batched=True, bandwidth_id=bw), 2, flush, warm=1)
+    b_ms = event_ms(lambda: model.encode_infer_ragged(rag, batched=False, bandwidth_id=bw), 2, flush, warm=1)
+    ragged_row["encode_only"] = {"batched_ms": round(e_ms, 2), "buckets_ms": round(b_ms, 2),
+                                 "batched_audio_s_per_s": round(rag_s / (e_ms * 1e-3), 1)}
+
+    def rag_batched():
+        enc = model.encode_infer_ragged(rag, batched=True, bandwidth_id=bw)
+        return model.decode_ragged([f for f, _ in enc], batched=True, bandwidth_id=bw)
+    r_ms = event_ms(rag_batched, 3, flush, warm=1)
+    ragged_row["batched"] = {"ms": round(r_ms, 2), "audio_s_per_s": round(rag_s / (r_ms * 1e-3), 1),
+                             "api": "wt_encode_ragged + wt_decode_ragged: one LSTM recurrence and one padded decoder row "
+                                    "space for all clips, per-clip lengths in the kernels that look across rows"}
     next_rows["ragged_batches"] = ragged_row
     del rag
     torch.cuda.empty_cache()

@@ -83,6 +83,17 @@ int wt_reserve(wt_handle* h, int32_t B, int32_t T);
 int wt_encode(wt_handle* h, const float* wav, int32_t B, int32_t T, float* features_out,
               int64_t* codes_out, void* stream);
 
+/* encode_infer of B clips of DIFFERENT lengths in one call (the caller pattern is the
+ * reference's one-file-at-a-time loop, infer.py:44-54, whose per-file results this reproduces exactly: nothing is padded
+ * to a common length, every clip keeps its own reflect padding and frame count). `lengths` [B] is HOST memory (samples per
+ * clip); wav (device) holds the clips back to back, sum(lengths) samples. Outputs are packed in the same order:
+ * features_out clip b as [dimension, L_b] (may be NULL), codes_out [sum_b L_b], L_b = wt_frames_for(lengths[b]).
+ * The conv front runs per run of equal-length clips; the LSTM, the last conv and the VQ run once for all clips (the
+ * recurrence is a latency chain whose cost does not depend on the batch). Clips too short for the tensor-core encoder
+ * layout (a few hundred samples) -> WT_ERR_VALUE: encode those one by one with wt_encode. */
+int wt_encode_ragged(wt_handle* h, const float* wav, const int32_t* lengths, int32_t B, float* features_out,
+                     int64_t* codes_out, void* stream);
+
 /* feature_extractor.encodec.encoder(wav[B,1,T]) (encoder/modules/seanet.py:143-144):
  * the pre-quantisation latent z [B, dimension, L]. */
 int wt_encoder_forward(wt_handle* h, const float* wav, int32_t B, int32_t T, float* z_out, void* stream);
@@ -103,6 +114,14 @@ int wt_check_errors(wt_handle* h);
  * audio [B, L*hop_length]. One bandwidth_id for the whole batch (decoder/modules.py:81-86). */
 int wt_decode(wt_handle* h, const float* features, int32_t B, int32_t L, int32_t bandwidth_id,
               float* audio_out, void* stream);
+
+/* decode of B feature maps of DIFFERENT lengths in one call (same caller pattern and exactness contract as
+ * wt_encode_ragged: clip b's audio equals a batch-of-one wt_decode). lengths [B]: HOST memory, frames per clip;
+ * features (device): clip b as [dimension, L_b], packed back to back; audio_out: clip b as L_b * hop_length samples,
+ * packed the same way. All clips share one padded row space (pitch = longest clip of the chunk + 3): the GEMMs run over
+ * it as usual; GroupNorm, attention, the depthwise conv and the overlap-add read each clip's own length. */
+int wt_decode_ragged(wt_handle* h, const float* features, const int32_t* lengths, int32_t B, int32_t bandwidth_id,
+                     float* audio_out, void* stream);
 
 /* EuclideanCodebook.quantize + dequantize (encoder/quantization/core_vq.py:175-190) on
  * row-major frames x [N, dimension] -> codes [N] int64, quantized [N, dimension] (may be NULL). */

@@ -102,3 +102,62 @@ def test_ragged_batch_matches_one_clip_at_a_time_oracle():
         f1, c1 = m.encode_infer(w.cuda().unsqueeze(0), bandwidth_id=bw.cuda())
         assert torch.equal(c1, c)
     assert launches_ragged < m.launch_count() - before
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["small320", "small600"])
+def test_ragged_batched_encode_equals_one_clip_at_a_time(tag):
+    """wt_encode_ragged (one LSTM recurrence for clips of different lengths, per-run conv fronts) returns bit for bit what
+    a batch-of-one encode_infer returns for every clip: rows of the recurrent GEMM are independent, the reflect padding
+    in front of the last conv is taken at each clip's own end, filler frames are dropped."""
+    from tests.gpu_util import native_model
+    from wavtokenizer_b200 import spec
+    m = native_model(tag, 2)
+    lens = [24000, 31111, 24000, 9000, 48017, 12345, 24000, 9000, 20000]
+    wavs = [spec.synthetic_audio(1, n, seed=170 + i)[0].cuda() for i, n in enumerate(lens)]
+    bw = torch.tensor([0]).cuda()
+    n0 = m.launch_count()
+    got = m.encode_infer_ragged(wavs, bandwidth_id=bw)
+    n_batched = m.launch_count() - n0
+    n0 = m.launch_count()
+    for w, (f, c) in zip(wavs, got):
+        f1, c1 = m.encode_infer(w.unsqueeze(0), bandwidth_id=bw)
+        assert c.shape == c1.shape and f.shape == f1.shape
+        assert torch.equal(c, c1) and torch.equal(f, f1)
+    assert n_batched < m.launch_count() - n0  # equal-length runs share a front pass; one recurrence for all clips
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["small320", "small600"])
+def test_ragged_batched_decode_equals_one_clip_at_a_time(tag):
+    """wt_decode_ragged (one padded row space, per-clip lengths in GroupNorm / attention / depthwise conv / overlap-add)
+    against batch-of-one decode calls of the same path, and one clip against the oracle."""
+    from oracle import wavtok_oracle as O
+    from tests import helpers
+    from tests.gpu_util import native_model
+    cfg, sd = helpers.model(tag)
+    m = native_model(tag, 2)
+    g = torch.Generator().manual_seed(21)
+    Ls = [75, 230, 75, 31, 150, 4, 97, 230, 1]
+    codes = [torch.randint(0, cfg.vq_bins, (1, 1, L), generator=g) for L in Ls]
+    feats = [m.codes_to_features(c.cuda())[0] for c in codes]
+    bw = torch.tensor([2]).cuda()
+    n0 = m.launch_count()
+    got = m.decode_ragged(feats, bandwidth_id=bw)
+    n_batched = m.launch_count() - n0
+    n0 = m.launch_count()
+    for f, a, L in zip(feats, got, Ls):
+        a1 = m.decode(f.unsqueeze(0), bandwidth_id=bw)
+        assert a.shape == a1.shape == (1, L * cfg.hop_length)
+        # same kernels on the same rows; the GroupNorm reduction order depends on the common pitch, and a 1e-7 difference
+        # upstream moves fp16 roundings of the single-pass ConvNeXt operands: agreement at the 95 dB level (bar: 60 dB)
+        assert helpers.snr_db(a1, a) >= 88.0, (L, helpers.snr_db(a1, a))
+    assert n_batched < (m.launch_count() - n0) // 4
+    i = 4
+    with torch.inference_mode():
+        ref = O.decode(sd, cfg, O.codes_to_features(sd, cfg, codes[i]), torch.tensor([2]))
+    assert helpers.snr_db(ref, got[i].cpu()) >= 60.0
+    # bucketed and batched paths agree, in input order
+    alt = m.decode_ragged(feats, batched=False, bandwidth_id=bw)
+    for a, b2 in zip(got, alt):
+        assert helpers.snr_db(b2, a) >= 88.0

@@ -42,9 +42,11 @@ SYMBOLS = {
     "wt_workspace_bytes": (_I64, [_P, _I32, _I32]),
     "wt_reserve": (ctypes.c_int, [_P, _I32, _I32]),
     "wt_encode": (ctypes.c_int, [_P, _P, _I32, _I32, _P, _P, _P]),
+    "wt_encode_ragged": (ctypes.c_int, [_P, _P, ctypes.POINTER(_I32), _I32, _P, _P, _P]),
     "wt_encoder_forward": (ctypes.c_int, [_P, _P, _I32, _I32, _P, _P]),
     "wt_codes_to_features": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
     "wt_decode": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
+    "wt_decode_ragged": (ctypes.c_int, [_P, _P, ctypes.POINTER(_I32), _I32, _I32, _P, _P]),
     "wt_vq": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P]),
     "wt_encode_decode_host": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P]),
     "wt_tap_request": (ctypes.c_int, [_P, ctypes.c_char_p, _P, _I64]),

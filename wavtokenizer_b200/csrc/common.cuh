@@ -102,8 +102,9 @@ void launch_conv0_planes(const float* wav, const float* w, const float* bias, __
 int resblock0_pack_floats();
 void launch_resblock0_fused(const float* wav, const float* pack, __half* ye_hi, __half* ye_lo, float* y_f32, int B, int T,
                             int Py, int left, int hr, cudaStream_t s);
+// len_tab (device, [B], optional): per-clip frame counts of a ragged batch; L is then the longest clip (the row pitch)
 void launch_lstm_skip_elu_pad(const float* y, const float* x, float* out_f32, __half* elu_hi, __half* elu_lo, int B,
-                              int L, int D, cudaStream_t s);
+                              int L, int D, cudaStream_t s, const int* len_tab = nullptr);
 
 // vq
 void launch_vq_simt(const float* x, const float* codebook, const float* cnorm, long long N, int D, int bins,
@@ -133,24 +134,34 @@ inline RowOut out_split(__half* hi, __half* lo, float* also_f32 = nullptr) {
     RowOut o; o.hi = hi; o.lo = lo; o.f32 = also_f32; return o;
 }
 
+// Ragged decoder batch: every clip keeps the common row pitch Lp = Lmax + 3, clip b holds len[b]
+// <= Lmax frames and everything from there to the pitch is halo (zeros wherever a k-tap conv reads it). off[b] = frames of
+// the clips before b: where clip b sits in the PACKED API tensors (features in, audio out). Null pointers: uniform batch.
+struct Ragged {
+    const int* len = nullptr;
+    const long long* off = nullptr;
+};
+
 // decoder (clip b owns rows [b*Lp, b*Lp + L); Lp - L halo rows after each clip are written as zeros)
-void launch_features_to_rows(const float* in /*[B,C,L]*/, RowOut out, int B, int C, int L, int Lp, cudaStream_t s);
+void launch_features_to_rows(const float* in /*[B,C,L]*/, RowOut out, int B, int C, int L, int Lp, cudaStream_t s,
+                             Ragged rg = Ragged{});
 void launch_groupnorm(const float* x, const float* w, const float* b, RowOut out, int B, int L, int Lp, int C,
-                      int groups, float eps, int swish, cudaStream_t s);
+                      int groups, float eps, int swish, cudaStream_t s, Ragged rg = Ragged{});
 void launch_layernorm(const float* x, const float* w, const float* b, RowOut out, long long M, int C, float eps,
                       cudaStream_t s);
 void launch_dwconv_ln(const float* x, const float* dw /*[7,C] (taps transposed at load)*/, const float* db, const float* scale,
-                      const float* shift, RowOut out, int B, int L, int Lp, int C, float eps, cudaStream_t s);
+                      const float* shift, RowOut out, int B, int L, int Lp, int C, float eps, cudaStream_t s,
+                      Ragged rg = Ragged{});
 void launch_attention(const float* qkv /*[B*Lp, 3C]*/, RowOut out /*[B*Lp, C]*/, int B, int L, int Lp, int C,
                       cudaStream_t s);
 // tensor-core attention helpers (scores and P.V run as batched tcgen05 GEMMs)
 void launch_softmax_planes(const float* S, int ldS, __half* p_hi, __half* p_lo, int Lpad, int B, int L, int Lp,
-                           float scale, cudaStream_t s);
+                           float scale, cudaStream_t s, Ragged rg = Ragged{});
 void launch_vt_planes(const __half* q_hi, const __half* q_lo, __half* vt_hi, __half* vt_lo, int B, int L, int Lp, int C,
-                      int Lpad, cudaStream_t s);
+                      int Lpad, cudaStream_t s, Ragged rg = Ragged{});
 void launch_spectral(const float* z /*[M, ldz]*/, int ldz, RowOut S /*[M, ldS]*/, long long M, int half, int ldS,
                      cudaStream_t s);
 void launch_overlap_add(const float* frames /*[B*Lp, n_fft]*/, const float* wsq /*[n_fft]*/, float* audio, int B, int L,
-                        int Lp, int n_fft, int hop, cudaStream_t s);
+                        int Lp, int n_fft, int hop, cudaStream_t s, Ragged rg = Ragged{});
 
 }  // namespace wt

@@ -79,11 +79,12 @@ constexpr int GN_GPB = 2, GN_LANES = GN_GPB * 6, GN_PH = 32, GN_THREADS = GN_LAN
 template <int RES>
 __global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                const float* __restrict__ bsh, RowOut out, int L, int Lp,
-                                                               int C, float eps, int swish) {
+                                                               int C, float eps, int swish, Ragged rg) {
     __shared__ float ps[GN_THREADS], pq[GN_THREADS];
     __shared__ double rs[GN_LANES], rq[GN_LANES];
     __shared__ float s_mean[GN_GPB], s_rstd[GN_GPB];
     const int b = blockIdx.y, slab = blockIdx.x;
+    if (rg.len) L = rg.len[b];  // ragged: statistics over the clip's own frames, zero rows from there to the pitch
     const int lane = threadIdx.x % GN_LANES, ph = threadIdx.x / GN_LANES;
     const int c = slab * (GN_GPB * 24) + lane * 4;
     const long long base = (long long)b * Lp * C + c;
@@ -248,11 +249,12 @@ __device__ __forceinline__ void warp_sum16(float (&v)[16], int lane) {
 __global__ void __launch_bounds__(DW_THREADS, 2) dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ dwT,
                                                                   const float* __restrict__ db, const float* __restrict__ scale,
                                                                   const float* __restrict__ shift, RowOut out, int L, int Lp,
-                                                                  float eps) {
+                                                                  float eps, Ragged rg) {
     constexpr int C = 768, NW = DW_THREADS / 32;
     __shared__ __align__(16) float red[2][DW_TT][8];  // [pass][frame][warp] partial sums (6 used)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y, t0 = blockIdx.x * DW_TT;
+    if (rg.len) L = rg.len[b];  // ragged: rows past the clip's own end read as the conv's zero padding and are written as zeros
     const int c = threadIdx.x * 4;
     const float* xb = x + (long long)b * Lp * C + c;
     float4 xr[DW_TT + 6];
@@ -409,9 +411,11 @@ __global__ void __launch_bounds__(256) spectral_kernel(const float* __restrict__
 // frames already carry the window (folded into the iDFT basis). Each output sample sums the <= n_fft/hop
 // frames that cover it and divides by the matching sum of squared window samples.
 __global__ void overlap_add_kernel(const float* __restrict__ frames, const float* __restrict__ wsq,
-                                   float* __restrict__ audio, int L, int Lp, int n_fft, int hop, int pad) {
+                                   float* __restrict__ audio, int L, int Lp, int n_fft, int hop, int pad, Ragged rg) {
     const int b = blockIdx.y;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long out0 = rg.off ? rg.off[b] * hop : (long long)b * L * hop;  // ragged: outputs packed back to back
+    if (rg.len) L = rg.len[b];
     const int len = L * hop;
     if (n >= len) return;
     const int p = n + pad;
@@ -425,14 +429,15 @@ __global__ void overlap_add_kernel(const float* __restrict__ frames, const float
         acc += frames[((long long)b * Lp + t) * n_fft + k];
         env += wsq[k];
     }
-    audio[(long long)b * len + n] = acc / env;
+    audio[out0 + n] = acc / env;
 }
 
 // features [B, C, L] (API layout) -> rows [B*Lp, C] (fp32 or split planes), halo rows zeroed.
-__global__ void features_to_rows_kernel(const float* __restrict__ in, RowOut out, int C, int L, int Lp) {
+__global__ void features_to_rows_kernel(const float* __restrict__ in, RowOut out, int C, int L, int Lp, Ragged rg) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
-    const float* ib = in + (long long)b * C * L;
+    const float* ib = in + (rg.off ? rg.off[b] * C : (long long)b * C * L);  // ragged: clip b is [C, len[b]] at off[b] * C
+    if (rg.len) L = rg.len[b];
     const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int c = c0 + i, t = t0 + threadIdx.x;
@@ -450,11 +455,12 @@ __global__ void features_to_rows_kernel(const float* __restrict__ in, RowOut out
 // (they are the K dimension of the P.V GEMM) and for halo query rows. One warp per query row.
 __global__ void __launch_bounds__(256) softmax_planes_kernel(const float* __restrict__ S, int ldS,
                                                              __half* __restrict__ p_hi, __half* __restrict__ p_lo,
-                                                             int Lpad, int B, int L, int Lp, float scale) {
+                                                             int Lpad, int B, int L, int Lp, float scale, Ragged rg) {
     const int lane = threadIdx.x & 31;
     long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= (long long)B * Lp) return;
     const int i = (int)(row % Lp);
+    if (rg.len) L = rg.len[row / Lp];  // ragged: keys and queries of clip b stop at len[b]
     __half* oh = p_hi + row * Lpad;
     __half* ol = p_lo + row * Lpad;
     if (i >= L) {
@@ -481,9 +487,10 @@ __global__ void __launch_bounds__(256) softmax_planes_kernel(const float* __rest
 // V^T planes for the P.V GEMM: qkv planes [B*Lp, 3C] (v = columns 2C..3C) -> vT [B*C, Lpad], zero for keys >= L.
 __global__ void vt_planes_kernel(const __half* __restrict__ q_hi, const __half* __restrict__ q_lo,
                                  __half* __restrict__ vt_hi, __half* __restrict__ vt_lo, int L, int Lp, int C,
-                                 int Lpad) {
+                                 int Lpad, Ragged rg) {
     __shared__ __half th[32][34], tl[32][34];
     const int b = blockIdx.z;
+    if (rg.len) L = rg.len[b];
     const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int j = j0 + r, c = c0 + threadIdx.x;
@@ -510,28 +517,28 @@ __global__ void vt_planes_kernel(const __half* __restrict__ q_hi, const __half* 
 }  // namespace
 
 void launch_softmax_planes(const float* S, int ldS, __half* p_hi, __half* p_lo, int Lpad, int B, int L, int Lp,
-                           float scale, cudaStream_t s) {
+                           float scale, cudaStream_t s, Ragged rg) {
     if (B <= 0 || L <= 0) return;
     long long rows = (long long)B * Lp;
-    softmax_planes_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(S, ldS, p_hi, p_lo, Lpad, B, L, Lp, scale);
+    softmax_planes_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(S, ldS, p_hi, p_lo, Lpad, B, L, Lp, scale, rg);
     WT_CUDA(cudaGetLastError());
 }
 
 void launch_vt_planes(const __half* q_hi, const __half* q_lo, __half* vt_hi, __half* vt_lo, int B, int L, int Lp, int C,
-                      int Lpad, cudaStream_t s) {
+                      int Lpad, cudaStream_t s, Ragged rg) {
     if (B <= 0 || L <= 0) return;
     dim3 grid((Lpad + 31) / 32, C / 32, B), block(32, 8);
-    vt_planes_kernel<<<grid, block, 0, s>>>(q_hi, q_lo, vt_hi, vt_lo, L, Lp, C, Lpad);
+    vt_planes_kernel<<<grid, block, 0, s>>>(q_hi, q_lo, vt_hi, vt_lo, L, Lp, C, Lpad, rg);
     WT_CUDA(cudaGetLastError());
 }
 
 void launch_groupnorm(const float* x, const float* w, const float* b, RowOut out, int B, int L, int Lp, int C,
-                      int groups, float eps, int swish, cudaStream_t s) {
+                      int groups, float eps, int swish, cudaStream_t s, Ragged rg) {
     if (B <= 0 || L <= 0) return;
     if (groups != 32 || C != 768) throw Error(1, "groupnorm: expected GroupNorm(32, 768)");
     dim3 grid(C / (GN_GPB * 24), B);
-    if (L <= GN_RES * GN_PH && Lp <= L + GN_PH) groupnorm_kernel<GN_RES><<<grid, GN_THREADS, 0, s>>>(x, w, b, out, L, Lp, C, eps, swish);
-    else groupnorm_kernel<0><<<grid, GN_THREADS, 0, s>>>(x, w, b, out, L, Lp, C, eps, swish);
+    if (L <= GN_RES * GN_PH && Lp <= L + GN_PH) groupnorm_kernel<GN_RES><<<grid, GN_THREADS, 0, s>>>(x, w, b, out, L, Lp, C, eps, swish, rg);
+    else groupnorm_kernel<0><<<grid, GN_THREADS, 0, s>>>(x, w, b, out, L, Lp, C, eps, swish, rg);
     WT_CUDA(cudaGetLastError());
 }
 
@@ -544,11 +551,11 @@ void launch_layernorm(const float* x, const float* w, const float* b, RowOut out
 }
 
 void launch_dwconv_ln(const float* x, const float* dw, const float* db, const float* scale, const float* shift,
-                      RowOut out, int B, int L, int Lp, int C, float eps, cudaStream_t s) {
+                      RowOut out, int B, int L, int Lp, int C, float eps, cudaStream_t s, Ragged rg) {
     if (B <= 0 || L <= 0) return;
     if (C != 768) throw Error(1, "dwconv_ln: backbone dim must be 768");
     dim3 grid((Lp + DW_TT - 1) / DW_TT, B);
-    dwconv_ln_kernel<<<grid, DW_THREADS, 0, s>>>(x, dw, db, scale, shift, out, L, Lp, eps);
+    dwconv_ln_kernel<<<grid, DW_THREADS, 0, s>>>(x, dw, db, scale, shift, out, L, Lp, eps, rg);
     WT_CUDA(cudaGetLastError());
 }
 
@@ -577,17 +584,17 @@ void launch_spectral(const float* z, int ldz, RowOut S, long long M, int half, i
 }
 
 void launch_overlap_add(const float* frames, const float* wsq, float* audio, int B, int L, int Lp, int n_fft, int hop,
-                        cudaStream_t s) {
+                        cudaStream_t s, Ragged rg) {
     if (B <= 0 || L <= 0) return;
     dim3 grid((L * hop + 255) / 256, B);
-    overlap_add_kernel<<<grid, 256, 0, s>>>(frames, wsq, audio, L, Lp, n_fft, hop, (n_fft - hop) / 2);
+    overlap_add_kernel<<<grid, 256, 0, s>>>(frames, wsq, audio, L, Lp, n_fft, hop, (n_fft - hop) / 2, rg);
     WT_CUDA(cudaGetLastError());
 }
 
-void launch_features_to_rows(const float* in, RowOut out, int B, int C, int L, int Lp, cudaStream_t s) {
+void launch_features_to_rows(const float* in, RowOut out, int B, int C, int L, int Lp, cudaStream_t s, Ragged rg) {
     if (B <= 0 || L <= 0) return;
     dim3 grid((Lp + 31) / 32, (C + 31) / 32, B), block(32, 8);
-    features_to_rows_kernel<<<grid, block, 0, s>>>(in, out, C, L, Lp);
+    features_to_rows_kernel<<<grid, block, 0, s>>>(in, out, C, L, Lp, rg);
     WT_CUDA(cudaGetLastError());
 }
 

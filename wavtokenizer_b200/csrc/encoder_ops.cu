@@ -340,21 +340,29 @@ resblock0_fused_kernel(const float* __restrict__ wav, const float* __restrict__ 
 // of the k7 conv (clip pitch L + 6, data at offset 3).
 __global__ void lstm_skip_elu_pad_kernel(const float* __restrict__ y, const float* __restrict__ x,
                                          float* __restrict__ out_f32, __half* __restrict__ elu_hi,
-                                         __half* __restrict__ elu_lo, int B, int L, int D) {
-    const int P = L + 6;
+                                         __half* __restrict__ elu_lo, int B, int Lmax, int D,
+                                         const int* __restrict__ len_tab) {
+    const int P = Lmax + 6;  // clip pitch of the padded rows; a ragged batch keeps ONE pitch, clip b is L = len_tab[b] long
     const int d8 = D / 8;
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)B * P * d8) return;
     int c8 = (int)(gid % d8);
     long long row = gid / d8;
     int b = (int)(row / P), p = (int)(row - (long long)b * P);
+    const int L = len_tab ? len_tab[b] : Lmax;
+    float v[8], e[8];
+    if (p >= L + 6) {  // past this clip's own padded rows (ragged batch only): finite filler, never read by a valid frame
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = 0.f;
+        split_store8(elu_hi, elu_lo, row * D + c8 * 8, e);
+        return;
+    }
     int t = p - 3;
     const bool interior = t >= 0 && t < L;
     if (t < 0) t = -t;
     if (t >= L) t = 2 * (L - 1) - t;
     const long long src = ((long long)t * B + b) * D + c8 * 8;   // y, x: time-major rows [t*B + b]
-    const long long dst = ((long long)b * L + t) * D + c8 * 8;   // fp32 copy: batch-major rows
-    float v[8], e[8];
+    const long long dst = ((long long)b * Lmax + t) * D + c8 * 8;   // fp32 copy: batch-major rows
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         v[i] = y[src + i] + x[src + i];
@@ -449,9 +457,9 @@ void launch_resblock0_fused(const float* wav, const float* pack, __half* ye_hi, 
 }
 
 void launch_lstm_skip_elu_pad(const float* y, const float* x, float* out_f32, __half* elu_hi, __half* elu_lo, int B,
-                              int L, int D, cudaStream_t s) {
+                              int L, int D, cudaStream_t s, const int* len_tab) {
     long long n = (long long)B * (L + 6) * (D / 8);
-    lstm_skip_elu_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y, x, out_f32, elu_hi, elu_lo, B, L, D);
+    lstm_skip_elu_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y, x, out_f32, elu_hi, elu_lo, B, L, D, len_tab);
     WT_CUDA(cudaGetLastError());
 }
 

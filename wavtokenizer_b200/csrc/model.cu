@@ -146,6 +146,8 @@ struct wt_handle {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t aux_stream = nullptr;   // second layer of the LSTM wavefront (encoder_back_tc)
     std::vector<cudaEvent_t> aux_evs;
+    std::vector<cudaStream_t> lane_streams;  // conv fronts of a ragged batch run on several streams (do_encode_ragged)
+    std::vector<cudaEvent_t> lane_evs;
     std::vector<cudaEvent_t> copy_evs;
     std::function<void(int /*first clip*/, int /*clips*/)> before_enc_chunk, after_dec_chunk;
     // Sticky device-side error flag (code out of range in a gather). It is NOT read back synchronously: the launch is
@@ -177,6 +179,8 @@ struct wt_handle {
         for (auto e : copy_evs) cudaEventDestroy(e);
         for (auto e : aux_evs) cudaEventDestroy(e);
         if (err_ev) cudaEventDestroy(err_ev);
+        for (auto e : lane_evs) cudaEventDestroy(e);
+        for (auto st : lane_streams) cudaStreamDestroy(st);
         if (aux_stream) cudaStreamDestroy(aux_stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         for (void* p : owned) cudaFree(p);
@@ -1063,8 +1067,12 @@ void encoder_front_tc(wt_handle* h, const float* wav, int Bc, int T, int b0, int
 
 // SLSTM + ELU + final k7 conv on the tensor cores: hoisted input projections, one GEMM launch per time
 // step whose epilogue is the LSTM cell (gates never leave the SM), final conv over the reflect-padded rows.
+// `len_tab` (device, [Bg], optional): a ragged group. Row b of every time step belongs to clip b of len_tab[b] <= L frames;
+// the recurrence runs all L steps for every row (steps past a clip's end compute on filler and are never read), the
+// reflect padding in front of the last conv is taken at each clip's own end, and the frames t >= len_tab[b] of z are
+// filler the caller drops.
 float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, const __half* pre_lo, int Bg, int L,
-                       int b0, __half** zc_hi_out, __half** zc_lo_out, cudaStream_t s) {
+                       int b0, __half** zc_hi_out, __half** zc_lo_out, cudaStream_t s, const int* len_tab = nullptr) {
     const wt_config& c = h->cfg;
     const int D = c.dimension;
     const long long M = (long long)Bg * L;
@@ -1181,8 +1189,8 @@ float* encoder_back_tc(wt_handle* h, const float* pre, const __half* pre_hi, con
     __half *e_hi = halves(nE), *e_lo = halves(nE);
     {
         Scope sc(h, CAT_LSTM, s, KERN_LSTM_SKIP, 0, (double)M * D * 12 + (double)nE * 4);
-        if (c.lstm_layers) launch_lstm_skip_elu_pad(ylast, pre, lo, e_hi, e_lo, Bg, L, D, s);
-        else launch_lstm_skip_elu_pad(pre, h->zero_rows /*unused*/, lo, e_hi, e_lo, Bg, L, D, s);
+        if (c.lstm_layers) launch_lstm_skip_elu_pad(ylast, pre, lo, e_hi, e_lo, Bg, L, D, s, len_tab);
+        else launch_lstm_skip_elu_pad(pre, h->zero_rows /*unused*/, lo, e_hi, e_lo, Bg, L, D, s, len_tab);
     }
     h->tap("enc13", lo, Bg, L, D, b0, s);
     float* z = h->alloc((size_t)M * D);
@@ -1271,8 +1279,11 @@ void decoder_chunk_simt(wt_handle* h, const float* features /*[Bc, Din, L]*/, in
 
 // tcgen05 plan: same dataflow in the padded row space (3 zero rows after each clip), every contraction on
 // the tensor cores with split-fp16 operands, every A operand written as hi/lo planes by its producer.
+// `rg` (optional): a ragged chunk. L is then the longest clip of the chunk (the common pitch is L + 3), rg.len[b] the frames
+// of clip b, rg.off[b] its place in the packed `features` / `audio` arrays. Row-wise work (GEMMs, LayerNorm, spectral) runs
+// over the padded row space; the kernels that look across rows of a clip read the clip's own length.
 void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int Bc, int L, int bw, float* audio,
-                      int b0, cudaStream_t s) {
+                      int b0, cudaStream_t s, Ragged rg = Ragged{}) {
     const wt_config& c = h->cfg;
     Runner r{h, s};
     const int D = c.dim, Hd = c.intermediate_dim, Din = c.dimension;
@@ -1308,16 +1319,16 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
         launch_tap_gemm_tc(g, s);
     };
 
-    { Scope sc(h, CAT_MEM, s, KERN_ROWS, 0, (double)Bc * L * Din * 8); launch_features_to_rows(features, out_split(xin_hi, xin_lo), Bc, Din, L, Lp, s); }
+    { Scope sc(h, CAT_MEM, s, KERN_ROWS, 0, (double)Bc * L * Din * 8); launch_features_to_rows(features, out_split(xin_hi, xin_lo), Bc, Din, L, Lp, s, rg); }
     r.cat = CAT_DEC_CONV;
     gemm(xin_hi, xin_lo, Din, 7, h->embed.w_hi, h->embed.w_lo, D, 3, h->embed.b, ACT_NONE, nullptr, nullptr, x, D,
          nullptr, nullptr, 0);
     h->tap("dec_embed", x, Bc, L, D, b0, s, Lp);
 
     auto resnet = [&](const wt_handle::Resnet& p) {
-        { Scope sc(h, CAT_MEM, s, KERN_GROUPNORM, 0, (double)Bc * L * D * 8); launch_groupnorm(x, p.n1w, p.n1b, out_split(a_hi, a_lo), Bc, L, Lp, D, 32, eps, 1, s); }
+        { Scope sc(h, CAT_MEM, s, KERN_GROUPNORM, 0, (double)Bc * L * D * 8); launch_groupnorm(x, p.n1w, p.n1b, out_split(a_hi, a_lo), Bc, L, Lp, D, 32, eps, 1, s, rg); }
         gemm(a_hi, a_lo, D, 3, p.c1.w_hi, p.c1.w_lo, D, 3, p.c1.b, ACT_NONE, nullptr, nullptr, t2, D, nullptr, nullptr, 0);
-        { Scope sc(h, CAT_MEM, s, KERN_GROUPNORM, 0, (double)Bc * L * D * 8); launch_groupnorm(t2, p.n2w, p.n2b, out_split(a_hi, a_lo), Bc, L, Lp, D, 32, eps, 1, s); }
+        { Scope sc(h, CAT_MEM, s, KERN_GROUPNORM, 0, (double)Bc * L * D * 8); launch_groupnorm(t2, p.n2w, p.n2b, out_split(a_hi, a_lo), Bc, L, Lp, D, 32, eps, 1, s, rg); }
         gemm(a_hi, a_lo, D, 3, p.c2.w_hi, p.c2.w_lo, D, 3, p.c2.b, ACT_NONE, nullptr, x, x, D, nullptr, nullptr, 0);
     };
     resnet(h->pos[0]); h->tap("dec_pos0", x, Bc, L, D, b0, s, Lp);
@@ -1328,7 +1339,7 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
         __half *p_hi = halves((size_t)R * Lpad), *p_lo = halves((size_t)R * Lpad);
         __half *vt_hi = halves((size_t)Bc * D * Lpad), *vt_lo = halves((size_t)Bc * D * Lpad);
         __half *qkv_hi = g_hi, *qkv_lo = g_lo;  // [R, 3D] planes (the GELU buffer is free here)
-        { Scope sc(h, CAT_MEM, s, KERN_GROUPNORM, 0, (double)Bc * L * D * 8); launch_groupnorm(x, h->attn.nw, h->attn.nb, out_split(a_hi, a_lo), Bc, L, Lp, D, 32, eps, 0, s); }
+        { Scope sc(h, CAT_MEM, s, KERN_GROUPNORM, 0, (double)Bc * L * D * 8); launch_groupnorm(x, h->attn.nw, h->attn.nb, out_split(a_hi, a_lo), Bc, L, Lp, D, 32, eps, 0, s, rg); }
         gemm(a_hi, a_lo, D, 1, h->attn.wqkv_h.hi, h->attn.wqkv_h.lo, 3 * D, 3, h->attn.bqkv, ACT_NONE, nullptr, nullptr,
              nullptr, 0, qkv_hi, qkv_lo, 3 * D);
         r.cat = CAT_ATTN;
@@ -1342,8 +1353,8 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
             Scope sc(h, CAT_ATTN, s);
             launch_tap_gemm_tc(g, s);
         }
-        { Scope sc(h, CAT_ATTN, s, KERN_SOFTMAX, 0, (double)Bc * L * L * 8); launch_softmax_planes(S, Lpad, p_hi, p_lo, Lpad, Bc, L, Lp, 1.0f / sqrtf((float)D), s); }
-        { Scope sc(h, CAT_ATTN, s, KERN_VT, 0, (double)Bc * L * D * 8); launch_vt_planes(qkv_hi, qkv_lo, vt_hi, vt_lo, Bc, L, Lp, D, Lpad, s); }
+        { Scope sc(h, CAT_ATTN, s, KERN_SOFTMAX, 0, (double)Bc * L * L * 8); launch_softmax_planes(S, Lpad, p_hi, p_lo, Lpad, Bc, L, Lp, 1.0f / sqrtf((float)D), s, rg); }
+        { Scope sc(h, CAT_ATTN, s, KERN_VT, 0, (double)Bc * L * D * 8); launch_vt_planes(qkv_hi, qkv_lo, vt_hi, vt_lo, Bc, L, Lp, D, Lpad, s, rg); }
         {   // out[b, i, :] = sum_j P[b, i, j] v_j
             TcGemm g;
             g.seg[0] = tc_taps(p_hi, p_lo, R, Lpad, Lpad, 1, 0);
@@ -1361,14 +1372,14 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
     }
     resnet(h->pos[2]); h->tap("dec_pos3", x, Bc, L, D, b0, s, Lp);
     resnet(h->pos[3]); h->tap("dec_pos4", x, Bc, L, D, b0, s, Lp);
-    { Scope sc(h, CAT_MEM, s, KERN_GROUPNORM, 0, (double)Bc * L * D * 8); launch_groupnorm(x, h->gn5w, h->gn5b, out_f32(t2), Bc, L, Lp, D, 32, eps, 0, s); }
+    { Scope sc(h, CAT_MEM, s, KERN_GROUPNORM, 0, (double)Bc * L * D * 8); launch_groupnorm(x, h->gn5w, h->gn5b, out_f32(t2), Bc, L, Lp, D, 32, eps, 0, s, rg); }
     h->tap("dec_pos5", t2, Bc, L, D, b0, s, Lp);
     { Scope sc(h, CAT_MEM, s, KERN_LAYERNORM, 0, (double)Bc * L * D * 8); launch_layernorm(t2, h->norm_scale + (size_t)bw * D, h->norm_shift + (size_t)bw * D, out_f32(x), R, D, eps, s); }
     h->tap("dec_norm", x, Bc, L, D, b0, s, Lp);
     r.cat = CAT_PWCONV;
     for (int i = 0; i < c.num_layers; ++i) {
         const auto& p = h->cnx[i];
-        { Scope sc(h, CAT_MEM, s, KERN_DWCONV_LN, 0, (double)Bc * L * D * (pw_passes == 3 ? 8 : 6)); launch_dwconv_ln(x, p.dw, p.db, p.scale + (size_t)bw * D, p.shift + (size_t)bw * D, out_split(a_hi, pw_passes == 3 ? a_lo : nullptr), Bc, L, Lp, D, eps, s); }
+        { Scope sc(h, CAT_MEM, s, KERN_DWCONV_LN, 0, (double)Bc * L * D * (pw_passes == 3 ? 8 : 6)); launch_dwconv_ln(x, p.dw, p.db, p.scale + (size_t)bw * D, p.shift + (size_t)bw * D, out_split(a_hi, pw_passes == 3 ? a_lo : nullptr), Bc, L, Lp, D, eps, s, rg); }
         gemm(a_hi, a_lo, D, 1, p.w1_h.hi, p.w1_h.lo, Hd, pw_passes, p.b1, ACT_GELU, nullptr, nullptr, nullptr, 0,
              g_hi, pw_passes == 3 ? g_lo : nullptr, Hd);
         gemm(g_hi, g_lo, Hd, 1, p.w2_h.hi, p.w2_h.lo, D, pw_passes, p.b2, ACT_NONE, p.gamma, x, x, D, nullptr, nullptr, 0);
@@ -1384,7 +1395,7 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
     { Scope sc(h, CAT_MEM, s, KERN_SPECTRAL, 0, (double)Bc * L * (N + 2) * 8); launch_spectral(bigA, h->ldz, out_split(S_hi, S_lo), R, half, h->Kp, s); }
     gemm(S_hi, S_lo, h->Kp, 1, h->basis_h.hi, h->basis_h.lo, N, 3, nullptr, ACT_NONE, nullptr, nullptr, bigA, N, nullptr,
          nullptr, 0);
-    { Scope sc(h, CAT_MEM, s, KERN_OLA, 0, (double)Bc * L * (N + c.hop_length) * 4); launch_overlap_add(bigA, h->wsq, audio, Bc, L, Lp, N, c.hop_length, s); }
+    { Scope sc(h, CAT_MEM, s, KERN_OLA, 0, (double)Bc * L * (N + c.hop_length) * 4); launch_overlap_add(bigA, h->wsq, audio, Bc, L, Lp, N, c.hop_length, s, rg); }
 }
 
 void decoder_chunk(wt_handle* h, const float* features, int Bc, int L, int bw, float* audio, int b0, cudaStream_t s) {
@@ -1470,6 +1481,110 @@ void do_encode(wt_handle* h, const float* wav, int B, int T, float* features_out
     }
 }
 
+// Ragged encode: B clips of DIFFERENT lengths in one call (the reference feeds one file at a time,
+// infer.py:44-54, so clip b's result is by definition that of a batch-of-one call). The conv front runs per run of
+// equal-length clips (reflect padding, strides and chunk shapes depend on the clip's own length); what makes a
+// batch-of-one slow is the LSTM, a latency chain of L steps per layer whatever the batch, so ALL clips share one
+// recurrence: their pre-LSTM rows sit side by side in the time-major group buffer (row t*B + b), shorter clips padded
+// with zero rows that only their own (dropped) steps read. Last conv and VQ run once over the padded frames.
+// `lengths` is host memory; wav holds the clips back to back; outputs are packed the same way:
+// features [sum_b D * L_b] (clip b as [D, L_b]), codes [sum_b L_b].
+void do_encode_ragged(wt_handle* h, const float* wav, const int32_t* lengths, int B, float* features_out,
+                      int64_t* codes_out, cudaStream_t s) {
+    const wt_config& c = h->cfg;
+    if (B <= 0) return;
+    if (h->plan < 1 || c.lstm_layers < 1) throw Error(WT_ERR_VALUE, "encode_ragged: needs the tcgen05 plan and an LSTM");
+    const int D = c.dimension;
+    std::vector<long long> woff(B + 1, 0), foff(B + 1, 0);
+    std::vector<int> Ls(B);
+    int Tmax = 0, Lmax = 0;
+    for (int b = 0; b < B; ++b) {
+        const int T = lengths[b];
+        if (T <= 0) throw Error(WT_ERR_VALUE, "encode_ragged: every clip needs T > 0");
+        if (!encoder_tc_supported(c, T)) throw Error(WT_ERR_VALUE, "encode_ragged: clip too short for the batched path");
+        Ls[b] = frames_for(c, T);
+        woff[b + 1] = woff[b] + T;
+        foff[b + 1] = foff[b] + Ls[b];
+        Tmax = std::max(Tmax, T);
+        Lmax = std::max(Lmax, Ls[b]);
+    }
+    for (int g0 = 0; g0 < B; g0 += ENC_GROUP) {
+        const int Bg = std::min(ENC_GROUP, B - g0);
+        int Lg = 0, Tg = 0, run_max = 1;
+        for (int b = g0, run = 0; b < g0 + Bg; ++b) {
+            Lg = std::max(Lg, Ls[b]);
+            Tg = std::max(Tg, (int)lengths[b]);
+            run = (b > g0 && lengths[b] == lengths[b - 1]) ? run + 1 : 1;
+            run_max = std::max(run_max, std::min(run, ENC_CHUNK));
+        }
+        // The fronts of single clips are chains of small launches (a 1 s clip has 1 - 30 tiles per GEMM at the deeper
+        // levels): they run on NL streams, each with its own scratch region, so that they fill the GPU together.
+        static const int NL = [] {
+            const char* e = std::getenv("WT_RAGGED_LANES");
+            const int v = e ? std::atoi(e) : 8;  // 64 clips of 64 lengths: 22.1 / 15.2 / 12.3 / 11.1 ms with 1 / 2 / 4 / 8 lanes
+            return v < 1 ? 1 : (v > 8 ? 8 : v);
+        }();
+        const size_t front_floats = enc_front_tc_floats(c, run_max, Tg) + 1024;
+        const size_t need = (enc_back_floats(c, Bg, Lg) + NL * front_floats +
+                             3 * align_up((size_t)Bg * Lg * D, 64) + (size_t)Bg * Lg * 2 + Bg + 4096) * sizeof(float);
+        h->ensure_arena(need);
+        h->arena_off = 0;
+        const size_t nPre = (size_t)Bg * Lg * D;
+        float* pre = h->alloc(nPre);
+        __half* pre_hi = reinterpret_cast<__half*>(h->alloc(nPre / 2));
+        __half* pre_lo = reinterpret_cast<__half*>(h->alloc(nPre / 2));
+        int* len_dev = reinterpret_cast<int*>(h->alloc(Bg));
+        long long* codes_tmp = reinterpret_cast<long long*>(h->alloc((size_t)Bg * Lg * 2));
+        WT_CUDA(cudaMemsetAsync(pre, 0, nPre * sizeof(float), s));
+        WT_CUDA(cudaMemsetAsync(pre_hi, 0, nPre * sizeof(__half), s));
+        WT_CUDA(cudaMemsetAsync(pre_lo, 0, nPre * sizeof(__half), s));
+        WT_CUDA(cudaMemcpyAsync(len_dev, Ls.data() + g0, Bg * sizeof(int), cudaMemcpyHostToDevice, s));
+        const size_t mark = h->arena_off;
+        while ((int)h->lane_streams.size() < NL - 1) {
+            cudaStream_t st;
+            WT_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            h->lane_streams.push_back(st);
+        }
+        while ((int)h->lane_evs.size() < NL) {
+            cudaEvent_t e;
+            WT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h->lane_evs.push_back(e);
+        }
+        WT_CUDA(cudaEventRecord(h->lane_evs[0], s));  // fork: the lanes start once the group buffers are cleared
+        for (int l = 1; l < NL; ++l) WT_CUDA(cudaStreamWaitEvent(h->lane_streams[l - 1], h->lane_evs[0], 0));
+        int run_idx = 0;
+        for (int b = g0; b < g0 + Bg; ++run_idx) {  // one front pass per run of equal-length clips
+            int e = b + 1;
+            while (e < g0 + Bg && lengths[e] == lengths[b] && e - b < ENC_CHUNK) ++e;
+            const int lane = run_idx % NL;
+            cudaStream_t ls = lane == 0 ? s : h->lane_streams[lane - 1];
+            h->arena_off = mark + (size_t)lane * front_floats * sizeof(float);  // a lane reuses its scratch in stream order
+            const size_t to = (size_t)(b - g0) * D;  // time-major: clip b - g0 starts at row b - g0 of every time step
+            encoder_front_tc(h, wav + woff[b], e - b, lengths[b], /*b0 (no taps)=*/1, Bg, pre + to, pre_hi + to, pre_lo + to, ls);
+            b = e;
+        }
+        for (int l = 1; l < NL; ++l) {  // join
+            WT_CUDA(cudaEventRecord(h->lane_evs[l], h->lane_streams[l - 1]));
+            WT_CUDA(cudaStreamWaitEvent(s, h->lane_evs[l], 0));
+        }
+        h->arena_off = mark;
+        __half *zc_hi = nullptr, *zc_lo = nullptr;
+        encoder_back_tc(h, pre, pre_hi, pre_lo, Bg, Lg, /*b0=*/1, &zc_hi, &zc_lo, s, len_dev);
+        const long long M = (long long)Bg * Lg;
+        unsigned long long* keys = reinterpret_cast<unsigned long long*>(h->alloc((size_t)M * 2));
+        vq_tc(h, zc_hi, zc_lo, M, keys, codes_tmp, s);
+        for (int b = g0; b < g0 + Bg; ++b) {  // drop the filler frames: clip b keeps its first L_b codes
+            long long* dst = reinterpret_cast<long long*>(codes_out) + foff[b];
+            WT_CUDA(cudaMemcpyAsync(dst, codes_tmp + (size_t)(b - g0) * Lg, (size_t)Ls[b] * sizeof(long long),
+                                    cudaMemcpyDeviceToDevice, s));
+            if (features_out) {
+                Scope sc(h, CAT_MEM, s, KERN_GATHER, 0, (double)Ls[b] * (D * 4 + 8));
+                launch_codes_to_features(h->codebooks, dst, features_out + foff[b] * D, 1, 1, Ls[b], D, c.vq_bins, nullptr, s);
+            }
+        }
+    }
+}
+
 void do_decode(wt_handle* h, const float* features, int B, int L, int bw, float* audio, cudaStream_t s) {
     const wt_config& c = h->cfg;
     if (B < 0 || L <= 0) throw Error(WT_ERR_VALUE, "decode: expected features [B, C, L] with L > 0");
@@ -1482,6 +1597,44 @@ void do_decode(wt_handle* h, const float* features, int B, int L, int bw, float*
         decoder_chunk(h, features + (size_t)b0 * c.dimension * L, Bc, L, bw,
                       audio + (size_t)b0 * L * c.hop_length, b0, s);
         if (h->after_dec_chunk) h->after_dec_chunk(b0, Bc);
+    }
+}
+
+// Ragged decode: B feature maps of DIFFERENT lengths in one call. Clip b's audio is by definition
+// what a batch-of-one decode returns (GroupNorm / attention over ITS frames, zero conv padding and iSTFT "same" trimming at
+// ITS ends; reference decoder/models.py:10-16,107-127, spectral_ops.py:58-73). `lengths` (host) = frames per clip;
+// features: clip b as [dimension, L_b], packed back to back; audio: clip b as L_b * hop samples, packed the same way.
+void do_decode_ragged(wt_handle* h, const float* features, const int32_t* lengths, int B, int bw, float* audio,
+                      cudaStream_t s) {
+    const wt_config& c = h->cfg;
+    if (B <= 0) return;
+    if (h->plan < 1) throw Error(WT_ERR_VALUE, "decode_ragged: needs the tcgen05 plan");
+    if (bw < 0 || bw >= c.adanorm_num_embeddings) throw Error(WT_ERR_INDEX, "index out of range in self (bandwidth_id)");
+    std::vector<long long> off(B + 1, 0);
+    for (int b = 0; b < B; ++b) {
+        if (lengths[b] <= 0) throw Error(WT_ERR_VALUE, "decode_ragged: every clip needs L > 0");
+        off[b + 1] = off[b] + lengths[b];
+    }
+    // chunks of clips whose padded rows (Bc * (Lmax + 3)) stay near one decoder chunk of the uniform path
+    const long long row_budget = (long long)DEC_CHUNK * 228;
+    for (int b0 = 0; b0 < B;) {
+        int e = b0, Lm = 0;
+        while (e < B) {
+            const int Ln = std::max(Lm, (int)lengths[e]);
+            if (e > b0 && (long long)(e - b0 + 1) * (Ln + 3) > row_budget) break;
+            Lm = Ln; ++e;
+        }
+        const int Bc = e - b0;
+        h->ensure_arena(dec_chunk_floats(c, Bc, Lm, h->Kp) * sizeof(float) + (size_t)Bc * 16 + 8192);
+        h->arena_off = 0;
+        int* len_dev = reinterpret_cast<int*>(h->alloc(Bc));
+        long long* off_dev = reinterpret_cast<long long*>(h->alloc((size_t)Bc * 2));
+        WT_CUDA(cudaMemcpyAsync(len_dev, lengths + b0, Bc * sizeof(int), cudaMemcpyHostToDevice, s));
+        WT_CUDA(cudaMemcpyAsync(off_dev, off.data() + b0, Bc * sizeof(long long), cudaMemcpyHostToDevice, s));
+        Ragged rg;
+        rg.len = len_dev; rg.off = off_dev;
+        decoder_chunk_tc(h, features, Bc, Lm, bw, audio, /*b0 (no taps)=*/1, s, rg);
+        b0 = e;
     }
 }
 
@@ -1584,6 +1737,14 @@ int wt_encode(wt_handle* h, const float* wav, int32_t B, int32_t T, float* featu
     });
 }
 
+int wt_encode_ragged(wt_handle* h, const float* wav, const int32_t* lengths, int32_t B, float* features_out,
+                     int64_t* codes_out, void* stream) {
+    return guarded(h, [&] {
+        if (!wav || !lengths || !codes_out) throw Error(WT_ERR_VALUE, "wt_encode_ragged: null buffer");
+        do_encode_ragged(h, wav, lengths, B, features_out, codes_out, (cudaStream_t)stream);
+    });
+}
+
 int wt_encoder_forward(wt_handle* h, const float* wav, int32_t B, int32_t T, float* z_out, void* stream) {
     return guarded(h, [&] {
         if (!wav || !z_out) throw Error(WT_ERR_VALUE, "wt_encoder_forward: null buffer");
@@ -1612,6 +1773,14 @@ int wt_decode(wt_handle* h, const float* features, int32_t B, int32_t L, int32_t
     return guarded(h, [&] {
         if (!features || !audio_out) throw Error(WT_ERR_VALUE, "wt_decode: null buffer");
         do_decode(h, features, B, L, bandwidth_id, audio_out, (cudaStream_t)stream);
+    });
+}
+
+int wt_decode_ragged(wt_handle* h, const float* features, const int32_t* lengths, int32_t B, int32_t bandwidth_id,
+                     float* audio_out, void* stream) {
+    return guarded(h, [&] {
+        if (!features || !lengths || !audio_out) throw Error(WT_ERR_VALUE, "wt_decode_ragged: null buffer");
+        do_decode_ragged(h, features, lengths, B, bandwidth_id, audio_out, (cudaStream_t)stream);
     });
 }
 

@@ -355,12 +355,18 @@ class WavTokenizer(nn.Module):
         return int(self.__dict__.get("_plan", 2))
 
     @torch.inference_mode()
-    def encode_infer_ragged(self, clips, max_bucket: int = 0, streams: int = 1, **kwargs: Any):
+    def encode_infer_ragged(self, clips, max_bucket: int = 0, streams: int = 1, batched: Optional[bool] = None,
+                            **kwargs: Any):
         """Clips of DIFFERENT lengths ([T_i] or [1, T_i] float32) -> per clip, in input order, exactly what the
         reference's one-file-at-a-time loop returns (infer.py:44-54): ``(features [1, 512, L_i], codes [1, 1, L_i])``.
-        Equal-length clips are stacked and share one C-ABI call (``ragged.length_buckets``); nothing is padded.
-        ``streams`` > 1 runs the buckets on that many CUDA streams (one model replica each) so that small buckets,
-        which cannot fill the GPU alone, overlap."""
+        Nothing is padded to a common length.
+
+        Default (``batched`` None/True, every clip long enough for the tensor-core encoder layout): ONE C-ABI call
+        (``wt_encode_ragged``): the conv front runs per run of equal-length clips and the LSTM - a latency chain whose
+        cost does not depend on the batch - runs once for all clips, as do the last conv and the VQ.
+        ``batched=False`` (or very short clips): equal-length clips are stacked and share one ``wt_encode`` call per
+        length bucket (``ragged.length_buckets``); ``streams`` > 1 then runs the buckets on that many CUDA streams (one
+        model replica each) so that small buckets, which cannot fill the GPU alone, overlap."""
         flat = []
         for i, c in enumerate(clips):
             if c.dim() == 2 and c.shape[0] == 1:
@@ -368,6 +374,10 @@ class WavTokenizer(nn.Module):
             if c.dim() != 1:
                 raise ValueError(f"clip {i}: expected [T] or [1, T], got {tuple(c.shape)}")
             flat.append(c)
+        if batched is None:
+            batched = streams <= 1
+        if batched and len(flat) > 1 and self.plan() >= 1 and all(self._ragged_ok(int(c.numel())) for c in flat):
+            return self._encode_ragged_native(flat, **kwargs)
 
         def make(model):
             def fn(batch):
@@ -382,10 +392,52 @@ class WavTokenizer(nn.Module):
             out = ragged.run_bucketed(flat, make(self), max_bucket)
         return [(f.unsqueeze(0), c.unsqueeze(1)) for f, c in out]
 
+    def _ragged_ok(self, T: int) -> bool:
+        """Same rule as the library's tensor-core encoder layout: every level's reflect halo stays inside the clip."""
+        Tc = T
+        for s in self.cfg.strides:
+            Tn = -(-Tc // s)
+            hr = s // 2 + (Tn * s - Tc)
+            if Tc < 4 or Tc <= hr + 1 or Tc <= s:
+                return False
+            Tc = Tn
+        return Tc >= 4
+
+    def _encode_ragged_native(self, flat, **kwargs: Any):
+        h = self.native()
+        self._bandwidth_index(kwargs, need_list_semantics=True)  # looked up, then ignored (vq.py:126-137)
+        for c in flat:
+            if c.dtype != torch.float32:
+                raise RuntimeError(f"Input type ({c.dtype}) and weight type (torch.float32) should be the same")
+            self._check_input(c, "audio_input")
+        # clips of equal length next to each other (one conv-front pass per run), longest first
+        order = sorted(range(len(flat)), key=lambda i: (-int(flat[i].numel()), i))
+        lens = [int(flat[i].numel()) for i in order]
+        wav = torch.cat([flat[i] for i in order]).contiguous()
+        Ls = [self.cfg.frames_for(n) for n in lens]
+        D = self.cfg.dimension
+        feats = torch.empty(sum(Ls) * D, dtype=torch.float32, device=wav.device)
+        codes = torch.empty(sum(Ls), dtype=torch.int64, device=wav.device)
+        arr = (ctypes.c_int32 * len(lens))(*lens)
+        with torch.cuda.device(wav.device):
+            _native.check(_native.lib().wt_encode_ragged(h.ptr, wav.data_ptr(), arr, len(lens), feats.data_ptr(),
+                                                         codes.data_ptr(), self._stream()))
+        out: List[Any] = [None] * len(flat)
+        off = 0
+        for i, L in zip(order, Ls):
+            out[i] = (feats[off * D:(off + L) * D].view(1, D, L), codes[off:off + L].view(1, 1, L))
+            off += L
+        return out
+
     @torch.inference_mode()
-    def decode_ragged(self, features, max_bucket: int = 0, streams: int = 1, **kwargs: Any):
+    def decode_ragged(self, features, max_bucket: int = 0, streams: int = 1, batched: Optional[bool] = None,
+                      **kwargs: Any):
         """Features of different lengths ([512, L_i] or [1, 512, L_i]) -> [audio [1, L_i * hop]] in input order,
-        each equal to a batch-of-one ``decode`` (reference decoder/pretrained.py:192-207)."""
+        each equal to a batch-of-one ``decode`` (reference decoder/pretrained.py:192-207).
+
+        Default (``batched`` None/True): ONE C-ABI call (``wt_decode_ragged``): all clips share one padded row space
+        whose GEMMs run at batch size, while GroupNorm, attention, the depthwise convs and the overlap-add read every
+        clip's own length. ``batched=False``: one ``wt_decode`` per length bucket, optionally on ``streams`` streams."""
         flat = []
         for i, f in enumerate(features):
             if f.dim() == 3 and f.shape[0] == 1:
@@ -393,6 +445,10 @@ class WavTokenizer(nn.Module):
             if f.dim() != 2:
                 raise ValueError(f"features {i}: expected [C, L] or [1, C, L], got {tuple(f.shape)}")
             flat.append(f)
+        if batched is None:
+            batched = streams <= 1
+        if batched and len(flat) > 1 and self.plan() >= 1:
+            return self._decode_ragged_native(flat, **kwargs)
 
         def make(model):
             return lambda batch: ((model.decode(batch, **kwargs), 0),)
@@ -403,6 +459,32 @@ class WavTokenizer(nn.Module):
         else:
             out = ragged.run_bucketed(flat, make(self), max_bucket)
         return [a.unsqueeze(0) for (a,) in out]
+
+    def _decode_ragged_native(self, flat, **kwargs: Any):
+        h = self.native()
+        bw = self._bandwidth_index(kwargs, need_list_semantics=False)
+        C = self.cfg.input_channels
+        for f in flat:
+            if f.shape[0] != C:
+                raise RuntimeError(f"expected features [{C}, L], got {tuple(f.shape)}")
+            if f.dtype != torch.float32:
+                raise RuntimeError(f"Input type ({f.dtype}) and weight type (torch.float32) should be the same")
+            self._check_input(f, "features_input")
+        order = sorted(range(len(flat)), key=lambda i: (-int(flat[i].shape[1]), i))  # similar lengths share a chunk
+        Ls = [int(flat[i].shape[1]) for i in order]
+        packed = torch.cat([flat[i].contiguous().reshape(-1) for i in order])
+        hop = self.cfg.hop_length
+        audio = torch.empty(sum(Ls) * hop, dtype=torch.float32, device=packed.device)
+        arr = (ctypes.c_int32 * len(Ls))(*Ls)
+        with torch.cuda.device(packed.device):
+            _native.check(_native.lib().wt_decode_ragged(h.ptr, packed.data_ptr(), arr, len(Ls), bw, audio.data_ptr(),
+                                                         self._stream()))
+        out: List[Any] = [None] * len(flat)
+        off = 0
+        for i, L in zip(order, Ls):
+            out[i] = audio[off * hop:(off + L) * hop].view(1, L * hop)
+            off += L
+        return out
 
     def encode_decode_host(self, wav_host: torch.Tensor, bandwidth_id: int = 0):
         """Whole hot path on HOST tensors (pinned recommended): H2D, encode, decode, D2H, sync.
