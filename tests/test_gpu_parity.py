@@ -240,6 +240,21 @@ def test_host_buffer_entry_point(setup):
 
 
 @pytest.mark.parametrize("plan", [0, 2])
+def test_host_buffer_entry_point_pieces_and_chunks(plan):
+    """150 clips: 10 copy pieces of 16 clips (the last one partial), 3 encoder chunks, 2 decoder chunks. The host-buffer
+    entry (H2D piece -> level-0 kernel of that piece, overlap-add of a piece -> its D2H) returns exactly what the
+    device-resident calls return."""
+    m = native_model("small320", plan)
+    wav = spec.synthetic_audio(150, 12000, seed=31).pin_memory()
+    codes_h, audio_h = m.encode_decode_host(wav, 1)
+    codes_h, audio_h = codes_h.clone(), audio_h.clone()
+    bw = torch.tensor([1]).cuda()
+    f, c = m.encode_infer(wav.cuda(), bandwidth_id=bw)
+    a = m.decode(f, bandwidth_id=bw)
+    assert torch.equal(codes_h, c.cpu()) and torch.equal(audio_h, a.cpu())
+
+
+@pytest.mark.parametrize("plan", [0, 2])
 def test_full_size_properties(plan):
     """BASELINE.json configs[1] size (small-320, 256 x 3 s): size-independent properties — features are
     exact codebook rows of the codes, decoding is deterministic and batch-order equivariant, and a

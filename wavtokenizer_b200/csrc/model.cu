@@ -55,6 +55,7 @@ inline int tc_prefetch() {
     return v;
 }
 constexpr int ENC_GROUP = 1024; // clips per LSTM / final-conv / VQ pass (the recurrent GEMM's M)
+constexpr int COPY_PIECE = 16;  // clips per H2D / D2H piece of the host-buffer entry point (4.6 MB of audio)
 constexpr int DEC_CHUNK_DEFAULT = 128;  // clips per decoder pass (29 k rows: fp32 row tensors of 90 MB stay L2-resident)
 inline int dec_chunk() {
     static const int v = [] {
@@ -149,7 +150,11 @@ struct wt_handle {
     std::vector<cudaStream_t> lane_streams;  // conv fronts of a ragged batch run on several streams (do_encode_ragged)
     std::vector<cudaEvent_t> lane_evs;
     std::vector<cudaEvent_t> copy_evs;
-    std::function<void(int /*first clip*/, int /*clips*/)> before_enc_chunk, after_dec_chunk;
+    // wav_ready(first clip, clips): called right before the first kernel that reads those clips' audio;
+    // audio_done(first clip, clips): called right after the kernel that wrote those clips' audio. Both work on PIECES of
+    // COPY_PIECE clips (finer than the compute chunks), so that only one piece of H2D stands in front of the first kernel
+    // and only one piece of D2H behind the last one.
+    std::function<void(int /*first clip*/, int /*clips*/)> wav_ready, audio_done;
     // Sticky device-side error flag (code out of range in a gather). It is NOT read back synchronously: the launch is
     // followed by an async copy into pinned memory plus an event, and the flag is examined when that event has
     // completed -- at the next call on the handle, at wt_check_errors(), or at the end of wt_encode_decode_host.
@@ -940,6 +945,7 @@ void encoder_levels_tc(wt_handle* h, const float* wav, int Bc, int Tin, int i0, 
         const size_t nX = (size_t)Bc * (Tc + 2) * C;
         const size_t nWin = (size_t)Bc * (Tc + 2) * 8;
         xr_hi = halves(nWin); xr_lo = halves(nWin); xe_hi = halves(nX); xe_lo = halves(nX);
+        if (h->wav_ready) h->wav_ready(b0, Bc);
         Scope sc(h, CAT_ENC_CONV, s);
         launch_conv0_planes(wav, h->conv0_w, h->conv0_b, xr_hi, xr_lo, xe_hi, xe_lo, Bc, Tc, C, s);
     }
@@ -971,9 +977,16 @@ void encoder_levels_tc(wt_handle* h, const float* wav, int Bc, int Tin, int i0, 
         __half *ye_hi = halves(nY), *ye_lo = halves(nY);
         float* y_tap = want("enc" + std::to_string(idx)) ? h->alloc(nY) : nullptr;
         if (fused) {
-            // algorithmic work per sample: conv0 224 + k3 1536 + 1x1 512 + shortcut 1024 MACs; 4 B in, 128 B of planes out
-            Scope sc(h, CAT_ENC_CONV, s, KERN_RB0, 6592.0 * Bc * Tc, 132.0 * Bc * Tc);
-            launch_resblock0_fused(wav, h->rb0_pack, ye_hi, ye_lo, y_tap, Bc, Tc, Py, left, right + extra, s);
+            // algorithmic work per sample: conv0 224 + k3 1536 + 1x1 512 + shortcut 1024 MACs; 4 B in, 128 B of planes out.
+            // Host-buffer entry: one launch per copy piece, each behind ITS piece of the H2D stream only.
+            const int piece = h->wav_ready ? COPY_PIECE : Bc;
+            for (int p0 = 0; p0 < Bc; p0 += piece) {
+                const int np = std::min(piece, Bc - p0);
+                if (h->wav_ready) h->wav_ready(b0 + p0, np);
+                Scope sc(h, CAT_ENC_CONV, s, KERN_RB0, 6592.0 * np * Tc, 132.0 * np * Tc);
+                launch_resblock0_fused(wav + (size_t)p0 * Tc, h->rb0_pack, ye_hi + (size_t)p0 * Py * C, ye_lo + (size_t)p0 * Py * C,
+                                       y_tap ? y_tap + (size_t)p0 * Py * C : nullptr, np, Tc, Py, left, right + extra, s);
+            }
         } else {
             TcGemm g;
             g.nseg = 2;
@@ -1395,7 +1408,17 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
     { Scope sc(h, CAT_MEM, s, KERN_SPECTRAL, 0, (double)Bc * L * (N + 2) * 8); launch_spectral(bigA, h->ldz, out_split(S_hi, S_lo), R, half, h->Kp, s); }
     gemm(S_hi, S_lo, h->Kp, 1, h->basis_h.hi, h->basis_h.lo, N, 3, nullptr, ACT_NONE, nullptr, nullptr, bigA, N, nullptr,
          nullptr, 0);
-    { Scope sc(h, CAT_MEM, s, KERN_OLA, 0, (double)Bc * L * (N + c.hop_length) * 4); launch_overlap_add(bigA, h->wsq, audio, Bc, L, Lp, N, c.hop_length, s, rg); }
+    if (h->audio_done && !rg.len) {  // host-buffer entry: overlap-add per copy piece, each followed by ITS D2H
+        for (int p0 = 0; p0 < Bc; p0 += COPY_PIECE) {
+            const int np = std::min(COPY_PIECE, Bc - p0);
+            { Scope sc(h, CAT_MEM, s, KERN_OLA, 0, (double)np * L * (N + c.hop_length) * 4);
+              launch_overlap_add(bigA + (size_t)p0 * Lp * N, h->wsq, audio + (size_t)p0 * L * c.hop_length, np, L, Lp, N, c.hop_length, s); }
+            h->audio_done(b0 + p0, np);
+        }
+    } else {
+        Scope sc(h, CAT_MEM, s, KERN_OLA, 0, (double)Bc * L * (N + c.hop_length) * 4);
+        launch_overlap_add(bigA, h->wsq, audio, Bc, L, Lp, N, c.hop_length, s, rg);
+    }
 }
 
 void decoder_chunk(wt_handle* h, const float* features, int Bc, int L, int bw, float* audio, int b0, cudaStream_t s) {
@@ -1450,7 +1473,7 @@ void do_encode(wt_handle* h, const float* wav, int B, int T, float* features_out
             h->arena_off = mark;
             const size_t ro = (size_t)b0 * L * D;
             const size_t to = (size_t)b0 * D;  // time-major: clip b0 starts at row b0 of every time step
-            if (h->before_enc_chunk) h->before_enc_chunk(g0 + b0, Bc);
+            if (!tc && h->wav_ready) h->wav_ready(g0 + b0, Bc);  // (the tensor-core front calls it per piece itself)
             if (tc) encoder_front_tc(h, wav + (size_t)(g0 + b0) * T, Bc, T, g0 + b0, Bg, pre + to, pre_hi + to, pre_lo + to, s);
             else encoder_front(h, wav + (size_t)(g0 + b0) * T, Bc, T, g0 + b0, pre + ro, s);
         }
@@ -1596,7 +1619,7 @@ void do_decode(wt_handle* h, const float* features, int B, int L, int bw, float*
         h->arena_off = 0;
         decoder_chunk(h, features + (size_t)b0 * c.dimension * L, Bc, L, bw,
                       audio + (size_t)b0 * L * c.hop_length, b0, s);
-        if (h->after_dec_chunk) h->after_dec_chunk(b0, Bc);
+        if (h->audio_done && h->plan < 1) h->audio_done(b0, Bc);  // (the tensor-core chunk calls it per copy piece itself)
     }
 }
 
@@ -1837,8 +1860,10 @@ int wt_encode_decode_host(wt_handle* h, const float* wav_host, int32_t B, int32_
         float* feat = (float*)p; p += align_up(n_feat * 4, 256);
         int64_t* codes = (int64_t*)p; p += align_up(n_codes * 8, 256);
         float* audio = (float*)p;
-        // Copies run on a second stream, chunk by chunk: the encoder front of chunk i waits only for ITS clips, and the
-        // audio of decoder chunk i leaves while chunk i+1 is computed (pinned host buffers make these true async DMAs).
+        // Copies run on a second stream in pieces of COPY_PIECE clips: the level-0 kernel of a piece waits only for ITS
+        // clips (0.09 ms of H2D in front of the first kernel instead of a whole 64-clip chunk), and the audio of a piece
+        // leaves right after its overlap-add while the next one is computed (pinned host buffers make these true async
+        // DMAs); what stays exposed at the end is the D2H of the last piece.
         if (!h->copy_stream) WT_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         cudaStream_t cs = h->copy_stream;
         size_t ev_next = 0;
@@ -1855,23 +1880,26 @@ int wt_encode_decode_host(wt_handle* h, const float* wav_host, int32_t B, int32_
             WT_CUDA(cudaEventRecord(e, s));
             WT_CUDA(cudaStreamWaitEvent(cs, e, 0));
         }
-        std::unordered_map<int, cudaEvent_t> h2d;  // first clip of an encoder chunk -> its wav is on the device
-        for (int g0 = 0; g0 < B; g0 += ENC_GROUP)  // same chunking as do_encode
-            for (int b0 = g0; b0 < std::min(B, g0 + ENC_GROUP); b0 += ENC_CHUNK) {
-                const int Bc = std::min(ENC_CHUNK, std::min(B, g0 + ENC_GROUP) - b0);
-                WT_CUDA(cudaMemcpyAsync(wav + (size_t)b0 * T, wav_host + (size_t)b0 * T, (size_t)Bc * T * 4,
-                                        cudaMemcpyHostToDevice, cs));
-                cudaEvent_t e = next_event();
-                WT_CUDA(cudaEventRecord(e, cs));
-                h2d[b0] = e;
-            }
+        // H2D in pieces of COPY_PIECE clips, in clip order: piece i of the wav is on the device when h2d[i] has fired
+        std::vector<cudaEvent_t> h2d;
+        for (int b0 = 0; b0 < B; b0 += COPY_PIECE) {
+            const int np = std::min(COPY_PIECE, B - b0);
+            WT_CUDA(cudaMemcpyAsync(wav + (size_t)b0 * T, wav_host + (size_t)b0 * T, (size_t)np * T * 4,
+                                    cudaMemcpyHostToDevice, cs));
+            cudaEvent_t e = next_event();
+            WT_CUDA(cudaEventRecord(e, cs));
+            h2d.push_back(e);
+        }
         struct Clear {
             wt_handle* h;
-            ~Clear() { h->before_enc_chunk = nullptr; h->after_dec_chunk = nullptr; }
+            ~Clear() { h->wav_ready = nullptr; h->audio_done = nullptr; }
         } clear{h};
-        h->before_enc_chunk = [&](int b0, int) { WT_CUDA(cudaStreamWaitEvent(s, h2d.at(b0), 0)); };
+        h->wav_ready = [&](int b0, int n) {  // the compute stream waits for exactly the pieces that hold these clips
+            for (int i = b0 / COPY_PIECE; i <= (b0 + n - 1) / COPY_PIECE && i < (int)h2d.size(); ++i)
+                WT_CUDA(cudaStreamWaitEvent(s, h2d[i], 0));
+        };
         do_encode(h, wav, B, T, feat, codes, nullptr, s);
-        h->before_enc_chunk = nullptr;
+        h->wav_ready = nullptr;
         {
             cudaEvent_t e = next_event();
             WT_CUDA(cudaEventRecord(e, s));
@@ -1879,15 +1907,15 @@ int wt_encode_decode_host(wt_handle* h, const float* wav_host, int32_t B, int32_
             WT_CUDA(cudaMemcpyAsync(codes_host, codes, n_codes * 8, cudaMemcpyDeviceToHost, cs));
         }
         const size_t per_clip = (size_t)L * c.hop_length;
-        h->after_dec_chunk = [&](int b0, int Bc) {
+        h->audio_done = [&](int b0, int n) {  // D2H of these clips' audio behind the overlap-add that wrote them
             cudaEvent_t e = next_event();
             WT_CUDA(cudaEventRecord(e, s));
             WT_CUDA(cudaStreamWaitEvent(cs, e, 0));
             WT_CUDA(cudaMemcpyAsync(audio_host + (size_t)b0 * per_clip, audio + (size_t)b0 * per_clip,
-                                    (size_t)Bc * per_clip * 4, cudaMemcpyDeviceToHost, cs));
+                                    (size_t)n * per_clip * 4, cudaMemcpyDeviceToHost, cs));
         };
         do_decode(h, feat, B, L, bandwidth_id, audio, s);
-        h->after_dec_chunk = nullptr;
+        h->audio_done = nullptr;
         WT_CUDA(cudaStreamSynchronize(s));
         WT_CUDA(cudaStreamSynchronize(cs));
         poll_err_flag(h, true);
