@@ -55,11 +55,13 @@ METRIC = "encode+decode audio-sec/sec (24 kHz)"
 UNIT = "audio-s/s"
 CPU_SAMPLE_CLIPS = 8
 PARITY_CLIPS = 4
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the modal launch shape, one `ncu --set full` capture each
-# (profiles/r01_final_summary.md, profiles/r01_ncu_table_*.txt); null where no capture of that kernel exists
-TRAFFIC = {"tap_gemm_tc_kernel<256, 3>": 249.5e6, "tap_gemm_tc_kernel<256, 1>": 135.0e6,
-           "tap_gemm_tc_kernel<64, 3>": 1.79e9, "tap_gemm_tc_kernel<32, 3>": 0.89e9, "tap_gemm_tc_kernel<128, 3>": 1.09e9,
-           "resblock0_fused_kernel": 0.58e9, "groupnorm_kernel": 135.2e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the modal launch shape, one `ncu --set full` capture each at
+# the end of round 2 (profiles/r02_ncu_table.txt; tools/ncu_targets.sh): decoder k3 conv 768 -> 768 over 128 clips,
+# ConvNeXt GEMM-1, encoder level-0 strided conv / level-1 strided conv / level-0 fused kernel over 64 clips, ...
+TRAFFIC = {"tap_gemm_tc_kernel<256, 3>": 127.3e6, "tap_gemm_tc_kernel<256, 1>": 132.9e6,
+           "tap_gemm_tc_kernel<64, 3>": 1.134e9, "tap_gemm_tc_kernel<128, 3>": 1.137e9,
+           "resblock0_fused_kernel": 0.555e9, "groupnorm_kernel": 136.5e6, "dwconv_ln_kernel": 106.6e6,
+           "lstm_persistent_kernel": 69.3e6}
 CATS = ["enc_conv", "lstm", "vq", "dec_conv", "pwconv", "head_idft", "attention", "memory_bound"]
 NAMED_KERNELS = {1: "lstm_persistent_kernel", 2: "resblock0_fused_kernel", 3: "groupnorm_kernel", 4: "dwconv_ln_kernel",
                  5: "layernorm_kernel", 6: "spectral_kernel", 7: "overlap_add_kernel", 8: "softmax_planes_kernel",

@@ -422,6 +422,7 @@ struct Cfg {
     static constexpr int STAGE = PLANES * (A_PLANE + B_PLANE);
     static constexpr int STAGES = (200 * 1024) / STAGE > 8 ? 8 : (200 * 1024) / STAGE;
     static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int BIAS_SMEM = 12 * 1024;  // GELU-only epilogue: the whole bias vector (N <= 3072) staged once per CTA
     // An SS-mode MMA (M = 128, K = 16) costs >= ~128 cycles whatever N is (A-tile fetch from shared memory), so
     // for N <= 128 the hi and lo weight tiles (adjacent in shared memory) are multiplied by A_hi in ONE MMA of
     // N = 2*BN: hh lands in accumulator columns [0, BN), hl in [BN, 2*BN); A_lo x W_hi then adds lh to [0, BN).
@@ -480,6 +481,13 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // GELU-only epilogue: bias[0, N) lives in shared memory behind the barriers (the per-chunk global loads of the bias sat
+    // on the epilogue's critical path: 18 % of its stall samples, profiles/r02_ncu_stalls.txt)
+    const float* sbias = reinterpret_cast<const float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
+    if (GELU_EPI) {
+        float* sb = const_cast<float*>(sbias);
+        for (int i = threadIdx.x; i < g.N; i += NUM_THREADS) sb[i] = g.bias[i];
+    }
     // per-CTA timeline stamps (tools/gemm_timeline.py) exist only in builds with -DWT_TIMELINE=1 (WT_TIMELINE=1 in the
     // environment of _native.build): in the shipped kernels they cost registers the 96-register cap does not have
 #if WT_TIMELINE
@@ -825,7 +833,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                     __syncwarp();
                     tmem_ld(tbase + (uint32_t)col, r);
                     if (row_ok) {
-                        const float* bp = g.bias + n0 + col;
+                        const float* bp = (GELU_EPI ? sbias : g.bias) + n0 + col;
                         __half* op = g.out_hi + (long long)m * g.ldh + n0 + col;
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
@@ -1311,11 +1319,13 @@ void launch_cfg(const TcGemm& g, cudaStream_t s) {
     static PerDevice<int> max_ctas_dev;  // cluster variant: CTAs that can be co-resident as pairs
     bool& attr = attr_dev.get();
     int& max_ctas = max_ctas_dev.get();
+    constexpr int SMEM = C::SMEM + (EPI == 2 ? C::BIAS_SMEM : 0);
+    if (EPI == 2 && g.N * (int)sizeof(float) > C::BIAS_SMEM) throw Error(4, "gemm_tc: GELU-only epilogue needs N <= 3072");
     if (!attr) {
-        WT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        WT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         if (CL2) {
             cudaLaunchConfig_t qc = {};
-            qc.gridDim = dim3(num_sms() & ~1); qc.blockDim = dim3(NUM_THREADS); qc.dynamicSmemBytes = C::SMEM;
+            qc.gridDim = dim3(num_sms() & ~1); qc.blockDim = dim3(NUM_THREADS); qc.dynamicSmemBytes = SMEM;
             cudaLaunchAttribute qa[1];
             qa[0].id = cudaLaunchAttributeClusterDimension;
             qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
@@ -1345,7 +1355,7 @@ void launch_cfg(const TcGemm& g, cudaStream_t s) {
         int grid = std::min(2 * items, std::min(num_sms() & ~1, max_ctas));
         if (g.max_ctas > 0) grid = std::max(2, std::min(grid, g.max_ctas & ~1));
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = s;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1355,7 +1365,7 @@ void launch_cfg(const TcGemm& g, cudaStream_t s) {
         const int tiles = m_tiles * n_tiles * g.batch;
         int grid = tiles < num_sms() ? tiles : num_sms();
         if (g.max_ctas > 0) grid = std::max(1, std::min(grid, g.max_ctas));
-        kernel<<<grid, NUM_THREADS, C::SMEM, s>>>(maps, g);
+        kernel<<<grid, NUM_THREADS, SMEM, s>>>(maps, g);
     }
     WT_CUDA(cudaGetLastError());
 }

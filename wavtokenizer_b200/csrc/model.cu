@@ -1393,9 +1393,29 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
     for (int i = 0; i < c.num_layers; ++i) {
         const auto& p = h->cnx[i];
         { Scope sc(h, CAT_MEM, s, KERN_DWCONV_LN, 0, (double)Bc * L * D * (pw_passes == 3 ? 8 : 6)); launch_dwconv_ln(x, p.dw, p.db, p.scale + (size_t)bw * D, p.shift + (size_t)bw * D, out_split(a_hi, pw_passes == 3 ? a_lo : nullptr), Bc, L, Lp, D, eps, s, rg); }
-        gemm(a_hi, a_lo, D, 1, p.w1_h.hi, p.w1_h.lo, Hd, pw_passes, p.b1, ACT_GELU, nullptr, nullptr, nullptr, 0,
-             g_hi, pw_passes == 3 ? g_lo : nullptr, Hd);
-        gemm(g_hi, g_lo, Hd, 1, p.w2_h.hi, p.w2_h.lo, D, pw_passes, p.b2, ACT_NONE, p.gamma, x, x, D, nullptr, nullptr, 0);
+        // pointwise MLP 768 -> 2304 -> 768. WT_PW_SPLIT = n runs GEMM-1 -> GEMM-2 over n row slices in turn, so that the
+        // 2304-wide fp16 plane of a slice (133 MB for a whole 128-clip chunk, more than the L2) is still L2-resident when
+        // GEMM-2 reads it (slices start at multiples of 256 rows = one CTA-pair tile).
+        static const int pw_split = [] { const char* e = std::getenv("WT_PW_SPLIT"); const int v = e ? std::atoi(e) : 1; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+        const long long slice = pw_split > 1 ? (long long)align_up((size_t)((R + pw_split - 1) / pw_split), 256) : R;
+        for (long long r0 = 0; r0 < R; r0 += slice) {
+            const long long nr = std::min(slice, R - r0);
+            for (int which = 0; which < 2; ++which) {
+                TcGemm g;
+                if (which == 0) {
+                    g.seg[0] = tc_taps(a_hi + r0 * D, a_lo + r0 * D, nr, D, D, 1, 0);
+                    g.W_hi = p.w1_h.hi; g.W_lo = p.w1_h.lo; g.N = Hd; g.K = D; g.bias = p.b1; g.act = ACT_GELU;
+                    g.out_hi = g_hi + r0 * Hd; g.out_lo = pw_passes == 3 ? g_lo + r0 * Hd : nullptr; g.ldh = Hd;
+                } else {
+                    g.seg[0] = tc_taps(g_hi + r0 * Hd, g_lo + r0 * Hd, nr, Hd, Hd, 1, 0);
+                    g.W_hi = p.w2_h.hi; g.W_lo = p.w2_h.lo; g.N = D; g.K = Hd; g.bias = p.b2; g.gamma = p.gamma;
+                    g.res = x + r0 * D; g.ldres = D; g.out_f32 = x + r0 * D; g.ldo = D;
+                }
+                g.M = (int)nr; g.passes = pw_passes; g.prefetch = tc_prefetch();
+                Scope sc(h, r.cat, s);
+                launch_tap_gemm_tc(g, s);
+            }
+        }
         h->tap(("dec_cnx" + std::to_string(i)).c_str(), x, Bc, L, D, b0, s, Lp);
     }
     { Scope sc(h, CAT_MEM, s, KERN_LAYERNORM, 0, (double)Bc * L * D * 8); launch_layernorm(x, h->fln_w, h->fln_b, out_split(a_hi, a_lo, t2), R, D, eps, s); }
