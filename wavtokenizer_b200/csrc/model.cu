@@ -1418,26 +1418,48 @@ void decoder_chunk_tc(wt_handle* h, const float* features /*[Bc, Din, L]*/, int 
         }
         h->tap(("dec_cnx" + std::to_string(i)).c_str(), x, Bc, L, D, b0, s, Lp);
     }
-    { Scope sc(h, CAT_MEM, s, KERN_LAYERNORM, 0, (double)Bc * L * D * 8); launch_layernorm(x, h->fln_w, h->fln_b, out_split(a_hi, a_lo, t2), R, D, eps, s); }
-    h->tap("dec_final", t2, Bc, L, D, b0, s, Lp);
+    // final LayerNorm -> head GEMM -> exp / sincos -> inverse DFT GEMM -> overlap-add. In the host-buffer entry this tail
+    // runs over SLICES of TAIL_SLICE clips in turn: the audio of a slice goes to the host (D2H on the copy stream) while
+    // the next slice is computed, so only the last slice's D2H stays exposed behind the last kernel of the call.
     const int N = c.n_fft, half = N / 2 + 1;
-    r.cat = CAT_HEAD;
-    gemm(a_hi, a_lo, D, 1, h->head_h.hi, h->head_h.lo, N + 2, 3, h->head_b, ACT_NONE, nullptr, nullptr, bigA, h->ldz,
-         nullptr, nullptr, 0);
-    h->tap("dec_headlin", bigA, Bc, L, N + 2, b0, s, Lp, h->ldz);
-    { Scope sc(h, CAT_MEM, s, KERN_SPECTRAL, 0, (double)Bc * L * (N + 2) * 8); launch_spectral(bigA, h->ldz, out_split(S_hi, S_lo), R, half, h->Kp, s); }
-    gemm(S_hi, S_lo, h->Kp, 1, h->basis_h.hi, h->basis_h.lo, N, 3, nullptr, ACT_NONE, nullptr, nullptr, bigA, N, nullptr,
-         nullptr, 0);
-    if (h->audio_done && !rg.len) {  // host-buffer entry: overlap-add per copy piece, each followed by ITS D2H
-        for (int p0 = 0; p0 < Bc; p0 += COPY_PIECE) {
-            const int np = std::min(COPY_PIECE, Bc - p0);
-            { Scope sc(h, CAT_MEM, s, KERN_OLA, 0, (double)np * L * (N + c.hop_length) * 4);
-              launch_overlap_add(bigA + (size_t)p0 * Lp * N, h->wsq, audio + (size_t)p0 * L * c.hop_length, np, L, Lp, N, c.hop_length, s); }
-            h->audio_done(b0 + p0, np);
+    constexpr int TAIL_SLICE = 2 * COPY_PIECE;
+    const bool sliced = h->audio_done && !rg.len && Bc > TAIL_SLICE;
+    const int step_clips = sliced ? TAIL_SLICE : Bc;
+    for (int c0 = 0; c0 < Bc; c0 += step_clips) {
+        const int nc = std::min(step_clips, Bc - c0);
+        const long long r0 = (long long)c0 * Lp, nr = (long long)nc * Lp;
+        auto gemm_rows = [&](const __half* ahi, const __half* alo, int Cin, const __half* whi, const __half* wlo, int Nn,
+                             const float* bias, float* of32, int ldo) {
+            TcGemm g;
+            g.seg[0] = tc_taps(ahi, alo, nr, Cin, Cin, 1, 0);
+            g.W_hi = whi; g.W_lo = wlo; g.M = (int)nr; g.N = Nn; g.K = Cin; g.passes = 3;
+            g.bias = bias; g.out_f32 = of32; g.ldo = ldo;
+            g.prefetch = tc_prefetch();
+            Scope sc(h, r.cat, s);
+            launch_tap_gemm_tc(g, s);
+        };
+        { Scope sc(h, CAT_MEM, s, KERN_LAYERNORM, 0, (double)nc * L * D * 8);
+          launch_layernorm(x + r0 * D, h->fln_w, h->fln_b, out_split(a_hi + r0 * D, a_lo + r0 * D, t2 + r0 * D), nr, D, eps, s); }
+        if (!sliced) h->tap("dec_final", t2, Bc, L, D, b0, s, Lp);
+        r.cat = CAT_HEAD;
+        float* zrows = bigA + r0 * h->ldz;   // z of this slice (pitch ldz >= N: it never reaches into an earlier slice's frames)
+        float* frames = bigA + r0 * N;       // windowed frames of this slice (pitch N), written when its z is dead
+        gemm_rows(a_hi + r0 * D, a_lo + r0 * D, D, h->head_h.hi, h->head_h.lo, N + 2, h->head_b, zrows, h->ldz);
+        if (!sliced) h->tap("dec_headlin", bigA, Bc, L, N + 2, b0, s, Lp, h->ldz);
+        { Scope sc(h, CAT_MEM, s, KERN_SPECTRAL, 0, (double)nc * L * (N + 2) * 8);
+          launch_spectral(zrows, h->ldz, out_split(S_hi + r0 * h->Kp, S_lo + r0 * h->Kp), nr, half, h->Kp, s); }
+        gemm_rows(S_hi + r0 * h->Kp, S_lo + r0 * h->Kp, h->Kp, h->basis_h.hi, h->basis_h.lo, N, nullptr, frames, N);
+        if (h->audio_done && !rg.len) {  // overlap-add per copy piece, each followed by ITS D2H
+            for (int p0 = c0; p0 < c0 + nc; p0 += COPY_PIECE) {
+                const int np = std::min(COPY_PIECE, c0 + nc - p0);
+                { Scope sc(h, CAT_MEM, s, KERN_OLA, 0, (double)np * L * (N + c.hop_length) * 4);
+                  launch_overlap_add(bigA + (size_t)p0 * Lp * N, h->wsq, audio + (size_t)p0 * L * c.hop_length, np, L, Lp, N, c.hop_length, s); }
+                h->audio_done(b0 + p0, np);
+            }
+        } else {
+            Scope sc(h, CAT_MEM, s, KERN_OLA, 0, (double)Bc * L * (N + c.hop_length) * 4);
+            launch_overlap_add(bigA, h->wsq, audio, Bc, L, Lp, N, c.hop_length, s, rg);
         }
-    } else {
-        Scope sc(h, CAT_MEM, s, KERN_OLA, 0, (double)Bc * L * (N + c.hop_length) * 4);
-        launch_overlap_add(bigA, h->wsq, audio, Bc, L, Lp, N, c.hop_length, s, rg);
     }
 }
 
