@@ -1,0 +1,91 @@
+"""-m gpu: the fused level 0 -> 1 encoder kernel (csrc/enc_fused.cu: strided conv + ResBlock of level 1 in one tcgen05
+kernel, reference encoder/modules/seanet.py:45-63,123-129) against the unfused launches of the same library, the reference
+goldens and the CPU oracle.
+
+The fused kernel has no x1 output, so a request for the enc3 tap selects the unfused launches: the same handle gives both
+paths. ResBlock-1 output (enc4) is compared as a FULL tensor (every clip end and tile seam), the later stages through the
+golden subsamples, and the codes through the tie report.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import wavtok_oracle as O  # checker only
+from tests import helpers
+from tests.gpu_util import Taps, golden_sub, native_model
+from wavtokenizer_b200 import spec
+
+pytestmark = pytest.mark.gpu
+
+TAGS = [t for t in helpers.TAGS if helpers.model(t)[0].strides[0] == 2]  # K = 2 * stride * 32 = 128 fits the kernel
+
+
+@pytest.fixture(scope="module", params=TAGS)
+def setup(request):
+    tag = request.param
+    cfg, sd = helpers.model(tag)
+    return tag, cfg, sd, helpers.golden(tag), native_model(tag, 1)
+
+
+def _enc4(m, wav, with_enc3):
+    names = ["enc4", "enc15"] + (["enc3"] if with_enc3 else [])
+    taps = Taps(m, names, capacity=48 << 20)
+    n0 = m.launch_count()
+    _, codes = m.encode_infer(wav, bandwidth_id=torch.tensor([0]).cuda())
+    torch.cuda.synchronize()
+    n = m.launch_count() - n0
+    y, z = taps.get("enc4"), taps.get("enc15")
+    taps.close()
+    return y, z, codes.cpu(), n
+
+
+@pytest.mark.parametrize("B,T", [(3, 72000), (2, 4801), (5, 1283), (1, 24000)])
+def test_fused_matches_unfused_full_tensor(setup, B, T):
+    tag, cfg, sd, g, m = setup
+    wav = spec.synthetic_audio(B, T, seed=77 + T).cuda()
+    y_f, z_f, c_f, n_f = _enc4(m, wav, with_enc3=False)
+    y_u, z_u, c_u, n_u = _enc4(m, wav, with_enc3=True)
+    assert n_u - n_f == 2, (n_u, n_f)  # three launches (strided conv, k3 conv, ResBlock tail) became one
+    assert y_f.shape == y_u.shape == (B, 64, (T + 1) // 2)
+    assert torch.isfinite(y_f).all()
+    # same operands, same 3-pass products; only the fp32 summation order of the k3 taps differs
+    assert helpers.snr_db(y_u, y_f) >= 110.0
+    assert float((y_u - y_f).abs().max()) <= 2e-5 * float(y_u.abs().max())
+    assert helpers.snr_db(z_u, z_f) >= 95.0
+    assert (c_f != c_u).float().mean().item() <= 0.01
+
+
+def test_fused_against_reference_goldens(setup):
+    tag, cfg, sd, g, m = setup
+    names = [str(n) for n in g["tap_names"] if str(n) not in {"enc0", "enc2", "enc3", "enc5", "enc8", "enc11", "enc14"}
+             and str(n).startswith("enc")]
+    taps = Taps(m, names)
+    wav = spec.synthetic_audio(2, int(g["e2e_T"]), seed=11).cuda()
+    _, codes = m.encode_infer(wav, bandwidth_id=torch.tensor([2]).cuda())
+    torch.cuda.synchronize()
+    for n in names:
+        snr = helpers.snr_db(torch.from_numpy(g["tap_" + n]), golden_sub(taps.get(n)))
+        assert snr >= 85.0, (n, snr)
+    z = taps.get("enc15")
+    taps.close()
+    assert helpers.snr_db(torch.from_numpy(g["e2e_z"]), z) >= 85.0
+    ref_codes = torch.from_numpy(g["e2e_codes"].astype(np.int64))
+    cb = sd[spec.CODEBOOK_PREFIX + "0._codebook.embed"]
+    rep = O.vq_tie_report(z.permute(0, 2, 1).reshape(-1, cfg.dimension), cb, codes.cpu(), ref_codes)
+    helpers.assert_code_parity(rep)
+
+
+def test_fused_against_oracle_one_clip(setup):
+    """ResBlock-1 output of a whole 1 s clip against the CPU oracle's fp32 stage (all positions, both clip ends)."""
+    tag, cfg, sd, g, m = setup
+    wav = spec.synthetic_audio(1, 24000, seed=5).cuda()
+    y_f, _, _, _ = _enc4(m, wav, with_enc3=False)
+    E = O.ENC
+    with torch.inference_mode():  # encoder.model[0..4]: conv0, ResBlock 0, ELU + strided conv, ResBlock 1
+        x = O.sconv1d(sd, E + "0.", wav.cpu().unsqueeze(1))
+        x = O.seanet_resblock(sd, E + "1.", x)
+        x = O.sconv1d(sd, E + "3.", F.elu(x), stride=cfg.strides[0])
+        y = O.seanet_resblock(sd, E + "4.", x)
+    assert y.shape == y_f.shape
+    assert helpers.snr_db(y, y_f) >= 85.0

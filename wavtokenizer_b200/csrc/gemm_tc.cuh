@@ -1,5 +1,6 @@
 // tcgen05 GEMM launch descriptor (see gemm_tc.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -102,6 +103,34 @@ void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_
 int lstm_ctas(int B, int D);
 void launch_split_f16(const float* x, __half* hi, __half* lo, long long rows, int cols, long long ld_in,
                       long long ld_out, cudaStream_t s);
+
+// Cached tensor map of a 2-D fp16 tensor (`rows` rows of `inner` elements, row r starting r*stride elements after the
+// base; stride < inner: overlapping rows) with a [box_rows, kw] box under the swizzle that matches kw (64 / 32 / 16).
+const CUtensorMap& tc_make_map(const __half* base, long long rows, long long inner, long long stride, int box_rows, int kw);
+int tc_num_sms();
+long long* tc_debug_timeline();
+
+// Levels 0 -> 1 of the SEANet encoder in ONE tcgen05 kernel (enc_fused.cu): strided conv (32 -> 64, k4, s2) of the ELU(y0)
+// planes, ELU, k3 conv (64 -> 32), ELU, 1x1 conv (32 -> 64) + composed shortcut, ELU -> planes in the padded layout of
+// the next strided conv. x1, ELU(x1) and ELU(h1) never leave the SM.
+struct EncL1Weights {
+    const __half* w1 = nullptr;  // [256, 128]: rows [Wc_lo | Wc_hi | Wd_hi | Wd_lo] (composed shortcut, strided conv)
+    const __half* w2 = nullptr;  // [192, 64]: rows [Wk3_hi | Wk3_lo], row = tap * 32 + cout
+    const __half* w3 = nullptr;  // [128, 32]: rows [W1x1_lo | W1x1_hi]
+    const float* bias = nullptr; // b_d[64] | b_k3[32] | b_tail[64]
+};
+struct EncL1Args {
+    const __half* y0_hi = nullptr;  // ELU(y0) planes of level 0: clip pitch 2 * (T1 + 2) rows of 32 channels
+    const __half* y0_lo = nullptr;
+    long long y0_elems = 0;
+    int Bc = 0, T1 = 0;             // clips, level-1 length; row space m = b * (T1 + 2) + t
+    RowMap map;                     // destination layout of ELU(y1) (Pin = T1 + 2, Tvalid = T1)
+    __half* ye_hi = nullptr;        // ELU(y1) planes, 64 channels per row
+    __half* ye_lo = nullptr;
+    float* y_f32 = nullptr;         // optional fp32 copy of y1 at the same rows (debug tap)
+};
+bool enc_l1_fused_supported(int cin, int stride);
+void launch_enc_l1_fused(const EncL1Weights& w, const EncL1Args& a, cudaStream_t s);
 
 // Convenience: a dense / tap-mode segment over rows [rows, Cin] with pitch lda.
 inline TcSeg tc_taps(const __half* hi, const __half* lo, long long rows, int Cin, int lda, int taps, int center) {

@@ -113,6 +113,7 @@ struct wt_handle {
     // LSTM weights with gate rows permuted so that each 64-wide tile holds [i | f | g | o] x 16 hidden units
     struct LstmTc { HalfW w_ih, w_hh; float* bias = nullptr; } lstm_tc[4];
     float* rb0_pack = nullptr;   // level-0 fused kernel weights (encoder_ops.cu resblock0_fused_kernel)
+    EncL1Weights l1_fused;       // level 0 -> 1 fused tcgen05 kernel weights (enc_fused.cu); w1 == nullptr: not available
     float* zero_rows = nullptr;  // zero planes standing in for h_{-1}
     // vq
     float* codebooks = nullptr;  // [num_quantizers * bins, D]
@@ -200,6 +201,14 @@ struct wt_handle {
         WT_CUDA(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(float)));
         owned.push_back(d);
         if (!v.empty()) WT_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+        return d;
+    }
+
+    __half* upload_halves(const std::vector<__half>& v) {
+        __half* d = nullptr;
+        WT_CUDA(cudaMalloc(&d, std::max<size_t>(v.size(), 8) * sizeof(__half)));
+        owned.push_back(d);
+        if (!v.empty()) WT_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(__half), cudaMemcpyHostToDevice));
         return d;
     }
 
@@ -431,6 +440,43 @@ void prepare(wt_handle* h, const Table& t) {
             }
             rt.w2 = h->upload_split(w2);
             rt.bias2 = h->upload(b2);
+            if (i == 1 && C == 64 && h->down[0].k * h->down[0].cin == 128 && enc_l1_fused_supported(C / 2, c.strides[0])) {
+                // fused level 0 -> 1 kernel (enc_fused.cu): the three weight tiles as single fp16 tensors whose rows
+                // stack the hi / lo planes in the order the MMAs address them
+                const ConvW& dn = h->down[0];
+                auto hi16 = [](float v) { return __float2half_rn(v); };
+                auto lo16 = [](float v) { const __half hh = __float2half_rn(v); return __float2half_rn(v - __half2float(hh)); };
+                std::vector<__half> p1((size_t)256 * 128), p2((size_t)192 * 64), p3((size_t)128 * 32);
+                for (int n = 0; n < 64; ++n)
+                    for (int j = 0; j < 128; ++j) {
+                        const float wc = w2[(size_t)n * K2 + off1 + j], wd = dn.hw[(size_t)n * 128 + j];
+                        p1[(size_t)(0 + n) * 128 + j] = lo16(wc);
+                        p1[(size_t)(64 + n) * 128 + j] = hi16(wc);
+                        p1[(size_t)(128 + n) * 128 + j] = hi16(wd);
+                        p1[(size_t)(192 + n) * 128 + j] = lo16(wd);
+                    }
+                for (int tap = 0; tap < 3; ++tap)
+                    for (int n = 0; n < 32; ++n)
+                        for (int k = 0; k < 64; ++k) {
+                            const float w = c1.hw[(size_t)n * 192 + tap * 64 + k];
+                            p2[(size_t)(tap * 32 + n) * 64 + k] = hi16(w);
+                            p2[(size_t)(96 + tap * 32 + n) * 64 + k] = lo16(w);
+                        }
+                for (int n = 0; n < 64; ++n)
+                    for (int k = 0; k < 32; ++k) {
+                        const float w = c2.hw[(size_t)n * 32 + k];
+                        p3[(size_t)n * 32 + k] = lo16(w);
+                        p3[(size_t)(64 + n) * 32 + k] = hi16(w);
+                    }
+                std::vector<float> fb(160);
+                for (int n = 0; n < 64; ++n) fb[n] = dn.hb[n];
+                for (int n = 0; n < 32; ++n) fb[64 + n] = c1.hb[n];
+                for (int n = 0; n < 64; ++n) fb[96 + n] = b2[n];
+                h->l1_fused.w1 = h->upload_halves(p1);
+                h->l1_fused.w2 = h->upload_halves(p2);
+                h->l1_fused.w3 = h->upload_halves(p3);
+                h->l1_fused.bias = h->upload(fb);
+            }
             if (i == 0 && C == 32) {
                 // fused level-0 kernel: w0t[7][32] b0[32] w1t[96][16] b1[16] w2t[16][32] wsct[8][32] b2[32]
                 std::vector<float> pk((size_t)resblock0_pack_floats(), 0.f);
@@ -714,7 +760,8 @@ enum Cat : int { CAT_ENC_CONV = 0, CAT_LSTM, CAT_VQ, CAT_DEC_CONV, CAT_PWCONV, C
 // through last_launch_info(); the other kernels of the step are named here.
 enum Kern : int {
     KERN_LSTM = 1, KERN_RB0 = 2, KERN_GROUPNORM = 3, KERN_DWCONV_LN = 4, KERN_LAYERNORM = 5, KERN_SPECTRAL = 6,
-    KERN_OLA = 7, KERN_SOFTMAX = 8, KERN_VT = 9, KERN_ROWS = 10, KERN_GATHER = 11, KERN_LSTM_SKIP = 12, KERN_VQ_MISC = 13
+    KERN_OLA = 7, KERN_SOFTMAX = 8, KERN_VT = 9, KERN_ROWS = 10, KERN_GATHER = 11, KERN_LSTM_SKIP = 12, KERN_VQ_MISC = 13,
+    KERN_ENC_L1F = 14
 };
 
 // Counts one kernel launch and, when timing is on, brackets it with CUDA events on its stream. `kern` / `flops` /
@@ -941,6 +988,10 @@ void encoder_levels_tc(wt_handle* h, const float* wav, int Bc, int Tin, int i0, 
     const bool composed1 = true;
     const __half *y0_hi = nullptr, *y0_lo = nullptr;  // ELU(y0) planes of level 0 and their size
     long long nY0 = 0;
+    // Level 0's strided conv and the whole ResBlock of level 1 in ONE kernel (enc_fused.cu): x1, ELU(x1) and ELU(h1) stay
+    // on the SM. The x1 tap (enc3) does not exist then, so a request for it selects the unfused launches.
+    const bool l1f = fused0 && i0 == 0 && i1 >= 2 && h->l1_fused.w1 != nullptr && C == 32 && !want("enc3") &&
+                     enc_l1_fused_supported(C, c.strides[0]);
     if (i0 == 0 && !fused0) {
         const size_t nX = (size_t)Bc * (Tc + 2) * C;
         const size_t nWin = (size_t)Bc * (Tc + 2) * 8;
@@ -959,8 +1010,9 @@ void encoder_levels_tc(wt_handle* h, const float* wav, int Bc, int Tin, int i0, 
         const bool fused = fused0 && i == 0;
         // ---- G1: h1 = conv_k3(ELU(x)) -> ELU(h1) planes, same row space ----
         const size_t nH = (size_t)rowsX * (C / 2);
-        __half *he_hi = fused ? nullptr : halves(nH), *he_lo = fused ? nullptr : halves(nH);
-        if (!fused) {
+        const bool l1f_here = l1f && i == 1;
+        __half *he_hi = (fused || l1f_here) ? nullptr : halves(nH), *he_lo = (fused || l1f_here) ? nullptr : halves(nH);
+        if (!fused && !l1f_here) {
             TcGemm g;
             g.kw = rt.kw1;
             g.seg[0] = tc_window(xe_hi, xe_lo, rowsX * C, 3 * C, C, 0, rt.kw1);
@@ -987,6 +1039,15 @@ void encoder_levels_tc(wt_handle* h, const float* wav, int Bc, int Tin, int i0, 
                 launch_resblock0_fused(wav + (size_t)p0 * Tc, h->rb0_pack, ye_hi + (size_t)p0 * Py * C, ye_lo + (size_t)p0 * Py * C,
                                        y_tap ? y_tap + (size_t)p0 * Py * C : nullptr, np, Tc, Py, left, right + extra, s);
             }
+        } else if (l1f_here) {
+            EncL1Args fa;
+            fa.y0_hi = y0_hi; fa.y0_lo = y0_lo; fa.y0_elems = nY0; fa.Bc = Bc; fa.T1 = Tc;
+            fa.map.Pin = P; fa.map.Tvalid = Tc; fa.map.Pout = Py; fa.map.off = left; fa.map.hl = left; fa.map.hr = right + extra;
+            fa.ye_hi = ye_hi; fa.ye_lo = ye_lo; fa.y_f32 = y_tap;
+            // algorithmic work per level-1 position: strided conv 64x128 + k3 32x192 + 1x1 64x32 + shortcut 64x64 MACs;
+            // two new level-0 rows (32 channels, split planes) in, one row of 64 channels out
+            Scope sc(h, CAT_ENC_CONV, s, KERN_ENC_L1F, 40960.0 * Bc * Tc, 512.0 * Bc * Tc);
+            launch_enc_l1_fused(h->l1_fused, fa, s);
         } else {
             TcGemm g;
             g.nseg = 2;
@@ -1007,6 +1068,11 @@ void encoder_levels_tc(wt_handle* h, const float* wav, int Bc, int Tin, int i0, 
         // ---- G3: z = strided conv(ELU(y)) -> next level's planes (x and ELU(x)), or the pre-LSTM rows ----
         if (i == 0) { y0_hi = ye_hi; y0_lo = ye_lo; nY0 = (long long)nY; }
         const int C2 = 2 * C;
+        if (l1f && i == 0) {  // the fused kernel of the next iteration reads the ELU(y0) planes directly
+            xr_hi = xr_lo = xe_hi = xe_lo = nullptr;
+            Tc = Tn; C = C2; idx += 3;
+            continue;
+        }
         TcGemm g;
         g.seg[0] = tc_window(ye_hi, ye_lo, (long long)nY, 2 * s_ * C, (long long)s_ * C);
         g.W_hi = h->down[i].w_hi; g.W_lo = h->down[i].w_lo; g.M = Bc * Q; g.N = C2; g.K = 2 * s_ * C; g.passes = 3;
