@@ -8,21 +8,25 @@
 //
 // The unfused path runs three GEMM launches for this and moves x1 / ELU(x1) / ELU(h1) / the y0 windows a second time
 // through HBM (3.4 GB per 64 clips); here a persistent CTA keeps all weights resident in shared memory (96 KB), reads a
-// tile of `a` once (TMA) and writes ELU(y1) once (1.1 GB per 64 clips). Intermediates live in TMEM and shared memory:
+// tile of `a` once (TMA, two 64 KB buffers) and writes ELU(y1) once (1.1 GB per 64 clips). Everything in between lives in
+// TENSOR MEMORY: the accumulators, and the A operands of the second and third product, which the epilogue warps write
+// back with tcgen05.st as packed fp16 pairs (A-from-TMEM form of tcgen05.mma: rows = lanes, a k-step = 8 columns):
 //
-//   GEMM1  [a_hi, a_lo] x [Wc_lo; Wc_hi; Wd_hi; Wd_lo]  -> TMEM  [sc_hl | sc_hh+lh | x1_hh+lh | x1_hl]   (N = 256 and 128)
-//   ep 1   x1 + b_d -> ELU -> split -> shared-memory tile E (128-byte swizzle, K-major: the A operand of GEMM2)
-//   GEMM2  E x [Wk3_hi; Wk3_lo] with the three taps as COLUMN blocks  -> P[r, tap*32 + c]               (N = 192 and 96)
-//   ep 2   h1[r] = P0[r-1] + P1[r] + P2[r+1] (+ reflect at the clip ends) -> ELU -> split -> tile A2 (64-byte swizzle)
-//   GEMM3  A2 x [W1x1_lo; W1x1_hi] accumulated onto the sc columns                                        (N = 128 and 64)
+//   GEMM1  [a_hi, a_lo] (smem) x [Wc; Wd]                     -> columns [sc | x1]            (N = 128, K = 128)
+//   ep 1   x1 + b_d -> ELU -> split -> E = [hi | lo] per k-step, IN PLACE over the x1 columns
+//   GEMM2  E (TMEM) x Wk3 with the three taps as COLUMN blocks -> P[r, tap*32 + c]             (N = 96, K = 64)
+//   ep 2   h1[r] = P0[r-1] + P1[r] + P2[r+1] (+ reflect at the clip ends) -> ELU -> split -> A2 in place over P
+//   GEMM3  A2 (TMEM) x W1x1 accumulated onto the sc columns                                    (N = 64, K = 32)
 //   ep 3   y1 + b_2 -> ELU -> split planes -> HBM (row re-map + mirrored halo rows, as the generic GEMM epilogue)
 //
 // The row shift of the k3 conv happens between ACCUMULATOR rows (warp shuffles), not between operand rows: a tile is four
-// independent groups of 32 rows (one per TMEM lane quarter = one epilogue warp row range), each loaded with its own
-// one-row halo, so 30 of every 32 rows produce output and no shift ever crosses a warp. All three products use the
+// independent groups of 32 rows (one per TMEM lane quarter = the rows one epilogue warp can read), each loaded with its
+// own one-row halo, so 30 of every 32 rows produce output and no shift ever crosses a warp. All three products use the
 // 3-pass split-fp16 scheme of gemm_tc.cu (hi*hi + hi*lo + lo*hi, fp32 accumulate).
-// TMEM: two regions of 256 columns; tile i keeps GEMM1 / GEMM3 in region i & 1 and P in the other one, so the last
-// epilogue of tile i overlaps GEMM1 of tile i + 1.
+// TWO tiles are in flight: tile slot s = (tile number of this CTA) & 1 owns 224 TMEM columns, one A buffer and one group of
+// 8 epilogue warps; the single MMA-issuing thread polls the barriers of both slots and issues whichever product is ready,
+// so the tensor pipe works on one tile while the epilogue warps of the other one run (v1 of this kernel ran the chain of
+// one tile at a time: 7.2 k cycles per tile, of which the tensor pipe was busy 2.3 k).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -39,26 +43,28 @@ namespace {
 
 constexpr int F_QROWS = 30;                 // output rows per lane quarter (32 rows loaded)
 constexpr int F_TILE = 4 * F_QROWS;         // output rows per tile
-constexpr int F_THREADS = 64 + 16 * 32;     // warp 0 TMA, warp 1 MMA, 16 epilogue warps (4 per lane quarter)
+constexpr int F_THREADS = 64 + 16 * 32;     // warp 0 TMA, warp 1 MMA, 2 groups of 8 epilogue warps (2 per lane quarter)
 
-constexpr uint32_t F_W1 = 0;                         // 2 k-blocks x [256 rows x 128 B]
+constexpr uint32_t F_W1 = 0;                         // 2 k-blocks x [256 rows x 128 B]: rows [Wc_hi | Wd_hi | Wc_lo | Wd_lo]
 constexpr uint32_t F_W1_KB = 256 * 128;
-constexpr uint32_t F_W2 = F_W1 + 2 * F_W1_KB;        // [192 rows x 128 B]
-constexpr uint32_t F_W3 = F_W2 + 192 * 128;          // [128 rows x 64 B]
-constexpr uint32_t F_A0 = F_W3 + 128 * 64;           // 2 planes x 2 k-blocks x [128 rows x 128 B]
+constexpr uint32_t F_W2 = F_W1 + 2 * F_W1_KB;        // [192 rows x 128 B]: rows [Wk3_hi | Wk3_lo]
+constexpr uint32_t F_W3 = F_W2 + 192 * 128;          // [128 rows x 64 B]: rows [W1x1_hi | W1x1_lo]
+constexpr uint32_t F_A0 = F_W3 + 128 * 64;           // 2 buffers x 2 planes x 2 k-blocks x [128 rows x 128 B]
 constexpr uint32_t F_A0_KB = 128 * 128;
 constexpr uint32_t F_A0_PLANE = 2 * F_A0_KB;
-constexpr uint32_t F_E = F_A0 + 2 * F_A0_PLANE;      // 2 planes x [128 rows x 128 B]
-constexpr uint32_t F_E_PLANE = 128 * 128;
-constexpr uint32_t F_A2 = F_E + 2 * F_E_PLANE;       // 2 planes x [128 rows x 64 B]
-constexpr uint32_t F_A2_PLANE = 128 * 64;
-constexpr uint32_t F_BAR = F_A2 + 2 * F_A2_PLANE;    // 9 mbarriers + TMEM slot
-constexpr uint32_t F_BIAS = F_BAR + 128;             // b_d[64] | b_1[32] | b_2[64]
+constexpr uint32_t F_A0_BUF = 2 * F_A0_PLANE;
+constexpr uint32_t F_BAR = F_A0 + 2 * F_A0_BUF;      // 17 mbarriers + TMEM slot
+constexpr uint32_t F_BIAS = F_BAR + 160;             // b_d[64] | b_1[32] | b_2[64]
 constexpr uint32_t F_SMEM = F_BIAS + 160 * 4 + 1024; // + alignment slack
 constexpr uint32_t F_W_BYTES = 2 * F_W1_KB + 192 * 128 + 128 * 64;
-static_assert(F_W2 % 1024 == 0 && F_W3 % 1024 == 0 && F_A0 % 1024 == 0 && F_E % 1024 == 0 && F_A2 % 1024 == 0,
+static_assert(F_W2 % 1024 == 0 && F_W3 % 1024 == 0 && F_A0 % 1024 == 0 && F_A0_BUF % 1024 == 0,
               "swizzled tiles start on 1024-byte boundaries");
 static_assert(F_SMEM <= 227 * 1024, "shared memory budget");
+
+// TMEM columns of a tile slot (two slots of 256 columns)
+constexpr uint32_t C_SC = 0;     // [0, 64)   shortcut accumulators, then y1
+constexpr uint32_t C_X1 = 64;    // [64, 128) x1 accumulators, then E: k-step k = [hi 8 cols | lo 8 cols] at 64 + 16 k
+constexpr uint32_t C_P = 128;    // [128, 224) P = three tap blocks of 32, then A2: k-step k at 128 + 16 k
 
 struct FArgs {
     const float* bias;
@@ -70,13 +76,68 @@ struct FArgs {
     long long* dbg;
 };
 
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// A operand from tensor memory (TS form): rows = TMEM lanes, the 16 K elements of a k-step packed two per 32-bit column
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+                 "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+// tcgen05.wait::ld with the loaded registers passing THROUGH it, so that no use can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld8(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void pin8(uint32_t (&r)[8]) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) : : "memory");
+}
+__device__ __forceinline__ void pin16(uint32_t (&r)[16]) {  // orders the uses of r[] after the preceding volatile asm
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                      "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
 }
 
 __global__ void __launch_bounds__(F_THREADS, 1)
@@ -86,31 +147,36 @@ enc_l1_fused_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
-    auto bar = [&](int i) { return sbase + F_BAR + 8u * i; };
-    enum { B_W = 0, B_A0_FULL, B_A0_EMPTY, B_G1, B_G2, B_G3, B_E1, B_E2, B_E3 };
-    const uint32_t tmem_slot = sbase + F_BAR + 80;
-    const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(sptr + F_BAR + 80);
+    // barriers: B_W, then per tile slot s: 1 + 8 s + {A0_FULL, A0_EMPTY, G1, G2, G3, E1, E2, E3}
+    enum { A0_FULL = 0, A0_EMPTY, G1, G2, G3, E1, E2, E3 };
+    auto bar = [&](int s, int i) { return sbase + F_BAR + 8u * (1 + 8 * s + i); };
+    const uint32_t bar_w = sbase + F_BAR;
+    const uint32_t tmem_slot = sbase + F_BAR + 8u * 17;
+    const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(sptr + F_BAR + 8u * 17);
     float* sbias = reinterpret_cast<float*>(sptr + F_BIAS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_local = a.n_tiles > (int)blockIdx.x ? (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 #if WT_TIMELINE
     long long* dbg = (a.dbg && blockIdx.x == 0) ? a.dbg : nullptr;
     const long long t_begin = dbg ? clock64() : 0;
-    auto stamp = [&](int it, int slot) { if (dbg && it >= 2 && it < 6) dbg[(it - 2) * 16 + slot] = clock64() - t_begin; };
+    auto stamp = [&](int it, int slot) { if (dbg && it >= 4 && it < 8) dbg[(it - 4) * 16 + slot] = clock64() - t_begin; };
 #else
     auto stamp = [](int, int) {};
 #endif
 
     for (int i = threadIdx.x; i < 160; i += F_THREADS) sbias[i] = a.bias[i];
     if (warp == 0 && lane == 0) {
-        mbar_init(bar(B_W), 1);
-        mbar_init(bar(B_A0_FULL), 1);
-        mbar_init(bar(B_A0_EMPTY), 1);
-        mbar_init(bar(B_G1), 1);
-        mbar_init(bar(B_G2), 1);
-        mbar_init(bar(B_G3), 1);
-        mbar_init(bar(B_E1), 16);
-        mbar_init(bar(B_E2), 16);
-        mbar_init(bar(B_E3), 16);
+        mbar_init(bar_w, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar(s, A0_FULL), 1);
+            mbar_init(bar(s, A0_EMPTY), 1);
+            mbar_init(bar(s, G1), 1);
+            mbar_init(bar(s, G2), 1);
+            mbar_init(bar(s, G3), 1);
+            mbar_init(bar(s, E1), 8);
+            mbar_init(bar(s, E2), 8);
+            mbar_init(bar(s, E3), 8);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -125,211 +191,239 @@ enc_l1_fused_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
-            mbar_expect_tx(bar(B_W), F_W_BYTES);
-            tma_load_2d(sbase + F_W1, &mapW1, 0, 0, bar(B_W));
-            tma_load_2d(sbase + F_W1 + F_W1_KB, &mapW1, 64, 0, bar(B_W));
-            tma_load_2d(sbase + F_W2, &mapW2, 0, 0, bar(B_W));
-            tma_load_2d(sbase + F_W3, &mapW3, 0, 0, bar(B_W));
-            int it = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-                mbar_wait(bar(B_A0_EMPTY), (uint32_t)(it & 1) ^ 1u);
-                mbar_expect_tx(bar(B_A0_FULL), 2 * F_A0_PLANE);
+            mbar_expect_tx(bar_w, F_W_BYTES);
+            tma_load_2d(sbase + F_W1, &mapW1, 0, 0, bar_w);
+            tma_load_2d(sbase + F_W1 + F_W1_KB, &mapW1, 64, 0, bar_w);
+            tma_load_2d(sbase + F_W2, &mapW2, 0, 0, bar_w);
+            tma_load_2d(sbase + F_W3, &mapW3, 0, 0, bar_w);
+            for (int it = 0; it < n_local; ++it) {
+                const int s = it & 1;
+                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                mbar_wait(bar(s, A0_EMPTY), ph ^ 1u);
+                mbar_expect_tx(bar(s, A0_FULL), F_A0_BUF);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int row = tile * F_TILE + q * F_QROWS - 1;  // one halo row in front of the quarter's 30 outputs
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb) {
-                        const uint32_t dst = sbase + F_A0 + kb * F_A0_KB + q * 4096;
-                        tma_load_2d(dst, &mapA_hi, kb * 64, row, bar(B_A0_FULL));
-                        tma_load_2d(dst + F_A0_PLANE, &mapA_lo, kb * 64, row, bar(B_A0_FULL));
+                        const uint32_t dst = sbase + F_A0 + s * F_A0_BUF + kb * F_A0_KB + q * 4096;
+                        tma_load_2d(dst, &mapA_hi, kb * 64, row, bar(s, A0_FULL));
+                        tma_load_2d(dst + F_A0_PLANE, &mapA_lo, kb * 64, row, bar(s, A0_FULL));
                     }
                 }
                 stamp(it, 0);
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer: one thread, both tile slots, whichever product is ready =====================
         if (elect_one()) {
             const uint64_t d128 = umma_desc_hi(64), d64 = umma_desc_hi(32);
-            constexpr uint32_t i256 = umma_idesc_f16(256), i192 = umma_idesc_f16(192), i128 = umma_idesc_f16(128),
-                               i96 = umma_idesc_f16(96), i64 = umma_idesc_f16(64);
-            mbar_wait(bar(B_W), 0);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-                const uint32_t ph = (uint32_t)(it & 1);
-                const uint32_t Rp = tmem_base + ph * 256u, Rq = tmem_base + (ph ^ 1u) * 256u;
-                // ---- GEMM1: strided conv + composed shortcut ----
-                mbar_wait(bar(B_A0_FULL), ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                stamp(it, 1);
+            constexpr uint32_t i128 = umma_idesc_f16(128), i96 = umma_idesc_f16(96), i64 = umma_idesc_f16(64);
+            mbar_wait(bar_w, 0);
+            int it_s[2] = {0, 1};   // next tile (local index) of each slot
+            int stage[2] = {0, 0};  // 0: GEMM1 next, 1: GEMM2, 2: GEMM3
+            uint32_t idle = 0;
+            while (it_s[0] < n_local || it_s[1] < n_local) {
+                bool progress = false;
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb) {
+                for (int s = 0; s < 2; ++s) {  // fully unrolled: the per-slot state stays in registers
+                    const int it = it_s[s];
+                    if (it >= n_local) continue;
+                    const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                    const uint32_t T = tmem_base + 256u * s;
+                    if (stage[s] == 0) {
+                        // ---- GEMM1: strided conv + composed shortcut (A from shared memory) ----
+                        if (!mbar_test(bar(s, A0_FULL), ph)) continue;
+                        if (it >= 2 && !mbar_test(bar(s, E3), ph ^ 1u)) continue;  // the slot's previous tile has been drained
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        stamp(it, 1);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t koff = k * 32;
-                        const uint32_t sa = sbase + F_A0 + kb * F_A0_KB + koff;
-                        const uint32_t sw = sbase + F_W1 + kb * F_W1_KB + koff;
-                        umma_f16(Rp, umma_desc_at(d128, sa), umma_desc_at(d128, sw), i256, (kb | k) != 0);
-                        umma_f16(Rp + 64, umma_desc_at(d128, sa + F_A0_PLANE), umma_desc_at(d128, sw + 64 * 128), i128, 1);
+                        for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t koff = k * 32;
+                                const uint32_t sa = sbase + F_A0 + s * F_A0_BUF + kb * F_A0_KB + koff;
+                                const uint32_t sw = sbase + F_W1 + kb * F_W1_KB + koff;
+                                const uint64_t a_hi = umma_desc_at(d128, sa), a_lo = umma_desc_at(d128, sa + F_A0_PLANE);
+                                const uint64_t w_hi = umma_desc_at(d128, sw), w_lo = umma_desc_at(d128, sw + 128 * 128);
+                                umma_f16(T + C_SC, a_hi, w_hi, i128, (kb | k) != 0);
+                                umma_f16(T + C_SC, a_hi, w_lo, i128, 1);
+                                umma_f16(T + C_SC, a_lo, w_hi, i128, 1);
+                            }
+                        }
+                        umma_commit(bar(s, A0_EMPTY));
+                        umma_commit(bar(s, G1));
+                        stage[s] = 1;
+                        progress = true;
+                    } else if (stage[s] == 1) {
+                        // ---- GEMM2: k3 conv, taps as column blocks (A = E from tensor memory) ----
+                        if (!mbar_test(bar(s, E1), ph)) continue;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        stamp(it, 2);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t sw = sbase + F_W2 + k * 32;
+                            const uint64_t w_hi = umma_desc_at(d128, sw), w_lo = umma_desc_at(d128, sw + 96 * 128);
+                            const uint32_t e_hi = T + C_X1 + 16 * k, e_lo = e_hi + 8;
+                            umma_f16_ts(T + C_P, e_hi, w_hi, i96, k != 0);
+                            umma_f16_ts(T + C_P, e_hi, w_lo, i96, 1);
+                            umma_f16_ts(T + C_P, e_lo, w_hi, i96, 1);
+                        }
+                        umma_commit(bar(s, G2));
+                        stage[s] = 2;
+                        progress = true;
+                    } else {
+                        // ---- GEMM3: 1x1 conv onto the shortcut columns (A = A2 from tensor memory) ----
+                        if (!mbar_test(bar(s, E2), ph)) continue;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        stamp(it, 3);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const uint32_t sw = sbase + F_W3 + k * 32;
+                            const uint64_t w_hi = umma_desc_at(d64, sw), w_lo = umma_desc_at(d64, sw + 64 * 64);
+                            const uint32_t h_hi = T + C_P + 16 * k, h_lo = h_hi + 8;
+                            umma_f16_ts(T + C_SC, h_hi, w_hi, i64, 1);
+                            umma_f16_ts(T + C_SC, h_hi, w_lo, i64, 1);
+                            umma_f16_ts(T + C_SC, h_lo, w_hi, i64, 1);
+                        }
+                        umma_commit(bar(s, G3));
+                        stage[s] = 0;
+                        it_s[s] = it + 2;
+                        progress = true;
                     }
                 }
-                umma_commit(bar(B_A0_EMPTY));
-                umma_commit(bar(B_G1));
-                // ---- GEMM2: k3 conv, taps as column blocks ----
-                mbar_wait(bar(B_E1), ph);
-                if (it > 0) mbar_wait(bar(B_E3), ph ^ 1u);  // y of the previous tile (region Rq) has been drained
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                stamp(it, 2);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t koff = k * 32;
-                    const uint64_t w = umma_desc_at(d128, sbase + F_W2 + koff);
-                    umma_f16(Rq, umma_desc_at(d128, sbase + F_E + koff), w, i192, k != 0);
-                    umma_f16(Rq, umma_desc_at(d128, sbase + F_E + F_E_PLANE + koff), w, i96, 1);
-                }
-                umma_commit(bar(B_G2));
-                // ---- GEMM3: 1x1 conv onto the shortcut columns ----
-                mbar_wait(bar(B_E2), ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                stamp(it, 3);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const uint32_t koff = k * 32;
-                    const uint32_t sw = sbase + F_W3 + koff;
-                    umma_f16(Rp, umma_desc_at(d64, sbase + F_A2 + koff), umma_desc_at(d64, sw), i128, 1);
-                    umma_f16(Rp + 64, umma_desc_at(d64, sbase + F_A2 + F_A2_PLANE + koff), umma_desc_at(d64, sw + 64 * 64), i64, 1);
-                }
-                umma_commit(bar(B_G3));
+                if (progress) idle = 0;
+                else if (++idle > SPIN_LIMIT) asm volatile("trap;");
             }
         }
     } else {
-        // ===================== epilogue warps =====================
-        const int q = warp & 3;            // TMEM lane quarter (hardware: warp id % 4)
-        const int cg = (warp - 2) >> 2;    // column share 0..3
-        const int row = q * 32 + lane;     // tile row = TMEM lane
+        // ===================== epilogue warps: group g (8 warps) serves tile slot g =====================
+        const int q = warp & 3;                   // TMEM lane quarter (hardware: warp id % 4)
+        const int g = (warp - 2) >> 3;            // tile slot
+        const int hh = ((warp - 2) >> 2) & 1;     // column half of the quarter's rows
         const int Pin = a.map.Pin, T1 = a.T1;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-            const uint32_t ph = (uint32_t)(it & 1);
-            const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-            const uint32_t Rp = tmem_base + lane_off + ph * 256u, Rq = tmem_base + lane_off + (ph ^ 1u) * 256u;
+        const uint32_t T = tmem_base + ((uint32_t)(q * 32) << 16) + 256u * g;
+        for (int it = g; it < n_local; it += 2) {
+            const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int m = tile * F_TILE + q * F_QROWS - 1 + lane;
             const int bq = m >= 0 ? m / Pin : 0;
             const int t = m - bq * Pin;
             const bool out_ok = lane >= 1 && lane <= F_QROWS && m >= 0 && m < a.Mtot && t < T1;
-            // ---- epilogue 1: ELU(x1) -> tile E ----
-            mbar_wait(bar(B_G1), ph);
+            // ---- epilogue 1: ELU(x1) -> E, in place over this warp's 32 x1 columns ----
+            mbar_wait(bar(g, G1), ph);
+            __syncwarp();  // tcgen05.ld / st are .sync.aligned: re-converge after the predicated stores of the last tile
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (threadIdx.x == 64) stamp(it, 4);
+            if ((threadIdx.x & 255) == 64) stamp(it, 4);
             {
-                uint32_t r[16], r2[16];
-                tmem_ld_pair(Rp + 128 + cg * 16, r, Rp + 192 + cg * 16, r2);
-                uint32_t hi[8], lo[8];
+                uint32_t r0[16], r1[16];
+                tmem_ld16_nowait(T + C_X1 + 32 * hh, r0);
+                tmem_ld16_nowait(T + C_X1 + 32 * hh + 16, r1);
+                tmem_wait_ld(r0);
+                pin16(r1);
+                const float* bd = sbias + 32 * hh;
+                {
+                    uint32_t e[16];  // [hi 8 | lo 8] of k-step 2 hh
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float v0 = elu1(__uint_as_float(r[2 * i]) + __uint_as_float(r2[2 * i]) + sbias[cg * 16 + 2 * i]);
-                    const float v1 = elu1(__uint_as_float(r[2 * i + 1]) + __uint_as_float(r2[2 * i + 1]) + sbias[cg * 16 + 2 * i + 1]);
-                    split2(v0, v1, hi[i], lo[i]);
+                    for (int i = 0; i < 8; ++i)
+                        split2(elu1(__uint_as_float(r0[2 * i]) + bd[2 * i]), elu1(__uint_as_float(r0[2 * i + 1]) + bd[2 * i + 1]), e[i], e[8 + i]);
+                    tmem_st16(T + C_X1 + 32 * hh, e);
                 }
-                const uint32_t rb = sbase + F_E + row * 128;
-                const uint32_t c0 = (uint32_t)((2 * cg) ^ (row & 7)) * 16, c1 = (uint32_t)((2 * cg + 1) ^ (row & 7)) * 16;
-                sts128(rb + c0, hi[0], hi[1], hi[2], hi[3]);
-                sts128(rb + c1, hi[4], hi[5], hi[6], hi[7]);
-                sts128(rb + F_E_PLANE + c0, lo[0], lo[1], lo[2], lo[3]);
-                sts128(rb + F_E_PLANE + c1, lo[4], lo[5], lo[6], lo[7]);
+                {
+                    uint32_t e[16];  // k-step 2 hh + 1
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        split2(elu1(__uint_as_float(r1[2 * i]) + bd[16 + 2 * i]), elu1(__uint_as_float(r1[2 * i + 1]) + bd[16 + 2 * i + 1]), e[i], e[8 + i]);
+                    tmem_st16(T + C_X1 + 32 * hh + 16, e);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core (async proxy) reads
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(B_E1));
-            // ---- epilogue 2: h1 = P0[r-1] + P1[r] + P2[r+1] -> ELU -> tile A2 ----
-            mbar_wait(bar(B_G2), ph);
+            if (lane == 0) mbar_arrive(bar(g, E1));
+            // ---- epilogue 2: h1 = P0[r-1] + P1[r] + P2[r+1] -> ELU -> A2, in place over this warp's tap-0 columns ----
+            mbar_wait(bar(g, G2), ph);
+            __syncwarp();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (threadIdx.x == 64) stamp(it, 5);
+            if ((threadIdx.x & 255) == 64) stamp(it, 5);
             {
-                uint32_t a0[8], a1[8], b0[8], b1[8], c0[8], c1[8];
-                tmem_ld8_nowait(Rq + 0 + cg * 8, a0);
-                tmem_ld8_nowait(Rq + 96 + cg * 8, a1);
-                tmem_ld8_nowait(Rq + 32 + cg * 8, b0);
-                tmem_ld8_nowait(Rq + 128 + cg * 8, b1);
-                tmem_ld8_nowait(Rq + 64 + cg * 8, c0);
-                tmem_ld8_nowait(Rq + 160 + cg * 8, c1);
-                asm volatile("tcgen05.wait::ld.sync.aligned;"
-                             : "+r"(a0[0]), "+r"(a0[1]), "+r"(a0[2]), "+r"(a0[3]), "+r"(a0[4]), "+r"(a0[5]), "+r"(a0[6]), "+r"(a0[7]),
-                               "+r"(a1[0]), "+r"(a1[1]), "+r"(a1[2]), "+r"(a1[3]), "+r"(a1[4]), "+r"(a1[5]), "+r"(a1[6]), "+r"(a1[7]),
-                               "+r"(b0[0]), "+r"(b0[1]), "+r"(b0[2]), "+r"(b0[3]), "+r"(b0[4]), "+r"(b0[5]), "+r"(b0[6]), "+r"(b0[7]),
-                               "+r"(b1[0]), "+r"(b1[1]), "+r"(b1[2]), "+r"(b1[3]), "+r"(b1[4]), "+r"(b1[5]), "+r"(b1[6]), "+r"(b1[7])
-                             :
-                             : "memory");
-                asm volatile("" : "+r"(c0[0]), "+r"(c0[1]), "+r"(c0[2]), "+r"(c0[3]), "+r"(c0[4]), "+r"(c0[5]), "+r"(c0[6]), "+r"(c0[7]),
-                                  "+r"(c1[0]), "+r"(c1[1]), "+r"(c1[2]), "+r"(c1[3]), "+r"(c1[4]), "+r"(c1[5]), "+r"(c1[6]), "+r"(c1[7])
-                             :
-                             : "memory");
                 // reflect padding of the k3 conv at the clip ends (conv.py:200-210): position -1 reads 1, T1 reads T1 - 2
                 const bool first = t == 0, last = t == T1 - 1;
-                float h[8];
+                const bool any_first = __any_sync(0xffffffffu, first), any_last = __any_sync(0xffffffffu, last);
+                const float* b1 = sbias + 64 + 16 * hh;
+                uint32_t h2[16];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float p0 = __uint_as_float(a0[i]) + __uint_as_float(a1[i]);
-                    const float p1 = __uint_as_float(b0[i]) + __uint_as_float(b1[i]);
-                    const float p2 = __uint_as_float(c0[i]) + __uint_as_float(c1[i]);
-                    const float p0u = __shfl_up_sync(0xffffffffu, p0, 1), p0d = __shfl_down_sync(0xffffffffu, p0, 1);
-                    const float p2u = __shfl_up_sync(0xffffffffu, p2, 1), p2d = __shfl_down_sync(0xffffffffu, p2, 1);
-                    h[i] = elu1((first ? p0d : p0u) + p1 + (last ? p2u : p2d) + sbias[64 + cg * 8 + i]);
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t p0[8], p1[8], p2[8];
+                    tmem_ld8_nowait(T + C_P + 16 * hh + 8 * half, p0);
+                    tmem_ld8_nowait(T + C_P + 32 + 16 * hh + 8 * half, p1);
+                    tmem_ld8_nowait(T + C_P + 64 + 16 * hh + 8 * half, p2);
+                    tmem_wait_ld8(p0);
+                    pin8(p1);
+                    pin8(p2);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float v[2];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const float c0 = __uint_as_float(p0[2 * i + j]), c2 = __uint_as_float(p2[2 * i + j]);
+                            float lo_tap = __shfl_up_sync(0xffffffffu, c0, 1);    // P0 of row r - 1
+                            float hi_tap = __shfl_down_sync(0xffffffffu, c2, 1);  // P2 of row r + 1
+                            if (any_first) { const float d = __shfl_down_sync(0xffffffffu, c0, 1); if (first) lo_tap = d; }
+                            if (any_last) { const float u = __shfl_up_sync(0xffffffffu, c2, 1); if (last) hi_tap = u; }
+                            v[j] = elu1(lo_tap + __uint_as_float(p1[2 * i + j]) + hi_tap + b1[8 * half + 2 * i + j]);
+                        }
+                        split2(v[0], v[1], h2[4 * half + i], h2[8 + 4 * half + i]);
+                    }
                 }
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) split2(h[2 * i], h[2 * i + 1], hi[i], lo[i]);
-                const uint32_t rb = sbase + F_A2 + row * 64 + (uint32_t)(cg ^ ((row >> 1) & 3)) * 16;
-                sts128(rb, hi[0], hi[1], hi[2], hi[3]);
-                sts128(rb + F_A2_PLANE, lo[0], lo[1], lo[2], lo[3]);
+                tmem_st16(T + C_P + 16 * hh, h2);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(B_E2));
+            if (lane == 0) mbar_arrive(bar(g, E2));
             // ---- epilogue 3: ELU(y1) planes -> HBM ----
-            mbar_wait(bar(B_G3), ph);
+            mbar_wait(bar(g, G3), ph);
+            __syncwarp();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (threadIdx.x == 64) stamp(it, 6);
+            if ((threadIdx.x & 255) == 64) stamp(it, 6);
             {
-                uint32_t r[16], r2[16];
-                tmem_ld_pair(Rp + 64 + cg * 16, r, Rp + 0 + cg * 16, r2);
+                uint32_t r0[16], r1[16];
+                tmem_ld16_nowait(T + C_SC + 32 * hh, r0);
+                tmem_ld16_nowait(T + C_SC + 32 * hh + 16, r1);
+                tmem_wait_ld(r0);
+                pin16(r1);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(g, E3));  // the accumulators are in registers: the slot may be refilled
                 if (out_ok) {
-                    float v[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        v[i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]) + sbias[96 + cg * 16 + i];
                     const long long sb = a.map.sb ? a.map.sb : a.map.Pout, st = a.map.st ? a.map.st : 1;
                     const long long base = (long long)bq * sb + (long long)a.map.off * st;
-                    const long long dst = base + t * st;
-                    long long mir_l = -1, mir_r = -1;
-                    if (t >= 1 && t <= a.map.hl) mir_l = base - t * st;
-                    if (t <= T1 - 2 && t >= T1 - 1 - a.map.hr) mir_r = base + (2 * (T1 - 1) - t) * st;
-                    if (a.y_f32) {
-                        float* o = a.y_f32 + dst * 64 + cg * 16;
+                    long long rows[3] = {base + t * st, -1, -1};
+                    if (t >= 1 && t <= a.map.hl) rows[1] = base - t * st;
+                    if (t <= T1 - 2 && t >= T1 - 1 - a.map.hr) rows[2] = base + (2 * (T1 - 1) - t) * st;
+                    const float* b2 = sbias + 96 + 32 * hh;
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        if (mir_l >= 0) {
-                            o = a.y_f32 + mir_l * 64 + cg * 16;
+                    for (int half = 0; half < 2; ++half) {
+                        float v[16];
 #pragma unroll
-                            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        }
-                        if (mir_r >= 0) {
-                            o = a.y_f32 + mir_r * 64 + cg * 16;
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(half ? r1[i] : r0[i]) + b2[16 * half + i];
 #pragma unroll
-                            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        for (int k = 0; k < 3; ++k) {
+                            if (rows[k] < 0) continue;
+                            const long long off = rows[k] * 64 + 32 * hh + 16 * half;
+                            if (a.y_f32) {
+                                float* o = a.y_f32 + off;
+#pragma unroll
+                                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            }
+                            store_planes<16, true>(a.ye_hi, a.ye_lo, off, v);
                         }
                     }
-                    store_planes<16, true>(a.ye_hi, a.ye_lo, dst * 64 + cg * 16, v);
-                    if (mir_l >= 0) store_planes<16, true>(a.ye_hi, a.ye_lo, mir_l * 64 + cg * 16, v);
-                    if (mir_r >= 0) store_planes<16, true>(a.ye_hi, a.ye_lo, mir_r * 64 + cg * 16, v);
                 }
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(B_E3));
-            if (threadIdx.x == 64) stamp(it, 7);
+            if ((threadIdx.x & 255) == 64) stamp(it, 7);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

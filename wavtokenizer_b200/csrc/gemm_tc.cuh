@@ -112,11 +112,11 @@ long long* tc_debug_timeline();
 
 // Levels 0 -> 1 of the SEANet encoder in ONE tcgen05 kernel (enc_fused.cu): strided conv (32 -> 64, k4, s2) of the ELU(y0)
 // planes, ELU, k3 conv (64 -> 32), ELU, 1x1 conv (32 -> 64) + composed shortcut, ELU -> planes in the padded layout of
-// the next strided conv. x1, ELU(x1) and ELU(h1) never leave the SM.
+// the next strided conv. x1, ELU(x1) and ELU(h1) never leave the SM (they live in tensor memory).
 struct EncL1Weights {
-    const __half* w1 = nullptr;  // [256, 128]: rows [Wc_lo | Wc_hi | Wd_hi | Wd_lo] (composed shortcut, strided conv)
+    const __half* w1 = nullptr;  // [256, 128]: rows [Wc_hi | Wd_hi | Wc_lo | Wd_lo] (composed shortcut, strided conv)
     const __half* w2 = nullptr;  // [192, 64]: rows [Wk3_hi | Wk3_lo], row = tap * 32 + cout
-    const __half* w3 = nullptr;  // [128, 32]: rows [W1x1_lo | W1x1_hi]
+    const __half* w3 = nullptr;  // [128, 32]: rows [W1x1_hi | W1x1_lo]
     const float* bias = nullptr; // b_d[64] | b_k3[32] | b_tail[64]
 };
 struct EncL1Args {

@@ -450,9 +450,9 @@ void prepare(wt_handle* h, const Table& t) {
                 for (int n = 0; n < 64; ++n)
                     for (int j = 0; j < 128; ++j) {
                         const float wc = w2[(size_t)n * K2 + off1 + j], wd = dn.hw[(size_t)n * 128 + j];
-                        p1[(size_t)(0 + n) * 128 + j] = lo16(wc);
-                        p1[(size_t)(64 + n) * 128 + j] = hi16(wc);
-                        p1[(size_t)(128 + n) * 128 + j] = hi16(wd);
+                        p1[(size_t)(0 + n) * 128 + j] = hi16(wc);
+                        p1[(size_t)(64 + n) * 128 + j] = hi16(wd);
+                        p1[(size_t)(128 + n) * 128 + j] = lo16(wc);
                         p1[(size_t)(192 + n) * 128 + j] = lo16(wd);
                     }
                 for (int tap = 0; tap < 3; ++tap)
@@ -465,8 +465,8 @@ void prepare(wt_handle* h, const Table& t) {
                 for (int n = 0; n < 64; ++n)
                     for (int k = 0; k < 32; ++k) {
                         const float w = c2.hw[(size_t)n * 32 + k];
-                        p3[(size_t)n * 32 + k] = lo16(w);
-                        p3[(size_t)(64 + n) * 32 + k] = hi16(w);
+                        p3[(size_t)n * 32 + k] = hi16(w);
+                        p3[(size_t)(64 + n) * 32 + k] = lo16(w);
                     }
                 std::vector<float> fb(160);
                 for (int n = 0; n < 64; ++n) fb[n] = dn.hb[n];
