@@ -649,7 +649,9 @@ struct LstmArgs {
     int* counters;       // [m_tiles * L * LSTM_KB * LSTM_CNT_PITCH], zeroed before launch
     int B, L, D, m_tiles;
     int t_begin, t_end;  // this launch runs steps [t_begin, t_end): h, c and the counters of earlier steps are in place
-    int publish;         // 0: every lane fences (fence.proxy.async + membar.gl) before the release; 1: one release per warp
+    int publish;         // 0: every lane fences (fence.proxy.async + membar.gl) before the release; 1: one release per warp;
+                         // 2: one release per CTA behind a named barrier of the epilogue warps
+    int poll_ns;         // back-off between two polls of the arrival counters (0: none)
     long long* dbg;      // optional timeline of CTA (0,0): 8 stamps per step for steps 4..7
 };
 
@@ -661,8 +663,17 @@ constexpr int LSTM_A_STAGE = 2 * BM * 128;               // hi + lo tile of h_{t
 constexpr int LSTM_STAGES = 3;
 constexpr int LSTM_SMEM = LSTM_W_BYTES + LSTM_STAGES * LSTM_A_STAGE + 1024 + 256;
 constexpr int LSTM_CTAS_PER_KB = 4 * 16;  // arrivals per k-block of 64 hidden units: four CTAs x 16 epilogue warps
-constexpr int LSTM_CNT_PITCH = 8;     // ints between counters (one 32-byte sector each)
+#ifndef WT_LSTM_CNT_PITCH
+#define WT_LSTM_CNT_PITCH 8
+#endif
+constexpr int LSTM_CNT_PITCH = WT_LSTM_CNT_PITCH;     // ints between counters (8: one 32-byte sector each; 32: one line each)
 
+// CL > 1: the kernel runs as clusters of CL CTAs along the gate-slice axis. The CL CTAs of a cluster share one batch tile,
+// i.e. they all stream the SAME h_{t-1} tile every step: each loads 128 / CL of its rows per k-block and multicasts them
+// into all CL shared memories, so the tile crosses L2 -> SM once per cluster instead of once per CTA (64 CTAs x 256 KB =
+// 16 MB per step and layer otherwise, which is what the load phase of a step was bound by, twice over with both layers of
+// the wavefront resident). A ring stage is recycled when the MMAs of all CL CTAs have read it (multicast commit).
+template <int CL>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid_constant__ CUtensorMap mapH_lo,
                        const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
@@ -688,7 +699,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
     auto stamp = [&](int t, int slot) { if (dbg && t >= 4 && t < 8) dbg[(t - 4) * 8 + slot] = clock64() - t_begin; };
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < LSTM_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < LSTM_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), LSTM_EPI_WARPS); }
         mbar_init(w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -699,8 +710,11 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // the peers' barriers exist before anything is multicast at them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    constexpr int QROWS = BM / CL;  // rows of a k-block this CTA loads (and multicasts)
 
     if (warp == 0) {
         // ---- producer: resident W slice once, then h_{t-1} tiles every step ----
@@ -733,6 +747,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                     while (n < LSTM_KB && ((ready >> n) & 1u)) ++n;
                     if (n == issued) {
                         if (++spins > (1u << 24)) asm volatile("trap;");
+                        if (a.poll_ns) __nanosleep(a.poll_ns);  // back-off: the polls share L2 lines with the arrivals they wait for
                         continue;
                     }
                     if (issued == 0 && lane == 0) stamp(t, 0);  // first k-block(s) of h_{t-1} published
@@ -742,8 +757,15 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                             if (kb == issued) asm volatile("fence.proxy.async;" ::: "memory");
                             const uint32_t sa = a_base + stage * LSTM_A_STAGE;
                             mbar_expect_tx(full_bar(stage), LSTM_A_STAGE);
-                            tma_load_2d(sa, &mapH_hi, kb * BK, r0, full_bar(stage));
-                            tma_load_2d(sa + BM * 128, &mapH_lo, kb * BK, r0, full_bar(stage));
+                            if (CL > 1) {
+                                const uint32_t off = crank * (uint32_t)(QROWS * 128);
+                                const int rq = r0 + (int)crank * QROWS;
+                                tma_load_2d_mc(sa + off, &mapH_hi, kb * BK, rq, full_bar(stage), (uint16_t)((1u << CL) - 1));
+                                tma_load_2d_mc(sa + BM * 128 + off, &mapH_lo, kb * BK, rq, full_bar(stage), (uint16_t)((1u << CL) - 1));
+                            } else {
+                                tma_load_2d(sa, &mapH_hi, kb * BK, r0, full_bar(stage));
+                                tma_load_2d(sa + BM * 128, &mapH_lo, kb * BK, r0, full_bar(stage));
+                            }
                             if (kb == LSTM_KB - 1) stamp(t, 1);  // last k-block issued
                         }
                         __syncwarp();
@@ -783,7 +805,8 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                             umma_f16(tmem_d, a_hi, b_hi, idesc2, (kb | k) != 0);  // [hh | hl] in one MMA (N = 128)
                             umma_f16(tmem_d, a_lo, b_hi, idesc, 1);               // + lh into columns [0, 64)
                         }
-                        umma_commit(empty_bar(stage));
+                        if (CL > 1) umma_commit_mc(empty_bar(stage), (uint16_t)((1u << CL) - 1));  // frees the stage in every CTA
+                        else umma_commit(empty_bar(stage));
                         if (kb == LSTM_KB - 1) umma_commit(tfull_bar(acc));
                     }
                     __syncwarp();
@@ -884,6 +907,16 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                 // publish = 1: the stores of the warp's lanes are ordered before lane 0's release by __syncwarp (the release
                 // is cumulative over writes that happen-before it), so ONE fence round trip per warp instead of two; the
                 // generic -> async proxy ordering is established on the consumer side (fence.proxy.async after its acquire)
+                if (a.publish == 2) {
+                    // ONE arrival per CTA: the 16 epilogue warps meet at a named barrier (which orders their h stores before
+                    // the releasing thread), then one thread adds all 16 arrivals. 4 atomics per k-block counter instead of
+                    // 64 (same-address atomics serialise in L2), one release fence per CTA instead of 16.
+                    asm volatile("bar.sync 1, %0;" ::"r"(LSTM_EPI_WARPS * 32) : "memory");
+                    if (threadIdx.x == 64) {
+                        int* cnt = a.counters + (((long long)mt * a.L + t) * LSTM_KB + (ns >> 2)) * LSTM_CNT_PITCH;
+                        asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(cnt), "r"(LSTM_EPI_WARPS) : "memory");
+                    }
+                } else {
                 if (a.publish == 0) {
                     asm volatile("fence.proxy.async;" ::: "memory");
                     __threadfence();
@@ -892,6 +925,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                 if (lane == 0) {
                     int* cnt = a.counters + (((long long)mt * a.L + t) * LSTM_KB + (ns >> 2)) * LSTM_CNT_PITCH;
                     asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(cnt) : "memory");
+                }
                 }
                 if (threadIdx.x == 64) stamp(t, 6);  // published
                 // c_t (read back by this same thread at step t + 1) and y_t (read after the kernel) are stored AFTER the
@@ -905,6 +939,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // peers may still multicast into this CTA's stages / commit onto its barriers
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
     }
@@ -1139,10 +1174,14 @@ void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_
                             const __half* w_hi, const __half* w_lo, int B, int L, int D, cudaStream_t s, int t_begin,
                             int t_end) {
     if (D != 512) throw Error(4, "lstm_persistent: hidden size must be 512");
+    // WT_LSTM_CLUSTER = 1 (default) / 2 / 4: CTAs per cluster sharing the multicast h tile (1: every CTA loads its own copy)
+    static const int cl = [] { const char* e = std::getenv("WT_LSTM_CLUSTER"); const int v = e ? std::atoi(e) : 1; return (v == 1 || v == 2 || v == 4) ? v : 1; }();
+    const void* kernel = cl == 4 ? (const void*)lstm_persistent_kernel<4> : cl == 2 ? (const void*)lstm_persistent_kernel<2>
+                                                                                       : (const void*)lstm_persistent_kernel<1>;
     static PerDevice<bool> attr_dev;
     bool& attr = attr_dev.get();
     if (!attr) {
-        WT_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LSTM_SMEM));
+        WT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LSTM_SMEM));
         attr = true;
     }
     LstmArgs a;
@@ -1151,8 +1190,11 @@ void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_
     if (t_end < 0) t_end = L;
     if (t_begin < 0 || t_begin >= t_end || t_end > L) throw Error(4, "lstm_persistent: bad step range");
     a.t_begin = t_begin; a.t_end = t_end;
-    static const int publish = [] { const char* e = std::getenv("WT_LSTM_PUBLISH"); return e ? std::atoi(e) : 0; }();
-    a.publish = publish;  // measured: 30.05 (0) vs 30.20 (1) ms per step, within noise -> the conservative form stays
+    // measured: publish 0 vs 1: 30.05 vs 30.20 ms per step (noise); 2 (one arrival per CTA): LSTM category 7.2-7.5 -> 6.3-6.6 ms
+    static const int publish = [] { const char* e = std::getenv("WT_LSTM_PUBLISH"); return e ? std::atoi(e) : 2; }();
+    a.publish = publish;
+    static const int poll_ns = [] { const char* e = std::getenv("WT_LSTM_POLL_NS"); return e ? std::atoi(e) : 0; }();
+    a.poll_ns = poll_ns;
     a.dbg = g_debug_timeline ? g_debug_timeline + 148 * 64 : nullptr;  // after the generic GEMMs' per-CTA slots
     const int n_slices = 4 * D / 64;
     int mgroups = a.m_tiles;
@@ -1162,11 +1204,18 @@ void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_
     CUtensorMap mw_hi = make_map(w_hi, 4LL * D, D, D, 64);
     CUtensorMap mw_lo = make_map(w_lo, 4LL * D, D, D, 64);
     if (t_begin == 0) WT_CUDA(cudaMemsetAsync(counters, 0, lstm_counter_ints(B, L) * sizeof(int), s));
-    CUtensorMap mh_hi = make_map(h_hi, (long long)L * B, D, D, BM);
-    CUtensorMap mh_lo = make_map(h_lo, (long long)L * B, D, D, BM);
+    CUtensorMap mh_hi = make_map(h_hi, (long long)L * B, D, D, BM / cl);
+    CUtensorMap mh_lo = make_map(h_lo, (long long)L * B, D, D, BM / cl);
     void* args[] = {&mh_hi, &mh_lo, &mw_hi, &mw_lo, &a};
-    WT_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_persistent_kernel, dim3(n_slices, mgroups), dim3(LSTM_THREADS),
-                                        args, (size_t)LSTM_SMEM, s));
+    // cooperative: every CTA must be co-resident (they wait on each other); clusters along the gate-slice axis
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_slices, mgroups); cfg.blockDim = dim3(LSTM_THREADS); cfg.dynamicSmemBytes = LSTM_SMEM; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = cl; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = cl > 1 ? 2 : 1;
+    WT_CUDA(cudaLaunchKernelExC(&cfg, kernel, args));
 }
 
 int lstm_ctas(int B, int D) {
