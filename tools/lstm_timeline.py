@@ -18,7 +18,7 @@ m.encode_infer(wav, bandwidth_id=bw)
 torch.cuda.synchronize()
 lib.wt_debug_timeline(None)
 d = dbg[148 * 64:].view(8, 8).cpu()  # last layer's launch overwrote the first
-names = ["published(t-1) seen", "last TMA issued", "first kb landed", "last kb landed", "acc ready", "cell done", "published"]
+names = ["published(t-1) seen", "last TMA issued", "first kb landed", "last kb landed", "acc ready", "cell done", "published", "all warps stored h"]
 for i in range(4):
     base = int(d[i][0])
     print(f"step {4+i}: t0={base}", {n: int(d[i][k]) - base for k, n in enumerate(names)})

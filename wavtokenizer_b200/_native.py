@@ -94,6 +94,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cflags = [f for f in NVCC_FLAGS if f != "-shared"]
     if os.environ.get("WT_TIMELINE"):  # instrumented build for tools/gemm_timeline.py (per-CTA clock64 stamps)
         cflags.append("-DWT_TIMELINE=1")
+    cflags += os.environ.get("WT_EXTRA_NVCC_FLAGS", "").split()  # experiments: compile-time tunables (-DWT_...=n)
 
     def compile_one(src: str):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")

@@ -652,6 +652,7 @@ struct LstmArgs {
     int publish;         // 0: every lane fences (fence.proxy.async + membar.gl) before the release; 1: one release per warp;
                          // 2: one release per CTA behind a named barrier of the epilogue warps
     int poll_ns;         // back-off between two polls of the arrival counters (0: none)
+    int keep_c;          // 1: c_t in registers between steps, y_t stored one step late (0: both stored every step)
     long long* dbg;      // optional timeline of CTA (0,0): 8 stamps per step for steps 4..7
 };
 
@@ -660,8 +661,13 @@ constexpr int LSTM_THREADS = 64 + LSTM_EPI_WARPS * 32;
 constexpr int LSTM_KB = 8;                               // D = 512 = 8 k-blocks of 64
 constexpr int LSTM_W_BYTES = LSTM_KB * 2 * 64 * 128;     // resident W slice: 8 kb x (hi, lo) x [64 rows x 128 B]
 constexpr int LSTM_A_STAGE = 2 * BM * 128;               // hi + lo tile of h_{t-1}
-constexpr int LSTM_STAGES = 3;
-constexpr int LSTM_SMEM = LSTM_W_BYTES + LSTM_STAGES * LSTM_A_STAGE + 1024 + 256;
+#ifndef WT_LSTM_STAGES
+#define WT_LSTM_STAGES 3  // measured: 2 and 3 ring stages give the same step time; with 2 the third stage's room holds the h staging tile of publish = 3
+#endif
+constexpr int LSTM_STAGES = WT_LSTM_STAGES;
+constexpr int LSTM_HST = LSTM_STAGES <= 2 ? 2 * BM * 32 : 0;  // staging tile of h_t (hi + lo, [128 rows x 16 units]) for the TMA store
+constexpr int LSTM_SMEM = LSTM_W_BYTES + LSTM_STAGES * LSTM_A_STAGE + LSTM_HST + 1024 + 256;
+static_assert(LSTM_SMEM <= 227 * 1024, "LSTM shared memory budget");
 constexpr int LSTM_CTAS_PER_KB = 4 * 16;  // arrivals per k-block of 64 hidden units: four CTAs x 16 epilogue warps
 #ifndef WT_LSTM_CNT_PITCH
 #define WT_LSTM_CNT_PITCH 8
@@ -677,12 +683,14 @@ template <int CL>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid_constant__ CUtensorMap mapH_lo,
                        const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
+                       const __grid_constant__ CUtensorMap mapS_hi, const __grid_constant__ CUtensorMap mapS_lo,
                        const LstmArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t w_base = smem_base;
     const uint32_t a_base = smem_base + LSTM_W_BYTES;
-    const uint32_t bar_base = a_base + LSTM_STAGES * LSTM_A_STAGE;
+    const uint32_t hst_base = a_base + LSTM_STAGES * LSTM_A_STAGE;  // h_t staging tile (publish = 3)
+    const uint32_t bar_base = hst_base + LSTM_HST;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (LSTM_STAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * LSTM_STAGES + s); };
@@ -822,6 +830,12 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
         const int u0 = ns * 16 + hw * 4;
         int acc = 0;
         uint32_t acc_phase = 0;
+        // One batch tile per CTA (the usual case): c_t stays in registers between the steps of a launch (it is read back only
+        // by the thread that wrote it). y_t is stored one step late, after the next accumulator wait: the release that
+        // publishes h_t waits for the outstanding writes of the SM, and only the h planes belong in front of it.
+        const bool c_in_regs = a.keep_c && a.m_tiles <= MG;
+        float4 c_keep = make_float4(0.f, 0.f, 0.f, 0.f), y_pend = c_keep;
+        long long y_pend_row = -1;
         for (int t = a.t_begin; t < a.t_end; ++t) {
             for (int mt = mg; mt < a.m_tiles; mt += MG) {
                 const int b = mt * BM + q * 32 + lane;
@@ -836,7 +850,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                     xf = *reinterpret_cast<const float4*>(xr + 16);
                     xg = *reinterpret_cast<const float4*>(xr + 32);
                     xo = *reinterpret_cast<const float4*>(xr + 48);
-                    if (t > 0) cv = *reinterpret_cast<const float4*>(cr);  // c_{-1} = 0
+                    if (t > 0) cv = (c_in_regs && t > a.t_begin) ? c_keep : *reinterpret_cast<const float4*>(cr);  // c_{-1} = 0
                 }
                 uint32_t ri[4] = {0u, 0u, 0u, 0u}, rf[4] = {0u, 0u, 0u, 0u}, rg[4] = {0u, 0u, 0u, 0u},
                          ro[4] = {0u, 0u, 0u, 0u};  // h_{-1} = 0
@@ -877,6 +891,10 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                     if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator is in registers: free it early
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
+                if (y_pend_row >= 0) {  // y of the previous step (see above)
+                    *reinterpret_cast<float4*>(a.y + y_pend_row * a.D + u0) = y_pend;
+                    y_pend_row = -1;
+                }
                 float4 c_out = cv, y_out = cv;
                 if (row_ok) {
                     const float xiv[4] = {xi.x, xi.y, xi.z, xi.w}, xfv[4] = {xf.x, xf.y, xf.z, xf.w};
@@ -895,8 +913,16 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                     uint32_t h01, l01, h23, l23;
                     split2(hv[0], hv[1], h01, l01);
                     split2(hv[2], hv[3], h23, l23);
+                    if (LSTM_HST > 0 && a.publish == 3 && (mt + 1) * BM <= a.B) {
+                        // staged: [128 rows x 32 B] per plane under the 32-byte TMA swizzle (16-byte chunk ^= bit 2 of the row)
+                        const int r = q * 32 + lane;
+                        const uint32_t so = (uint32_t)(r * 32 + ((((hw >> 1) ^ (r >> 2)) & 1) << 4) + (hw & 1) * 8);
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(hst_base + so), "r"(h01), "r"(h23) : "memory");
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(hst_base + BM * 32 + so), "r"(l01), "r"(l23) : "memory");
+                    } else {
                     *reinterpret_cast<uint2*>(a.h_hi + row * a.D + u0) = make_uint2(h01, h23);
                     *reinterpret_cast<uint2*>(a.h_lo + row * a.D + u0) = make_uint2(l01, l23);
+                    }
                     c_out = make_float4(cvv[0], cvv[1], cvv[2], cvv[3]);
                     y_out = make_float4(hv[0], hv[1], hv[2], hv[3]);
                 }
@@ -907,12 +933,26 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                 // publish = 1: the stores of the warp's lanes are ordered before lane 0's release by __syncwarp (the release
                 // is cumulative over writes that happen-before it), so ONE fence round trip per warp instead of two; the
                 // generic -> async proxy ordering is established on the consumer side (fence.proxy.async after its acquire)
-                if (a.publish == 2) {
+                if (a.publish >= 2) {
                     // ONE arrival per CTA: the 16 epilogue warps meet at a named barrier (which orders their h stores before
                     // the releasing thread), then one thread adds all 16 arrivals. 4 atomics per k-block counter instead of
                     // 64 (same-address atomics serialise in L2), one release fence per CTA instead of 16.
                     asm volatile("bar.sync 1, %0;" ::"r"(LSTM_EPI_WARPS * 32) : "memory");
+                    if (threadIdx.x == 64) stamp(t, 7);  // all 16 epilogue warps have stored their h
                     if (threadIdx.x == 64) {
+                        if (LSTM_HST > 0 && a.publish == 3 && (mt + 1) * BM <= a.B) {
+                            // publish = 3: the CTA's [128 x 16] slice of h_t leaves as TWO bulk tensor stores from the staging
+                            // tile instead of 1024 scattered 8-byte stores; the release then has nothing else to wait for
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            const int r0 = (int)((long long)t * a.B) + mt * BM;
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                         ::"l"(reinterpret_cast<uint64_t>(&mapS_hi)), "r"(ns * 16), "r"(r0), "r"(hst_base) : "memory");
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                         ::"l"(reinterpret_cast<uint64_t>(&mapS_lo)), "r"(ns * 16), "r"(r0), "r"(hst_base + BM * 32) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                            asm volatile("fence.proxy.async;" ::: "memory");
+                        }
                         int* cnt = a.counters + (((long long)mt * a.L + t) * LSTM_KB + (ns >> 2)) * LSTM_CNT_PITCH;
                         asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(cnt), "r"(LSTM_EPI_WARPS) : "memory");
                     }
@@ -931,11 +971,18 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap mapH_hi, const __grid
                 // c_t (read back by this same thread at step t + 1) and y_t (read after the kernel) are stored AFTER the
                 // release: the fences above then only wait for the two h-plane stores the other CTAs are waiting for
                 if (row_ok) {
-                    *reinterpret_cast<float4*>(cr) = c_out;
-                    *reinterpret_cast<float4*>(a.y + row * a.D + u0) = y_out;
+                    if (c_in_regs) {
+                        c_keep = c_out;
+                        if (t == a.t_end - 1) *reinterpret_cast<float4*>(cr) = c_out;
+                    } else {
+                        *reinterpret_cast<float4*>(cr) = c_out;
+                    }
+                    if (a.keep_c) { y_pend = y_out; y_pend_row = row; }
+                    else *reinterpret_cast<float4*>(a.y + row * a.D + u0) = y_out;
                 }
             }
         }
+        if (y_pend_row >= 0) *reinterpret_cast<float4*>(a.y + y_pend_row * a.D + u0) = y_pend;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -1191,10 +1238,13 @@ void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_
     if (t_begin < 0 || t_begin >= t_end || t_end > L) throw Error(4, "lstm_persistent: bad step range");
     a.t_begin = t_begin; a.t_end = t_end;
     // measured: publish 0 vs 1: 30.05 vs 30.20 ms per step (noise); 2 (one arrival per CTA): LSTM category 7.2-7.5 -> 6.3-6.6 ms
+    // 3 (needs -DWT_LSTM_STAGES=2: bulk tensor store of the staged h slice behind the one release): LSTM kernel 4.76 vs 4.65 ms, not kept
     static const int publish = [] { const char* e = std::getenv("WT_LSTM_PUBLISH"); return e ? std::atoi(e) : 2; }();
     a.publish = publish;
     static const int poll_ns = [] { const char* e = std::getenv("WT_LSTM_POLL_NS"); return e ? std::atoi(e) : 0; }();
     a.poll_ns = poll_ns;
+    static const int keep_c = [] { const char* e = std::getenv("WT_LSTM_KEEP_C"); return e ? std::atoi(e) : 1; }();
+    a.keep_c = keep_c;
     a.dbg = g_debug_timeline ? g_debug_timeline + 148 * 64 : nullptr;  // after the generic GEMMs' per-CTA slots
     const int n_slices = 4 * D / 64;
     int mgroups = a.m_tiles;
@@ -1206,7 +1256,9 @@ void launch_lstm_persistent(const float* xin, float* y, __half* h_hi, __half* h_
     if (t_begin == 0) WT_CUDA(cudaMemsetAsync(counters, 0, lstm_counter_ints(B, L) * sizeof(int), s));
     CUtensorMap mh_hi = make_map(h_hi, (long long)L * B, D, D, BM / cl);
     CUtensorMap mh_lo = make_map(h_lo, (long long)L * B, D, D, BM / cl);
-    void* args[] = {&mh_hi, &mh_lo, &mw_hi, &mw_lo, &a};
+    CUtensorMap ms_hi = make_map(h_hi, (long long)L * B, D, D, BM, 16);  // store maps: [128 rows x 16 units] boxes
+    CUtensorMap ms_lo = make_map(h_lo, (long long)L * B, D, D, BM, 16);
+    void* args[] = {&mh_hi, &mh_lo, &mw_hi, &mw_lo, &ms_hi, &ms_lo, &a};
     // cooperative: every CTA must be co-resident (they wait on each other); clusters along the gate-slice axis
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_slices, mgroups); cfg.blockDim = dim3(LSTM_THREADS); cfg.dynamicSmemBytes = LSTM_SMEM; cfg.stream = s;
