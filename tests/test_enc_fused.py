@@ -89,3 +89,23 @@ def test_fused_against_oracle_one_clip(setup):
         y = O.seanet_resblock(sd, E + "4.", x)
     assert y.shape == y_f.shape
     assert helpers.snr_db(y, y_f) >= 85.0
+
+
+@pytest.mark.parametrize("B,T", [(2, 24000), (3, 4801), (4, 1283)])
+def test_level0_and_level1_against_fp32_plan_full_tensors(setup, B, T):
+    """Level 0 (csrc/enc_l0_tc.cu: k3 / 1x1 products of ResBlock 0 as A-from-TMEM MMAs) and the fused level 1 against the
+    fp32 CUDA-core plan of the same library, every position of every clip (clip ends, tile seams, quarter seams)."""
+    tag, cfg, sd, g, m = setup
+    m0 = native_model(tag, 0)
+    wav = spec.synthetic_audio(B, T, seed=900 + T).cuda()
+    out = {}
+    for name, mod in (("tc", m), ("fp32", m0)):
+        taps = Taps(mod, ["enc1", "enc4"], capacity=48 << 20)
+        mod.encode_infer(wav, bandwidth_id=torch.tensor([0]).cuda())
+        torch.cuda.synchronize()
+        out[name] = (taps.get("enc1"), taps.get("enc4"))
+        taps.close()
+    assert out["tc"][0].shape == out["fp32"][0].shape == (B, 32, T)
+    assert helpers.snr_db(out["fp32"][0], out["tc"][0]) >= 100.0
+    assert helpers.snr_db(out["fp32"][1], out["tc"][1]) >= 95.0
+    assert float((out["fp32"][0] - out["tc"][0]).abs().max()) <= 1e-4 * float(out["fp32"][0].abs().max())

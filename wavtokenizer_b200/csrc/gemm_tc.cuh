@@ -132,6 +132,17 @@ struct EncL1Args {
 bool enc_l1_fused_supported(int cin, int stride);
 void launch_enc_l1_fused(const EncL1Weights& w, const EncL1Args& a, cudaStream_t s);
 
+// Level 0 of the SEANet encoder (conv0 + ResBlock 0) with the k3 and 1x1 products on the tensor cores (enc_l0_tc.cu);
+// conv0 and the composed shortcut stay on the CUDA cores with their weights in the kernel-parameter constant bank.
+struct EncL0Weights {
+    const __half* wk3 = nullptr;   // [96, 32]: rows [Wk3_hi | Wk3_lo], row = tap * 16 + cout
+    const __half* w1x1 = nullptr;  // [64, 16]: rows [W1x1_hi | W1x1_lo]
+    const float* consts = nullptr; // HOST: w0[7][32] | b0[32] | wsc[7][32] | b1[16] | b2[32]
+};
+bool enc_l0_tc_supported();
+void launch_enc_l0_tc(const EncL0Weights& w, const float* wav, __half* ye_hi, __half* ye_lo, float* y_f32, int B, int T,
+                      const RowMap& map, cudaStream_t s);
+
 // Convenience: a dense / tap-mode segment over rows [rows, Cin] with pitch lda.
 inline TcSeg tc_taps(const __half* hi, const __half* lo, long long rows, int Cin, int lda, int taps, int center) {
     TcSeg s;

@@ -114,6 +114,8 @@ struct wt_handle {
     struct LstmTc { HalfW w_ih, w_hh; float* bias = nullptr; } lstm_tc[4];
     float* rb0_pack = nullptr;   // level-0 fused kernel weights (encoder_ops.cu resblock0_fused_kernel)
     EncL1Weights l1_fused;       // level 0 -> 1 fused tcgen05 kernel weights (enc_fused.cu); w1 == nullptr: not available
+    EncL0Weights l0_tc;          // level 0 with tensor-core k3 / 1x1 products (enc_l0_tc.cu); wk3 == nullptr: not available
+    std::vector<float> l0_consts;
     float* zero_rows = nullptr;  // zero planes standing in for h_{-1}
     // vq
     float* codebooks = nullptr;  // [num_quantizers * bins, D]
@@ -499,6 +501,36 @@ void prepare(wt_handle* h, const Table& t) {
                 q += 256;
                 for (int n = 0; n < 32; ++n) q[n] = b2[n];
                 h->rb0_pack = h->upload(pk);
+                {   // tensor-core level 0 (enc_l0_tc.cu): MMA weight tiles as stacked hi / lo rows, the rest as constants
+                    auto hi16 = [](float v) { return __float2half_rn(v); };
+                    auto lo16 = [](float v) { const __half hh = __float2half_rn(v); return __float2half_rn(v - __half2float(hh)); };
+                    std::vector<__half> pk3((size_t)96 * 32), p11((size_t)64 * 16);
+                    for (int tap = 0; tap < 3; ++tap)
+                        for (int n = 0; n < 16; ++n)
+                            for (int k = 0; k < 32; ++k) {
+                                const float w = c1.hw[(size_t)n * 96 + tap * 32 + k];
+                                pk3[(size_t)(tap * 16 + n) * 32 + k] = hi16(w);
+                                pk3[(size_t)(48 + tap * 16 + n) * 32 + k] = lo16(w);
+                            }
+                    for (int n = 0; n < 32; ++n)
+                        for (int k = 0; k < 16; ++k) {
+                            const float w = c2.hw[(size_t)n * 16 + k];
+                            p11[(size_t)n * 16 + k] = hi16(w);
+                            p11[(size_t)(32 + n) * 16 + k] = lo16(w);
+                        }
+                    h->l0_consts.assign(528, 0.f);
+                    float* kc = h->l0_consts.data();
+                    for (int j = 0; j < 7; ++j)
+                        for (int n = 0; n < 32; ++n) {
+                            kc[j * 32 + n] = h_conv0_w[(size_t)n * 7 + j];
+                            kc[256 + j * 32 + n] = w2[(size_t)n * K2 + off1 + j];
+                        }
+                    for (int n = 0; n < 32; ++n) { kc[224 + n] = h_conv0_b[n]; kc[496 + n] = b2[n]; }
+                    for (int n = 0; n < 16; ++n) kc[480 + n] = c1.hb[n];
+                    h->l0_tc.wk3 = h->upload_halves(pk3);
+                    h->l0_tc.w1x1 = h->upload_halves(p11);
+                    h->l0_tc.consts = h->l0_consts.data();
+                }
             }
             C *= 2;
         }
@@ -1036,6 +1068,12 @@ void encoder_levels_tc(wt_handle* h, const float* wav, int Bc, int Tin, int i0, 
                 const int np = std::min(piece, Bc - p0);
                 if (h->wav_ready) h->wav_ready(b0 + p0, np);
                 Scope sc(h, CAT_ENC_CONV, s, KERN_RB0, 6592.0 * np * Tc, 132.0 * np * Tc);
+                if (h->l0_tc.wk3 && enc_l0_tc_supported()) {
+                    RowMap mp;
+                    mp.Pin = Tc + 2; mp.Tvalid = Tc; mp.Pout = Py; mp.off = left; mp.hl = left; mp.hr = right + extra;
+                    launch_enc_l0_tc(h->l0_tc, wav + (size_t)p0 * Tc, ye_hi + (size_t)p0 * Py * C, ye_lo + (size_t)p0 * Py * C,
+                                     y_tap ? y_tap + (size_t)p0 * Py * C : nullptr, np, Tc, mp, s);
+                } else
                 launch_resblock0_fused(wav + (size_t)p0 * Tc, h->rb0_pack, ye_hi + (size_t)p0 * Py * C, ye_lo + (size_t)p0 * Py * C,
                                        y_tap ? y_tap + (size_t)p0 * Py * C : nullptr, np, Tc, Py, left, right + extra, s);
             }
