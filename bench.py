@@ -66,7 +66,7 @@ CATS = ["enc_conv", "lstm", "vq", "dec_conv", "pwconv", "head_idft", "attention"
 NAMED_KERNELS = {1: "lstm_persistent_kernel", 2: "resblock0_fused_kernel", 3: "groupnorm_kernel", 4: "dwconv_ln_kernel",
                  5: "layernorm_kernel", 6: "spectral_kernel", 7: "overlap_add_kernel", 8: "softmax_planes_kernel",
                  9: "vt_planes_kernel", 10: "features_to_rows_kernel", 11: "codes_to_features_kernel",
-                 12: "lstm_skip_elu_pad_kernel", 14: "enc_l1_fused_kernel"}
+                 12: "lstm_skip_elu_pad_kernel", 14: "enc_l1_fused_kernel", 15: "enc_l0_tc_kernel"}
 
 
 def cfg_path(name: str) -> str:
@@ -346,6 +346,10 @@ def kernel_records(lib, hptr, step_ms: float, peaks: dict) -> tuple:
                 r["note"] = ("level-0 strided conv + level-1 ResBlock in one tcgen05 kernel: 256 B of ELU(y0) planes in + "
                              "256 B of ELU(y1) planes out per level-1 position, intermediates in TMEM / shared memory; "
                              f"{d['tflops_per_s']} algorithmic TFLOP/s (3-pass split fp16)")
+            if kname == "enc_l0_tc_kernel":
+                r["note"] = ("conv0 + ResBlock 0: 4 B in + 128 B of split-fp16 planes out per sample; k3 / 1x1 products as "
+                             "A-from-TMEM tcgen05 MMAs, conv0 + composed shortcut (448 FMA per sample) and the ELU / split "
+                             f"epilogues on the CUDA cores, which bound it: {d['tflops_per_s']} algorithmic TFLOP/s")
             if kname == "resblock0_fused_kernel":
                 r["note"] = ("4 B in + 128 B of split-fp16 planes out per sample; the kernel is fp32-FMA bound before it "
                              f"is HBM bound: {d['tflops_per_s']} algorithmic TFLOP/s on the CUDA cores")

@@ -793,7 +793,7 @@ enum Cat : int { CAT_ENC_CONV = 0, CAT_LSTM, CAT_VQ, CAT_DEC_CONV, CAT_PWCONV, C
 enum Kern : int {
     KERN_LSTM = 1, KERN_RB0 = 2, KERN_GROUPNORM = 3, KERN_DWCONV_LN = 4, KERN_LAYERNORM = 5, KERN_SPECTRAL = 6,
     KERN_OLA = 7, KERN_SOFTMAX = 8, KERN_VT = 9, KERN_ROWS = 10, KERN_GATHER = 11, KERN_LSTM_SKIP = 12, KERN_VQ_MISC = 13,
-    KERN_ENC_L1F = 14
+    KERN_ENC_L1F = 14, KERN_ENC_L0TC = 15
 };
 
 // Counts one kernel launch and, when timing is on, brackets it with CUDA events on its stream. `kern` / `flops` /
@@ -1067,8 +1067,9 @@ void encoder_levels_tc(wt_handle* h, const float* wav, int Bc, int Tin, int i0, 
             for (int p0 = 0; p0 < Bc; p0 += piece) {
                 const int np = std::min(piece, Bc - p0);
                 if (h->wav_ready) h->wav_ready(b0 + p0, np);
-                Scope sc(h, CAT_ENC_CONV, s, KERN_RB0, 6592.0 * np * Tc, 132.0 * np * Tc);
-                if (h->l0_tc.wk3 && enc_l0_tc_supported()) {
+                const bool l0tc = h->l0_tc.wk3 && enc_l0_tc_supported();
+                Scope sc(h, CAT_ENC_CONV, s, l0tc ? KERN_ENC_L0TC : KERN_RB0, 6592.0 * np * Tc, 132.0 * np * Tc);
+                if (l0tc) {
                     RowMap mp;
                     mp.Pin = Tc + 2; mp.Tvalid = Tc; mp.Pout = Py; mp.off = left; mp.hl = left; mp.hr = right + extra;
                     launch_enc_l0_tc(h->l0_tc, wav + (size_t)p0 * Tc, ye_hi + (size_t)p0 * Py * C, ye_lo + (size_t)p0 * Py * C,
