@@ -509,6 +509,41 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                 // ConvNeXt GEMM-1 fast path (reference decoder/modules.py:54-55): bias + exact-erf GELU -> fp16 plane,
                 // 32 columns per tcgen05.ld so that the fixed per-chunk cost is paid half as often; nothing else live.
                 static_assert(BN / C::G == 64 || BN != 256 || PASSES != 1, "two 32-column chunks per warp");
+                if constexpr (GELU_EPI) {
+                    // 16-column chunks, the tcgen05.ld of chunk c + 1 in flight while chunk c is computed (a chunk's load
+                    // latency under 16 warps reading tensor memory is of the order of its ~250 instructions of math)
+                    constexpr int NCH = BN / C::G / 16;
+                    const int col0 = cg * (BN / C::G);
+                    const float* bp0 = sbias + n0 + col0;
+                    __half* op0 = g.out_hi + (long long)m * g.ldh + n0 + col0;
+                    uint32_t ra[16], rb[16];
+                    __syncwarp();
+                    tmem_ld16_nowait(tbase + (uint32_t)col0, ra);
+                    tmem_wait_ld(ra);
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        uint32_t(&cur)[16] = (c & 1) ? rb : ra;
+                        uint32_t(&nxt)[16] = (c & 1) ? ra : rb;
+                        if (c + 1 < NCH) tmem_ld16_nowait(tbase + (uint32_t)(col0 + 16 * (c + 1)), nxt);
+                        if (row_ok) {
+                            uint32_t w[8];
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 b = *reinterpret_cast<const float4*>(bp0 + 16 * c + i);
+                                const float v0 = gelu_erf(__uint_as_float(cur[i]) + b.x);
+                                const float v1 = gelu_erf(__uint_as_float(cur[i + 1]) + b.y);
+                                const float v2 = gelu_erf(__uint_as_float(cur[i + 2]) + b.z);
+                                const float v3 = gelu_erf(__uint_as_float(cur[i + 3]) + b.w);
+                                const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+                                w[i / 2] = *reinterpret_cast<const uint32_t*>(&h01);
+                                w[i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                            }
+                            st256(op0 + 16 * c, w);
+                        }
+                        __syncwarp();
+                        if (c + 1 < NCH) tmem_wait_ld(nxt);
+                    }
+                } else {
 #pragma unroll 1
                 for (int c2 = 0; c2 < BN / C::G / 32; ++c2) {
                     const int col = cg * (BN / C::G) + c2 * 32;
@@ -535,6 +570,7 @@ tap_gemm_tc_kernel(const __grid_constant__ Maps maps, const TcGemm g) {
                             st256(op + 16 * j, w);
                         }
                     }
+                }
                 }
             } else if constexpr (!GELU_EPI) {
 #pragma unroll 1
