@@ -169,27 +169,37 @@ enc_l0_tc_kernel(const __grid_constant__ CUtensorMap mapWk, const __grid_constan
         const int g = (warp - 2) >> 2;
         const int Pin = a.map.Pin, T = a.T;
         const uint32_t TM = tmem_base + ((uint32_t)(q * 32) << 16) + 128u * g;
-        for (int it = g; it < n_local; it += Z_GROUPS) {
-            const uint32_t ph = (uint32_t)(it >> 2) & 1u;
+        // the 7 audio samples of a position, reflect-padded at the clip ends (conv.py:79-96); loaded one tile ahead so that the
+        // first FMA of step A does not wait for them (5 % of the stall samples sat there, profiles/r02_ncu_stalls_final.txt)
+        auto load_samples = [&](int it, float (&sv)[7], int& bq_o, int& t_o, bool& ok_o) {
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int m = tile * Z_TILE + q * Z_QROWS - 1 + lane;
-            int bq = m >= 0 ? m / Pin : 0;
+            int bq = (m >= 0 && it < n_local) ? m / Pin : 0;
             const int t = m - bq * Pin;
-            const bool out_ok = lane >= 1 && lane <= Z_QROWS && m >= 0 && m < a.Mtot && t < T;
+            ok_o = lane >= 1 && lane <= Z_QROWS && m >= 0 && m < a.Mtot && t < T;
             if (bq >= a.Bc) bq = a.Bc - 1;  // rows past the last clip: any readable address (their results are dropped)
-            // the 7 audio samples of this position, reflect-padded at the clip ends (conv.py:79-96)
-            float s[7];
-            {
-                const float* x = a.wav + (long long)bq * T;
-                const int tc = t < T ? t : T - 1;
+            bq_o = bq; t_o = t;
+            const float* x = a.wav + (long long)bq * T;
+            const int tc = (t >= 0 && t < T) ? t : T - 1;
 #pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    int idx = tc - 3 + j;
-                    if (idx < 0) idx = -idx;
-                    if (idx >= T) idx = 2 * (T - 1) - idx;
-                    s[j] = __ldg(x + idx);
-                }
+            for (int j = 0; j < 7; ++j) {
+                int idx = tc - 3 + j;
+                if (idx < 0) idx = -idx;
+                if (idx >= T) idx = 2 * (T - 1) - idx;
+                sv[j] = __ldg(x + idx);
             }
+        };
+        float sn[7];
+        int bq_n, t_n;
+        bool ok_n;
+        load_samples(g, sn, bq_n, t_n, ok_n);
+        for (int it = g; it < n_local; it += Z_GROUPS) {
+            const uint32_t ph = (uint32_t)(it >> 2) & 1u;
+            float s[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) s[j] = sn[j];
+            const int bq = bq_n, t = t_n;
+            const bool out_ok = ok_n;
             __syncwarp();
             // ---- step A: ELU(conv0) -> packed planes in tensor memory ----
 #pragma unroll
@@ -212,6 +222,7 @@ enc_l0_tc_kernel(const __grid_constant__ CUtensorMap mapWk, const __grid_constan
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(g, E_READY));
+            load_samples(it + Z_GROUPS, sn, bq_n, t_n, ok_n);  // next tile's samples: in flight behind steps B and C
             // ---- step B: h1 = P0[r-1] + P1[r] + P2[r+1] -> ELU -> packed planes ----
             mbar_wait(bar(g, P_READY), ph);
             __syncwarp();
