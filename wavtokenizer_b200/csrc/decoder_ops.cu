@@ -80,9 +80,7 @@ template <int RES>
 __global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                const float* __restrict__ bsh, RowOut out, int L, int Lp,
                                                                int C, float eps, int swish, Ragged rg) {
-    __shared__ float ps[GN_THREADS], pq[GN_THREADS];
-    __shared__ double rs[GN_LANES], rq[GN_LANES];
-    __shared__ float s_mean[GN_GPB], s_rstd[GN_GPB];
+    __shared__ double part[GN_THREADS / 32][4];  // per warp: (sum, sum of squares) of group 0 and of group 1
     const int b = blockIdx.y, slab = blockIdx.x;
     if (rg.len) L = rg.len[b];  // ragged: statistics over the clip's own frames, zero rows from there to the pitch
     const int lane = threadIdx.x % GN_LANES, ph = threadIdx.x / GN_LANES;
@@ -110,31 +108,36 @@ __global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __re
             q = fmaf(v.x, v.x, q); q = fmaf(v.y, v.y, q); q = fmaf(v.z, v.z, q); q = fmaf(v.w, v.w, q);
         }
     }
-    ps[threadIdx.x] = s;
-    pq[threadIdx.x] = q;
-    __syncthreads();
-    if (threadIdx.x < GN_LANES) {  // column sums over the phases
-        double ds = 0, dq = 0;
-        for (int p = 0; p < GN_PH; ++p) {
-            ds += ps[p * GN_LANES + threadIdx.x];
-            dq += pq[p * GN_LANES + threadIdx.x];
+    // group sums: lanes 6g..6g+5 of every row phase belong to group g of the slab. Warp-level sums of the two groups in
+    // fp64 (shuffles), one partial per warp in shared memory, then every thread adds the 12 partials of ITS group: one
+    // barrier and no serial tail (the column-sum loops of the first version cost about as much as the loads)
+    {
+        const int wl = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        const bool g1 = lane >= 6;
+        double a0 = g1 ? 0.0 : (double)s, b0 = g1 ? 0.0 : (double)q, a1 = g1 ? (double)s : 0.0, b1 = g1 ? (double)q : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+            b0 += __shfl_xor_sync(0xffffffffu, b0, off);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+            b1 += __shfl_xor_sync(0xffffffffu, b1, off);
         }
-        rs[threadIdx.x] = ds;
-        rq[threadIdx.x] = dq;
+        if (wl == 0) { part[wid][0] = a0; part[wid][1] = b0; part[wid][2] = a1; part[wid][3] = b1; }
     }
     __syncthreads();
-    if (threadIdx.x < GN_GPB) {  // group g of the slab = lanes 6g..6g+5
+    float mean, rstd;
+    {
+        const int g = lane >= 6 ? 1 : 0;
         double ds = 0, dq = 0;
-        for (int l = 0; l < 6; ++l) { ds += rs[threadIdx.x * 6 + l]; dq += rq[threadIdx.x * 6 + l]; }
+#pragma unroll
+        for (int w_ = 0; w_ < GN_THREADS / 32; ++w_) { ds += part[w_][2 * g]; dq += part[w_][2 * g + 1]; }
         const double n = (double)L * 24.0;
-        const double mean = ds / n;
-        double var = dq / n - mean * mean;
+        const double m_ = ds / n;
+        double var = dq / n - m_ * m_;
         if (var < 0) var = 0;
-        s_mean[threadIdx.x] = (float)mean;
-        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+        mean = (float)m_;
+        rstd = (float)(1.0 / sqrt(var + (double)eps));
     }
-    __syncthreads();
-    const float mean = s_mean[lane / 6], rstd = s_rstd[lane / 6];
     const float4 wv = *reinterpret_cast<const float4*>(w + c), bv = *reinterpret_cast<const float4*>(bsh + c);
     auto emit = [&](int t, const float4& v) {  // row t of the slab: normalised (+ swish) or, past L, a zero halo row
         float y[4] = {0.f, 0.f, 0.f, 0.f};

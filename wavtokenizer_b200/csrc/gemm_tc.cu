@@ -1177,7 +1177,16 @@ void launch_bn(const TcGemm& g, cudaStream_t s) {
     if (g.N <= 16) return launch_cfg<16, PASSES>(g, s);
     if (g.N <= 32) return launch_cfg<32, PASSES>(g, s);
     if (g.N <= 64) return launch_cfg<64, PASSES>(g, s);
-    if (g.N <= 128) return launch_cfg<128, PASSES>(g, s);
+    if (g.N <= 128) {
+        // WT_TC_N128_MC=1: 128-column tiles with a long K (the level-1 strided conv: K = 512, W re-read per tile from L2,
+        // 4 x the DRAM bytes) as CTA pairs with the W halves multicast into both CTAs
+        if constexpr (PASSES == 3) {
+            static const int mc = [] { const char* e = std::getenv("WT_TC_N128_MC"); return e ? std::atoi(e) : 0; }();
+            const int mt = (g.M + BM - 1) / BM;
+            if (mc && g.N == 128 && g.K >= 256 && g.batch == 1 && g.kw == 64 && mt >= 2) return launch_cfg<128, 3, 0, 1>(g, s);
+        }
+        return launch_cfg<128, PASSES>(g, s);
+    }
     const bool wide = g.N % 256 == 0 || g.N > 1024;
     if (!wide) return launch_cfg<128, PASSES>(g, s);
     // wide tiles run as CTA pairs: WT_TC_CLUSTER=2 one tcgen05.mma.cta_group::2 of M = 256 per pair (each CTA holds half of
