@@ -15,7 +15,7 @@ own clips; the only collective is the all-gather of codes). Prints ONE JSON line
   other_configs  the same measurement on small-600 (the configuration north_star's target is quoted on) and on the
                  medium model at 1024 clips per rank (configs[2]); the VQ-only sweep at 1e7 frames per GPU
                  (configs[4]); decode-only detokenisation of 512 x 10 s token streams per GPU (configs[3])
-  next_rows      SURVEY.md 8(f): convert_audio, the save_audio limiter + PCM16 back-end, ragged batches
+  next_rows      SURVEY.md 8(f): convert_audio, the save_audio limiter + PCM16 back-end, ragged batches, SEANet decoder
 
 `--impl reference` drives the unmodified reference's own public API (decoder/pretrained.py:186-239) on the host CPU
 with all host threads, on a bounded sample of the same workload (falls back to the oracle port, kind "port", when
@@ -611,6 +611,25 @@ def extras(m: dict, args, dev, rank: int, world: int, flush, peaks: dict) -> tup
                                     "space for all clips, per-clip lengths in the kernels that look across rows"}
     next_rows["ragged_batches"] = ragged_row
     del rag
+    # ---- the SEANet decoder (feature_extractor.encodec.decoder), fp32 CUDA-core kernels ----
+    try:
+        from wavtokenizer_b200.pretrained import WavTokenizer
+        m4 = WavTokenizer(cfg)
+        full = dict(m4.state_dict())
+        full.update(sd)
+        full.update(spec.synthetic_seanet_decoder(cfg, 7))
+        m4.load_state_dict(full)
+        m4 = m4.to(dev)
+        n4, l4 = 16, cfg.frames_for(T)
+        z4 = 0.03 * torch.randn(n4, cfg.dimension, l4, device=dev, generator=g)
+        s_ms = event_ms(lambda: m4.feature_extractor.encodec.decoder(z4), 2, flush, warm=1)
+        next_rows["seanet_decoder"] = {
+            "workload": f"feature_extractor.encodec.decoder on {n4} x 3 s latents (L = {l4}), random-init weights",
+            "ms": round(s_ms, 3), "audio_s_per_s": round(n4 * l4 * cfg.hop_length / SR / (s_ms * 1e-3), 1),
+            "note": "next to the hot path, not on it: fp32 CUDA-core tap GEMMs, one launch per LSTM step"}
+        del m4, z4
+    except Exception as e:  # the row is informational
+        next_rows["seanet_decoder"] = {"error": str(e)[:200]}
     torch.cuda.empty_cache()
     return other, next_rows
 

@@ -98,6 +98,12 @@ int wt_encode_ragged(wt_handle* h, const float* wav, const int32_t* lengths, int
  * the pre-quantisation latent z [B, dimension, L]. */
 int wt_encoder_forward(wt_handle* h, const float* wav, int32_t B, int32_t T, float* z_out, void* stream);
 
+/* SEANet decoder, `model.feature_extractor.encodec.decoder(z)` of the reference (encoder/modules/seanet.py:189-238,
+ * built by decoder/feature_extractors.py:76-79): z [B, dimension, L] -> audio [B, L * hop].
+ * Its weights (`feature_extractor.encodec.decoder.*`) are optional in wt_create: WT_ERR_RUNTIME when they were not given.
+ * Next to the hot path, not on it: fp32 CUDA-core kernels. */
+int wt_seanet_decoder(wt_handle* h, const float* z, int32_t B, int32_t L, float* audio_out, void* stream);
+
 /* WavTokenizer.codes_to_features (decoder/pretrained.py:209-239).
  * codes [K, B, L] int64 (device) -> features [B, dimension, L] (sum over the K codebooks). */
 int wt_codes_to_features(wt_handle* h, const int64_t* codes, int32_t K, int32_t B, int32_t L,

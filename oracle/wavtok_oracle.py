@@ -142,6 +142,35 @@ def seanet_encoder(sd: Dict[str, Tensor], cfg, audio: Tensor, library_lstm: bool
     return x
 
 
+def sconvtr1d(sd: Dict[str, Tensor], prefix: str, x: Tensor, stride: int) -> Tensor:
+    """SConvTranspose1d.forward, non-causal branch (encoder/modules/conv.py:232-253) on a weight-normed
+    ConvTranspose1d (conv.py:125-139; weight_norm over dim 0 = input channels): full transposed conv, then the fixed
+    padding kernel - stride is trimmed, right = total // 2, left = total - right."""
+    dt = x.dtype
+    w = weight_norm_fold(_w(sd, prefix + "convtr.convtr.weight_g", dt), _w(sd, prefix + "convtr.convtr.weight_v", dt))
+    b = _w(sd, prefix + "convtr.convtr.bias", dt)
+    k = w.shape[-1]
+    y = F.conv_transpose1d(x, w, b, stride=stride)
+    total = k - stride
+    right = total // 2
+    left = total - right
+    return y[..., left: y.shape[-1] - right]
+
+
+def seanet_decoder(sd: Dict[str, Tensor], cfg, z: Tensor, library_lstm: bool = True) -> Tensor:
+    """SEANetDecoder.forward (encoder/modules/seanet.py:189-238) on z [B, 512, L]; returns audio [B, 1, L * hop].
+    SURVEY.md section 8(f) row 4: next to the hot path, not on it."""
+    DEC = "feature_extractor.encodec.decoder.model."
+    x = sconv1d(sd, DEC + "0.", z)
+    x = (slstm_library if library_lstm else slstm)(sd, DEC + "1.", x, cfg.lstm_layers)
+    idx = 2
+    for s in reversed(list(cfg.strides)):
+        x = sconvtr1d(sd, f"{DEC}{idx + 1}.", F.elu(x), s)
+        x = seanet_resblock(sd, f"{DEC}{idx + 2}.", x)
+        idx += 3
+    return sconv1d(sd, f"{DEC}{idx + 1}.", F.elu(x))
+
+
 # ----------------------------------------------------------------------------------
 # vector quantiser
 # ----------------------------------------------------------------------------------

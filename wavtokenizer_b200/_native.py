@@ -44,6 +44,7 @@ SYMBOLS = {
     "wt_encode": (ctypes.c_int, [_P, _P, _I32, _I32, _P, _P, _P]),
     "wt_encode_ragged": (ctypes.c_int, [_P, _P, ctypes.POINTER(_I32), _I32, _P, _P, _P]),
     "wt_encoder_forward": (ctypes.c_int, [_P, _P, _I32, _I32, _P, _P]),
+    "wt_seanet_decoder": (ctypes.c_int, [_P, _P, _I32, _I32, _P, _P]),
     "wt_codes_to_features": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
     "wt_decode": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
     "wt_decode_ragged": (ctypes.c_int, [_P, _P, ctypes.POINTER(_I32), _I32, _I32, _P, _P]),

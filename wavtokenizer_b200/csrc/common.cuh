@@ -106,6 +106,11 @@ void launch_resblock0_fused(const float* wav, const float* pack, __half* ye_hi, 
 void launch_lstm_skip_elu_pad(const float* y, const float* x, float* out_f32, __half* elu_hi, __half* elu_lo, int B,
                               int L, int D, cudaStream_t s, const int* len_tab = nullptr);
 
+// SEANet decoder: gather of a transposed conv's per-tap GEMM output g [B*L, 2*stride*Cout] into
+// y [B, L*stride, Cout] (+ bias), trimmed by `left` samples in front (reference encoder/modules/conv.py:232-253)
+void launch_convtr_gather(const float* g, const float* bias, float* y, int B, int L, int Cout, int stride, int left,
+                          cudaStream_t s);
+
 // vq
 void launch_vq_simt(const float* x, const float* codebook, const float* cnorm, long long N, int D, int bins,
                     long long* codes, cudaStream_t s);

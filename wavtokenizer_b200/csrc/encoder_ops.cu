@@ -490,4 +490,37 @@ void launch_transpose_blc_to_bcl(const float* in, float* out, int B, int L, int 
     WT_CUDA(cudaGetLastError());
 }
 
+namespace {
+
+// Transposed conv as a GEMM + this gather (reference encoder/modules/conv.py:232-253, SConvTranspose1d non-causal):
+// g[b, t, j*Cout + co] = sum_ci W[ci, co, j] x[b, t, ci] (one GEMM, N = k*Cout, k = 2*stride), then
+// y[b, m, co] = bias[co] + g[b, n/s, n%s] + g[b, n/s - 1, n%s + s] with n = m + left, for m in [0, L*stride): the full
+// transposed conv trimmed by left = ceil((k - s) / 2) in front and (k - s) / 2 at the end.
+__global__ void convtr_gather_kernel(const float* __restrict__ g, const float* __restrict__ bias, float* __restrict__ y,
+                                     int L, int Cout, int stride, int left, long long total) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int co = (int)(gid % Cout);
+    const long long bm = gid / Cout;
+    const long long Tout = (long long)L * stride;
+    const long long b = bm / Tout;
+    const int m = (int)(bm - b * Tout);
+    const int n = m + left;
+    const int t0 = n / stride, j0 = n - t0 * stride;
+    const long long ldg = 2LL * stride * Cout;
+    float v = bias[co];
+    if (t0 < L) v += g[(b * L + t0) * ldg + (long long)j0 * Cout + co];
+    if (t0 >= 1 && t0 - 1 < L) v += g[(b * L + t0 - 1) * ldg + (long long)(j0 + stride) * Cout + co];
+    y[gid] = v;
+}
+}  // namespace
+
+void launch_convtr_gather(const float* g, const float* bias, float* y, int B, int L, int Cout, int stride, int left,
+                          cudaStream_t s) {
+    const long long total = (long long)B * L * stride * Cout;
+    if (total <= 0) return;
+    convtr_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(g, bias, y, L, Cout, stride, left, total);
+    WT_CUDA(cudaGetLastError());
+}
+
 }  // namespace wt

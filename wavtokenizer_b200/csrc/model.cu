@@ -114,6 +114,14 @@ struct wt_handle {
     struct LstmTc { HalfW w_ih, w_hh; float* bias = nullptr; } lstm_tc[4];
     float* rb0_pack = nullptr;   // level-0 fused kernel weights (encoder_ops.cu resblock0_fused_kernel)
     EncL1Weights l1_fused;       // level 0 -> 1 fused tcgen05 kernel weights (enc_fused.cu); w1 == nullptr: not available
+    // SEANet decoder (feature_extractor.encodec.decoder): optional, fp32 CUDA-core plan only
+    struct SeanetDec {
+        bool present = false;
+        ConvW first, last;
+        Lstm lstm[4];
+        struct Up { float* w = nullptr; float* b = nullptr; int cin = 0, cout = 0, stride = 1; } up[4];
+        ResBlk rb[4];
+    } sdec;
     EncL0Weights l0_tc;          // level 0 with tensor-core k3 / 1x1 products (enc_l0_tc.cu); wk3 == nullptr: not available
     std::vector<float> l0_consts;
     float* zero_rows = nullptr;  // zero planes standing in for h_{-1}
@@ -276,6 +284,7 @@ namespace {
 // ---------------------------------------------------------------------------------------
 struct Table {
     std::unordered_map<std::string, std::pair<const float*, int64_t>> m;
+    bool has(const std::string& name) const { return m.find(name) != m.end(); }
     const float* get(const std::string& name, int64_t numel) const {
         auto it = m.find(name);
         if (it == m.end()) throw Error(WT_ERR_VALUE, "missing checkpoint tensor: " + name);
@@ -555,6 +564,57 @@ void prepare(wt_handle* h, const Table& t) {
                 h->lstm_tc[l].w_hh = h->upload_split(pwh);
                 h->lstm_tc[l].bias = h->upload(pb);
             }
+        }
+    }
+
+    // ---- SEANet decoder, when the checkpoint carries it (reference encoder/modules/seanet.py:189-238) ----
+    {
+        const std::string Dp = "feature_extractor.encodec.decoder.model.";
+        if (t.has(Dp + "0.conv.conv.weight_v")) {
+            auto& sd = h->sdec;
+            int chd = c.n_filters * 16;
+            sd.first = load_wn_conv(h, t, Dp + "0.", chd, c.dimension, 7, 1);
+            for (int l = 0; l < c.lstm_layers; ++l) {
+                const std::string p = Dp + "1.lstm.";
+                const std::string sfx = "_l" + std::to_string(l);
+                const int64_t D = chd;
+                sd.lstm[l].w_ih = load_vec(h, t, p + "weight_ih" + sfx, 4 * D * D);
+                sd.lstm[l].w_hh = load_vec(h, t, p + "weight_hh" + sfx, 4 * D * D);
+                const float* bi = t.get(p + "bias_ih" + sfx, 4 * D);
+                const float* bh = t.get(p + "bias_hh" + sfx, 4 * D);
+                std::vector<float> bias(4 * D);
+                for (int64_t i = 0; i < 4 * D; ++i) bias[i] = bi[i] + bh[i];
+                sd.lstm[l].bias = h->upload(bias);
+            }
+            int didx = 2;
+            for (int i = 0; i < 4; ++i) {
+                const int s_ = c.strides[3 - i], k = 2 * s_, cin = chd, cout = chd / 2;
+                const std::string p = Dp + std::to_string(didx + 1) + ".convtr.convtr.";
+                const float* g = t.get(p + "weight_g", cin);
+                const float* v = t.get(p + "weight_v", (int64_t)cin * cout * k);
+                const float* b = t.get(p + "bias", cout);
+                // weight_norm over dim 0 (input channels), then GEMM form W2[j*cout + co][ci] = w[ci][co][j]
+                std::vector<float> w2((size_t)k * cout * cin);
+                for (int ci = 0; ci < cin; ++ci) {
+                    const float* vi = v + (size_t)ci * cout * k;
+                    double ss = 0;
+                    for (int e = 0; e < cout * k; ++e) ss += (double)vi[e] * vi[e];
+                    const float sc = g[ci] / (float)std::sqrt(ss);
+                    for (int co = 0; co < cout; ++co)
+                        for (int j = 0; j < k; ++j) w2[((size_t)j * cout + co) * cin + ci] = sc * vi[(size_t)co * k + j];
+                }
+                sd.up[i].w = h->upload(w2);
+                sd.up[i].b = h->upload(std::vector<float>(b, b + cout));
+                sd.up[i].cin = cin; sd.up[i].cout = cout; sd.up[i].stride = s_;
+                const std::string rp = Dp + std::to_string(didx + 2) + ".";
+                sd.rb[i].c1 = load_wn_conv(h, t, rp + "block.1.", cout / 2, cout, 3, 1);
+                sd.rb[i].c2 = load_wn_conv(h, t, rp + "block.3.", cout, cout / 2, 1, 1);
+                sd.rb[i].sc = load_wn_conv(h, t, rp + "shortcut.", cout, cout, 1, 1);
+                chd = cout;
+                didx += 3;
+            }
+            sd.last = load_wn_conv(h, t, Dp + std::to_string(didx + 1) + ".", 1, chd, 7, 1);
+            sd.present = true;
         }
     }
 
@@ -951,6 +1011,102 @@ float* encoder_back(wt_handle* h, const float* pre, int Bg, int L, int b0, cudaS
     r.conv(h->enc_last, lo, z, Bg, L, true, PRO_ELU);
     h->tap("enc15", z, Bg, L, D, b0, s);
     return z;
+}
+
+// SEANetDecoder.forward (reference encoder/modules/seanet.py:189-238) on z [B, dimension, L] -> audio [B, L * hop]
+// (fp32 CUDA-core kernels: this entry is next to the hot path, not on it).
+size_t seanet_decoder_floats(const wt_config& c, int B, int L) {
+    size_t per_clip = 0;
+    long long T = L;
+    int ch = c.n_filters * 16;
+    per_clip += (size_t)L * (c.dimension + 5 * ch + 4 * ch) + (size_t)(4 + 1) * ch;  // rows, conv, LSTM y (x2) / skip / xin, gates, cell
+    for (int i = 0; i < 4; ++i) {
+        const int s_ = c.strides[3 - i];
+        per_clip += (size_t)T * 2 * s_ * (ch / 2);                 // per-tap products
+        T *= s_;
+        ch /= 2;
+        per_clip += (size_t)T * ch * 4 + (size_t)T * (ch / 2);     // y, shortcut, block output, next x; hidden
+    }
+    per_clip += (size_t)T;
+    return per_clip * (size_t)B + 64 * 64;
+}
+
+void seanet_decoder(wt_handle* h, const float* z_bcl, int B, int L, float* audio, cudaStream_t s) {
+    const wt_config& c = h->cfg;
+    const auto& sd = h->sdec;
+    if (!sd.present)
+        throw Error(WT_ERR_RUNTIME, "seanet_decoder: the checkpoint holds no feature_extractor.encodec.decoder weights");
+    if (B <= 0 || L <= 0) throw Error(WT_ERR_VALUE, "seanet_decoder: expected z [B, C, L] with B, L > 0");
+    h->ensure_arena(seanet_decoder_floats(c, B, L) * sizeof(float) + (1 << 20));
+    h->arena_off = 0;
+    Runner r{h, s};
+    r.cat = CAT_ENC_CONV;
+    int ch = c.n_filters * 16;
+    const long long M = (long long)B * L;
+    float* zr = h->alloc((size_t)M * c.dimension);
+    { Scope sc(h, CAT_MEM, s); launch_transpose_bcl_to_blc(z_bcl, zr, B, c.dimension, L, s); }
+    float* x = h->alloc((size_t)M * ch);
+    r.conv(sd.first, zr, x, B, L, true, PRO_NONE);
+    {   // SLSTM (reference encoder/modules/lstm.py:31-39): rows are clip-major [b*L + t]
+        const int D = ch;
+        float* xin = h->alloc((size_t)M * 4 * D);
+        float* ybuf[4];
+        for (int l = 0; l < c.lstm_layers; ++l) ybuf[l] = h->alloc((size_t)M * D);
+        float* gates = h->alloc((size_t)B * 4 * D);
+        float* cst = h->alloc((size_t)B * D);
+        const float* lin = x;
+        r.cat = CAT_LSTM;
+        for (int l = 0; l < c.lstm_layers; ++l) {
+            r.linear(lin, sd.lstm[l].w_ih, sd.lstm[l].bias, xin, M, 4 * D, D, ACT_NONE, nullptr, nullptr);
+            WT_CUDA(cudaMemsetAsync(cst, 0, (size_t)B * D * sizeof(float), s));
+            for (int t = 0; t < L; ++t) {
+                const float* g_in;
+                long long ldg;
+                if (t == 0) {
+                    g_in = xin; ldg = (long long)L * 4 * D;  // h_{-1} = 0
+                } else {
+                    r.linear(ybuf[l] + (size_t)(t - 1) * D, sd.lstm[l].w_hh, nullptr, gates, B, 4 * D, D, ACT_NONE, nullptr,
+                             xin + (size_t)t * 4 * D, L * D, 4 * D, L * 4 * D);
+                    g_in = gates; ldg = 4 * D;
+                }
+                { Scope sc(h, CAT_LSTM, s); launch_lstm_pointwise(g_in, cst, ybuf[l] + (size_t)t * D, B, D, ldg, (long long)L * D, s); }
+            }
+            lin = ybuf[l];
+        }
+        float* lo = h->alloc((size_t)M * D);
+        { Scope sc(h, CAT_LSTM, s); launch_add(lin, x, lo, M * D, s); }
+        x = lo;
+        r.cat = CAT_ENC_CONV;
+    }
+    int T = L;
+    for (int i = 0; i < 4; ++i) {
+        const auto& up = sd.up[i];
+        const int s_ = up.stride, k = 2 * s_;
+        // ELU + SConvTranspose1d: per-tap products as one GEMM (ELU in the loader), then the overlap gather
+        float* g2 = h->alloc((size_t)B * T * k * up.cout);
+        {
+            TapGemm g;
+            g.A = x; g.W = up.w; g.bias = nullptr; g.out = g2;
+            g.M = B * T; g.N = k * up.cout; g.K = up.cin; g.Cin = up.cin; g.taps = 1; g.stride = 1; g.pad_left = 0;
+            g.Tin = 1; g.Tout = 1; g.Trefl = 1; g.pad_mode = PAD_ZERO; g.pro = PRO_ELU; g.act = ACT_NONE;
+            g.lda = up.cin; g.ldo = k * up.cout; g.ldres = k * up.cout;
+            r.gemm(g);
+        }
+        const int total = k - s_, right = total / 2, left = total - right;
+        const int Tn = T * s_;
+        float* y = h->alloc((size_t)B * Tn * up.cout);
+        { Scope sc(h, CAT_MEM, s); launch_convtr_gather(g2, up.b, y, B, T, up.cout, s_, left, s); }
+        // SEANetResnetBlock (seanet.py:45-63)
+        const int C = up.cout;
+        float* h1 = h->alloc((size_t)B * Tn * (C / 2));
+        float* scb = h->alloc((size_t)B * Tn * C);
+        float* yo = h->alloc((size_t)B * Tn * C);
+        r.conv(sd.rb[i].c1, y, h1, B, Tn, true, PRO_ELU);
+        r.conv(sd.rb[i].sc, y, scb, B, Tn, true, PRO_NONE);
+        r.conv(sd.rb[i].c2, h1, yo, B, Tn, true, PRO_ELU, ACT_NONE, scb);
+        x = yo; T = Tn; ch = C;
+    }
+    r.conv(sd.last, x, audio, B, T, true, PRO_ELU);  // [B*T, 1] rows = audio [B, T]
 }
 
 // Nearest-code search on the tensor cores: (x - mu).(c - mu) with 3-pass split-fp16 operands, argmin of
@@ -1919,6 +2075,13 @@ int wt_encoder_forward(wt_handle* h, const float* wav, int32_t B, int32_t T, flo
     return guarded(h, [&] {
         if (!wav || !z_out) throw Error(WT_ERR_VALUE, "wt_encoder_forward: null buffer");
         do_encode(h, wav, B, T, nullptr, nullptr, z_out, (cudaStream_t)stream);
+    });
+}
+
+int wt_seanet_decoder(wt_handle* h, const float* z, int32_t B, int32_t L, float* audio_out, void* stream) {
+    return guarded(h, [&] {
+        if (!z || !audio_out) throw Error(WT_ERR_VALUE, "wt_seanet_decoder: null buffer");
+        seanet_decoder(h, z, B, L, audio_out, (cudaStream_t)stream);
     });
 }
 

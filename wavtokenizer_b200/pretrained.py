@@ -40,6 +40,34 @@ class _Encoder(_Node):
         return self._root._encoder_forward(x.reshape(B, T))
 
 
+class _SeanetDecoder(nn.Module):
+    """``model.feature_extractor.encodec.decoder`` — callable on z [B, 512, L] like the reference SEANetDecoder
+    (reference encoder/modules/seanet.py:189-238). Its weights are the
+    ``feature_extractor.encodec.decoder.*`` tensors of a checkpoint; they are optional and do not appear in
+    ``state_dict()`` (the hot path never reads them). Without them every call raises."""
+
+    def __init__(self, root: "WavTokenizer"):
+        super().__init__()
+        object.__setattr__(self, "_root", root)
+
+    @torch.inference_mode()
+    def forward(self, z: torch.Tensor) -> torch.Tensor:
+        root = self._root
+        if not root._seanet_dec:
+            raise RuntimeError("this model holds no feature_extractor.encodec.decoder weights (load a checkpoint that has them)")
+        B, C, L = z.shape
+        if C != root.cfg.dimension:
+            raise RuntimeError(f"expected input[{B}, {C}, {L}] to have {root.cfg.dimension} channels")
+        if z.dtype != torch.float32:
+            raise RuntimeError(f"Input type ({z.dtype}) and weight type (torch.float32) should be the same")
+        root._check_input(z, "z")
+        z = z.contiguous()
+        out = torch.empty(B, 1, L * root.cfg.hop_length, dtype=torch.float32, device=z.device)
+        with torch.cuda.device(z.device):
+            _native.check(_native.lib().wt_seanet_decoder(root.native().ptr, z.data_ptr(), B, L, out.data_ptr(), root._stream()))
+        return out
+
+
 class _VQLayer(_Node):
     @property
     def codebook(self) -> torch.Tensor:  # reference core_vq.py:286-288
@@ -55,6 +83,7 @@ class WavTokenizer(nn.Module):
         self.config_path = config_path
         self._handle: Optional[_native.Handle] = None
         self._kinds: Dict[str, str] = {}
+        self._seanet_dec: Dict[str, torch.Tensor] = {}  # optional SEANet-decoder weights
         init = spec.synthetic_state_dict(cfg, seed=0)  # a fresh (random-init) model, like from_hparams0802
         for name, (shape, kind) in spec.state_spec(cfg).items():
             self._register(name, init[name], kind)
@@ -65,6 +94,7 @@ class WavTokenizer(nn.Module):
         q.dimension = cfg.dimension
         self.feature_extractor.bandwidths = list(cfg.bandwidths)
         self.feature_extractor.frame_rate = 25  # "not use" (feature_extractors.py:68)
+        self.feature_extractor.encodec.add_module("decoder", _SeanetDecoder(self))
         self.eval()
 
     # ------------------------------------------------------------------ module tree
@@ -139,9 +169,16 @@ class WavTokenizer(nn.Module):
         return model
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
-        """Strict on the hot-path keys; the SEANet-decoder keys every reference checkpoint
-        carries (feature_extractors.py:76-79) are accepted and ignored."""
+        """Strict on the hot-path keys. The SEANet-decoder keys every reference checkpoint carries
+        (feature_extractors.py:76-79) are optional: a COMPLETE set is kept for ``feature_extractor.encodec.decoder``
+        (SURVEY.md section 8(f) row 4), anything else under that prefix is accepted and ignored as before."""
         filtered = {k: v for k, v in state_dict.items() if not k.startswith(spec.UNUSED_PREFIX)}
+        want = spec.seanet_decoder_spec(self.cfg)
+        have = {k: v for k, v in state_dict.items() if k in want}
+        if len(have) == len(want) and all(tuple(have[k].shape) == tuple(s) for k, s in want.items()):
+            self._seanet_dec = {k: have[k].detach().to(torch.float32).cpu().clone() for k in want}
+        else:
+            self._seanet_dec = {}
         out = super().load_state_dict(filtered, strict=strict, assign=assign)
         self._invalidate()
         return out
@@ -182,7 +219,9 @@ class WavTokenizer(nn.Module):
                 raise RuntimeError(
                     "codebook is not initialised (inited == 0): the reference would run k-means inside infer "
                     "(core_vq.py:140-151); load a checkpoint or install a codebook first")
-            self._handle = _native.Handle(self.cfg, {k: v for k, v in self.state_dict().items()}, idx)
+            tensors = {k: v for k, v in self.state_dict().items()}
+            tensors.update(self._seanet_dec)
+            self._handle = _native.Handle(self.cfg, tensors, idx)
         return self._handle
 
     def _stream(self) -> ctypes.c_void_p:

@@ -345,3 +345,85 @@ def expand_codebook(base_rows_bf16: torch.Tensor, bins: int, seed: int = 5, jitt
     noise = torch.randn(bins, dim, generator=g, dtype=torch.float32) * jitter
     idx = torch.arange(bins) % n_base
     return (base[idx] + noise).contiguous()
+
+# ----------------------------------------------------------------------------------
+# SEANet decoder: feature_extractor.encodec.decoder, the waveform decoder every reference
+# checkpoint carries (decoder/feature_extractors.py:76-79) and the fork's enhancement experiments call. NOT on the
+# WavTokenizer hot path: its weights are optional (loaded when the checkpoint has them, run through wt_seanet_decoder).
+# ----------------------------------------------------------------------------------
+def seanet_decoder_layout(cfg: ModelConfig) -> List[dict]:
+    """The 16-entry ``decoder.model`` Sequential (reference encoder/modules/seanet.py:189-238) as plain records; the
+    decoder walks the ratios in the constructor's order, i.e. the encoder's strides reversed."""
+    out: List[dict] = []
+    ch = cfg.n_filters * 2 ** len(cfg.strides)
+    out.append(dict(idx=0, kind="conv", cin=cfg.dimension, cout=ch, k=7))
+    out.append(dict(idx=1, kind="lstm", dim=ch, layers=cfg.lstm_layers))
+    idx = 2
+    for s in reversed(list(cfg.strides)):
+        out.append(dict(idx=idx, kind="elu"))
+        out.append(dict(idx=idx + 1, kind="convtr", cin=ch, cout=ch // 2, k=2 * s, stride=s))
+        out.append(dict(idx=idx + 2, kind="resblock", dim=ch // 2, hidden=ch // 4))
+        ch //= 2
+        idx += 3
+    out.append(dict(idx=idx, kind="elu"))
+    out.append(dict(idx=idx + 1, kind="conv", cin=ch, cout=1, k=7))
+    return out
+
+
+def seanet_decoder_spec(cfg: ModelConfig) -> "OrderedDict[str, Tuple[int, ...]]":
+    """name -> shape of the SEANet decoder's parameters, named as in the reference's ``state_dict()``
+    (old-style weight_norm; for ConvTranspose1d the norm runs over dim 0 = INPUT channels, conv.py:25-34, 125-139)."""
+    spec: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+
+    def wn_conv(prefix: str, cout: int, cin: int, k: int) -> None:
+        spec[prefix + "conv.conv.bias"] = (cout,)
+        spec[prefix + "conv.conv.weight_g"] = (cout, 1, 1)
+        spec[prefix + "conv.conv.weight_v"] = (cout, cin, k)
+
+    for ent in seanet_decoder_layout(cfg):
+        p = f"{UNUSED_PREFIX}model.{ent['idx']}."
+        if ent["kind"] == "conv":
+            wn_conv(p, ent["cout"], ent["cin"], ent["k"])
+        elif ent["kind"] == "convtr":
+            spec[p + "convtr.convtr.bias"] = (ent["cout"],)
+            spec[p + "convtr.convtr.weight_g"] = (ent["cin"], 1, 1)
+            spec[p + "convtr.convtr.weight_v"] = (ent["cin"], ent["cout"], ent["k"])
+        elif ent["kind"] == "resblock":
+            wn_conv(p + "block.1.", ent["hidden"], ent["dim"], 3)
+            wn_conv(p + "block.3.", ent["dim"], ent["hidden"], 1)
+            wn_conv(p + "shortcut.", ent["dim"], ent["dim"], 1)
+        elif ent["kind"] == "lstm":
+            d = ent["dim"]
+            for layer in range(ent["layers"]):
+                spec[f"{p}lstm.weight_ih_l{layer}"] = (4 * d, d)
+                spec[f"{p}lstm.weight_hh_l{layer}"] = (4 * d, d)
+                spec[f"{p}lstm.bias_ih_l{layer}"] = (4 * d,)
+                spec[f"{p}lstm.bias_hh_l{layer}"] = (4 * d,)
+    return spec
+
+
+def synthetic_seanet_decoder(cfg: ModelConfig, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """Seeded random-init SEANet-decoder weights with the constructors' statistics (uniform +-1/sqrt(fan_in);
+    weight_g = ||weight_v|| per norm slice, jittered so that the fold is observable)."""
+    shapes = seanet_decoder_spec(cfg)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for name, shape in shapes.items():
+        g = _gen(seed, name)
+        leaf = name.rsplit(".", 1)[1]
+        if leaf == "weight_g":
+            continue
+        if leaf == "weight_v":
+            fan_in = shape[1] * shape[2]
+        elif leaf == "bias":
+            v = shapes[name[: -len("bias")] + "weight_v"]
+            fan_in = v[1] * v[2]
+        else:
+            fan_in = shape[-1] if leaf.startswith("weight") else shapes[name.replace("bias_", "weight_")][-1]
+        sd[name] = (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) / math.sqrt(fan_in)
+    for name, shape in shapes.items():
+        if name.endswith("weight_g"):
+            v = sd[name[: -len("weight_g")] + "weight_v"]
+            nrm = v.reshape(v.shape[0], -1).norm(dim=1).reshape(shape)
+            g = _gen(seed, name)
+            sd[name] = nrm * (1.0 + 0.1 * torch.randn(shape, generator=g, dtype=torch.float32))
+    return OrderedDict((k, sd[k]) for k in shapes)
