@@ -18,7 +18,7 @@ from wavtokenizer_b200 import spec
 
 pytestmark = pytest.mark.gpu
 
-TAGS = [t for t in helpers.TAGS if helpers.model(t)[0].strides[0] == 2]  # K = 2 * stride * 32 = 128 fits the kernel
+TAGS = [t for t in helpers.TAGS if helpers.model(t)[0].strides[0] in (2, 4)]  # window K = 2 * stride * 32 = 128 / 256
 
 
 @pytest.fixture(scope="module", params=TAGS)
@@ -43,11 +43,14 @@ def _enc4(m, wav, with_enc3):
 @pytest.mark.parametrize("B,T", [(3, 72000), (2, 4801), (5, 1283), (1, 24000)])
 def test_fused_matches_unfused_full_tensor(setup, B, T):
     tag, cfg, sd, g, m = setup
+    if cfg.strides[0] == 4 and T < 2400:
+        T = 2411  # clips this short fall back to the fp32 encoder under the 4-5-5-6 strides (reflect halo > clip)
     wav = spec.synthetic_audio(B, T, seed=77 + T).cuda()
     y_f, z_f, c_f, n_f = _enc4(m, wav, with_enc3=False)
     y_u, z_u, c_u, n_u = _enc4(m, wav, with_enc3=True)
     assert n_u - n_f == 2, (n_u, n_f)  # three launches (strided conv, k3 conv, ResBlock tail) became one
-    assert y_f.shape == y_u.shape == (B, 64, (T + 1) // 2)
+    s0 = cfg.strides[0]
+    assert y_f.shape == y_u.shape == (B, 64, (T + s0 - 1) // s0)
     assert torch.isfinite(y_f).all()
     # same operands, same 3-pass products; only the fp32 summation order of the k3 taps differs
     assert helpers.snr_db(y_u, y_f) >= 110.0

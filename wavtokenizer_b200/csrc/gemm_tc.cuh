@@ -110,17 +110,18 @@ const CUtensorMap& tc_make_map(const __half* base, long long rows, long long inn
 int tc_num_sms();
 long long* tc_debug_timeline();
 
-// Levels 0 -> 1 of the SEANet encoder in ONE tcgen05 kernel (enc_fused.cu): strided conv (32 -> 64, k4, s2) of the ELU(y0)
+// Levels 0 -> 1 of the SEANet encoder in ONE tcgen05 kernel (enc_fused.cu): strided conv (32 -> 64, k4 s2 or k8 s4) of the ELU(y0)
 // planes, ELU, k3 conv (64 -> 32), ELU, 1x1 conv (32 -> 64) + composed shortcut, ELU -> planes in the padded layout of
 // the next strided conv. x1, ELU(x1) and ELU(h1) never leave the SM (they live in tensor memory).
 struct EncL1Weights {
-    const __half* w1 = nullptr;  // [256, 128]: rows [Wc_hi | Wd_hi | Wc_lo | Wd_lo] (composed shortcut, strided conv)
+    const __half* w1 = nullptr;  // [256, k0]: rows [Wc_hi | Wd_hi | Wc_lo | Wd_lo] (composed shortcut, strided conv)
     const __half* w2 = nullptr;  // [192, 64]: rows [Wk3_hi | Wk3_lo], row = tap * 32 + cout
     const __half* w3 = nullptr;  // [128, 32]: rows [W1x1_hi | W1x1_lo]
     const float* bias = nullptr; // b_d[64] | b_k3[32] | b_tail[64]
+    int k0 = 128;                // window width 2 * stride * 32: 128 (stride 2) or 256 (stride 4) = row length of w1
 };
 struct EncL1Args {
-    const __half* y0_hi = nullptr;  // ELU(y0) planes of level 0: clip pitch 2 * (T1 + 2) rows of 32 channels
+    const __half* y0_hi = nullptr;  // ELU(y0) planes of level 0: clip pitch stride * (T1 + 2) rows of 32 channels
     const __half* y0_lo = nullptr;
     long long y0_elems = 0;
     int Bc = 0, T1 = 0;             // clips, level-1 length; row space m = b * (T1 + 2) + t

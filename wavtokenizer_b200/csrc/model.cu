@@ -451,20 +451,22 @@ void prepare(wt_handle* h, const Table& t) {
             }
             rt.w2 = h->upload_split(w2);
             rt.bias2 = h->upload(b2);
-            if (i == 1 && C == 64 && h->down[0].k * h->down[0].cin == 128 && enc_l1_fused_supported(C / 2, c.strides[0])) {
+            if (i == 1 && C == 64 && (h->down[0].k * h->down[0].cin == 128 || h->down[0].k * h->down[0].cin == 256) &&
+                enc_l1_fused_supported(C / 2, c.strides[0])) {
                 // fused level 0 -> 1 kernel (enc_fused.cu): the three weight tiles as single fp16 tensors whose rows
                 // stack the hi / lo planes in the order the MMAs address them
                 const ConvW& dn = h->down[0];
                 auto hi16 = [](float v) { return __float2half_rn(v); };
                 auto lo16 = [](float v) { const __half hh = __float2half_rn(v); return __float2half_rn(v - __half2float(hh)); };
-                std::vector<__half> p1((size_t)256 * 128), p2((size_t)192 * 64), p3((size_t)128 * 32);
+                const int K0 = dn.k * dn.cin;  // 128 (stride 2) or 256 (stride 4)
+                std::vector<__half> p1((size_t)256 * K0), p2((size_t)192 * 64), p3((size_t)128 * 32);
                 for (int n = 0; n < 64; ++n)
-                    for (int j = 0; j < 128; ++j) {
-                        const float wc = w2[(size_t)n * K2 + off1 + j], wd = dn.hw[(size_t)n * 128 + j];
-                        p1[(size_t)(0 + n) * 128 + j] = hi16(wc);
-                        p1[(size_t)(64 + n) * 128 + j] = hi16(wd);
-                        p1[(size_t)(128 + n) * 128 + j] = lo16(wc);
-                        p1[(size_t)(192 + n) * 128 + j] = lo16(wd);
+                    for (int j = 0; j < K0; ++j) {
+                        const float wc = w2[(size_t)n * K2 + off1 + j], wd = dn.hw[(size_t)n * K0 + j];
+                        p1[(size_t)(0 + n) * K0 + j] = hi16(wc);
+                        p1[(size_t)(64 + n) * K0 + j] = hi16(wd);
+                        p1[(size_t)(128 + n) * K0 + j] = lo16(wc);
+                        p1[(size_t)(192 + n) * K0 + j] = lo16(wd);
                     }
                 for (int tap = 0; tap < 3; ++tap)
                     for (int n = 0; n < 32; ++n)
@@ -487,6 +489,7 @@ void prepare(wt_handle* h, const Table& t) {
                 h->l1_fused.w2 = h->upload_halves(p2);
                 h->l1_fused.w3 = h->upload_halves(p3);
                 h->l1_fused.bias = h->upload(fb);
+                h->l1_fused.k0 = K0;
             }
             if (i == 0 && C == 32) {
                 // fused level-0 kernel: w0t[7][32] b0[32] w1t[96][16] b1[16] w2t[16][32] wsct[8][32] b2[32]
@@ -1241,7 +1244,8 @@ void encoder_levels_tc(wt_handle* h, const float* wav, int Bc, int Tin, int i0, 
             fa.ye_hi = ye_hi; fa.ye_lo = ye_lo; fa.y_f32 = y_tap;
             // algorithmic work per level-1 position: strided conv 64x128 + k3 32x192 + 1x1 64x32 + shortcut 64x64 MACs;
             // two new level-0 rows (32 channels, split planes) in, one row of 64 channels out
-            Scope sc(h, CAT_ENC_CONV, s, KERN_ENC_L1F, 40960.0 * Bc * Tc, 512.0 * Bc * Tc);
+            const double k0 = (double)h->l1_fused.k0;
+            Scope sc(h, CAT_ENC_CONV, s, KERN_ENC_L1F, (2.0 * 64 * k0 + 24576.0) * Bc * Tc, (2.0 * k0 + 256.0) * Bc * Tc);
             launch_enc_l1_fused(h->l1_fused, fa, s);
         } else {
             TcGemm g;
