@@ -56,12 +56,13 @@ UNIT = "audio-s/s"
 CPU_SAMPLE_CLIPS = 8
 PARITY_CLIPS = 4
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the modal launch shape, one `ncu --set full` capture each at
-# the end of round 2 (profiles/r02_ncu_table.txt; tools/ncu_targets.sh): decoder k3 conv 768 -> 768 over 128 clips,
-# ConvNeXt GEMM-1, encoder level-0 strided conv / level-1 strided conv / level-0 fused kernel over 64 clips, ...
+# the end of round 2 (profiles/r02_ncu_table.txt, r02_ncu_table_final.txt; tools/ncu_targets.sh, ncu_round2_final.sh):
+# decoder k3 conv 768 -> 768 over 128 clips, ConvNeXt GEMM-1, encoder level-1 strided conv / level-0 kernel / fused
+# level-0 -> 1 kernel over 64 clips, one LSTM segment, ...
 TRAFFIC = {"tap_gemm_tc_kernel<256, 3>": 127.3e6, "tap_gemm_tc_kernel<256, 1>": 132.9e6,
            "tap_gemm_tc_kernel<64, 3>": 1.134e9, "tap_gemm_tc_kernel<128, 3>": 1.137e9,
            "resblock0_fused_kernel": 0.555e9, "groupnorm_kernel": 136.5e6, "dwconv_ln_kernel": 106.6e6,
-           "lstm_persistent_kernel": 69.3e6}
+           "lstm_persistent_kernel": 70.2e6, "enc_l0_tc_kernel": 0.556e9, "enc_l1_fused_kernel": 1.137e9}
 CATS = ["enc_conv", "lstm", "vq", "dec_conv", "pwconv", "head_idft", "attention", "memory_bound"]
 NAMED_KERNELS = {1: "lstm_persistent_kernel", 2: "resblock0_fused_kernel", 3: "groupnorm_kernel", 4: "dwconv_ln_kernel",
                  5: "layernorm_kernel", 6: "spectral_kernel", 7: "overlap_add_kernel", 8: "softmax_planes_kernel",
