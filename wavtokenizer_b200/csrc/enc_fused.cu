@@ -211,59 +211,61 @@ enc_l1_fused_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_co
                     if (stage[s] == 0) {
                         // ---- GEMM1: strided conv + composed shortcut (A from the ring, consumed in tile order) ----
                         constexpr int NG = KB0 / L::KPS;  // ring stages per tile: global stage index n = it * NG + kg
-                        // NG == 1: each slot has its own stage, so the slots' GEMM1s may overtake each other (a slot that is
-                        // drained early does not wait for the other one; forcing tile order cost 7 %); NG == 4: the two
-                        // stages are shared, the ring is consumed in tile order
-                        if (NG > 1 && it != it1) continue;
-#pragma unroll 1
-                        for (int turn = 0; turn < NG; ++turn) {
-                            const int kg = kb1 / L::KPS;
-                            // NG == 1: stage = it & 1 = s, phase = ph; NG == 4 (two stages): stage = kg & 1, phase = (kg >> 1) & 1
-                            const uint32_t st = NG == 1 ? (uint32_t)s : (uint32_t)(kg & 1);
-                            const uint32_t php = NG == 1 ? ph : (uint32_t)((kg >> 1) & 1);
-                            if (!mbar_test(bar_full(st), php)) break;
-                            // first stage of a tile: the slot's previous tile must have been drained
-                            if (kg == 0 && it >= 2 && !mbar_test(bar(s, E3), ph ^ 1u)) break;
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            if (kg == 0) stamp(it, 1);
-                            // the MMA-issuing thread is a serial resource: every address below is a compile-time constant
-                            // (a run-time k-block index cost 7 % of the kernel)
-                            auto issue = [&](auto KBASE, const uint32_t stc) {
-                                constexpr int kbase = decltype(KBASE)::value;
+                        // the MMA-issuing thread is a serial resource: every address below is a compile-time constant
+                        auto issue = [&](auto KBASE, const uint32_t stc) {
+                            constexpr int kbase = decltype(KBASE)::value;
 #pragma unroll
-                                for (int j = 0; j < L::KPS; ++j) {
+                            for (int j = 0; j < L::KPS; ++j) {
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        const uint32_t koff = k * 32;
-                                        const uint32_t sa = sbase + L::RING + stc * L::STG + j * L::KBLK + koff;
-                                        const uint32_t sw = sbase + L::W1 + (kbase + j) * L::W1_KB + koff;
-                                        const uint64_t a_hi = umma_desc_at(d128, sa), a_lo = umma_desc_at(d128, sa + L::PLANE);
-                                        const uint64_t w_hi = umma_desc_at(d128, sw), w_lo = umma_desc_at(d128, sw + 128 * 128);
-                                        umma_f16(T + C_SC, a_hi, w_hi, i128, (kbase | j | k) != 0);
-                                        umma_f16(T + C_SC, a_hi, w_lo, i128, 1);
-                                        umma_f16(T + C_SC, a_lo, w_hi, i128, 1);
-                                    }
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint32_t koff = k * 32;
+                                    const uint32_t sa = sbase + L::RING + stc * L::STG + j * L::KBLK + koff;
+                                    const uint32_t sw = sbase + L::W1 + (kbase + j) * L::W1_KB + koff;
+                                    const uint64_t a_hi = umma_desc_at(d128, sa), a_lo = umma_desc_at(d128, sa + L::PLANE);
+                                    const uint64_t w_hi = umma_desc_at(d128, sw), w_lo = umma_desc_at(d128, sw + 128 * 128);
+                                    umma_f16(T + C_SC, a_hi, w_hi, i128, (kbase | j | k) != 0);
+                                    umma_f16(T + C_SC, a_hi, w_lo, i128, 1);
+                                    umma_f16(T + C_SC, a_lo, w_hi, i128, 1);
                                 }
-                            };
-                            if constexpr (NG == 1) {
-                                issue(IC<0>{}, (uint32_t)s);  // s is a constant after the unrolling of the slot loop
-                            } else {
+                            }
+                        };
+                        if constexpr (NG == 1) {
+                            // each slot owns a stage (stage = it & 1 = s, phase = ph): the slots' GEMM1s may overtake each other
+                            if (!mbar_test(bar_full(s), ph)) continue;
+                            if (it >= 2 && !mbar_test(bar(s, E3), ph ^ 1u)) continue;  // the slot's previous tile has been drained
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            stamp(it, 1);
+                            issue(IC<0>{}, (uint32_t)s);  // s is a constant after the unrolling of the slot loop
+                            umma_commit(bar_empty(s));
+                            umma_commit(bar(s, G1));
+                            stage[s] = 1;
+                            progress = true;
+                        } else {
+                            // the two stages are shared by the slots: the ring is consumed in tile order, one k-block per stage
+                            if (it != it1) continue;
+#pragma unroll 1
+                            for (int turn = 0; turn < NG; ++turn) {
+                                const int kg = kb1;  // KPS == 1
+                                const uint32_t st = (uint32_t)(kg & 1), php = (uint32_t)((kg >> 1) & 1);  // n = 4 it + kg, two stages
+                                if (!mbar_test(bar_full(st), php)) break;
+                                if (kg == 0 && it >= 2 && !mbar_test(bar(s, E3), ph ^ 1u)) break;
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                if (kg == 0) stamp(it, 1);
                                 switch (kg) {
                                     case 0: issue(IC<0>{}, 0u); break;
                                     case 1: issue(IC<1>{}, 1u); break;
                                     case 2: issue(IC<2>{}, 0u); break;
                                     default: issue(IC<3>{}, 1u); break;
                                 }
-                            }
-                            umma_commit(bar_empty(st));
-                            kb1 += L::KPS;
-                            progress = true;
-                            if (kb1 == KB0) {
-                                umma_commit(bar(s, G1));
-                                kb1 = 0;
-                                ++it1;
-                                stage[s] = 1;
-                                break;
+                                umma_commit(bar_empty(st));
+                                progress = true;
+                                if (++kb1 == KB0) {
+                                    umma_commit(bar(s, G1));
+                                    kb1 = 0;
+                                    ++it1;
+                                    stage[s] = 1;
+                                    break;
+                                }
                             }
                         }
                         if (stage[s] == 0) continue;
