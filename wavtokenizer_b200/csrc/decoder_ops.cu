@@ -7,6 +7,8 @@
 // of the next GEMM directly, so no separate conversion pass touches HBM.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace wt {
@@ -334,6 +336,79 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dwconv_ln_kernel(const float* _
     }
 }
 
+// Same operator for the single-plane consumer (plan 2: the ConvNeXt GEMM-1 reads ONE fp16 plane, so the output carries 11
+// bits): runs of 8 frames, 14 input rows per thread, mean and E[x^2] reduced TOGETHER (one 16-value butterfly, one barrier;
+// var = E[x^2] - mean^2 in fp32 is exact to ~1e-6 relative here, far below the fp16 rounding of the result), <= 112
+// registers so that three blocks share an SM (the 16-frame kernel above holds 168 registers: two blocks, 18 % occupancy,
+// and its two statistics passes cost a second barrier).
+constexpr int DW8_TT = 8;
+__global__ void __launch_bounds__(DW_THREADS, 3) dwconv_ln_hi_kernel(const float* __restrict__ x, const float* __restrict__ dwT,
+                                                                     const float* __restrict__ db, const float* __restrict__ scale,
+                                                                     const float* __restrict__ shift, __half* __restrict__ out_hi,
+                                                                     int L, int Lp, float eps, Ragged rg) {
+    constexpr int C = 768, NW = DW_THREADS / 32;
+    static_assert(NW == 6, "six warps cover the 768 channels");
+    __shared__ __align__(16) float red[2 * DW8_TT][8];  // [sum of frame i | sum of squares of frame i][warp]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, t0 = blockIdx.x * DW8_TT;
+    if (rg.len) L = rg.len[b];
+    const int c = threadIdx.x * 4;
+    const float* xb = x + (long long)b * Lp * C + c;
+    float4 xr[DW8_TT + 6];
+#pragma unroll
+    for (int r = 0; r < DW8_TT + 6; ++r) {
+        const int t = t0 - 3 + r;
+        xr[r] = (t >= 0 && t < L) ? *reinterpret_cast<const float4*>(xb + (long long)t * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float4 bias = *reinterpret_cast<const float4*>(db + c);
+    float4 v[DW8_TT];
+#pragma unroll
+    for (int i = 0; i < DW8_TT; ++i) v[i] = bias;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {  // tap-major: one weight vector live at a time
+        const float4 w = *reinterpret_cast<const float4*>(dwT + j * C + c);
+#pragma unroll
+        for (int i = 0; i < DW8_TT; ++i) {
+            v[i].x = fmaf(w.x, xr[i + j].x, v[i].x);
+            v[i].y = fmaf(w.y, xr[i + j].y, v[i].y);
+            v[i].z = fmaf(w.z, xr[i + j].z, v[i].z);
+            v[i].w = fmaf(w.w, xr[i + j].w, v[i].w);
+        }
+    }
+    float part[16];
+#pragma unroll
+    for (int i = 0; i < DW8_TT; ++i) {
+        part[i] = (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        part[DW8_TT + i] = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, v[i].w * v[i].w)));
+    }
+    warp_sum16(part, lane);
+    if ((lane & 1) == 0) red[lane >> 1][warp] = part[0];
+    __syncthreads();
+    const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+#pragma unroll
+    for (int i = 0; i < DW8_TT; ++i) {
+        const int t = t0 + i;
+        if (t >= Lp) break;
+        float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+        if (t < L) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&red[i][0]);
+            const float2 a1 = *reinterpret_cast<const float2*>(&red[i][4]);
+            const float4 q0 = *reinterpret_cast<const float4*>(&red[DW8_TT + i][0]);
+            const float2 q1 = *reinterpret_cast<const float2*>(&red[DW8_TT + i][4]);
+            const float mean = (((a0.x + a0.y) + (a0.z + a0.w)) + (a1.x + a1.y)) * (1.f / (float)C);
+            const float ex2 = (((q0.x + q0.y) + (q0.z + q0.w)) + (q1.x + q1.y)) * (1.f / (float)C);
+            const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + eps);
+            y0 = (v[i].x - mean) * rstd * sc.x + sh.x;
+            y1 = (v[i].y - mean) * rstd * sc.y + sh.y;
+            y2 = (v[i].z - mean) * rstd * sc.z + sh.z;
+            y3 = (v[i].w - mean) * rstd * sc.w + sh.w;
+        }  // else: halo row of the padded row space, written as zeros
+        const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
+        *reinterpret_cast<uint2*>(out_hi + ((long long)b * Lp + t) * C + c) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    }
+}
+
 // AttnBlock core (reference decoder/models.py:115-123): softmax(q k^T * C^-0.5) v, one head of width C
 // over the L frames of a clip. One warp per query row, 8 queries per block; scores live in shared memory.
 template <int PER>
@@ -557,6 +632,13 @@ void launch_dwconv_ln(const float* x, const float* dw, const float* db, const fl
                       RowOut out, int B, int L, int Lp, int C, float eps, cudaStream_t s, Ragged rg) {
     if (B <= 0 || L <= 0) return;
     if (C != 768) throw Error(1, "dwconv_ln: backbone dim must be 768");
+    static const bool hi8 = [] { const char* e = std::getenv("WT_DW_HI8"); return !e || std::atoi(e) != 0; }();
+    if (hi8 && out.hi && !out.lo && !out.f32) {  // single-plane consumer (plan 2)
+        dim3 grid8((Lp + DW8_TT - 1) / DW8_TT, B);
+        dwconv_ln_hi_kernel<<<grid8, DW_THREADS, 0, s>>>(x, dw, db, scale, shift, out.hi, L, Lp, eps, rg);
+        WT_CUDA(cudaGetLastError());
+        return;
+    }
     dim3 grid((Lp + DW_TT - 1) / DW_TT, B);
     dwconv_ln_kernel<<<grid, DW_THREADS, 0, s>>>(x, dw, db, scale, shift, out, L, Lp, eps, rg);
     WT_CUDA(cudaGetLastError());
