@@ -120,6 +120,10 @@ void launch_gather_rows(const float* codebook, const long long* codes, float* ou
 void launch_codes_to_features(const float* codebooks, const long long* codes, float* out, int K, int B, int L, int D,
                               int bins, int* err_flag, cudaStream_t s);
 
+// codebook rows (split planes) of codes [B, L] -> decoder row planes [B*Lp, D] with zero halo rows
+void launch_codes_to_row_planes(const __half* cb_hi, const __half* cb_lo, const long long* codes, __half* hi, __half* lo,
+                                int B, int L, int Lp, int D, int bins, cudaStream_t s);
+
 // tcgen05 VQ helpers
 void launch_center_split(const float* x, const float* mu, __half* hi, __half* lo, long long N, int D, cudaStream_t s);
 void launch_best_to_codes(const unsigned long long* best, long long* codes, long long N, cudaStream_t s);

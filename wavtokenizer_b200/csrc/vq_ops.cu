@@ -268,4 +268,38 @@ void launch_codes_to_features(const float* codebooks, const long long* codes, fl
     WT_CUDA(cudaGetLastError());
 }
 
+namespace {
+// Codebook rows of a batch of codes straight into the decoder's padded row planes (what codes_to_features followed by
+// features_to_rows produce, without the [B, D, L] fp32 round trip): row b*Lp + t <- planes of codebook[codes[b*L + t]] for
+// t < L, zeros for the halo rows. One thread per 16 bytes of a plane row.
+__global__ void codes_to_row_planes_kernel(const __half* __restrict__ cb_hi, const __half* __restrict__ cb_lo,
+                                           const long long* __restrict__ codes, __half* __restrict__ hi,
+                                           __half* __restrict__ lo, int L, int Lp, int D, int bins, long long total) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int per_row = D / 8;
+    const long long row = gid / per_row;
+    const int c8 = (int)(gid - row * per_row) * 8;
+    const long long b = row / Lp;
+    const int t = (int)(row - b * Lp);
+    uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
+    if (t < L) {
+        long long code = codes[b * L + t];
+        code = code < 0 ? 0 : (code >= bins ? bins - 1 : code);  // codes come from this library's own argmin
+        vh = *reinterpret_cast<const uint4*>(cb_hi + code * D + c8);
+        vl = *reinterpret_cast<const uint4*>(cb_lo + code * D + c8);
+    }
+    *reinterpret_cast<uint4*>(hi + row * D + c8) = vh;
+    *reinterpret_cast<uint4*>(lo + row * D + c8) = vl;
+}
+}  // namespace
+
+void launch_codes_to_row_planes(const __half* cb_hi, const __half* cb_lo, const long long* codes, __half* hi, __half* lo,
+                                int B, int L, int Lp, int D, int bins, cudaStream_t s) {
+    const long long total = (long long)B * Lp * (D / 8);
+    if (total <= 0) return;
+    codes_to_row_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(cb_hi, cb_lo, codes, hi, lo, L, Lp, D, bins, total);
+    WT_CUDA(cudaGetLastError());
+}
+
 }  // namespace wt
