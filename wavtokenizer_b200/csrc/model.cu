@@ -27,14 +27,18 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 
 namespace {
 
-constexpr int ENC_CHUNK_DEFAULT = 64;  // clips per encoder-front pass (early SEANet tensors: 9.2 MB per clip each)
+// Clips per encoder-front pass (early SEANet tensors: 9.2 MB per clip each). Device-resident calls use 128 (fewer, longer
+// launches: -0.3..-0.45 ms per 256-clip step against 64); the host-buffer entry point uses 64: its H2D pieces and the
+// per-piece level-0 launches pipeline at the finer grain (same e2e time either way, half the workspace).
+constexpr int ENC_CHUNK_DEFAULT = 128, ENC_CHUNK_HOST = 64;
+thread_local bool g_host_entry = false;  // set by wt_encode_decode_host for the duration of the call
 inline int enc_chunk() {
-    static int v = [] {
+    static int env = [] {
         const char* e = std::getenv("WT_ENC_CHUNK");
-        int n = e ? std::atoi(e) : ENC_CHUNK_DEFAULT;
-        return n >= 1 && n <= 256 ? n : ENC_CHUNK_DEFAULT;
+        int n = e ? std::atoi(e) : 0;
+        return n >= 1 && n <= 256 ? n : 0;
     }();
-    return v;
+    return env ? env : (g_host_entry ? ENC_CHUNK_HOST : ENC_CHUNK_DEFAULT);
 }
 #define ENC_CHUNK enc_chunk()
 // clips per sub-chunk of encoder levels 0-1 (encoder_front_tc); 0 = off. Measured (profiles/r02_enc_subchunk_sweep.md):
@@ -56,14 +60,17 @@ inline int tc_prefetch() {
 }
 constexpr int ENC_GROUP = 1024; // clips per LSTM / final-conv / VQ pass (the recurrent GEMM's M)
 constexpr int COPY_PIECE = 16;  // clips per H2D / D2H piece of the host-buffer entry point (4.6 MB of audio)
-constexpr int DEC_CHUNK_DEFAULT = 128;  // clips per decoder pass (29 k rows: fp32 row tensors of 90 MB stay L2-resident)
+// Clips per decoder pass. Device-resident calls: 256 (29 k -> 58 k rows: the 768-wide GEMMs fill 9.2 -> 18.5 waves of CTA
+// pairs, -1.0 ms per 256-clip step); host-buffer entry: 128, so that the audio of the first chunk leaves while the
+// second one is computed (same e2e time as 256, measured).
+constexpr int DEC_CHUNK_DEFAULT = 256, DEC_CHUNK_HOST = 128;
 inline int dec_chunk() {
-    static const int v = [] {
+    static int env = [] {
         const char* e = std::getenv("WT_DEC_CHUNK");
-        int n = e ? std::atoi(e) : DEC_CHUNK_DEFAULT;
-        return n >= 1 && n <= 1024 ? n : DEC_CHUNK_DEFAULT;
+        int n = e ? std::atoi(e) : 0;
+        return n >= 1 && n <= 1024 ? n : 0;
     }();
-    return v;
+    return env ? env : (g_host_entry ? DEC_CHUNK_HOST : DEC_CHUNK_DEFAULT);
 }
 #define DEC_CHUNK dec_chunk()
 
@@ -1930,10 +1937,11 @@ void do_decode(wt_handle* h, const float* features, int B, int L, int bw, float*
     const wt_config& c = h->cfg;
     if (B < 0 || L <= 0) throw Error(WT_ERR_VALUE, "decode: expected features [B, C, L] with L > 0");
     if (bw < 0 || bw >= c.adanorm_num_embeddings) throw Error(WT_ERR_INDEX, "index out of range in self (bandwidth_id)");
-    size_t need = dec_chunk_floats(c, std::min(B, DEC_CHUNK), L, h->Kp) * sizeof(float) + 4096;
+    const int chunk = L <= 256 ? DEC_CHUNK : std::min(DEC_CHUNK, DEC_CHUNK_HOST);  // long streams: rows per pass stay bounded
+    size_t need = dec_chunk_floats(c, std::min(B, chunk), L, h->Kp) * sizeof(float) + 4096;
     h->ensure_arena(need);
-    for (int b0 = 0; b0 < B; b0 += DEC_CHUNK) {
-        const int Bc = std::min(DEC_CHUNK, B - b0);
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int Bc = std::min(chunk, B - b0);
         h->arena_off = 0;
         decoder_chunk(h, features + (size_t)b0 * c.dimension * L, Bc, L, bw,
                       audio + (size_t)b0 * L * c.hop_length, b0, s);
@@ -2166,6 +2174,7 @@ int wt_encode_decode_host(wt_handle* h, const float* wav_host, int32_t B, int32_
                           int64_t* codes_host, float* audio_host, void* stream) {
     return guarded(h, [&] {
         if (!wav_host || !codes_host || !audio_host) throw Error(WT_ERR_VALUE, "wt_encode_decode_host: null buffer");
+        struct HostMode { HostMode() { g_host_entry = true; } ~HostMode() { g_host_entry = false; } } host_mode;
         cudaStream_t s = (cudaStream_t)stream;
         const wt_config& c = h->cfg;
         const int L = frames_for(c, T);
