@@ -485,6 +485,38 @@ __global__ void __launch_bounds__(256) spectral_kernel(const float* __restrict__
     }
 }
 
+// Same step, one WARP per row: no 64-bit index division per element, four bins per lane in flight (the loads of a run of
+// 128 bins are issued before the exp / sincos of the first one). Same expf / sincosf, so the values are identical.
+__global__ void __launch_bounds__(256) spectral_rows_kernel(const float* __restrict__ z, int ldz, RowOut S, long long M,
+                                                            int half, int ldS) {
+    const int lane = threadIdx.x & 31;
+    const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (m >= M) return;
+    const float* zr = z + m * ldz;
+    const long long o = m * ldS;
+    for (int i0 = 0; i0 < half; i0 += 128) {
+        float mg[4], ph[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + lane;
+            mg[u] = i < half ? zr[i] : 0.f;
+            ph[u] = i < half ? zr[half + i] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + lane;
+            if (i < half) {
+                const float mag = fminf(expf(mg[u]), 100.f);
+                float sn, cs;
+                sincosf(ph[u], &sn, &cs);
+                put(S, o + i, mag * cs);
+                put(S, o + half + i, mag * sn);
+            }
+        }
+    }
+    for (int i = 2 * half + lane; i < ldS; i += 32) put(S, o + i, 0.f);
+}
+
 // ISTFT "same" overlap-add + envelope normalisation (reference decoder/spectral_ops.py:58-73).
 // frames already carry the window (folded into the iDFT basis). Each output sample sums the <= n_fft/hop
 // frames that cover it and divides by the matching sum of squared window samples.
@@ -508,6 +540,32 @@ __global__ void overlap_add_kernel(const float* __restrict__ frames, const float
         env += wsq[k];
     }
     audio[out0 + n] = acc / env;
+}
+
+// Four consecutive samples per thread (hop, n_fft and the padding are multiples of 4: the four samples share their frame
+// range and sit in one 16-byte group of every frame and of the envelope table). Same summation order as above.
+__global__ void __launch_bounds__(256) overlap_add4_kernel(const float* __restrict__ frames, const float* __restrict__ wsq,
+                                                           float* __restrict__ audio, int L, int Lp, int n_fft, int hop, int pad,
+                                                           Ragged rg) {
+    const int b = blockIdx.y;
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const long long out0 = rg.off ? rg.off[b] * hop : (long long)b * L * hop;
+    if (rg.len) L = rg.len[b];
+    if (n >= L * hop) return;
+    const int p = n + pad;
+    int t_hi = p / hop;
+    int t_lo = p < n_fft ? 0 : (p - n_fft + hop) / hop;
+    if (t_hi > L - 1) t_hi = L - 1;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), env = acc;
+    const float* fb = frames + (long long)b * Lp * n_fft;
+    for (int t = t_lo; t <= t_hi; ++t) {
+        const int k = p - t * hop;
+        const float4 f = *reinterpret_cast<const float4*>(fb + (long long)t * n_fft + k);
+        const float4 w = *reinterpret_cast<const float4*>(wsq + k);
+        acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+        env.x += w.x; env.y += w.y; env.z += w.z; env.w += w.w;
+    }
+    *reinterpret_cast<float4*>(audio + out0 + n) = make_float4(acc.x / env.x, acc.y / env.y, acc.z / env.z, acc.w / env.w);
 }
 
 // features [B, C, L] (API layout) -> rows [B*Lp, C] (fp32 or split planes), halo rows zeroed.
@@ -592,6 +650,42 @@ __global__ void vt_planes_kernel(const __half* __restrict__ q_hi, const __half* 
     }
 }
 
+// Same transpose on 64 x 64 tiles with two halves per thread on both sides (128-byte rows per warp instead of 64).
+__global__ void __launch_bounds__(256) vt_planes2_kernel(const __half* __restrict__ q_hi, const __half* __restrict__ q_lo,
+                                                         __half* __restrict__ vt_hi, __half* __restrict__ vt_lo, int L, int Lp,
+                                                         int C, int Lpad, Ragged rg) {
+    __shared__ __half th[64][66], tl[64][66];
+    const int b = blockIdx.z;
+    if (rg.len) L = rg.len[b];
+    const int j0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    for (int r = threadIdx.y; r < 64; r += 8) {
+        const int j = j0 + r, c = c0 + 2 * threadIdx.x;
+        __half2 h = __floats2half2_rn(0.f, 0.f), l = h;
+        if (j < L) {
+            const long long src = ((long long)b * Lp + j) * 3 * C + 2 * C + c;
+            h = *reinterpret_cast<const __half2*>(q_hi + src);
+            l = *reinterpret_cast<const __half2*>(q_lo + src);
+        }
+        *reinterpret_cast<__half2*>(&th[r][2 * threadIdx.x]) = h;
+        *reinterpret_cast<__half2*>(&tl[r][2 * threadIdx.x]) = l;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 64; r += 8) {
+        const int c = c0 + r, j = j0 + 2 * threadIdx.x;
+        if (j < Lpad) {
+            const long long dst = ((long long)b * C + c) * Lpad + j;
+            *reinterpret_cast<__half2*>(vt_hi + dst) = __halves2half2(th[2 * threadIdx.x][r], th[2 * threadIdx.x + 1][r]);
+            *reinterpret_cast<__half2*>(vt_lo + dst) = __halves2half2(tl[2 * threadIdx.x][r], tl[2 * threadIdx.x + 1][r]);
+        }
+    }
+}
+
+// WT_MEM_V1=1 selects the one-element-per-thread forms of the spectral, overlap-add and V-transpose kernels.
+inline bool mem_v1() {
+    static const bool v = [] { const char* e = std::getenv("WT_MEM_V1"); return e && std::atoi(e) != 0; }();
+    return v;
+}
+
 }  // namespace
 
 void launch_softmax_planes(const float* S, int ldS, __half* p_hi, __half* p_lo, int Lpad, int B, int L, int Lp,
@@ -605,8 +699,14 @@ void launch_softmax_planes(const float* S, int ldS, __half* p_hi, __half* p_lo, 
 void launch_vt_planes(const __half* q_hi, const __half* q_lo, __half* vt_hi, __half* vt_lo, int B, int L, int Lp, int C,
                       int Lpad, cudaStream_t s, Ragged rg) {
     if (B <= 0 || L <= 0) return;
-    dim3 grid((Lpad + 31) / 32, C / 32, B), block(32, 8);
-    vt_planes_kernel<<<grid, block, 0, s>>>(q_hi, q_lo, vt_hi, vt_lo, L, Lp, C, Lpad, rg);
+    dim3 block(32, 8);
+    if (!mem_v1() && C % 64 == 0 && Lpad % 2 == 0) {
+        dim3 grid((Lpad + 63) / 64, C / 64, B);
+        vt_planes2_kernel<<<grid, block, 0, s>>>(q_hi, q_lo, vt_hi, vt_lo, L, Lp, C, Lpad, rg);
+    } else {
+        dim3 grid((Lpad + 31) / 32, C / 32, B);
+        vt_planes_kernel<<<grid, block, 0, s>>>(q_hi, q_lo, vt_hi, vt_lo, L, Lp, C, Lpad, rg);
+    }
     WT_CUDA(cudaGetLastError());
 }
 
@@ -663,16 +763,28 @@ void launch_attention(const float* qkv, RowOut out, int B, int L, int Lp, int C,
 void launch_spectral(const float* z, int ldz, RowOut S, long long M, int half, int ldS, cudaStream_t s) {
     if (M <= 0) return;
     if (ldS < 2 * half) throw Error(1, "spectral: ldS must cover both halves");
-    long long n = M * (ldS - half);
-    spectral_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(z, ldz, S, M, half, ldS);
+    if (!mem_v1()) {
+        spectral_rows_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(z, ldz, S, M, half, ldS);
+    } else {
+        long long n = M * (ldS - half);
+        spectral_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(z, ldz, S, M, half, ldS);
+    }
     WT_CUDA(cudaGetLastError());
 }
 
 void launch_overlap_add(const float* frames, const float* wsq, float* audio, int B, int L, int Lp, int n_fft, int hop,
                         cudaStream_t s, Ragged rg) {
     if (B <= 0 || L <= 0) return;
-    dim3 grid((L * hop + 255) / 256, B);
-    overlap_add_kernel<<<grid, 256, 0, s>>>(frames, wsq, audio, L, Lp, n_fft, hop, (n_fft - hop) / 2, rg);
+    const int pad = (n_fft - hop) / 2;
+    const bool vec4 = !mem_v1() && hop % 4 == 0 && n_fft % 4 == 0 && pad % 4 == 0 &&
+                      (((uintptr_t)frames | (uintptr_t)wsq | (uintptr_t)audio) & 15) == 0;
+    if (vec4) {
+        dim3 grid((L * hop / 4 + 255) / 256, B);
+        overlap_add4_kernel<<<grid, 256, 0, s>>>(frames, wsq, audio, L, Lp, n_fft, hop, pad, rg);
+    } else {
+        dim3 grid((L * hop + 255) / 256, B);
+        overlap_add_kernel<<<grid, 256, 0, s>>>(frames, wsq, audio, L, Lp, n_fft, hop, pad, rg);
+    }
     WT_CUDA(cudaGetLastError());
 }
 
