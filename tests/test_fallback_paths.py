@@ -31,7 +31,8 @@ torch.save({"codes": c.cpu(), "audio": a.cpu()}, sys.argv[2])
     {"WT_ENC_L0_FUSED_TC": "0", "WT_ENC_L1_FUSED": "0"},                  # CUDA-core level 0, three-launch level 1
     {"WT_LSTM_PUBLISH": "0", "WT_LSTM_KEEP_C": "0"},                      # per-warp release, c / y stored every step
     {"WT_LSTM_CLUSTER": "4", "WT_LSTM_POLL_NS": "30", "WT_TC_N128_MC": "1"},  # multicast variants
-], ids=["encoder-unfused", "lstm-round1-handover", "multicast"])
+    {"WT_MEM_V1": "1"},               # one-element-per-thread spectral / overlap-add / V-transpose, scalar-FMA dwconv + AdaLN
+], ids=["encoder-unfused", "lstm-round1-handover", "multicast", "memory-bound-forms"])
 def test_replaced_kernels_still_agree(tmp_path, env):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = str(tmp_path / "child.pt")
@@ -48,3 +49,5 @@ def test_replaced_kernels_still_agree(tmp_path, env):
     # same operands and the same 3-pass products: only fp32 summation orders differ between the variants
     assert (c.cpu() != child["codes"]).float().mean().item() <= 0.005
     assert helpers.snr_db(child["audio"], a.cpu()) >= 100.0
+    if "WT_MEM_V1" in env:  # decoder-side kernels only: the codes cannot move, the audio agrees to fp32 rounding
+        assert torch.equal(c.cpu(), child["codes"]) and helpers.snr_db(child["audio"], a.cpu()) >= 110.0

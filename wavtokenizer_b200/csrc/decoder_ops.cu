@@ -6,6 +6,7 @@
 // Every producer can write fp32 rows or the split-fp16 operand planes (hi = fp16(x), lo = fp16(x - hi))
 // of the next GEMM directly, so no separate conversion pass touches HBM.
 #include <cuda_fp16.h>
+#include <algorithm>
 
 #include <cstdlib>
 
@@ -409,6 +410,92 @@ __global__ void __launch_bounds__(DW_THREADS, 3) dwconv_ln_hi_kernel(const float
     }
 }
 
+// The same arithmetic with half the issue slots: the kernel above issues ~1000
+// instructions per thread and run (31 per output value) and is bound by exactly that (2.1 IPC at 18 warps per SM, 3.2 TB/s).
+// Here the 224 conv FMAs and the normalisation run as packed fp32 pairs (FFMA2 / FADD2 / FMUL2: two channels per
+// instruction), and the cross-warp sums of the 16 statistics are finished by 16 lanes (one statistic each) and handed
+// round by shuffles instead of every thread adding up all 16 x 6 partials.
+template <bool EDGE>  // EDGE = false: all 14 input rows and all 8 output rows of the run lie inside the clip (no masks)
+__device__ __forceinline__ void dwconv_ln_hi2_run(const float* __restrict__ xb, const float* __restrict__ dwT,
+                                                  const float* __restrict__ db, const float* __restrict__ scale,
+                                                  const float* __restrict__ shift, __half* __restrict__ ob, int t0, int L, int Lp,
+                                                  float eps, float (*red)[8]) {
+    constexpr int C = 768;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = threadIdx.x * 4;
+    float4 xr[DW8_TT + 6];
+#pragma unroll
+    for (int r = 0; r < DW8_TT + 6; ++r) {
+        const int t = t0 - 3 + r;
+        xr[r] = (!EDGE || (t >= 0 && t < L)) ? *reinterpret_cast<const float4*>(xb + (long long)t * C + c)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float4 bias = *reinterpret_cast<const float4*>(db + c);
+    float2 va[DW8_TT], vb[DW8_TT];  // channels (c, c+1) and (c+2, c+3)
+#pragma unroll
+    for (int i = 0; i < DW8_TT; ++i) { va[i] = make_float2(bias.x, bias.y); vb[i] = make_float2(bias.z, bias.w); }
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {  // tap-major: one weight vector live at a time
+        const float4 w = *reinterpret_cast<const float4*>(dwT + j * C + c);
+        const float2 wa = make_float2(w.x, w.y), wb = make_float2(w.z, w.w);
+#pragma unroll
+        for (int i = 0; i < DW8_TT; ++i) {
+            va[i] = __ffma2_rn(wa, make_float2(xr[i + j].x, xr[i + j].y), va[i]);
+            vb[i] = __ffma2_rn(wb, make_float2(xr[i + j].z, xr[i + j].w), vb[i]);
+        }
+    }
+    float part[16];
+#pragma unroll
+    for (int i = 0; i < DW8_TT; ++i) {
+        part[i] = (va[i].x + va[i].y) + (vb[i].x + vb[i].y);
+        part[DW8_TT + i] = fmaf(va[i].x, va[i].x, fmaf(va[i].y, va[i].y, fmaf(vb[i].x, vb[i].x, vb[i].y * vb[i].y)));
+    }
+    warp_sum16(part, lane);
+    if ((lane & 1) == 0) red[lane >> 1][warp] = part[0];
+    __syncthreads();
+    // lane l < 16 finishes statistic l (same order of additions as above); lanes 0..7 then hold mean and rstd of frame l
+    float tot = 0.f;
+    if (lane < 2 * DW8_TT) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&red[lane][0]);
+        const float2 a1 = *reinterpret_cast<const float2*>(&red[lane][4]);
+        tot = (((a0.x + a0.y) + (a0.z + a0.w)) + (a1.x + a1.y)) * (1.f / (float)C);
+    }
+    const float ex2 = __shfl_down_sync(0xffffffffu, tot, DW8_TT);
+    const float rstd_l = rsqrtf(fmaxf(ex2 - tot * tot, 0.f) + eps);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+    const float2 sca = make_float2(sc.x, sc.y), scb = make_float2(sc.z, sc.w);
+    const float2 sha = make_float2(sh.x, sh.y), shb = make_float2(sh.z, sh.w);
+#pragma unroll
+    for (int i = 0; i < DW8_TT; ++i) {
+        const int t = t0 + i;
+        if (EDGE && t >= Lp) break;
+        const float nmean = -__shfl_sync(0xffffffffu, tot, i), rstd = __shfl_sync(0xffffffffu, rstd_l, i);
+        float2 ya = make_float2(0.f, 0.f), yb = ya;
+        if (!EDGE || t < L) {
+            const float2 nm = make_float2(nmean, nmean), rs = make_float2(rstd, rstd);
+            ya = __ffma2_rn(__fmul2_rn(__fadd2_rn(va[i], nm), rs), sca, sha);
+            yb = __ffma2_rn(__fmul2_rn(__fadd2_rn(vb[i], nm), rs), scb, shb);
+        }  // else: halo row of the padded row space, written as zeros
+        const __half2 h01 = __floats2half2_rn(ya.x, ya.y), h23 = __floats2half2_rn(yb.x, yb.y);
+        *reinterpret_cast<uint2*>(ob + (long long)t * C + c) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    }
+}
+
+__global__ void __launch_bounds__(DW_THREADS, 3) dwconv_ln_hi2_kernel(const float* __restrict__ x, const float* __restrict__ dwT,
+                                                                      const float* __restrict__ db, const float* __restrict__ scale,
+                                                                      const float* __restrict__ shift, __half* __restrict__ out_hi,
+                                                                      int L, int Lp, float eps, Ragged rg) {
+    static_assert(DW_THREADS / 32 == 6, "six warps cover the 768 channels");
+    __shared__ __align__(16) float red[2 * DW8_TT][8];  // [sum of frame i | sum of squares of frame i][warp]
+    const int b = blockIdx.y, t0 = blockIdx.x * DW8_TT;
+    if (rg.len) L = rg.len[b];
+    const float* xb = x + (long long)b * Lp * 768;
+    __half* ob = out_hi + (long long)b * Lp * 768;
+    if (t0 >= 3 && t0 + DW8_TT + 3 <= L) dwconv_ln_hi2_run<false>(xb, dwT, db, scale, shift, ob, t0, L, Lp, eps, red);
+    else dwconv_ln_hi2_run<true>(xb, dwT, db, scale, shift, ob, t0, L, Lp, eps, red);
+}
+
 // AttnBlock core (reference decoder/models.py:115-123): softmax(q k^T * C^-0.5) v, one head of width C
 // over the L frames of a clip. One warp per query row, 8 queries per block; scores live in shared memory.
 template <int PER>
@@ -735,7 +822,8 @@ void launch_dwconv_ln(const float* x, const float* dw, const float* db, const fl
     static const bool hi8 = [] { const char* e = std::getenv("WT_DW_HI8"); return !e || std::atoi(e) != 0; }();
     if (hi8 && out.hi && !out.lo && !out.f32) {  // single-plane consumer (plan 2)
         dim3 grid8((Lp + DW8_TT - 1) / DW8_TT, B);
-        dwconv_ln_hi_kernel<<<grid8, DW_THREADS, 0, s>>>(x, dw, db, scale, shift, out.hi, L, Lp, eps, rg);
+        if (mem_v1()) dwconv_ln_hi_kernel<<<grid8, DW_THREADS, 0, s>>>(x, dw, db, scale, shift, out.hi, L, Lp, eps, rg);
+        else dwconv_ln_hi2_kernel<<<grid8, DW_THREADS, 0, s>>>(x, dw, db, scale, shift, out.hi, L, Lp, eps, rg);
         WT_CUDA(cudaGetLastError());
         return;
     }
