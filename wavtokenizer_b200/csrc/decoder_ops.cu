@@ -79,8 +79,8 @@ __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
 // RES > 0: L <= RES * GN_PH, the thread's <= RES rows stay in registers between the two passes (all RES loads in
 // flight at once, no second read); RES == 0: any L, pass 2 re-reads the slab.
 constexpr int GN_GPB = 2, GN_LANES = GN_GPB * 6, GN_PH = 32, GN_THREADS = GN_LANES * GN_PH, GN_RES = 8;
-template <int RES>
-__global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+template <int RES, int MINB = 3>  // MINB = 3: 56 registers, three blocks (36 warps) per SM instead of two at 66 registers
+__global__ void __launch_bounds__(GN_THREADS, MINB) groupnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                const float* __restrict__ bsh, RowOut out, int L, int Lp,
                                                                int C, float eps, int swish, Ragged rg) {
     __shared__ double part[GN_THREADS / 32][4];  // per warp: (sum, sum of squares) of group 0 and of group 1
@@ -134,21 +134,30 @@ __global__ void __launch_bounds__(GN_THREADS) groupnorm_kernel(const float* __re
         double ds = 0, dq = 0;
 #pragma unroll
         for (int w_ = 0; w_ < GN_THREADS / 32; ++w_) { ds += part[w_][2 * g]; dq += part[w_][2 * g + 1]; }
+        // 1 / n and 1 / sqrt(var + eps) from the fp32 special-function unit + one Newton step in fp64 (relative error
+        // ~1e-14: the fp32 results are the correctly rounded ones) instead of three fp64 divisions and a square root,
+        // which every thread of the block would execute (~100 issue slots of ~800)
         const double n = (double)L * 24.0;
-        const double m_ = ds / n;
-        double var = dq / n - m_ * m_;
+        const double r0 = (double)__frcp_rn((float)n);
+        const double rn = r0 * (2.0 - n * r0);
+        const double m_ = ds * rn;
+        double var = dq * rn - m_ * m_;
         if (var < 0) var = 0;
+        const double ve = var + (double)eps;
+        const double y0 = (double)rsqrtf((float)ve);
         mean = (float)m_;
-        rstd = (float)(1.0 / sqrt(var + (double)eps));
+        rstd = (float)(y0 * (1.5 - 0.5 * ve * y0 * y0));
     }
+    // y = (v - mean) * rstd * w + b as ONE packed FMA per channel pair: y = v * a + d, a = rstd * w, d = b - mean * a
     const float4 wv = *reinterpret_cast<const float4*>(w + c), bv = *reinterpret_cast<const float4*>(bsh + c);
+    const float2 a01 = make_float2(rstd * wv.x, rstd * wv.y), a23 = make_float2(rstd * wv.z, rstd * wv.w);
+    const float2 d01 = make_float2(fmaf(-mean, a01.x, bv.x), fmaf(-mean, a01.y, bv.y));
+    const float2 d23 = make_float2(fmaf(-mean, a23.x, bv.z), fmaf(-mean, a23.y, bv.w));
     auto emit = [&](int t, const float4& v) {  // row t of the slab: normalised (+ swish) or, past L, a zero halo row
         float y[4] = {0.f, 0.f, 0.f, 0.f};
         if (t < L) {
-            y[0] = (v.x - mean) * rstd * wv.x + bv.x;
-            y[1] = (v.y - mean) * rstd * wv.y + bv.y;
-            y[2] = (v.z - mean) * rstd * wv.z + bv.z;
-            y[3] = (v.w - mean) * rstd * wv.w + bv.w;
+            const float2 y01 = __ffma2_rn(make_float2(v.x, v.y), a01, d01), y23 = __ffma2_rn(make_float2(v.z, v.w), a23, d23);
+            y[0] = y01.x; y[1] = y01.y; y[2] = y23.x; y[3] = y23.y;
             if (swish) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) y[i] = __fdividef(y[i], 1.f + __expf(-y[i]));
@@ -802,7 +811,11 @@ void launch_groupnorm(const float* x, const float* w, const float* b, RowOut out
     if (B <= 0 || L <= 0) return;
     if (groups != 32 || C != 768) throw Error(1, "groupnorm: expected GroupNorm(32, 768)");
     dim3 grid(C / (GN_GPB * 24), B);
-    if (L <= GN_RES * GN_PH && Lp <= L + GN_PH) groupnorm_kernel<GN_RES><<<grid, GN_THREADS, 0, s>>>(x, w, b, out, L, Lp, C, eps, swish, rg);
+    static const bool minb2 = [] { const char* e = std::getenv("WT_GN_MINB"); return e && std::atoi(e) == 2; }();
+    if (L <= GN_RES * GN_PH && Lp <= L + GN_PH) {
+        if (minb2) groupnorm_kernel<GN_RES, 2><<<grid, GN_THREADS, 0, s>>>(x, w, b, out, L, Lp, C, eps, swish, rg);
+        else groupnorm_kernel<GN_RES><<<grid, GN_THREADS, 0, s>>>(x, w, b, out, L, Lp, C, eps, swish, rg);
+    }
     else groupnorm_kernel<0><<<grid, GN_THREADS, 0, s>>>(x, w, b, out, L, Lp, C, eps, swish, rg);
     WT_CUDA(cudaGetLastError());
 }
