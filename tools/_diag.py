@@ -1,3 +1,4 @@
+"""Decode repeatability check (run on a B200): same codes decoded repeatedly, after other work, and in child processes."""
 import os, subprocess, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests.gpu_util import native_model, Taps
