@@ -55,14 +55,15 @@ METRIC = "encode+decode audio-sec/sec (24 kHz)"
 UNIT = "audio-s/s"
 CPU_SAMPLE_CLIPS = 8
 PARITY_CLIPS = 4
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the modal launch shape, one `ncu --set full` capture each at
-# the end of round 2 (profiles/r02_ncu_table.txt, r02_ncu_table_final.txt; tools/ncu_targets.sh, ncu_round2_final.sh):
-# decoder k3 conv 768 -> 768 over 128 clips, ConvNeXt GEMM-1, encoder level-1 strided conv / level-0 kernel / fused
-# level-0 -> 1 kernel over 64 clips, one LSTM segment, ...
-TRAFFIC = {"tap_gemm_tc_kernel<256, 3>": 127.3e6, "tap_gemm_tc_kernel<256, 1>": 132.9e6,
-           "tap_gemm_tc_kernel<64, 3>": 1.134e9, "tap_gemm_tc_kernel<128, 3>": 1.137e9,
-           "resblock0_fused_kernel": 0.555e9, "groupnorm_kernel": 136.5e6, "dwconv_ln_kernel": 106.6e6,
-           "lstm_persistent_kernel": 70.2e6, "enc_l0_tc_kernel": 0.556e9, "enc_l1_fused_kernel": 1.137e9}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the modal launch shape, one `ncu --set full` capture each with
+# the pass sizes of the device-resident step (128-clip encoder passes, one 256-clip decoder pass):
+# profiles/r02_ncu_table_traffic_final2.txt (tools/ncu_round2_traffic.sh) and r02_ncu_table_mem_final2.txt
+# (tools/ncu_round2_mem.sh). <256, 3>: decoder k3 conv 768 -> 768 (197 MB read + 147 MB written; algorithmic 366 MB);
+# <256, 1>: mean of ConvNeXt GEMM-1 (93 + 219 MB) and GEMM-2 (455 + 143 MB), 12 launches each; <128, 3>: level-1 strided
+# conv; LSTM: one time segment (same shape as before: profiles/r02_ncu_table_final.txt).
+TRAFFIC = {"tap_gemm_tc_kernel<256, 3>": 343.8e6, "tap_gemm_tc_kernel<256, 1>": 454.9e6,
+           "tap_gemm_tc_kernel<128, 3>": 2.326e9, "groupnorm_kernel": 312.3e6, "dwconv_ln_kernel": 239.9e6,
+           "lstm_persistent_kernel": 70.2e6, "enc_l0_tc_kernel": 1.163e9, "enc_l1_fused_kernel": 2.326e9}
 CATS = ["enc_conv", "lstm", "vq", "dec_conv", "pwconv", "head_idft", "attention", "memory_bound"]
 NAMED_KERNELS = {1: "lstm_persistent_kernel", 2: "resblock0_fused_kernel", 3: "groupnorm_kernel", 4: "dwconv_ln_kernel",
                  5: "layernorm_kernel", 6: "spectral_kernel", 7: "overlap_add_kernel", 8: "softmax_planes_kernel",
