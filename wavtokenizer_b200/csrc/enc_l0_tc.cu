@@ -66,6 +66,7 @@ struct ZArgs {
 };
 
 
+template <bool PK>  // PK: conv0 and the composed shortcut as packed fp32 pairs (FFMA2); false: one FFMA per channel (WT_ENC_L0_FFMA2=0)
 __global__ void __launch_bounds__(Z_THREADS, 1)
 enc_l0_tc_kernel(const __grid_constant__ CUtensorMap mapWk, const __grid_constant__ CUtensorMap mapW1,
                  const __grid_constant__ L0Const K, const ZArgs a) {
@@ -208,13 +209,19 @@ enc_l0_tc_kernel(const __grid_constant__ CUtensorMap mapWk, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int c = 16 * k + 2 * i;
-                    float v0 = K.b0[c], v1 = K.b0[c + 1];
+                    // two channels per instruction (FFMA2: the weight pair comes from a uniform-register pair of the constant
+                    // bank, the sample is the broadcast scalar operand): 224 instead of 448 FMA issue slots per position
+                    float2 v = make_float2(K.b0[c], K.b0[c + 1]);
 #pragma unroll
                     for (int j = 0; j < 7; ++j) {
-                        v0 = fmaf(K.w0[j * 32 + c], s[j], v0);
-                        v1 = fmaf(K.w0[j * 32 + c + 1], s[j], v1);
+                        if (PK) {
+                            v = __ffma2_rn(make_float2(K.w0[j * 32 + c], K.w0[j * 32 + c + 1]), make_float2(s[j], s[j]), v);
+                        } else {
+                            v.x = fmaf(K.w0[j * 32 + c], s[j], v.x);
+                            v.y = fmaf(K.w0[j * 32 + c + 1], s[j], v.y);
+                        }
                     }
-                    split2(elu1(v0), elu1(v1), e[i], e[8 + i]);
+                    split2(elu1(v.x), elu1(v.y), e[i], e[8 + i]);
                 }
                 tmem_st16(TM + ZC_E + 16 * k, e);
             }
@@ -279,12 +286,20 @@ enc_l0_tc_kernel(const __grid_constant__ CUtensorMap mapWk, const __grid_constan
                     for (int half = 0; half < 2; ++half) {
                         float v[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
+                        for (int i = 0; i < 16; i += 2) {
                             const int c = 16 * half + i;
-                            float acc = __uint_as_float(half ? r1[i] : r0[i]) + K.b2[c];
+                            float2 acc = make_float2(__uint_as_float(half ? r1[i] : r0[i]) + K.b2[c],
+                                                     __uint_as_float(half ? r1[i + 1] : r0[i + 1]) + K.b2[c + 1]);
 #pragma unroll
-                            for (int j = 0; j < 7; ++j) acc = fmaf(K.wsc[j * 32 + c], s[j], acc);
-                            v[i] = acc;
+                            for (int j = 0; j < 7; ++j) {
+                                if (PK) {
+                                    acc = __ffma2_rn(make_float2(K.wsc[j * 32 + c], K.wsc[j * 32 + c + 1]), make_float2(s[j], s[j]), acc);
+                                } else {
+                                    acc.x = fmaf(K.wsc[j * 32 + c], s[j], acc.x);
+                                    acc.y = fmaf(K.wsc[j * 32 + c + 1], s[j], acc.y);
+                                }
+                            }
+                            v[i] = acc.x; v[i + 1] = acc.y;
                         }
 #pragma unroll
                         for (int k = 0; k < 3; ++k) {
@@ -321,9 +336,11 @@ void launch_enc_l0_tc(const EncL0Weights& w, const float* wav, __half* ye_hi, __
     static PerDevice<bool> attr_dev;
     bool& attr = attr_dev.get();
     if (!attr) {
-        WT_CUDA(cudaFuncSetAttribute(enc_l0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Z_SMEM));
+        WT_CUDA(cudaFuncSetAttribute(enc_l0_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Z_SMEM));
+        WT_CUDA(cudaFuncSetAttribute(enc_l0_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Z_SMEM));
         attr = true;
     }
+    static const bool packed = [] { const char* e = std::getenv("WT_ENC_L0_FFMA2"); return !e || std::atoi(e) != 0; }();
     if (map.Pin != T + 2 || map.Tvalid != T) throw Error(4, "enc_l0_tc: row map must describe T + 2 slots per clip");
     const long long Mtot = (long long)B * (T + 2);
     if (Mtot > (1LL << 30)) throw Error(4, "enc_l0_tc: chunk too large");
@@ -336,7 +353,8 @@ void launch_enc_l0_tc(const EncL0Weights& w, const float* wav, __half* ye_hi, __
     z.wav = wav; z.Bc = B; z.T = T; z.Mtot = (int)Mtot; z.n_tiles = (int)((Mtot + Z_TILE - 1) / Z_TILE);
     z.map = map; z.ye_hi = ye_hi; z.ye_lo = ye_lo; z.y_f32 = y_f32;
     const int grid = std::min(z.n_tiles, tc_num_sms());
-    enc_l0_tc_kernel<<<grid, Z_THREADS, Z_SMEM, s>>>(mWk, mW1, K, z);
+    if (packed) enc_l0_tc_kernel<true><<<grid, Z_THREADS, Z_SMEM, s>>>(mWk, mW1, K, z);
+    else enc_l0_tc_kernel<false><<<grid, Z_THREADS, Z_SMEM, s>>>(mWk, mW1, K, z);
     WT_CUDA(cudaGetLastError());
 }
 
